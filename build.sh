@@ -1,0 +1,12 @@
+#!/bin/bash
+# Builds the product library (sm_100a only) and the CPU oracle. Used by __graft_entry__.build().
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+OUT=dusk-blindbidproof_b200/libbbp_b200.so
+SRC=dusk-blindbidproof_b200/csrc
+if [ ! -f $OUT ] || [ -n "$(find $SRC include -newer $OUT -type f | head -1)" ]; then
+  $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xptxas -v -Xcompiler -fPIC -shared \
+    -o $OUT $SRC/bbp_capi.cu 2> build_ptxas.log || { tail -50 build_ptxas.log; exit 1; }
+fi
+make -s -C oracle liboracle.so

@@ -1,0 +1,260 @@
+// C ABI of the B200 backend (include/bbp.h): context, resident generator tables, base tables, MSM entry points,
+// point codecs and the primitive test hooks. The protocol layer (R1CS prove / verify, blind-bid drivers) lives in
+// r1cs.cuh / blindbid.cuh and is exported from the bottom of this translation unit.
+#include "../../include/bbp.h"
+#include "codec.cuh"
+#include "ctx.cuh"
+#include "msm.cuh"
+
+using namespace bbp;
+
+extern "C" {
+
+int bbp_init(bbp_ctx **out, int device, uint32_t gens_capacity, uint32_t party_capacity) {
+    if (!out) return BBP_ERR_INPUT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        fprintf(stderr, "bbp_init: no usable CUDA device %d (found %d); this backend has no CPU fallback\n", device, count);
+        return BBP_ERR_CUDA;
+    }
+    bbp_ctx *ctx = new bbp_ctx();
+    ctx->device = device;
+    int rc = ctx->init(gens_capacity, party_capacity);
+    if (rc) { delete ctx; return rc; }
+    *out = ctx;
+    return BBP_OK;
+}
+
+void bbp_free(bbp_ctx *ctx) {
+    if (!ctx) return;
+    ctx->destroy();
+    delete ctx;
+}
+
+uint64_t bbp_launch_count(const bbp_ctx *ctx) { return ctx ? ctx->launches + ctx->msm.launches : 0; }
+uint64_t bbp_stream(const bbp_ctx *ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+int bbp_sync(bbp_ctx *ctx) {
+    if (!ctx) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return BBP_OK;
+}
+
+int bbp_pedersen_gens(bbp_ctx *ctx, uint8_t B[32], uint8_t B_blinding[32]) {
+    if (!ctx || !B || !B_blinding) return BBP_ERR_INPUT;
+    memcpy(B, ctx->pc_compressed, 32);
+    memcpy(B_blinding, ctx->pc_compressed + 32, 32);
+    return BBP_OK;
+}
+
+int bbp_bulletproof_gens(bbp_ctx *ctx, int which, uint32_t party, uint32_t first, uint32_t count, uint8_t *out) {
+    if (!ctx || !out || (which != 'G' && which != 'H')) return BBP_ERR_INPUT;
+    if (party >= ctx->party_capacity || (uint64_t)first + count > ctx->gens_capacity) return BBP_ERR_INVALID_GENERATORS_LENGTH;
+    cudaSetDevice(ctx->device);
+    size_t idx = ctx->gen_index(which, party, first);
+    uint8_t *d_tmp = nullptr;
+    BBP_CUDA_OK(cudaMalloc(&d_tmp, (size_t)count * 32));
+    k_compress<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_gens_ext + 128 * idx, (uint32_t *)d_tmp, count);
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(out, d_tmp, (size_t)count * 32, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_tmp);
+    return e == cudaSuccess ? BBP_OK : BBP_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------- base tables
+int bbp_points_from_compressed(bbp_ctx *ctx, const uint8_t *points, size_t n, bbp_points **out, int *all_valid) {
+    if (!ctx || !points || !out || n == 0 || n > 0x7fffffffu) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    bbp_points *p = new bbp_points();
+    p->ctx = ctx; p->n = n;
+    uint8_t *d_in = nullptr;
+    int *d_valid = nullptr;
+    int rc = BBP_OK, h_valid = 1;
+    if (cudaMalloc(&p->d_niels, n * 96) != cudaSuccess || cudaMalloc(&d_in, n * 32) != cudaSuccess || cudaMalloc(&d_valid, 4) != cudaSuccess) rc = BBP_ERR_CUDA;
+    if (!rc && cudaMemcpyAsync(d_in, points, n * 32, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = BBP_ERR_CUDA;
+    if (!rc && cudaMemcpyAsync(d_valid, &h_valid, 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = BBP_ERR_CUDA;
+    if (!rc) {
+        k_decompress_to_niels<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const uint32_t *)d_in, p->d_niels, (uint32_t)n, d_valid, nullptr);
+        ctx->launches++;
+        if (cudaMemcpyAsync(&h_valid, d_valid, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = BBP_ERR_CUDA;
+    }
+    cudaFree(d_in); cudaFree(d_valid);
+    if (rc) { cudaFree(p->d_niels); delete p; return rc; }
+    if (all_valid) *all_valid = h_valid;
+    *out = p;
+    return BBP_OK;
+}
+
+int bbp_points_from_extended(bbp_ctx *ctx, const uint8_t *points_ext, size_t n, bbp_points **out) {
+    if (!ctx || !points_ext || !out || n == 0 || n > 0x7fffffffu) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    bbp_points *p = new bbp_points();
+    p->ctx = ctx; p->n = n;
+    uint8_t *d_in = nullptr;
+    int rc = BBP_OK;
+    if (cudaMalloc(&p->d_niels, n * 96) != cudaSuccess || cudaMalloc(&d_in, n * 128) != cudaSuccess) rc = BBP_ERR_CUDA;
+    if (!rc && cudaMemcpyAsync(d_in, points_ext, n * 128, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = BBP_ERR_CUDA;
+    if (!rc) {
+        size_t threads = (n + BBP_NIELS_BATCH - 1) / BBP_NIELS_BATCH;
+        k_ext_to_niels<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(d_in, p->d_niels, (uint32_t)n);
+        ctx->launches++;
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = BBP_ERR_CUDA;
+    }
+    cudaFree(d_in);
+    if (rc) { cudaFree(p->d_niels); delete p; return rc; }
+    *out = p;
+    return BBP_OK;
+}
+
+size_t bbp_points_len(const bbp_points *p) { return p ? p->n : 0; }
+void bbp_points_free(bbp_points *p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaFree(p->d_niels);
+    delete p;
+}
+
+// ---------------------------------------------------------------- MSM
+int bbp_msm_points_device(bbp_ctx *ctx, const void *scalars_device, size_t n, const bbp_points *points, void *out_device) {
+    if (!ctx || !scalars_device || !points || !out_device || n == 0 || n != points->n) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    msm_shape sh = msm_engine::make_shape((uint32_t)n, (uint32_t)n, (uint32_t)n, false, 0, 0, 0);
+    return ctx->msm.run(sh, (const uint8_t *)scalars_device, points->d_niels, nullptr, (uint8_t *)out_device);
+}
+
+int bbp_msm_points_batched(bbp_ctx *ctx, const uint8_t *scalars, size_t n_per_slot, size_t n_slots, const bbp_points *points, uint8_t *out) {
+    if (!ctx || !scalars || !points || !out || n_per_slot == 0 || n_slots == 0 || n_per_slot != points->n) return BBP_ERR_INPUT;
+    size_t n = n_per_slot * n_slots;
+    if (n > 0x7fffffffu) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    int rc = ctx->stage_in(scalars, n * 32);
+    if (rc) return rc;
+    rc = ctx->reserve_out(n_slots * 32);
+    if (rc) return rc;
+    msm_shape sh = msm_engine::make_shape((uint32_t)n, (uint32_t)n_per_slot, (uint32_t)n_per_slot, false, 0, 0, 0);
+    rc = ctx->msm.run(sh, ctx->d_in, points->d_niels, nullptr, ctx->d_out);
+    if (rc) return rc;
+    BBP_CUDA_OK(cudaMemcpyAsync(out, ctx->d_out, n_slots * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return BBP_OK;
+}
+
+int bbp_msm_points(bbp_ctx *ctx, const uint8_t *scalars, size_t n, const bbp_points *points, uint8_t out[32]) {
+    return bbp_msm_points_batched(ctx, scalars, n, 1, points, out);
+}
+
+int bbp_msm_vartime(bbp_ctx *ctx, const uint8_t *scalars, const uint8_t *points_ext, size_t n, uint8_t out[32]) {
+    bbp_points *p = nullptr;
+    int rc = bbp_points_from_extended(ctx, points_ext, n, &p);
+    if (rc) return rc;
+    rc = bbp_msm_points(ctx, scalars, n, p, out);
+    bbp_points_free(p);
+    return rc;
+}
+
+int bbp_msm_optional(bbp_ctx *ctx, const uint8_t *scalars, const uint8_t *points_compressed, size_t n, uint8_t out[32]) {
+    bbp_points *p = nullptr;
+    int valid = 1;
+    int rc = bbp_points_from_compressed(ctx, points_compressed, n, &p, &valid);
+    if (rc) return rc;
+    if (!valid) { bbp_points_free(p); return BBP_ERR_DECOMPRESS; }
+    rc = bbp_msm_points(ctx, scalars, n, p, out);
+    bbp_points_free(p);
+    return rc;
+}
+
+// ---------------------------------------------------------------- codecs
+int bbp_decompress(bbp_ctx *ctx, const uint8_t *compressed, size_t n, uint8_t *out_ext, uint8_t *valid) {
+    if (!ctx || !compressed || !out_ext || n == 0 || n > 0x7fffffffu) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    int rc = ctx->stage_in(compressed, n * 32);
+    if (rc) return rc;
+    size_t all_off = (n * 129 + 3) & ~(size_t)3;   // [n x 128 ext][n flags][pad][int all_valid]
+    rc = ctx->reserve_out(all_off + 4);
+    if (rc) return rc;
+    uint8_t *d_flags = ctx->d_out + n * 128;
+    int *d_all = (int *)(ctx->d_out + all_off);
+    BBP_CUDA_OK(cudaMemsetAsync(d_all, 1, 4, ctx->stream));
+    k_decompress_to_ext<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const uint32_t *)ctx->d_in, ctx->d_out, (uint32_t)n, d_all, d_flags);
+    ctx->launches++;
+    BBP_CUDA_OK(cudaMemcpyAsync(out_ext, ctx->d_out, n * 128, cudaMemcpyDeviceToHost, ctx->stream));
+    if (valid) BBP_CUDA_OK(cudaMemcpyAsync(valid, d_flags, n, cudaMemcpyDeviceToHost, ctx->stream));
+    BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return BBP_OK;
+}
+
+int bbp_compress(bbp_ctx *ctx, const uint8_t *points_ext, size_t n, uint8_t *out_compressed) {
+    if (!ctx || !points_ext || !out_compressed || n == 0 || n > 0x7fffffffu) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    int rc = ctx->stage_in(points_ext, n * 128);
+    if (rc) return rc;
+    rc = ctx->reserve_out(n * 32);
+    if (rc) return rc;
+    k_compress<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_in, (uint32_t *)ctx->d_out, (uint32_t)n);
+    ctx->launches++;
+    BBP_CUDA_OK(cudaMemcpyAsync(out_compressed, ctx->d_out, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return BBP_OK;
+}
+
+int bbp_from_uniform_bytes(bbp_ctx *ctx, const uint8_t *bytes64, size_t n, uint8_t *out_compressed) {
+    if (!ctx || !bytes64 || !out_compressed || n == 0 || n > 0x7fffffffu) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    int rc = ctx->stage_in(bytes64, n * 64);
+    if (rc) return rc;
+    rc = ctx->reserve_out(n * 160);
+    if (rc) return rc;
+    k_from_uniform<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const uint32_t *)ctx->d_in, ctx->d_out, (uint32_t)n);
+    k_compress<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_out, (uint32_t *)(ctx->d_out + n * 128), (uint32_t)n);
+    ctx->launches += 2;
+    BBP_CUDA_OK(cudaMemcpyAsync(out_compressed, ctx->d_out + n * 128, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return BBP_OK;
+}
+
+// ---------------------------------------------------------------- test hooks
+int bbp_test_fe(bbp_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, int op, uint8_t *out) {
+    if (!ctx || !a || !b || !out || n == 0) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    uint8_t *d = nullptr;
+    BBP_CUDA_OK(cudaMalloc(&d, n * 96));
+    cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d + n * 32, b, n * 32, cudaMemcpyHostToDevice, ctx->stream);
+    k_test_fe<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const uint32_t *)d, (const uint32_t *)(d + n * 32), (uint32_t *)(d + n * 64), (uint32_t)n, op);
+    ctx->launches++;
+    cudaMemcpyAsync(out, d + n * 64, n * 32, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    return e == cudaSuccess ? BBP_OK : BBP_ERR_CUDA;
+}
+
+int bbp_test_ge(bbp_ctx *ctx, const uint8_t *a_compressed, const uint8_t *b_compressed, size_t n, int op, uint8_t *out_compressed) {
+    if (!ctx || !a_compressed || !b_compressed || !out_compressed || n == 0) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    uint8_t *d = nullptr;
+    int *d_valid = nullptr;
+    // layout: a_c | b_c | a_ext | b_ext | r_ext | r_c
+    BBP_CUDA_OK(cudaMalloc(&d, n * (32 + 32 + 128 * 3 + 32)));
+    BBP_CUDA_OK(cudaMalloc(&d_valid, 4));
+    uint8_t *ac = d, *bc = d + n * 32, *ae = d + n * 64, *be = ae + n * 128, *re = be + n * 128, *rc_ = re + n * 128;
+    int one = 1;
+    cudaMemcpyAsync(d_valid, &one, 4, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(ac, a_compressed, n * 32, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(bc, b_compressed, n * 32, cudaMemcpyHostToDevice, ctx->stream);
+    unsigned g = (unsigned)((n + 127) / 128);
+    k_decompress_to_ext<<<g, 128, 0, ctx->stream>>>((const uint32_t *)ac, ae, (uint32_t)n, d_valid, nullptr);
+    k_decompress_to_ext<<<g, 128, 0, ctx->stream>>>((const uint32_t *)bc, be, (uint32_t)n, d_valid, nullptr);
+    k_test_ge<<<g, 128, 0, ctx->stream>>>(ae, be, re, (uint32_t)n, op);
+    k_compress<<<g, 128, 0, ctx->stream>>>(re, (uint32_t *)rc_, (uint32_t)n);
+    ctx->launches += 4;
+    cudaMemcpyAsync(out_compressed, rc_, n * 32, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(&one, d_valid, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d); cudaFree(d_valid);
+    if (e != cudaSuccess) return BBP_ERR_CUDA;
+    return one ? BBP_OK : BBP_ERR_DECOMPRESS;
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+// Batch point codecs: Ristretto decompress / compress, hash-to-group, and conversions into the 96-byte affine
+// niels layout the MSM kernels stream (Appendix A). One thread per point; each does one field
+// exponentiation (sqrt_ratio_i or inversion), so these kernels are pure FMA-pipe work.
+#pragma once
+#include "ge25519.cuh"
+
+namespace bbp {
+
+// compressed (n x 32 B) -> niels (n x 96 B); invalid encodings clear *all_valid and write the identity
+__global__ void __launch_bounds__(128) k_decompress_to_niels(const uint32_t *__restrict__ in, uint8_t *__restrict__ out, uint32_t n,
+                                                             int *__restrict__ all_valid, uint8_t *__restrict__ valid_flags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[8];
+    const uint4 *q = (const uint4 *)(in + 8 * (size_t)i);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    ge p;
+    bool ok = ge_decompress_words(p, w);
+    if (!ok) { p = ge_identity(); atomicAnd(all_valid, 0); }
+    if (valid_flags) valid_flags[i] = ok ? 1 : 0;
+    niels_store(out + 96 * (size_t)i, ge_affine_to_niels(p.X, p.Y, p.T));
+}
+
+// compressed -> extended (n x 128 B)
+__global__ void __launch_bounds__(128) k_decompress_to_ext(const uint32_t *__restrict__ in, uint8_t *__restrict__ out, uint32_t n,
+                                                           int *__restrict__ all_valid, uint8_t *__restrict__ valid_flags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[8];
+    const uint4 *q = (const uint4 *)(in + 8 * (size_t)i);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    ge p;
+    bool ok = ge_decompress_words(p, w);
+    if (!ok) { p = ge_identity(); atomicAnd(all_valid, 0); }
+    if (valid_flags) valid_flags[i] = ok ? 1 : 0;
+    ge_store(out + 128 * (size_t)i, p);
+}
+
+// extended (n x 128 B, any Z != 0) -> niels. Montgomery's trick over K points per thread: one inversion per K.
+#define BBP_NIELS_BATCH 8
+__global__ void __launch_bounds__(128) k_ext_to_niels(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, uint32_t n) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t i0 = t * BBP_NIELS_BATCH;
+    if (i0 >= n) return;
+    uint32_t cnt = min((uint32_t)BBP_NIELS_BATCH, n - i0);
+    fe prefix[BBP_NIELS_BATCH];
+    fe acc = fe_one();
+#pragma unroll 1
+    for (uint32_t k = 0; k < cnt; k++) {
+        prefix[k] = acc;
+        acc = fe_mul(acc, fe_load(in + 128 * (size_t)(i0 + k) + 64));
+    }
+    fe inv = fe_invert(acc);
+#pragma unroll 1
+    for (uint32_t k = cnt; k-- > 0;) {
+        ge p = ge_load(in + 128 * (size_t)(i0 + k));
+        fe zinv = fe_mul(inv, prefix[k]);
+        inv = fe_mul(inv, p.Z);
+        niels_store(out + 96 * (size_t)(i0 + k), ge_to_niels(p, zinv));
+    }
+}
+
+// extended -> compressed
+__global__ void __launch_bounds__(128) k_compress(const uint8_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ge p = ge_load(in + 128 * (size_t)i);
+    uint32_t w[8];
+    ge_compress_words(w, p);
+    uint4 *q = (uint4 *)(out + 8 * (size_t)i);
+    q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// 64 uniform bytes -> extended point (RistrettoPoint::from_uniform_bytes)
+__global__ void __launch_bounds__(128) k_from_uniform(const uint32_t *__restrict__ in, uint8_t *__restrict__ out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) w[k] = in[16 * (size_t)i + k];
+    ge_store(out + 128 * (size_t)i, ge_from_uniform_words(w));
+}
+
+// fixed-base window table: row w of `out` (stride entries of 96 B) = niels(2^(c*w) * P_i), built from extended inputs.
+// One thread per point walks the windows (c doublings each) and normalises each multiple with its own inversion.
+__global__ void __launch_bounds__(128) k_build_window_table(const uint8_t *__restrict__ in_ext, uint8_t *__restrict__ out, uint32_t n, uint32_t c,
+                                                            uint32_t W, uint32_t stride) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ge p = ge_load(in_ext + 128 * (size_t)i);
+#pragma unroll 1
+    for (uint32_t w = 0; w < W; w++) {
+        fe zinv = fe_invert(p.Z);
+        niels_store(out + 96 * ((size_t)w * stride + i), ge_to_niels(p, zinv));
+        if (w + 1 < W) {
+#pragma unroll 1
+            for (uint32_t k = 0; k < c; k++) p = ge_dbl(p);
+        }
+    }
+}
+
+__global__ void k_store_basepoint(uint8_t *out) { ge_store(out, ge_basepoint()); }
+
+// ---- unit-test kernels (driven by the bbp_test_* entry points; compared against the oracle in tests/)
+// op: 0 mul, 1 add, 2 sub, 3 invert(a), 4 sq(a), 5 neg(a)
+__global__ void k_test_fe(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, uint32_t *__restrict__ out, uint32_t n, int op) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe x, y, r;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { x.v[k] = a[8 * (size_t)i + k]; y.v[k] = b[8 * (size_t)i + k]; }
+    switch (op) {
+        case 0: r = fe_mul(x, y); break;
+        case 1: r = fe_add(x, y); break;
+        case 2: r = fe_sub(x, y); break;
+        case 3: r = fe_invert(x); break;
+        case 4: r = fe_sq(x); break;
+        default: r = fe_neg(x); break;
+    }
+    fe_tobytes_words(out + 8 * (size_t)i, r);
+}
+// op: 0 add (ext+ext), 1 double, 2 madd via niels of b, 3 msub via niels of b, 4 from_niels(b)
+__global__ void k_test_ge(const uint8_t *__restrict__ a_ext, const uint8_t *__restrict__ b_ext, uint8_t *__restrict__ out_ext, uint32_t n, int op) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ge p = ge_load(a_ext + 128 * (size_t)i), q = ge_load(b_ext + 128 * (size_t)i), r;
+    niels qn = ge_to_niels(q, fe_invert(q.Z));
+    switch (op) {
+        case 0: r = ge_add(p, q); break;
+        case 1: r = ge_dbl(p); break;
+        case 2: r = ge_madd(p, qn, false); break;
+        case 3: r = ge_madd(p, qn, true); break;
+        default: r = ge_from_niels(qn, false); break;
+    }
+    ge_store(out_ext + 128 * (size_t)i, r);
+}
+
+}  // namespace bbp

@@ -1,0 +1,429 @@
+// Signed-digit Pippenger multiscalar multiplication on one B200: sum_i s_i * P_i over Ristretto255.
+// Replaces curve25519-dalek 1.2.3's VartimeMultiscalarMul / MultiscalarMul as bulletproofs calls them underneath
+// src/blindbid/proof.rs:88 and src/blindbid/verify.rs:88. The compressed
+// result is algorithm independent, so the decomposition below is free to be GPU shaped.
+//
+// Pipeline (all on one stream, no host synchronisation between stages):
+//   1 recode     scalar -> mod l -> W signed radix-2^c digits; histogram of (slot, window, |digit|) keys
+//   2 scan       exclusive scan of the histogram (bucket offsets) and of ceil(count / S) (task offsets)
+//   3 scatter    counting sort of (point ref | sign) entries by key
+//   4 accumulate one thread per task (<= S entries of one bucket): 7M mixed additions from the niels table
+//   5 chunk      one thread per CH consecutive buckets: merge task partials, running sums (acc_k, run_k)
+//   6 window     one block per (slot, window): suffix scan + tree reduction in shared memory
+//   7 combine    Horner over windows (c doublings each), Ristretto compression
+// Two base layouts share the kernels: "variable" bases (one niels entry per point, W bucket sets per slot) and
+// "fixed" bases (a precomputed table of 2^(c*w) * P_i, all windows of a slot share ONE bucket set, no doublings).
+#pragma once
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+#include "ge25519.cuh"
+#include "sc25519.cuh"
+
+namespace bbp {
+
+#define BBP_CUDA_OK(expr)                                                                  \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            fprintf(stderr, "bbp: CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return -100;                                                                   \
+        }                                                                                  \
+    } while (0)
+
+struct msm_shape {
+    uint32_t n;            // scalars in this launch (all slots together)
+    uint32_t n_per_slot;   // scalars per slot (slot = i / n_per_slot)
+    uint32_t n_slots;
+    uint32_t base_mod;     // point ref of scalar i = i % base_mod (bases shared between slots) ; = n for distinct bases
+    uint32_t c;            // window bits
+    uint32_t W;            // windows
+    uint32_t B;            // buckets per bucket set = 2^(c-1)
+    uint32_t fixed;        // 1: table[w * table_stride + ref] holds 2^(c*w) * P_ref, one bucket set per slot
+    uint32_t table_stride; // entries per window row of a fixed table
+    uint32_t sets_per_slot;// W (variable) or 1 (fixed)
+    uint32_t nkeys;        // n_slots * sets_per_slot * B
+    uint32_t S;            // max entries per task
+    uint32_t CH;           // buckets per chunk (power of two)
+    uint32_t n_ch;         // chunks per bucket set = B / CH
+};
+
+// ---------------------------------------------------------------- recode + histogram
+// digits are stored window-major: digits[w * n + i]
+__global__ void k_recode(const uint32_t *__restrict__ scalars, int32_t *__restrict__ digits, uint32_t *__restrict__ hist, msm_shape sh) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sh.n) return;
+    uint32_t w8[8];
+    const uint4 *q = (const uint4 *)(scalars + 8 * (size_t)i);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    w8[0] = a.x; w8[1] = a.y; w8[2] = a.z; w8[3] = a.w; w8[4] = b.x; w8[5] = b.y; w8[6] = b.z; w8[7] = b.w;
+    sc s = sc_reduce_words(w8);
+    uint32_t slot = i / sh.n_per_slot;
+    uint32_t carry = 0;
+    const uint32_t c = sh.c, half = 1u << (c - 1), mask = (1u << c) - 1;
+    for (uint32_t w = 0; w < sh.W; w++) {
+        uint32_t bit = w * c, word = bit >> 5, off = bit & 31;
+        uint32_t chunk = 0;
+        if (word < 8) {
+            chunk = s.v[word] >> off;
+            if (off + c > 32 && word < 7) chunk |= s.v[word + 1] << (32 - off);
+        }
+        chunk = (chunk & mask) + carry;
+        carry = (chunk > half) ? 1u : 0u;                   // digits in [-(2^(c-1) - 1), 2^(c-1)]
+        int32_t d = (int32_t)chunk - (int32_t)(carry << c);
+        digits[(size_t)w * sh.n + i] = d;
+        if (d != 0) {
+            uint32_t mag = (uint32_t)(d < 0 ? -d : d) - 1;
+            uint32_t set = sh.fixed ? slot : slot * sh.W + w;
+            atomicAdd(&hist[set * sh.B + mag], 1u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- exclusive scan (tiles of 4096)
+// mode 0: in[i]; mode 1: ceil(in[i] / S)
+__device__ __forceinline__ uint32_t scan_xform(uint32_t x, uint32_t S) { return S ? (x + S - 1) / S : x; }
+
+__global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t *__restrict__ tile_sums,
+                                                     uint32_t n, uint32_t S) {
+    __shared__ uint32_t warp_sums[32];
+    uint32_t base = blockIdx.x * 4096u + threadIdx.x * 4u;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = (base + k < n) ? scan_xform(in[base + k], S) : 0u;
+    uint32_t tsum = v[0] + v[1] + v[2] + v[3];
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = warp_sums[lane], winc = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= (uint32_t)o) winc += t;
+        }
+        warp_sums[lane] = winc - ws;
+        if (lane == 31) tile_sums[blockIdx.x] = winc;
+    }
+    __syncthreads();
+    uint32_t ex = warp_sums[wid] + inc - tsum;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+    }
+}
+// single block: exclusive scan of the tile sums in place; writes the grand total to total_out
+__global__ void __launch_bounds__(1024) k_scan_tile_sums(uint32_t *__restrict__ tile_sums, uint32_t n_tiles, uint32_t *__restrict__ total_out) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n_tiles; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t x = i < n_tiles ? tile_sums[i] : 0u, inc = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += t;
+        }
+        if (lane == 31) warp_sums[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t ws = warp_sums[lane], winc = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= (uint32_t)o) winc += t;
+            }
+            warp_sums[lane] = winc - ws;
+        }
+        __syncthreads();
+        uint32_t carry = carry_s;
+        if (i < n_tiles) tile_sums[i] = carry + warp_sums[wid] + inc - x;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_sums[wid] + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry_s;
+}
+__global__ void k_scan_add(uint32_t *__restrict__ out, const uint32_t *__restrict__ tile_sums, uint32_t n, const uint32_t *__restrict__ total) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] += tile_sums[i >> 12];
+    if (i == n) out[n] = *total;   // one extra slot: out[n] = grand total
+}
+
+// ---------------------------------------------------------------- scatter (counting sort) + task table
+__global__ void k_scatter(const int32_t *__restrict__ digits, const uint32_t *__restrict__ offs, uint32_t *__restrict__ cursor,
+                          uint32_t *__restrict__ entries, msm_shape sh) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sh.n) return;
+    uint32_t slot = i / sh.n_per_slot;
+    uint32_t ref = i % sh.base_mod;
+    for (uint32_t w = 0; w < sh.W; w++) {
+        int32_t d = digits[(size_t)w * sh.n + i];
+        if (d == 0) continue;
+        uint32_t mag = (uint32_t)(d < 0 ? -d : d) - 1;
+        uint32_t set = sh.fixed ? slot : slot * sh.W + w;
+        uint32_t key = set * sh.B + mag;
+        uint32_t pos = atomicAdd(&cursor[key], 1u);
+        uint32_t r = sh.fixed ? (w * sh.table_stride + ref) : ref;
+        entries[offs[key] + pos] = r | (d < 0 ? 0x80000000u : 0u);
+    }
+}
+__global__ void k_task_fill(const uint32_t *__restrict__ toffs, uint32_t *__restrict__ task_key, uint32_t nkeys) {
+    uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= nkeys) return;
+    uint32_t t0 = toffs[key], t1 = toffs[key + 1];
+    for (uint32_t t = t0; t < t1; t++) task_key[t] = key;
+}
+
+// ---------------------------------------------------------------- bucket accumulation: one thread per task
+__global__ void __launch_bounds__(128) k_accumulate(const uint8_t *__restrict__ table, const uint32_t *__restrict__ entries,
+                                                    const uint32_t *__restrict__ offs, const uint32_t *__restrict__ toffs,
+                                                    const uint32_t *__restrict__ task_key, uint8_t *__restrict__ partial, msm_shape sh) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n_tasks = toffs[sh.nkeys];
+    if (t >= n_tasks) return;
+    uint32_t key = task_key[t];
+    uint32_t start = offs[key] + (t - toffs[key]) * sh.S;
+    uint32_t end = min(start + sh.S, offs[key + 1]);
+    uint32_t e = entries[start];
+    ge acc = ge_from_niels(niels_load_ro(table + 96 * (size_t)(e & 0x7fffffffu)), (e >> 31) != 0);
+    for (uint32_t j = start + 1; j < end; j++) {
+        e = entries[j];
+        niels q = niels_load_ro(table + 96 * (size_t)(e & 0x7fffffffu));
+        acc = ge_madd(acc, q, (e >> 31) != 0);
+    }
+    ge_store(partial + 128 * (size_t)t, acc);
+}
+
+// ---------------------------------------------------------------- chunk reduce: CH buckets -> (acc, run)
+//   run = sum_b bucket_b, acc = sum_b (b - b0 + 1) * bucket_b   over the chunk's buckets b0 .. b0+CH-1
+__global__ void __launch_bounds__(128) k_chunk_reduce(const uint8_t *__restrict__ partial, const uint32_t *__restrict__ toffs,
+                                                      uint8_t *__restrict__ chunk_acc, uint8_t *__restrict__ chunk_run, msm_shape sh) {
+    uint32_t ck = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n_chunks = sh.nkeys / sh.CH;
+    if (ck >= n_chunks) return;
+    uint32_t k0 = ck * sh.CH;
+    ge run = ge_identity(), acc = ge_identity();
+    bool run_nz = false, acc_nz = false;
+    for (uint32_t k = k0 + sh.CH; k-- > k0;) {
+        uint32_t t0 = toffs[k], t1 = toffs[k + 1];
+        for (uint32_t t = t0; t < t1; t++) {
+            ge p = ge_load(partial + 128 * (size_t)t);
+            if (run_nz) run = ge_add(run, p);
+            else { run = p; run_nz = true; }
+        }
+        if (run_nz) {
+            if (acc_nz) acc = ge_add(acc, run);
+            else { acc = run; acc_nz = true; }
+        }
+    }
+    ge_store(chunk_acc + 128 * (size_t)ck, acc);
+    ge_store(chunk_run + 128 * (size_t)ck, run);
+}
+
+// ---------------------------------------------------------------- window reduce: one block per bucket set
+//   total = sum_k acc_k + CH * sum_k k * run_k over the set's n_ch chunks. 256 threads; thread j owns the r = n_ch/256
+//   (>= 1) consecutive chunks [j*r, j*r + r):  A_j = sum acc_k, R_j = sum run_k, W_j = sum (k - j*r) * run_k, so that
+//   sum_k k*run_k = sum_j W_j + r * sum_j j*R_j, and sum_j j*R_j = sum_{j>=1} Sfx_j with Sfx the suffix sums of R
+//   (Hillis-Steele scan in shared memory), followed by a tree sum.
+#define BBP_WR_THREADS 256
+__global__ void __launch_bounds__(BBP_WR_THREADS) k_window_reduce(const uint8_t *__restrict__ chunk_acc, const uint8_t *__restrict__ chunk_run,
+                                                                  uint8_t *__restrict__ set_total, msm_shape sh) {
+    __shared__ uint4 smem_u4[BBP_WR_THREADS * 8];
+    uint8_t *sm = (uint8_t *)smem_u4;
+    const uint32_t j = threadIdx.x;
+    const uint32_t r = sh.n_ch > BBP_WR_THREADS ? sh.n_ch / BBP_WR_THREADS : 1;
+    const uint32_t nthr = sh.n_ch / r;           // active threads (power of two <= 256)
+    const size_t base = (size_t)blockIdx.x * sh.n_ch + (size_t)j * r;
+    ge A = ge_identity(), R = ge_identity(), Wt = ge_identity();
+    if (j < nthr) {
+        // high chunk to low: Wt accumulates the running sum before the current chunk is added (weights r-1 .. 0)
+        for (uint32_t k = r; k-- > 0;) {
+            if (k != r - 1) Wt = ge_add(Wt, R);
+            R = (k == r - 1) ? ge_load(chunk_run + 128 * (base + k)) : ge_add(R, ge_load(chunk_run + 128 * (base + k)));
+            A = (k == r - 1) ? ge_load(chunk_acc + 128 * (base + k)) : ge_add(A, ge_load(chunk_acc + 128 * (base + k)));
+        }
+        ge_store(sm + 128 * j, R);
+    }
+    __syncthreads();
+    ge s = R;
+    for (uint32_t off = 1; off < nthr; off <<= 1) {
+        ge t;
+        bool has = j + off < nthr;
+        if (has) t = ge_load(sm + 128 * (j + off));
+        __syncthreads();
+        if (has) { s = ge_add(s, t); ge_store(sm + 128 * j, s); }
+        __syncthreads();
+    }
+    // y_j = A_j + CH * (W_j + r * [j >= 1] Sfx_j)
+    if (j < nthr) {
+        ge w = Wt;
+        if (j >= 1) {
+            for (uint32_t m = r; m > 1; m >>= 1) s = ge_dbl(s);
+            w = (r > 1) ? ge_add(w, s) : s;
+        }
+        if (r > 1 || j >= 1) {
+            for (uint32_t m = sh.CH; m > 1; m >>= 1) w = ge_dbl(w);
+            A = ge_add(A, w);
+        }
+        ge_store(sm + 128 * j, A);
+    }
+    __syncthreads();
+    for (uint32_t stride = nthr >> 1; stride >= 1; stride >>= 1) {
+        if (j < stride) {
+            ge a = ge_load(sm + 128 * j), b = ge_load(sm + 128 * (j + stride));
+            ge_store(sm + 128 * j, ge_add(a, b));
+        }
+        __syncthreads();
+    }
+    if (j == 0) ge_store(set_total + 128 * (size_t)blockIdx.x, ge_load(sm));
+}
+
+// ---------------------------------------------------------------- final combine: one thread per slot
+// variable bases: Horner over the W window totals; fixed bases: the single set total. Optionally adds a carried-in
+// point (extended, 128 B per slot) before compressing; writes compressed (32 B) and extended (128 B) results.
+__global__ void __launch_bounds__(32) k_combine(const uint8_t *__restrict__ set_total, uint8_t *__restrict__ out_ext,
+                                                uint32_t *__restrict__ out_compressed, msm_shape sh) {
+    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= sh.n_slots) return;
+    ge acc;
+    if (sh.fixed) {
+        acc = ge_load(set_total + 128 * (size_t)slot);
+    } else {
+        const uint8_t *st = set_total + 128 * (size_t)slot * sh.W;
+        acc = ge_load(st + 128 * (size_t)(sh.W - 1));
+        for (uint32_t w = sh.W - 1; w-- > 0;) {
+            for (uint32_t j = 0; j < sh.c; j++) acc = ge_dbl(acc);
+            acc = ge_add(acc, ge_load(st + 128 * (size_t)w));
+        }
+    }
+    if (out_ext) ge_store(out_ext + 128 * (size_t)slot, acc);
+    if (out_compressed) ge_compress_words(out_compressed + 8 * (size_t)slot, acc);
+}
+
+// ---------------------------------------------------------------- host-side engine
+struct msm_engine {
+    cudaStream_t stream = nullptr;
+    // capacities
+    size_t cap_pairs = 0, cap_keys = 0, cap_tasks = 0, cap_chunks = 0, cap_sets = 0;
+    int32_t *digits = nullptr;
+    uint32_t *hist = nullptr, *offs = nullptr, *cursor = nullptr, *toffs = nullptr, *entries = nullptr, *task_key = nullptr;
+    uint32_t *tile_sums = nullptr, *total = nullptr;
+    uint8_t *partial = nullptr, *chunk_acc = nullptr, *chunk_run = nullptr, *set_total = nullptr;
+    uint64_t launches = 0;
+
+    static size_t max_tasks(const msm_shape &sh) { return ((size_t)sh.n * sh.W + sh.S - 1) / sh.S + sh.nkeys; }
+
+    void release() {
+        cudaFree(digits); cudaFree(hist); cudaFree(offs); cudaFree(cursor); cudaFree(toffs); cudaFree(entries); cudaFree(task_key);
+        cudaFree(tile_sums); cudaFree(total); cudaFree(partial); cudaFree(chunk_acc); cudaFree(chunk_run); cudaFree(set_total);
+        digits = nullptr; hist = offs = cursor = toffs = entries = task_key = tile_sums = total = nullptr;
+        partial = chunk_acc = chunk_run = set_total = nullptr;
+        cap_pairs = cap_keys = cap_tasks = cap_chunks = cap_sets = 0;
+    }
+
+    int reserve(const msm_shape &sh) {
+        size_t pairs = (size_t)sh.n * sh.W, keys = sh.nkeys, tasks = max_tasks(sh), chunks = keys / sh.CH, sets = (size_t)sh.n_slots * sh.sets_per_slot;
+        if (pairs > cap_pairs) {
+            cudaFree(digits); cudaFree(entries);
+            BBP_CUDA_OK(cudaMalloc(&digits, pairs * 4));
+            BBP_CUDA_OK(cudaMalloc(&entries, pairs * 4));
+            cap_pairs = pairs;
+        }
+        if (keys > cap_keys) {
+            cudaFree(hist); cudaFree(offs); cudaFree(cursor); cudaFree(toffs); cudaFree(tile_sums);
+            BBP_CUDA_OK(cudaMalloc(&hist, (keys + 1) * 4));
+            BBP_CUDA_OK(cudaMalloc(&offs, (keys + 1) * 4));
+            BBP_CUDA_OK(cudaMalloc(&cursor, (keys + 1) * 4));
+            BBP_CUDA_OK(cudaMalloc(&toffs, (keys + 1) * 4));
+            BBP_CUDA_OK(cudaMalloc(&tile_sums, (keys / 4096 + 2) * 4));
+            if (!total) BBP_CUDA_OK(cudaMalloc(&total, 4));
+            cap_keys = keys;
+        }
+        if (tasks > cap_tasks) {
+            cudaFree(task_key); cudaFree(partial);
+            BBP_CUDA_OK(cudaMalloc(&task_key, tasks * 4));
+            BBP_CUDA_OK(cudaMalloc(&partial, tasks * 128));
+            cap_tasks = tasks;
+        }
+        if (chunks > cap_chunks) {
+            cudaFree(chunk_acc); cudaFree(chunk_run);
+            BBP_CUDA_OK(cudaMalloc(&chunk_acc, chunks * 128));
+            BBP_CUDA_OK(cudaMalloc(&chunk_run, chunks * 128));
+            cap_chunks = chunks;
+        }
+        if (sets > cap_sets) {
+            cudaFree(set_total);
+            BBP_CUDA_OK(cudaMalloc(&set_total, sets * 128));
+            cap_sets = sets;
+        }
+        return 0;
+    }
+
+    int scan(const uint32_t *in, uint32_t *out, uint32_t n, uint32_t S) {
+        uint32_t tiles = (n + 4095) / 4096;
+        k_scan_tiles<<<tiles, 1024, 0, stream>>>(in, out, tile_sums, n, S);
+        k_scan_tile_sums<<<1, 1024, 0, stream>>>(tile_sums, tiles, total);
+        k_scan_add<<<(n + 1 + 255) / 256, 256, 0, stream>>>(out, tile_sums, n, total);
+        launches += 3;
+        return 0;
+    }
+
+    // window size heuristic (pairs per bucket set kept around 16-64)
+    static msm_shape make_shape(uint32_t n, uint32_t n_per_slot, uint32_t base_mod, bool fixed, uint32_t table_c, uint32_t table_W, uint32_t table_stride) {
+        msm_shape sh;
+        sh.n = n; sh.n_per_slot = n_per_slot; sh.n_slots = (n + n_per_slot - 1) / n_per_slot; sh.base_mod = base_mod;
+        sh.fixed = fixed ? 1 : 0;
+        if (fixed) {
+            sh.c = table_c; sh.W = table_W; sh.table_stride = table_stride; sh.sets_per_slot = 1;
+        } else {
+            uint32_t c = 5;
+            while (c < 16 && ((size_t)n_per_slot >> (c + 3)) >= 1) c++;   // ~16+ points per bucket
+            sh.c = c; sh.W = 253 / c + 1; sh.table_stride = 0; sh.sets_per_slot = sh.W;
+        }
+        sh.B = 1u << (sh.c - 1);
+        sh.nkeys = sh.n_slots * sh.sets_per_slot * sh.B;
+        size_t pairs_per_set = fixed ? (size_t)n_per_slot * sh.W : n_per_slot;
+        size_t avg = pairs_per_set / sh.B + 1;
+        sh.S = (uint32_t)std::min<size_t>(std::max<size_t>(2 * avg, 16), 64);
+        sh.CH = std::max(1u, std::min(32u, sh.B / 256));   // power of two; n_ch = B / CH is a power of two as well
+        sh.n_ch = sh.B / sh.CH;
+        return sh;
+    }
+
+    // d_scalars: n x 32 B on device; d_table: niels table; outputs on device (either may be null)
+    int run(const msm_shape &sh, const uint8_t *d_scalars, const uint8_t *d_table, uint8_t *d_out_ext, uint8_t *d_out_compressed) {
+        if (sh.n == 0) return -1;
+        int rc = reserve(sh);
+        if (rc) return rc;
+        BBP_CUDA_OK(cudaMemsetAsync(hist, 0, ((size_t)sh.nkeys + 1) * 4, stream));
+        BBP_CUDA_OK(cudaMemsetAsync(cursor, 0, ((size_t)sh.nkeys + 1) * 4, stream));
+        k_recode<<<(sh.n + 127) / 128, 128, 0, stream>>>((const uint32_t *)d_scalars, digits, hist, sh);
+        scan(hist, offs, sh.nkeys, 0);
+        scan(hist, toffs, sh.nkeys, sh.S);
+        k_scatter<<<(sh.n + 127) / 128, 128, 0, stream>>>(digits, offs, cursor, entries, sh);
+        k_task_fill<<<(sh.nkeys + 255) / 256, 256, 0, stream>>>(toffs, task_key, sh.nkeys);
+        size_t mt = max_tasks(sh);
+        k_accumulate<<<(unsigned)((mt + 127) / 128), 128, 0, stream>>>(d_table, entries, offs, toffs, task_key, partial, sh);
+        uint32_t n_chunks = sh.nkeys / sh.CH;
+        k_chunk_reduce<<<(n_chunks + 127) / 128, 128, 0, stream>>>(partial, toffs, chunk_acc, chunk_run, sh);
+        uint32_t sets = sh.n_slots * sh.sets_per_slot;
+        k_window_reduce<<<sets, BBP_WR_THREADS, 0, stream>>>(chunk_acc, chunk_run, set_total, sh);
+        k_combine<<<(sh.n_slots + 31) / 32, 32, 0, stream>>>(set_total, d_out_ext, (uint32_t *)d_out_compressed, sh);
+        launches += 6;
+        BBP_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+};
+
+}  // namespace bbp
