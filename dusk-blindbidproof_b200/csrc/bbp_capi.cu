@@ -63,6 +63,49 @@ int bbp_bulletproof_gens(bbp_ctx *ctx, int which, uint32_t party, uint32_t first
     return e == cudaSuccess ? BBP_OK : BBP_ERR_CUDA;
 }
 
+// ---------------------------------------------------------------- measurement hooks
+int bbp_set_profiling(bbp_ctx *ctx, int on) {
+    if (!ctx) return BBP_ERR_INPUT;
+    ctx->msm.profile = on != 0;
+    return BBP_OK;
+}
+int bbp_msm_stage_ms(bbp_ctx *ctx, float *ms, size_t n_stages) {
+    if (!ctx || !ms || n_stages != (size_t)msm_engine::N_STAGES) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    return ctx->msm.collect(ms) ? BBP_ERR_CUDA : BBP_OK;
+}
+int bbp_msm_plan(size_t n, uint32_t out[4]) {
+    if (!out || n == 0 || n > 0x7fffffffu) return BBP_ERR_INPUT;
+    msm_shape sh = msm_engine::make_shape((uint32_t)n, (uint32_t)n, (uint32_t)n, false, 0, 0, 0);
+    out[0] = sh.c; out[1] = sh.W; out[2] = sh.S; out[3] = sh.CH;
+    return BBP_OK;
+}
+int bbp_int_peak(bbp_ctx *ctx, double *wide_mads_per_s) {
+    if (!ctx || !wide_mads_per_s) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    cudaDeviceProp prop;
+    BBP_CUDA_OK(cudaGetDeviceProperties(&prop, ctx->device));
+    int blocks = prop.multiProcessorCount * 2, threads = 1024;
+    uint32_t *d = nullptr;
+    BBP_CUDA_OK(cudaMalloc(&d, (size_t)blocks * threads * 4));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; rep++) {
+        cudaEventRecord(e0, ctx->stream);
+        k_int_peak<<<blocks, threads, 0, ctx->stream>>>(d, rep + 1);
+        cudaEventRecord(e1, ctx->stream);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return BBP_ERR_CUDA; }
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep && ms < best) best = ms;
+    }
+    ctx->launches += 6;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *wide_mads_per_s = (double)blocks * threads * (double)BBP_PEAK_ITERS * BBP_PEAK_ILP / (best * 1e-3);
+    return BBP_OK;
+}
+
 // ---------------------------------------------------------------- base tables
 int bbp_points_from_compressed(bbp_ctx *ctx, const uint8_t *points, size_t n, bbp_points **out, int *all_valid) {
     if (!ctx || !points || !out || n == 0 || n > 0x7fffffffu) return BBP_ERR_INPUT;
@@ -117,11 +160,20 @@ void bbp_points_free(bbp_points *p) {
 }
 
 // ---------------------------------------------------------------- MSM
-int bbp_msm_points_device(bbp_ctx *ctx, const void *scalars_device, size_t n, const bbp_points *points, void *out_device) {
-    if (!ctx || !scalars_device || !points || !out_device || n == 0 || n != points->n) return BBP_ERR_INPUT;
+int bbp_msm_points_device(bbp_ctx *ctx, const void *scalars_device, size_t n, const bbp_points *points, void *out_device, void *out_ext_device) {
+    if (!ctx || !scalars_device || !points || (!out_device && !out_ext_device) || n == 0 || n != points->n) return BBP_ERR_INPUT;
     cudaSetDevice(ctx->device);
     msm_shape sh = msm_engine::make_shape((uint32_t)n, (uint32_t)n, (uint32_t)n, false, 0, 0, 0);
-    return ctx->msm.run(sh, (const uint8_t *)scalars_device, points->d_niels, nullptr, (uint8_t *)out_device);
+    return ctx->msm.run(sh, (const uint8_t *)scalars_device, points->d_niels, (uint8_t *)out_ext_device, (uint8_t *)out_device);
+}
+
+int bbp_sum_compress_device(bbp_ctx *ctx, const void *points_ext_device, size_t n, void *out_device) {
+    if (!ctx || !points_ext_device || !out_device || n == 0 || n > 1024) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    k_sum_compress<<<1, 32, 0, ctx->stream>>>((const uint8_t *)points_ext_device, (uint32_t)n, (uint32_t *)out_device);
+    ctx->launches++;
+    BBP_CUDA_OK(cudaGetLastError());
+    return BBP_OK;
 }
 
 int bbp_msm_points_batched(bbp_ctx *ctx, const uint8_t *scalars, size_t n_per_slot, size_t n_slots, const bbp_points *points, uint8_t *out) {

@@ -102,6 +102,44 @@ __global__ void __launch_bounds__(128) k_build_window_table(const uint8_t *__res
     }
 }
 
+// integer-pipe ceiling: BBP_PEAK_ILP independent chains of the same mad.lo.cc / madc.hi pair the field multiplier is
+// built from (ptxas fuses each pair into one IMAD.WIDE.U32), at full occupancy. The roofline denominator of the MSM.
+#define BBP_PEAK_ILP 8
+#define BBP_PEAK_ITERS 4096
+__global__ void __launch_bounds__(1024, 2) k_int_peak(uint32_t *out, uint32_t seed) {
+    uint32_t lo[BBP_PEAK_ILP], hi[BBP_PEAK_ILP];
+    uint32_t x = seed + threadIdx.x, y = seed * 3 + blockIdx.x + 1;
+#pragma unroll
+    for (int i = 0; i < BBP_PEAK_ILP; i++) { lo[i] = x + i; hi[i] = y + 7 * i; }
+#pragma unroll 1
+    for (int it = 0; it < BBP_PEAK_ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < BBP_PEAK_ILP; i++)
+            asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(lo[i]), "+r"(hi[i]) : "r"(x), "r"(y));
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < BBP_PEAK_ILP; i++) r ^= lo[i] ^ hi[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+// sum of n (<= 1024) extended points, compressed: the local tail of a sharded MSM after the all-gather of the
+// per-GPU partial sums. One warp: lane sums, then a shuffle-free tree through shared memory.
+__global__ void __launch_bounds__(32) k_sum_compress(const uint8_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ out) {
+    __shared__ uint4 sm_u4[32 * 8];
+    uint8_t *sm = (uint8_t *)sm_u4;
+    uint32_t lane = threadIdx.x;
+    ge acc = ge_identity();
+    for (uint32_t i = lane; i < n; i += 32) acc = ge_add(acc, ge_load(in + 128 * (size_t)i));
+    ge_store(sm + 128 * lane, acc);
+    __syncwarp();
+    for (uint32_t stride = 16; stride >= 1; stride >>= 1) {
+        if (lane < stride) ge_store(sm + 128 * lane, ge_add(ge_load(sm + 128 * lane), ge_load(sm + 128 * (lane + stride))));
+        __syncwarp();
+    }
+    if (lane == 0) ge_compress_words(out, ge_load(sm));
+}
+
 __global__ void k_store_basepoint(uint8_t *out) { ge_store(out, ge_basepoint()); }
 
 // ---- unit-test kernels (driven by the bbp_test_* entry points; compared against the oracle in tests/)

@@ -321,6 +321,30 @@ struct msm_engine {
     uint32_t *tile_sums = nullptr, *total = nullptr;
     uint8_t *partial = nullptr, *chunk_acc = nullptr, *chunk_run = nullptr, *set_total = nullptr;
     uint64_t launches = 0;
+    // optional per-stage timing (bbp_set_profiling): events around recode / scans / scatter+fill / accumulate /
+    // chunk reduce / window reduce / combine on the launching stream
+    static const int N_STAGES = 7;
+    bool profile = false;
+    cudaEvent_t ev[N_STAGES + 1] = {};
+    float stage_ms[N_STAGES] = {};
+    bool stage_pending = false;
+
+    int mark(int i) {
+        if (!profile) return 0;
+        if (!ev[i]) BBP_CUDA_OK(cudaEventCreate(&ev[i]));
+        BBP_CUDA_OK(cudaEventRecord(ev[i], stream));
+        return 0;
+    }
+    // blocks until the last profiled run has finished; ms[0..N_STAGES)
+    int collect(float *ms) {
+        if (stage_pending) {
+            BBP_CUDA_OK(cudaEventSynchronize(ev[N_STAGES]));
+            for (int i = 0; i < N_STAGES; i++) BBP_CUDA_OK(cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]));
+            stage_pending = false;
+        }
+        for (int i = 0; i < N_STAGES; i++) ms[i] = stage_ms[i];
+        return 0;
+    }
 
     static size_t max_tasks(const msm_shape &sh) { return ((size_t)sh.n * sh.W + sh.S - 1) / sh.S + sh.nkeys; }
 
@@ -330,6 +354,7 @@ struct msm_engine {
         digits = nullptr; hist = offs = cursor = toffs = entries = task_key = tile_sums = total = nullptr;
         partial = chunk_acc = chunk_run = set_total = nullptr;
         cap_pairs = cap_keys = cap_tasks = cap_chunks = cap_sets = 0;
+        for (int i = 0; i <= N_STAGES; i++) if (ev[i]) { cudaEventDestroy(ev[i]); ev[i] = nullptr; }
     }
 
     int reserve(const msm_shape &sh) {
@@ -408,18 +433,27 @@ struct msm_engine {
         if (rc) return rc;
         BBP_CUDA_OK(cudaMemsetAsync(hist, 0, ((size_t)sh.nkeys + 1) * 4, stream));
         BBP_CUDA_OK(cudaMemsetAsync(cursor, 0, ((size_t)sh.nkeys + 1) * 4, stream));
+        if (mark(0)) return -100;
         k_recode<<<(sh.n + 127) / 128, 128, 0, stream>>>((const uint32_t *)d_scalars, digits, hist, sh);
+        if (mark(1)) return -100;
         scan(hist, offs, sh.nkeys, 0);
         scan(hist, toffs, sh.nkeys, sh.S);
+        if (mark(2)) return -100;
         k_scatter<<<(sh.n + 127) / 128, 128, 0, stream>>>(digits, offs, cursor, entries, sh);
         k_task_fill<<<(sh.nkeys + 255) / 256, 256, 0, stream>>>(toffs, task_key, sh.nkeys);
+        if (mark(3)) return -100;
         size_t mt = max_tasks(sh);
         k_accumulate<<<(unsigned)((mt + 127) / 128), 128, 0, stream>>>(d_table, entries, offs, toffs, task_key, partial, sh);
+        if (mark(4)) return -100;
         uint32_t n_chunks = sh.nkeys / sh.CH;
         k_chunk_reduce<<<(n_chunks + 127) / 128, 128, 0, stream>>>(partial, toffs, chunk_acc, chunk_run, sh);
+        if (mark(5)) return -100;
         uint32_t sets = sh.n_slots * sh.sets_per_slot;
         k_window_reduce<<<sets, BBP_WR_THREADS, 0, stream>>>(chunk_acc, chunk_run, set_total, sh);
+        if (mark(6)) return -100;
         k_combine<<<(sh.n_slots + 31) / 32, 32, 0, stream>>>(set_total, d_out_ext, (uint32_t *)d_out_compressed, sh);
+        if (mark(7)) return -100;
+        if (profile) stage_pending = true;
         launches += 6;
         BBP_CUDA_OK(cudaGetLastError());
         return 0;

@@ -49,6 +49,16 @@ uint64_t bbp_launch_count(const bbp_ctx *ctx);
 uint64_t bbp_stream(const bbp_ctx *ctx);
 int bbp_sync(bbp_ctx *ctx);
 
+/* ---- measurement hooks (bench.py): per-stage MSM timing with CUDA events on the context stream, the MSM plan for a
+ * size, and the measured integer-multiply ceiling of the device (no reference counterpart) */
+int bbp_set_profiling(bbp_ctx *ctx, int on);
+/* ms[0..7): recode, scans, scatter+task table, bucket accumulation, chunk reduce, window reduce, combine+compress */
+int bbp_msm_stage_ms(bbp_ctx *ctx, float *ms, size_t n_stages);
+/* out = {window bits c, windows W, max entries per task S, buckets per chunk CH} chosen for an n-point MSM */
+int bbp_msm_plan(size_t n, uint32_t out[4]);
+/* sustained 32x32->64 multiply-accumulates per second (IMAD.WIDE.U32), all SMs, 8 independent chains per thread */
+int bbp_int_peak(bbp_ctx *ctx, double *wide_mads_per_s);
+
 /* ---- generators (bulletproofs PedersenGens / BulletproofGens, used at src/blindbid/mod.rs:35-36) ------------------- */
 /* compressed B, B_blinding */
 int bbp_pedersen_gens(bbp_ctx *ctx, uint8_t B[32], uint8_t B_blinding[32]);
@@ -71,9 +81,14 @@ int bbp_msm_points(bbp_ctx *ctx, const uint8_t *scalars, size_t n, const bbp_poi
 int bbp_msm_vartime(bbp_ctx *ctx, const uint8_t *scalars, const uint8_t *points_ext, size_t n, uint8_t out[32]);
 /* VartimeMultiscalarMul::optional_multiscalar_mul over compressed points: BBP_ERR_DECOMPRESS if any fails (None) */
 int bbp_msm_optional(bbp_ctx *ctx, const uint8_t *scalars, const uint8_t *points_compressed, size_t n, uint8_t out[32]);
-/* device-pointer variant for callers that already hold scalars in HBM (n x 32 B) and want the result left in HBM
- * (32 B compressed); fully asynchronous on the context stream */
-int bbp_msm_points_device(bbp_ctx *ctx, const void *scalars_device, size_t n, const bbp_points *points, void *out_device);
+/* device-pointer variant for callers that already hold scalars in HBM (n x 32 B) and want the result left in HBM:
+ * out_device = 32 B compressed and/or out_ext_device = 128 B extended partial sum (either may be NULL); fully
+ * asynchronous on the context stream */
+int bbp_msm_points_device(bbp_ctx *ctx, const void *scalars_device, size_t n, const bbp_points *points, void *out_device,
+                          void *out_ext_device);
+/* tail of a sharded MSM: sum of n <= 1024 extended partial sums (n x 128 B in HBM, e.g. the all-gather
+ * of every GPU's out_ext_device) -> 32 B compressed in HBM; asynchronous on the context stream */
+int bbp_sum_compress_device(bbp_ctx *ctx, const void *points_ext_device, size_t n, void *out_device);
 /* batched form: n_slots independent MSMs of n_per_slot scalars each over the SAME resident bases (slot-major scalars);
  * out = n_slots x 32 B compressed */
 int bbp_msm_points_batched(bbp_ctx *ctx, const uint8_t *scalars, size_t n_per_slot, size_t n_slots, const bbp_points *points, uint8_t *out);
