@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(128) k_decompress_to_ext(const uint32_t *__res
     bool ok = ge_decompress_words(p, w);
     if (!ok) { p = ge_identity(); atomicAnd(all_valid, 0); }
     if (valid_flags) valid_flags[i] = ok ? 1 : 0;
+    // API-facing: canonical field encodings (internal tables keep the lazy representation)
+    p.X = fe_canon(p.X); p.Y = fe_canon(p.Y); p.Z = fe_canon(p.Z); p.T = fe_canon(p.T);
     ge_store(out + 128 * (size_t)i, p);
 }
 
@@ -102,24 +104,26 @@ __global__ void __launch_bounds__(128) k_build_window_table(const uint8_t *__res
     }
 }
 
-// integer-pipe ceiling: BBP_PEAK_ILP independent chains of the same mad.lo.cc / madc.hi pair the field multiplier is
-// built from (ptxas fuses each pair into one IMAD.WIDE.U32), at full occupancy. The roofline denominator of the MSM.
+// integer-pipe ceiling: BBP_PEAK_ILP independent chains of the IMAD.WIDE.U32 (32x32+64) the field multiplier is built
+// from (ptxas fuses each mad.lo.cc / madc.hi pair into one), at full occupancy. The roofline denominator of the MSM.
 #define BBP_PEAK_ILP 8
 #define BBP_PEAK_ITERS 4096
 __global__ void __launch_bounds__(1024, 2) k_int_peak(uint32_t *out, uint32_t seed) {
-    uint32_t lo[BBP_PEAK_ILP], hi[BBP_PEAK_ILP];
-    uint32_t x = seed + threadIdx.x, y = seed * 3 + blockIdx.x + 1;
+    uint64_t acc[BBP_PEAK_ILP];
+    uint32_t x = seed + threadIdx.x;
 #pragma unroll
-    for (int i = 0; i < BBP_PEAK_ILP; i++) { lo[i] = x + i; hi[i] = y + 7 * i; }
+    for (int i = 0; i < BBP_PEAK_ILP; i++) acc[i] = ((uint64_t)(seed * 3 + blockIdx.x + 7 * i) << 32) | (x + i);
 #pragma unroll 1
-    for (int it = 0; it < BBP_PEAK_ITERS; it++) {
+    for (int it = 0; it < BBP_PEAK_ITERS; it += 4) {
 #pragma unroll
-        for (int i = 0; i < BBP_PEAK_ILP; i++)
-            asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(lo[i]), "+r"(hi[i]) : "r"(x), "r"(y));
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int i = 0; i < BBP_PEAK_ILP; i++) acc[i] += (uint64_t)(uint32_t)acc[i] * x;   // IMAD.WIDE.U32 Rd, Ra.lo, x, Rd
+        }
     }
     uint32_t r = 0;
 #pragma unroll
-    for (int i = 0; i < BBP_PEAK_ILP; i++) r ^= lo[i] ^ hi[i];
+    for (int i = 0; i < BBP_PEAK_ILP; i++) r ^= (uint32_t)acc[i] ^ (uint32_t)(acc[i] >> 32);
     out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
