@@ -216,3 +216,133 @@ class Backend:
         out = _out(32 * n)
         _chk(lib().bbp_test_ge(self.ctx, a, b, _sz(n), int(op), out), "bbp_test_ge")
         return out.raw
+
+
+# ---------------------------------------------------------------------------------------------- blind-bid entry points
+class ProveReq(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_char_p) for n in ("d", "k", "y", "y_inv", "q", "z_img", "seed", "pub_list")] + [
+        ("L", ctypes.c_size_t), ("toggle", ctypes.c_uint64), ("blindings", ctypes.c_char_p), ("rng_seed", ctypes.c_char_p),
+        ("proof_out", ctypes.c_void_p), ("proof_cap", ctypes.c_size_t), ("proof_len", ctypes.c_size_t),
+        ("commitments_out", ctypes.c_void_p), ("t_c_out", ctypes.c_void_p), ("status", ctypes.c_int)]
+
+
+class VerifyReq(ctypes.Structure):
+    _fields_ = [("proof", ctypes.c_char_p), ("proof_len", ctypes.c_size_t), ("commitments", ctypes.c_char_p), ("n_commitments", ctypes.c_size_t),
+                ("t_c", ctypes.c_char_p), ("n_t_c", ctypes.c_size_t), ("score", ctypes.c_char_p), ("z_img", ctypes.c_char_p), ("seed", ctypes.c_char_p),
+                ("pub_list", ctypes.c_char_p), ("L", ctypes.c_size_t), ("rng_seed", ctypes.c_char_p), ("status", ctypes.c_int)]
+
+
+PROOF_CAP = 2048
+
+
+def _prove_reqs(bids):
+    """bids: dicts with d,k,y,y_inv,q,z_img,seed,pub_list (bytes), toggle (int), blindings (bytes), rng_seed (bytes)."""
+    n = len(bids)
+    arr = (ProveReq * n)()
+    keep = []
+    for i, b in enumerate(bids):
+        L = len(b["pub_list"]) // 32
+        proof, comm, tc = _out(PROOF_CAP), _out(4 * 32), _out(32 * max(L, 1))
+        keep.append((proof, comm, tc))
+        r = arr[i]
+        for f in ("d", "k", "y", "y_inv", "q", "z_img", "seed", "pub_list", "blindings", "rng_seed"):
+            setattr(r, f, b[f])
+        r.L, r.toggle = L, b["toggle"]
+        r.proof_out, r.proof_cap = ctypes.cast(proof, ctypes.c_void_p), PROOF_CAP
+        r.commitments_out, r.t_c_out = ctypes.cast(comm, ctypes.c_void_p), ctypes.cast(tc, ctypes.c_void_p)
+    return arr, keep
+
+
+def _verify_reqs(items):
+    """items: dicts with proof, commitments, t_c, score, z_img, seed, pub_list, rng_seed (bytes)."""
+    n = len(items)
+    arr = (VerifyReq * n)()
+    for i, v in enumerate(items):
+        r = arr[i]
+        r.proof, r.proof_len = v["proof"], len(v["proof"])
+        r.commitments, r.n_commitments = v["commitments"], len(v["commitments"]) // 32
+        r.t_c, r.n_t_c = v["t_c"], len(v["t_c"]) // 32
+        r.score, r.z_img, r.seed = v["score"], v["z_img"], v["seed"]
+        r.pub_list, r.L = v["pub_list"], len(v["pub_list"]) // 32
+        r.rng_seed = v["rng_seed"]
+    return arr
+
+
+def _backend_methods():
+    def set_proof_format(self, versioned):
+        _chk(lib().bbp_set_proof_format(self.ctx, int(versioned)), "bbp_set_proof_format")
+
+    def blindbid_prove_batch(self, bids):
+        """Proof::prove for a list of bids in one GPU pass. Returns [(status, proof, commitments, t_c)]."""
+        arr, keep = _prove_reqs(bids)
+        _chk(lib().bbp_blindbid_prove_batch(self.ctx, _sz(len(bids)), arr), "bbp_blindbid_prove_batch")
+        out = []
+        for i, (proof, comm, tc) in enumerate(keep):
+            L = len(bids[i]["pub_list"]) // 32
+            out.append((arr[i].status, proof.raw[:arr[i].proof_len], comm.raw, tc.raw[:32 * L]))
+        return out
+
+    def blindbid_prove(self, bid):
+        return self.blindbid_prove_batch([bid])[0]
+
+    def blindbid_verify_each(self, items):
+        """Verify::verify for every item independently; returns the list of statuses (0 = accept)."""
+        arr = _verify_reqs(items)
+        _chk(lib().bbp_blindbid_verify_each(self.ctx, _sz(len(items)), arr), "bbp_blindbid_verify_each")
+        return [arr[i].status for i in range(len(items))]
+
+    def blindbid_verify(self, item):
+        return lib().bbp_blindbid_verify(self.ctx, item["proof"], _sz(len(item["proof"])), item["commitments"], _sz(len(item["commitments"]) // 32),
+                                         item["t_c"], _sz(len(item["t_c"]) // 32), item["score"], item["z_img"], item["seed"], item["pub_list"],
+                                         _sz(len(item["pub_list"]) // 32), item["rng_seed"])
+
+    def blindbid_verify_batch(self, items, batch_seed):
+        """One combined mega-check; returns (all_ok, statuses)."""
+        arr = _verify_reqs(items)
+        ok = ctypes.c_int(0)
+        _chk(lib().bbp_blindbid_verify_batch(self.ctx, _sz(len(items)), arr, batch_seed, ctypes.byref(ok)), "bbp_blindbid_verify_batch")
+        return bool(ok.value), [arr[i].status for i in range(len(items))]
+
+    def blindbid_verify_batch_partial(self, items, batch_seed, partial_dev_ptr):
+        arr = _verify_reqs(items)
+        ok = ctypes.c_int(0)
+        _chk(lib().bbp_blindbid_verify_batch_partial(self.ctx, _sz(len(items)), arr, batch_seed, ctypes.c_void_p(partial_dev_ptr), ctypes.byref(ok)),
+             "bbp_blindbid_verify_batch_partial")
+        return bool(ok.value), [arr[i].status for i in range(len(items))]
+
+    def pedersen_commit(self, values, blindings):
+        n = len(values) // 32
+        out = _out(32 * n)
+        _chk(lib().bbp_pedersen_commit(self.ctx, values, blindings, _sz(n), out), "bbp_pedersen_commit")
+        return out.raw
+
+    def msm_gens(self, scalars, slot_len, n_slots):
+        out = _out(32 * n_slots)
+        _chk(lib().bbp_msm_gens(self.ctx, scalars, _sz(slot_len), _sz(n_slots), out), "bbp_msm_gens")
+        return out.raw
+
+    for f in (set_proof_format, blindbid_prove_batch, blindbid_prove, blindbid_verify_each, blindbid_verify, blindbid_verify_batch,
+              blindbid_verify_batch_partial, pedersen_commit, msm_gens):
+        setattr(Backend, f.__name__, f)
+
+
+_backend_methods()
+
+
+# host-only helpers of the library (no GPU needed)
+def mimc_hash(left, right):
+    out = _out(32)
+    _chk(lib().bbp_mimc_hash(left, right, out), "bbp_mimc_hash")
+    return out.raw
+
+
+def mimc_constants():
+    out = _out(90 * 32)
+    _chk(lib().bbp_mimc_constants(out), "bbp_mimc_constants")
+    return out.raw
+
+
+def circuit_shape(n_commitments, n_toggles):
+    out = (ctypes.c_size_t * 3)()
+    _chk(lib().bbp_blindbid_circuit_shape(_sz(n_commitments), _sz(n_toggles), out), "bbp_blindbid_circuit_shape")
+    return out[0], out[1], out[2]

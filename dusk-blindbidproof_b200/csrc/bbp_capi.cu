@@ -5,6 +5,7 @@
 #include "codec.cuh"
 #include "ctx.cuh"
 #include "msm.cuh"
+#include "protocol.cuh"
 
 using namespace bbp;
 
@@ -307,6 +308,194 @@ int bbp_test_ge(bbp_ctx *ctx, const uint8_t *a_compressed, const uint8_t *b_comp
     cudaFree(d); cudaFree(d_valid);
     if (e != cudaSuccess) return BBP_ERR_CUDA;
     return one ? BBP_OK : BBP_ERR_DECOMPRESS;
+}
+
+// ---------------------------------------------------------------- blind-bid entry points
+static sc load_scalar(const uint8_t *p) { return sc_from_bytes_mod_order(p); }
+
+int bbp_set_proof_format(bbp_ctx *ctx, int versioned) {
+    if (!ctx) return BBP_ERR_INPUT;
+    proto_get(ctx)->proof_versioned = versioned ? 1 : 0;
+    return BBP_OK;
+}
+
+int bbp_blindbid_prove_batch(bbp_ctx *ctx, size_t n, bbp_prove_req *reqs) {
+    if (!ctx || !reqs || n == 0) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    std::vector<prove_job> jobs(n);
+    for (size_t i = 0; i < n; i++) {
+        bbp_prove_req &R = reqs[i];
+        prove_job &J = jobs[i];
+        R.status = BBP_ERR_INPUT;
+        R.proof_len = 0;
+        if (!R.d || !R.k || !R.y || !R.y_inv || !R.q || !R.z_img || !R.seed || !R.pub_list || !R.blindings || !R.rng_seed || !R.proof_out ||
+            !R.commitments_out || !R.t_c_out || R.L == 0 || R.toggle >= R.L + (uint64_t)0x100000000ull)
+            continue;
+        J.d = load_scalar(R.d); J.k = load_scalar(R.k); J.y = load_scalar(R.y); J.y_inv = load_scalar(R.y_inv);
+        J.q = load_scalar(R.q); J.z_img = load_scalar(R.z_img); J.seed = load_scalar(R.seed);
+        J.pub_list.resize(R.L);
+        for (size_t k = 0; k < R.L; k++) J.pub_list[k] = sc_from_bits(R.pub_list + 32 * k);   // Bid::from (src/blindbid/bid.rs:20-29)
+        J.toggle = R.toggle;
+        J.blindings.resize(4 + R.L);
+        for (size_t k = 0; k < 4 + R.L; k++) J.blindings[k] = load_scalar(R.blindings + 32 * k);
+        memcpy(J.rng_seed, R.rng_seed, 32);
+        J.status = 1;   // marked runnable
+    }
+    std::vector<prove_job> run;
+    std::vector<size_t> map;
+    for (size_t i = 0; i < n; i++)
+        if (jobs[i].status == 1) { map.push_back(i); run.push_back(std::move(jobs[i])); }
+    if (!run.empty()) {
+        int rc = prove_batch(ctx, run);
+        if (rc) return rc;
+    }
+    for (size_t k = 0; k < run.size(); k++) {
+        bbp_prove_req &R = reqs[map[k]];
+        prove_job &J = run[k];
+        R.status = J.status;
+        if (J.status) continue;
+        if (J.proof.size() > R.proof_cap) { R.status = BBP_ERR_INPUT; R.proof_len = J.proof.size(); continue; }
+        memcpy(R.proof_out, J.proof.data(), J.proof.size());
+        R.proof_len = J.proof.size();
+        memcpy(R.commitments_out, J.commitments.data(), J.commitments.size());
+        memcpy(R.t_c_out, J.t_c.data(), J.t_c.size());
+    }
+    return BBP_OK;
+}
+
+int bbp_blindbid_prove(bbp_ctx *ctx, const uint8_t d[32], const uint8_t k[32], const uint8_t y[32], const uint8_t y_inv[32], const uint8_t q[32],
+                       const uint8_t z_img[32], const uint8_t seed[32], const uint8_t *pub_list, size_t L, uint64_t toggle, const uint8_t *blindings,
+                       const uint8_t rng_seed[32], uint8_t *proof_out, size_t *proof_len, uint8_t *commitments_out, uint8_t *t_c_out) {
+    if (!proof_len) return BBP_ERR_INPUT;
+    bbp_prove_req R;
+    memset(&R, 0, sizeof R);
+    R.d = d; R.k = k; R.y = y; R.y_inv = y_inv; R.q = q; R.z_img = z_img; R.seed = seed; R.pub_list = pub_list; R.L = L; R.toggle = toggle;
+    R.blindings = blindings; R.rng_seed = rng_seed; R.proof_out = proof_out; R.proof_cap = *proof_len; R.commitments_out = commitments_out; R.t_c_out = t_c_out;
+    int rc = bbp_blindbid_prove_batch(ctx, 1, &R);
+    if (rc) return rc;
+    *proof_len = R.proof_len;
+    return R.status;
+}
+
+static int load_verify_jobs(size_t n, bbp_verify_req *reqs, std::vector<verify_job> &jobs, std::vector<size_t> &map) {
+    for (size_t i = 0; i < n; i++) {
+        bbp_verify_req &R = reqs[i];
+        R.status = BBP_ERR_INPUT;
+        if (!R.proof || !R.commitments || !R.t_c || !R.score || !R.z_img || !R.seed || (!R.pub_list && R.L) || !R.rng_seed) continue;
+        verify_job J;
+        J.proof.assign(R.proof, R.proof + R.proof_len);
+        J.commitments.assign(R.commitments, R.commitments + 32 * R.n_commitments);
+        J.t_c.assign(R.t_c, R.t_c + 32 * R.n_t_c);
+        J.score = load_scalar(R.score); J.z_img = load_scalar(R.z_img); J.seed = load_scalar(R.seed);
+        J.pub_list.resize(R.L);
+        for (size_t k = 0; k < R.L; k++) J.pub_list[k] = sc_from_bits(R.pub_list + 32 * k);   // src/blindbid/verify.rs:112-116
+        memcpy(J.rng_seed, R.rng_seed, 32);
+        map.push_back(i);
+        jobs.push_back(std::move(J));
+    }
+    return 0;
+}
+
+int bbp_blindbid_verify_each(bbp_ctx *ctx, size_t n, bbp_verify_req *reqs) {
+    if (!ctx || !reqs || n == 0) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    std::vector<verify_job> jobs;
+    std::vector<size_t> map;
+    load_verify_jobs(n, reqs, jobs, map);
+    if (!jobs.empty()) {
+        int rc = verify_each(ctx, jobs);
+        if (rc) return rc;
+    }
+    for (size_t k = 0; k < jobs.size(); k++) reqs[map[k]].status = jobs[k].status;
+    return BBP_OK;
+}
+
+int bbp_blindbid_verify(bbp_ctx *ctx, const uint8_t *proof, size_t proof_len, const uint8_t *commitments, size_t n_commitments, const uint8_t *t_c,
+                        size_t n_t_c, const uint8_t score[32], const uint8_t z_img[32], const uint8_t seed[32], const uint8_t *pub_list, size_t L,
+                        const uint8_t rng_seed[32]) {
+    bbp_verify_req R;
+    memset(&R, 0, sizeof R);
+    R.proof = proof; R.proof_len = proof_len; R.commitments = commitments; R.n_commitments = n_commitments; R.t_c = t_c; R.n_t_c = n_t_c;
+    R.score = score; R.z_img = z_img; R.seed = seed; R.pub_list = pub_list; R.L = L; R.rng_seed = rng_seed;
+    int rc = bbp_blindbid_verify_each(ctx, 1, &R);
+    return rc ? rc : R.status;
+}
+
+int bbp_blindbid_verify_batch(bbp_ctx *ctx, size_t n, bbp_verify_req *reqs, const uint8_t batch_seed[32], int *all_ok) {
+    if (!ctx || !reqs || n == 0 || !batch_seed) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    std::vector<verify_job> jobs;
+    std::vector<size_t> map;
+    load_verify_jobs(n, reqs, jobs, map);
+    int ok = 1;
+    if (!jobs.empty()) {
+        int rc = verify_batch(ctx, jobs, batch_seed, &ok, false, nullptr);
+        if (rc) return rc;
+    }
+    for (size_t k = 0; k < jobs.size(); k++) reqs[map[k]].status = jobs[k].status;
+    if (jobs.size() != n) ok = 0;
+    if (all_ok) *all_ok = ok;
+    return BBP_OK;
+}
+
+int bbp_blindbid_verify_batch_partial(bbp_ctx *ctx, size_t n, bbp_verify_req *reqs, const uint8_t batch_seed[32], void *partial_ext_device, int *local_ok) {
+    if (!ctx || !reqs || n == 0 || !batch_seed || !partial_ext_device) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    std::vector<verify_job> jobs;
+    std::vector<size_t> map;
+    load_verify_jobs(n, reqs, jobs, map);
+    if (jobs.size() != n) return BBP_ERR_INPUT;
+    int ok = 1;
+    int rc = verify_batch(ctx, jobs, batch_seed, &ok, true, (uint8_t *)partial_ext_device);
+    if (rc) return rc;
+    for (size_t k = 0; k < jobs.size(); k++) reqs[map[k]].status = jobs[k].status;
+    if (local_ok) *local_ok = ok;
+    return BBP_OK;
+}
+
+int bbp_mimc_hash(const uint8_t left[32], const uint8_t right[32], uint8_t out[32]) {
+    if (!left || !right || !out) return BBP_ERR_INPUT;
+    sc_tobytes(out, mimc_hash(load_scalar(left), load_scalar(right)));
+    return BBP_OK;
+}
+
+int bbp_mimc_constants(uint8_t out[90 * 32]) {
+    if (!out) return BBP_ERR_INPUT;
+    const std::vector<sc> &c = mimc_constants();
+    for (size_t i = 0; i < c.size(); i++) sc_tobytes(out + 32 * i, c[i]);
+    return BBP_OK;
+}
+
+int bbp_blindbid_circuit_shape(size_t n_commitments, size_t n_toggles, size_t out[3]) {
+    if (!out || n_commitments < 4 || n_toggles < 1 || n_toggles > 100000) return BBP_ERR_INPUT;
+    std::shared_ptr<const circuit_template> t = blindbid_template((uint32_t)n_commitments, (uint32_t)n_toggles);
+    out[0] = t->n1; out[1] = t->q; out[2] = t->m;
+    return BBP_OK;
+}
+
+// test hook: Pedersen commitments v*B + r*B_blinding for n (value, blinding) pairs
+int bbp_pedersen_commit(bbp_ctx *ctx, const uint8_t *values, const uint8_t *blindings, size_t n, uint8_t *out) {
+    if (!ctx || !values || !blindings || !out || n == 0) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    int rc = proto_tables(ctx);
+    if (rc) return rc;
+    std::vector<sc> vals(2 * n);
+    for (size_t i = 0; i < n; i++) { vals[2 * i] = load_scalar(values + 32 * i); vals[2 * i + 1] = load_scalar(blindings + 32 * i); }
+    return pedersen_commit_host(ctx, vals.data(), n, out);
+}
+
+// n_slots MSMs over the resident generator table [B, B_blinding, G.., H..]; scalars = n_slots x slot_len x 32 B (host)
+int bbp_msm_gens(bbp_ctx *ctx, const uint8_t *scalars, size_t slot_len, size_t n_slots, uint8_t *out) {
+    if (!ctx || !scalars || !out || slot_len == 0 || n_slots == 0 || slot_len * n_slots > 0x7fffffffu) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    int rc = proto_tables(ctx);
+    if (rc) return rc;
+    if ((rc = ctx->stage_in(scalars, slot_len * n_slots * 32))) return rc;
+    if ((rc = ctx->reserve_out(n_slots * 32))) return rc;
+    if ((rc = msm_gens_device(ctx, (const sc *)ctx->d_in, (uint32_t)slot_len, (uint32_t)n_slots, ctx->d_out, nullptr))) return rc;
+    BBP_CUDA_OK(cudaMemcpyAsync(out, ctx->d_out, n_slots * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return BBP_OK;
 }
 
 }  // extern "C"

@@ -8,6 +8,8 @@
 #include "keccak.h"
 #include "msm.cuh"
 
+namespace bbp { struct proto_state; void proto_release(proto_state *); }
+
 struct bbp_points {
     bbp_ctx *ctx = nullptr;
     size_t n = 0;
@@ -28,6 +30,8 @@ struct bbp_ctx {
     // fixed-base window table over the generator set (built on demand)
     uint8_t *d_gens_wtable = nullptr;
     uint32_t wtable_c = 0, wtable_W = 0;
+    // protocol layer state (templates, tables, scratch): protocol.cuh
+    bbp::proto_state *proto = nullptr;
     // staging
     uint8_t *d_in = nullptr, *d_out = nullptr;
     size_t cap_in = 0, cap_out = 0;
@@ -104,6 +108,8 @@ struct bbp_ctx {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         msm.release();
+        bbp::proto_release(proto);
+        proto = nullptr;
         cudaFree(d_gens_ext); cudaFree(d_gens_niels); cudaFree(d_gens_wtable); cudaFree(d_in); cudaFree(d_out);
         if (stream) cudaStreamDestroy(stream);
         stream = nullptr;

@@ -1,0 +1,714 @@
+// Batched blind-bid prover and verifier on one B200 (host orchestration; kernels in sc_kernels.cuh / msm.cuh /
+// fixedbase.cuh). Mirrors Proof::prove (src/blindbid/proof.rs:36-91) and Verify::verify (src/blindbid/verify.rs:47-89)
+// including everything bulletproofs does underneath them (SURVEY.md §8 a-4 .. a-8), for a whole batch of requests at
+// once: the reference serves one request per pool thread (src/futures/main.rs:52-62), here one launch serves them all.
+//
+// Division of labour
+//   host (one thread per proof, std::thread)  Merlin transcripts, TranscriptRng draws, witness evaluation, (de)serialisation
+//   GPU                                       every group operation and every O(n) scalar vector operation
+// There is no CPU implementation of the group: without the kernels nothing here can produce a point.
+//
+// RNG contract: callers pass the commitment blindings and the 32 "external" bytes that the reference
+// takes from thread_rng inside TranscriptRngBuilder::finalize; with those fixed every proof byte is deterministic.
+#pragma once
+#include <atomic>
+#include <map>
+#include <memory>
+#include <thread>
+#include "circuit.h"
+#include "ctx.cuh"
+#include "fixedbase.cuh"
+#include "sc_kernels.cuh"
+
+namespace bbp {
+
+// ---------------------------------------------------------------- small host utilities
+template <class F>
+inline void parallel_for(size_t n, F fn) {
+    size_t hw = std::thread::hardware_concurrency();
+    size_t nt = std::min<size_t>(std::max<size_t>(hw, 1), std::min<size_t>(n, 64));
+    if (nt <= 1) { for (size_t i = 0; i < n; i++) fn(i); return; }
+    std::atomic<size_t> next(0);
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++)
+        th.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < n;) fn(i); });
+    for (auto &x : th) x.join();
+}
+
+struct dev_buf {
+    uint8_t *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4;
+        if (cudaMalloc(&p, want) != cudaSuccess) { fprintf(stderr, "bbp: cudaMalloc(%zu) failed\n", want); return BBP_ERR_CUDA; }
+        cap = want;
+        return 0;
+    }
+    void release() { cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+struct dev_template {
+    std::shared_ptr<const circuit_template> tpl;
+    uint32_t *row_ptr = nullptr, *entries = nullptr, *const_j = nullptr, *const_idx = nullptr;
+};
+
+static const uint32_t WT_C = 11, WT_W = 24;   // window table over the generators: 24 windows of 11 bits (264 >= 254 bits)
+
+struct proto_state {
+    std::map<uint64_t, dev_template> templates;
+    uint8_t *comb = nullptr;       // Pedersen comb table
+    uint8_t *wtable = nullptr;     // generator window table, WT_W rows of n_gens niels entries
+    dev_buf chal, zpow, ypow, yinvpow, wit, vbl, blind3, poly, tout, a, b, sG, sH, slots, ab, pub, dyn_sc, dyn_pts, dyn_niels, stat, stat_red,
+        msm_out, msm_ext, flags, valid, commit_in, commit_out;
+    int proof_versioned = 1;       // R1CSProof::to_bytes layout (SURVEY.md §8c risk R1): 1 = leading phase byte, 0 = legacy 14-point form
+};
+
+inline proto_state *proto_get(bbp_ctx *ctx) {
+    if (!ctx->proto) ctx->proto = new proto_state();
+    return ctx->proto;
+}
+
+void proto_release(proto_state *ps) {
+    if (!ps) return;
+    for (auto &kv : ps->templates) { cudaFree(kv.second.row_ptr); cudaFree(kv.second.entries); cudaFree(kv.second.const_j); cudaFree(kv.second.const_idx); }
+    cudaFree(ps->comb); cudaFree(ps->wtable);
+    dev_buf *all[] = {&ps->chal, &ps->zpow, &ps->ypow, &ps->yinvpow, &ps->wit, &ps->vbl, &ps->blind3, &ps->poly, &ps->tout, &ps->a, &ps->b, &ps->sG, &ps->sH,
+                      &ps->slots, &ps->ab, &ps->pub, &ps->dyn_sc, &ps->dyn_pts, &ps->dyn_niels, &ps->stat, &ps->stat_red, &ps->msm_out, &ps->msm_ext,
+                      &ps->flags, &ps->valid, &ps->commit_in, &ps->commit_out};
+    for (dev_buf *b : all) b->release();
+    delete ps;
+}
+
+// one-time tables that need the generator set of the context
+inline int proto_tables(bbp_ctx *ctx) {
+    proto_state *ps = proto_get(ctx);
+    if (ctx->n_gens < 2) return BBP_ERR_INVALID_GENERATORS_LENGTH;
+    if (!ps->comb) {
+        BBP_CUDA_OK(cudaMalloc(&ps->comb, (size_t)BBP_COMB_ENTRIES * 96));
+        k_build_comb<<<1, 128, 0, ctx->stream>>>(ctx->d_gens_ext, ps->comb);
+        ctx->launches++;
+    }
+    if (!ps->wtable && ctx->n_gens > 2) {
+        BBP_CUDA_OK(cudaMalloc(&ps->wtable, (size_t)WT_W * ctx->n_gens * 96));
+        k_build_window_table<<<(unsigned)((ctx->n_gens + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_gens_ext, ps->wtable, (uint32_t)ctx->n_gens, WT_C, WT_W,
+                                                                                              (uint32_t)ctx->n_gens);
+        ctx->launches++;
+    }
+    BBP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+inline int proto_template(bbp_ctx *ctx, uint32_t n_commit, uint32_t n_toggle, dev_template **out) {
+    proto_state *ps = proto_get(ctx);
+    uint64_t key = ((uint64_t)n_commit << 32) | n_toggle;
+    auto it = ps->templates.find(key);
+    if (it == ps->templates.end()) {
+        dev_template dt;
+        dt.tpl = blindbid_template(n_commit, n_toggle);
+        const circuit_template &t = *dt.tpl;
+        BBP_CUDA_OK(cudaMalloc(&dt.row_ptr, t.row_ptr.size() * 4));
+        BBP_CUDA_OK(cudaMalloc(&dt.entries, std::max<size_t>(t.entries.size(), 1) * 4));
+        BBP_CUDA_OK(cudaMalloc(&dt.const_j, std::max<size_t>(t.const_j.size(), 1) * 4));
+        BBP_CUDA_OK(cudaMalloc(&dt.const_idx, std::max<size_t>(t.const_idx.size(), 1) * 4));
+        BBP_CUDA_OK(cudaMemcpyAsync(dt.row_ptr, t.row_ptr.data(), t.row_ptr.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        BBP_CUDA_OK(cudaMemcpyAsync(dt.entries, t.entries.data(), t.entries.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        BBP_CUDA_OK(cudaMemcpyAsync(dt.const_j, t.const_j.data(), t.const_j.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        BBP_CUDA_OK(cudaMemcpyAsync(dt.const_idx, t.const_idx.data(), t.const_idx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        it = ps->templates.emplace(key, dt).first;
+    }
+    *out = &it->second;
+    return 0;
+}
+
+inline uint32_t next_pow2_u32(uint32_t n) { uint32_t p = 1; while (p < n) p <<= 1; return p; }
+inline uint32_t log2_u32(uint32_t n) { uint32_t l = 0; while ((1u << l) < n) l++; return l; }
+
+inline int h2d(bbp_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (!bytes) return 0;
+    BBP_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+inline int d2h_sync(bbp_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (bytes) BBP_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// n commitments v*B + r*B_blinding; vals = n x (value, blinding) reduced scalars on the host; out = n x 32 B on the host
+inline int pedersen_commit_host(bbp_ctx *ctx, const sc *vals, size_t n, uint8_t *out) {
+    proto_state *ps = proto_get(ctx);
+    int rc;
+    if ((rc = ps->commit_in.ensure(n * 64)) || (rc = ps->commit_out.ensure(n * 32))) return rc;
+    if ((rc = h2d(ctx, ps->commit_in.p, vals, n * 64))) return rc;
+    k_pedersen_commit<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ps->commit_in.as<sc>(), ps->comb, ps->commit_out.as<uint32_t>(), (uint32_t)n);
+    ctx->launches++;
+    return d2h_sync(ctx, out, ps->commit_out.p, n * 32);
+}
+
+// n_slots MSMs over the generator window table; scalars: n_slots x slot_len on the device (slot_len <= n_gens, column i
+// of a slot multiplies generator i). Results: compressed (n_slots x 32 B) and / or extended (n_slots x 128 B), on device.
+inline int msm_gens_device(bbp_ctx *ctx, const sc *d_scalars, uint32_t slot_len, uint32_t n_slots, uint8_t *d_out_compressed, uint8_t *d_out_ext) {
+    proto_state *ps = proto_get(ctx);
+    if (slot_len > ctx->n_gens || !ps->wtable) return BBP_ERR_INVALID_GENERATORS_LENGTH;
+    msm_shape sh = msm_engine::make_shape(n_slots * slot_len, slot_len, slot_len, true, WT_C, WT_W, (uint32_t)ctx->n_gens);
+    return ctx->msm.run(sh, (const uint8_t *)d_scalars, ps->wtable, d_out_ext, d_out_compressed);
+}
+
+// ================================================================ R1CSProof (de)serialisation
+struct r1cs_proof_host {
+    uint8_t A_I1[32], A_O1[32], S1[32], A_I2[32], A_O2[32], S2[32], T_1[32], T_3[32], T_4[32], T_5[32], T_6[32];
+    sc t_x, t_x_blinding, e_blinding;
+    std::vector<uint8_t> LR;   // L_0 R_0 L_1 R_1 ...
+    sc a, b;
+};
+
+inline bool all_zero32(const uint8_t *p) { uint8_t acc = 0; for (int i = 0; i < 32; i++) acc |= p[i]; return acc == 0; }
+
+// R1CSProof::to_bytes (call site src/blindbid/proof.rs:125)
+inline std::vector<uint8_t> r1cs_to_bytes(const r1cs_proof_host &p, bool versioned) {
+    std::vector<uint8_t> out;
+    auto put = [&](const uint8_t *b) { out.insert(out.end(), b, b + 32); };
+    auto puts = [&](const sc &s) { uint8_t t[32]; sc_tobytes(t, s); put(t); };
+    bool one_phase = all_zero32(p.A_I2) && all_zero32(p.A_O2) && all_zero32(p.S2);
+    if (versioned) out.push_back(one_phase ? 0 : 1);
+    put(p.A_I1); put(p.A_O1); put(p.S1);
+    if (!versioned || !one_phase) { put(p.A_I2); put(p.A_O2); put(p.S2); }
+    put(p.T_1); put(p.T_3); put(p.T_4); put(p.T_5); put(p.T_6);
+    puts(p.t_x); puts(p.t_x_blinding); puts(p.e_blinding);
+    out.insert(out.end(), p.LR.begin(), p.LR.end());
+    puts(p.a); puts(p.b);
+    return out;
+}
+
+// R1CSProof::from_bytes (call site src/blindbid/proof.rs:154); false = FormatError
+inline bool r1cs_from_bytes(r1cs_proof_host &p, const uint8_t *in, size_t len, bool versioned) {
+    int version = 1;
+    if (versioned) {
+        if (len < 1) return false;
+        version = in[0];
+        in++; len--;
+    }
+    if (len % 32 != 0) return false;
+    size_t minlen;
+    if (version == 0) minlen = 11 * 32;
+    else if (version == 1) minlen = 14 * 32;
+    else return false;
+    if (len < minlen) return false;
+    size_t pos = 0;
+    auto get = [&](uint8_t *b) { memcpy(b, in + pos, 32); pos += 32; };
+    get(p.A_I1); get(p.A_O1); get(p.S1);
+    if (version == 0) { memset(p.A_I2, 0, 32); memset(p.A_O2, 0, 32); memset(p.S2, 0, 32); }
+    else { get(p.A_I2); get(p.A_O2); get(p.S2); }
+    get(p.T_1); get(p.T_3); get(p.T_4); get(p.T_5); get(p.T_6);
+    if (!sc_from_canonical(p.t_x, in + pos)) return false;
+    pos += 32;
+    if (!sc_from_canonical(p.t_x_blinding, in + pos)) return false;
+    pos += 32;
+    if (!sc_from_canonical(p.e_blinding, in + pos)) return false;
+    pos += 32;
+    // InnerProductProof::from_bytes
+    size_t rest = len - pos, ne = rest / 32;
+    if (ne < 2 || (ne - 2) % 2 != 0) return false;
+    size_t lg_n = (ne - 2) / 2;
+    if (lg_n >= 32) return false;
+    p.LR.assign(in + pos, in + pos + 64 * lg_n);
+    if (!sc_from_canonical(p.a, in + pos + 64 * lg_n)) return false;
+    if (!sc_from_canonical(p.b, in + pos + 64 * lg_n + 32)) return false;
+    return true;
+}
+
+// ================================================================ prover
+struct prove_job {
+    // inputs (all reduced / parsed by the caller of prove_batch)
+    sc d, k, y, y_inv, q, z_img, seed;
+    std::vector<sc> pub_list;       // L items (Scalar::from_bits semantics applied)
+    uint64_t toggle = 0;
+    std::vector<sc> blindings;      // 4 + L
+    uint8_t rng_seed[32];
+    // outputs
+    int status = 0;
+    std::vector<uint8_t> proof;
+    std::vector<uint8_t> commitments, t_c;   // 4 x 32, L x 32
+};
+
+// proves jobs[idx[0..B)] — all with the same list length L
+inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::vector<size_t> &idx) {
+    proto_state *ps = proto_get(ctx);
+    const uint32_t B = (uint32_t)idx.size();
+    const uint32_t L = (uint32_t)jobs[idx[0]].pub_list.size();
+    int rc;
+    if ((rc = proto_tables(ctx))) return rc;
+    dev_template *dt;
+    if ((rc = proto_template(ctx, 4, L, &dt))) return rc;
+    const circuit_template &T = *dt->tpl;
+    const uint32_t n1 = T.n1, m = T.m, n = next_pow2_u32(n1), lg = log2_u32(n), slot_len = 2 + 2 * n;
+    if (n > ctx->gens_capacity || ctx->party_capacity < 1) {   // bp_gens.gens_capacity < padded_n -> InvalidGeneratorsLength
+        for (size_t i : idx) jobs[i].status = BBP_ERR_INVALID_GENERATORS_LENGTH;
+        return 0;
+    }
+
+    struct hstate {
+        std::unique_ptr<merlin_transcript> tr;
+        std::unique_ptr<merlin_rng> rng;
+        evaluator ev;
+        std::vector<sc> pub, v;
+        r1cs_proof_host pf;
+        sc i_bl, o_bl, s_bl, tbl[6];   // tbl[1] (t_2 blinding) comes from the device
+    };
+    std::vector<hstate> hs(B);
+
+    // ---- phase 0: witness + V commitments
+    std::vector<sc> commit_vals((size_t)B * m * 2);
+    parallel_for(B, [&](size_t bi) {
+        prove_job &J = jobs[idx[bi]];
+        hstate &H = hs[bi];
+        H.v = {J.d, J.k, J.y, J.y_inv};
+        for (uint32_t i = 0; i < L; i++) H.v.push_back(sc_from_u64((uint64_t)i == J.toggle ? 1 : 0));
+        for (uint32_t i = 0; i < m; i++) { commit_vals[((size_t)bi * m + i) * 2] = H.v[i]; commit_vals[((size_t)bi * m + i) * 2 + 1] = J.blindings[i]; }
+        fill_public_values(H.pub, J.seed, J.q, J.z_img, J.pub_list.data(), L);
+        H.ev.pub = H.pub.data();
+        H.ev.a_L.reserve(n1); H.ev.a_R.reserve(n1); H.ev.a_O.reserve(n1);
+        std::vector<sc> toggles(H.v.begin() + 4, H.v.end()), items(J.pub_list.begin(), J.pub_list.end());
+        proof_gadget(H.ev, H.v[0], H.v[1], H.v[3], J.q, J.z_img, J.seed, toggles, items);
+    });
+    std::vector<uint8_t> V((size_t)B * m * 32);
+    if ((rc = pedersen_commit_host(ctx, commit_vals.data(), (size_t)B * m, V.data()))) return rc;
+
+    // ---- phase 1: transcript up to the blinding draws; upload witness
+    std::vector<sc> wit((size_t)B * 5 * n1), vbl((size_t)B * m), blind3((size_t)B * 3);
+    parallel_for(B, [&](size_t bi) {
+        prove_job &J = jobs[idx[bi]];
+        hstate &H = hs[bi];
+        H.tr.reset(new merlin_transcript("BlindBidProofGadget"));   // src/blindbid/mod.rs:37
+        H.tr->r1cs_domain_sep();                                      // Prover::new
+        for (uint32_t i = 0; i < m; i++) H.tr->append_point("V", &V[((size_t)bi * m + i) * 32]);
+        J.commitments.assign(&V[(size_t)bi * m * 32], &V[(size_t)bi * m * 32] + 4 * 32);
+        J.t_c.assign(&V[((size_t)bi * m + 4) * 32], &V[((size_t)bi * m + 4) * 32] + (size_t)L * 32);
+        H.tr->append_u64("m", m);
+        merlin_rng_builder rb = H.tr->build_rng();
+        for (uint32_t i = 0; i < m; i++) {
+            uint8_t b[32];
+            sc_tobytes(b, J.blindings[i]);
+            rb.rekey_with_witness_bytes("v_blinding", b, 32);
+            vbl[(size_t)bi * m + i] = J.blindings[i];
+        }
+        H.rng.reset(new merlin_rng(rb.finalize(J.rng_seed)));
+        H.i_bl = H.rng->random_scalar(); H.o_bl = H.rng->random_scalar(); H.s_bl = H.rng->random_scalar();
+        blind3[bi * 3] = H.i_bl; blind3[bi * 3 + 1] = H.o_bl; blind3[bi * 3 + 2] = H.s_bl;
+        // witness layout: vector-major [a_L | a_R | a_O | s_L | s_R], each B x n1
+        auto W = [&](uint32_t k) { return &wit[((size_t)k * B + bi) * n1]; };
+        for (uint32_t i = 0; i < n1; i++) { W(0)[i] = H.ev.a_L[i]; W(1)[i] = H.ev.a_R[i]; W(2)[i] = H.ev.a_O[i]; }
+        for (uint32_t i = 0; i < n1; i++) W(3)[i] = H.rng->random_scalar();   // s_L
+        for (uint32_t i = 0; i < n1; i++) W(4)[i] = H.rng->random_scalar();   // s_R
+    });
+
+    // device buffers
+    if ((rc = ps->chal.ensure((size_t)B * CH_N * 32)) || (rc = ps->zpow.ensure((size_t)B * T.q * 32)) || (rc = ps->ypow.ensure((size_t)B * n * 32)) ||
+        (rc = ps->yinvpow.ensure((size_t)B * n * 32)) || (rc = ps->wit.ensure((size_t)B * 5 * n1 * 32)) || (rc = ps->vbl.ensure((size_t)B * m * 32)) ||
+        (rc = ps->blind3.ensure((size_t)B * 96)) || (rc = ps->poly.ensure((size_t)B * 6 * n1 * 32)) || (rc = ps->tout.ensure((size_t)B * 8 * 32)) ||
+        (rc = ps->a.ensure((size_t)B * n * 32)) || (rc = ps->b.ensure((size_t)B * n * 32)) || (rc = ps->sG.ensure((size_t)B * n * 32)) ||
+        (rc = ps->sH.ensure((size_t)B * n * 32)) || (rc = ps->slots.ensure((size_t)B * 3 * slot_len * 32)) || (rc = ps->ab.ensure((size_t)B * 64)) ||
+        (rc = ps->msm_out.ensure((size_t)B * 3 * 32)))
+        return rc;
+    if ((rc = h2d(ctx, ps->wit.p, wit.data(), wit.size() * 32)) || (rc = h2d(ctx, ps->vbl.p, vbl.data(), vbl.size() * 32)) ||
+        (rc = h2d(ctx, ps->blind3.p, blind3.data(), blind3.size() * 32)))
+        return rc;
+
+    sc_batch SB;
+    memset(&SB, 0, sizeof SB);
+    SB.n_proofs = B; SB.n1 = n1; SB.q = T.q; SB.m = m; SB.n = n; SB.lg_n = lg; SB.n_pub = T.n_pub;
+    SB.row_ptr = dt->row_ptr; SB.entries = dt->entries; SB.const_j = dt->const_j; SB.const_idx = dt->const_idx; SB.n_const = (uint32_t)T.const_j.size();
+    SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>();
+    const sc *dw = ps->wit.as<sc>();
+    const size_t vs = (size_t)B * n1;
+    SB.aL = dw; SB.aR = dw + vs; SB.aO = dw + 2 * vs; SB.sL = dw + 3 * vs; SB.sR = dw + 4 * vs;
+    SB.vbl = ps->vbl.as<sc>(); SB.blind3 = ps->blind3.as<sc>(); SB.poly = ps->poly.as<sc>(); SB.tout = ps->tout.as<sc>();
+    SB.a = ps->a.as<sc>(); SB.b = ps->b.as<sc>(); SB.sG = ps->sG.as<sc>(); SB.sH = ps->sH.as<sc>(); SB.slots = ps->slots.as<sc>(); SB.ab_out = ps->ab.as<sc>();
+
+    // ---- phase 2 (GPU): A_I1, A_O1, S1
+    k_commit_slots<<<3 * B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+    ctx->launches++;
+    if ((rc = msm_gens_device(ctx, SB.slots, slot_len, 3 * B, ps->msm_out.p, nullptr))) return rc;
+    std::vector<uint8_t> pts((size_t)B * 3 * 32);
+    if ((rc = d2h_sync(ctx, pts.data(), ps->msm_out.p, pts.size()))) return rc;
+
+    // ---- phase 3 (host): y, z
+    std::vector<sc> chal((size_t)B * CH_N, sc_zero());
+    parallel_for(B, [&](size_t bi) {
+        hstate &H = hs[bi];
+        r1cs_proof_host &P = H.pf;
+        memcpy(P.A_I1, &pts[(bi * 3) * 32], 32); memcpy(P.A_O1, &pts[(bi * 3 + 1) * 32], 32); memcpy(P.S1, &pts[(bi * 3 + 2) * 32], 32);
+        H.tr->append_point("A_I1", P.A_I1); H.tr->append_point("A_O1", P.A_O1); H.tr->append_point("S1", P.S1);
+        H.tr->r1cs_1phase_domain_sep();     // the circuit has no randomised (second phase) constraints
+        memset(P.A_I2, 0, 32); memset(P.A_O2, 0, 32); memset(P.S2, 0, 32);
+        H.tr->append_point("A_I2", P.A_I2); H.tr->append_point("A_O2", P.A_O2); H.tr->append_point("S2", P.S2);
+        sc *c = &chal[bi * CH_N];
+        c[CH_Y] = H.tr->challenge_scalar("y");
+        c[CH_Z] = H.tr->challenge_scalar("z");
+        c[CH_YINV] = sc_invert(c[CH_Y]);
+    });
+    if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32))) return rc;
+
+    // ---- phase 4 (GPU): power tables, flattened constraints, l / r polynomials, t_1 .. t_6
+    k_powers<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+    k_polys<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+    ctx->launches += 2;
+    std::vector<sc> tout((size_t)B * 8);
+    if ((rc = d2h_sync(ctx, tout.data(), ps->tout.p, tout.size() * 32))) return rc;
+
+    // ---- phase 5: T_1, T_3, T_4, T_5, T_6
+    std::vector<sc> tvals((size_t)B * 5 * 2);
+    parallel_for(B, [&](size_t bi) {
+        hstate &H = hs[bi];
+        static const int tk[5] = {0, 2, 3, 4, 5};   // t_1, t_3, t_4, t_5, t_6
+        for (int k = 0; k < 5; k++) {
+            H.tbl[tk[k]] = H.rng->random_scalar();
+            tvals[(bi * 5 + k) * 2] = tout[bi * 8 + tk[k]];
+            tvals[(bi * 5 + k) * 2 + 1] = H.tbl[tk[k]];
+        }
+        H.tbl[1] = tout[bi * 8 + 6];   // t_2 blinding = <wV, v_blinding>
+    });
+    std::vector<uint8_t> Tp((size_t)B * 5 * 32);
+    if ((rc = pedersen_commit_host(ctx, tvals.data(), (size_t)B * 5, Tp.data()))) return rc;
+
+    // ---- phase 6 (host): u, x, t(x), blindings, w
+    parallel_for(B, [&](size_t bi) {
+        hstate &H = hs[bi];
+        r1cs_proof_host &P = H.pf;
+        memcpy(P.T_1, &Tp[(bi * 5) * 32], 32); memcpy(P.T_3, &Tp[(bi * 5 + 1) * 32], 32); memcpy(P.T_4, &Tp[(bi * 5 + 2) * 32], 32);
+        memcpy(P.T_5, &Tp[(bi * 5 + 3) * 32], 32); memcpy(P.T_6, &Tp[(bi * 5 + 4) * 32], 32);
+        H.tr->append_point("T_1", P.T_1); H.tr->append_point("T_3", P.T_3); H.tr->append_point("T_4", P.T_4);
+        H.tr->append_point("T_5", P.T_5); H.tr->append_point("T_6", P.T_6);
+        sc *c = &chal[bi * CH_N];
+        sc u = H.tr->challenge_scalar("u"), x = H.tr->challenge_scalar("x");
+        c[CH_U] = u; c[CH_X] = x;
+        const sc *t = &tout[bi * 8];
+        auto horner6 = [&](const sc *v) {   // x * (v0 + x (v1 + ... x v5))
+            sc acc = v[5];
+            for (int k = 4; k >= 0; k--) acc = sc_add(v[k], sc_mul(x, acc));
+            return sc_mul(x, acc);
+        };
+        P.t_x = horner6(t);
+        P.t_x_blinding = horner6(H.tbl);
+        P.e_blinding = sc_mul(x, sc_add(H.i_bl, sc_mul(x, sc_add(H.o_bl, sc_mul(x, H.s_bl)))));
+        H.tr->append_scalar("t_x", P.t_x);
+        H.tr->append_scalar("t_x_blinding", P.t_x_blinding);
+        H.tr->append_scalar("e_blinding", P.e_blinding);
+        c[CH_W] = H.tr->challenge_scalar("w");
+        H.tr->innerproduct_domain_sep(n);
+        P.LR.resize((size_t)64 * lg);
+    });
+    if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32))) return rc;
+
+    // ---- phase 7: inner-product argument, lg n rounds
+    k_ipp_init<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+    ctx->launches++;
+    std::vector<uint8_t> lr((size_t)B * 64);
+    for (uint32_t j = 0; j < lg; j++) {
+        k_ipp_round<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB, j, 0);
+        ctx->launches++;
+        if ((rc = msm_gens_device(ctx, SB.slots, slot_len, 2 * B, ps->msm_out.p, nullptr))) return rc;
+        if ((rc = d2h_sync(ctx, lr.data(), ps->msm_out.p, lr.size()))) return rc;
+        parallel_for(B, [&](size_t bi) {
+            hstate &H = hs[bi];
+            memcpy(&H.pf.LR[(size_t)64 * j], &lr[bi * 64], 64);
+            H.tr->append_point("L", &lr[bi * 64]);
+            H.tr->append_point("R", &lr[bi * 64 + 32]);
+            sc *c = &chal[bi * CH_N];
+            c[CH_UJ] = H.tr->challenge_scalar("u");
+            c[CH_UJINV] = sc_invert(c[CH_UJ]);
+        });
+        if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32))) return rc;
+    }
+    k_ipp_round<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB, lg, 1);
+    ctx->launches++;
+    std::vector<sc> ab((size_t)B * 2);
+    if ((rc = d2h_sync(ctx, ab.data(), ps->ab.p, ab.size() * 32))) return rc;
+    for (uint32_t bi = 0; bi < B; bi++) {
+        prove_job &J = jobs[idx[bi]];
+        hs[bi].pf.a = ab[bi * 2]; hs[bi].pf.b = ab[bi * 2 + 1];
+        J.proof = r1cs_to_bytes(hs[bi].pf, ps->proof_versioned != 0);
+        J.status = 0;
+    }
+    return 0;
+}
+
+// Proof::prove for a batch of requests; groups by list length
+inline int prove_batch(bbp_ctx *ctx, std::vector<prove_job> &jobs) {
+    std::map<size_t, std::vector<size_t>> groups;
+    for (size_t i = 0; i < jobs.size(); i++) {
+        prove_job &J = jobs[i];
+        size_t L = J.pub_list.size();
+        if (L == 0 || J.blindings.size() != 4 + L) { J.status = BBP_ERR_INPUT; continue; }   // the reference panics (gadgets.rs:103)
+        groups[L].push_back(i);
+    }
+    for (auto &g : groups) {
+        // bound the device footprint: at most 1024 proofs per launch group
+        for (size_t off = 0; off < g.second.size(); off += 1024) {
+            std::vector<size_t> part(g.second.begin() + off, g.second.begin() + std::min(g.second.size(), off + 1024));
+            int rc = prove_group(ctx, jobs, part);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+
+// ================================================================ verifier
+struct verify_job {
+    std::vector<uint8_t> proof, commitments, t_c;   // R1CSProof bytes, nc x 32, nt x 32
+    sc score, z_img, seed;
+    std::vector<sc> pub_list;
+    uint8_t rng_seed[32];
+    int status = 0;    // 0 = accept; BBP_ERR_FORMAT / BBP_ERR_VERIFICATION / BBP_ERR_INVALID_GENERATORS_LENGTH / BBP_ERR_INPUT otherwise
+};
+
+struct verify_prepared {
+    bool live = false;              // passed every host-side check; takes part in the GPU check
+    r1cs_proof_host pf;
+    uint32_t nc = 0, nt = 0, m = 0, n1 = 0, n = 0, lg = 0;
+    std::vector<sc> chal;           // CH_N
+    std::vector<sc> pub;
+    std::vector<sc> dyn_sc;         // dyn_stride host-side dynamic scalars (entries [0, m) are filled on the device)
+    std::vector<uint8_t> dyn_pts;   // dyn_stride x 32 compressed
+};
+
+// host part of Verifier::verify for one request: parse, replay the transcript, derive every challenge
+inline void verify_prepare(bbp_ctx *ctx, verify_job &J, verify_prepared &P, bool versioned) {
+    P.live = false;
+    if (!r1cs_from_bytes(P.pf, J.proof.data(), J.proof.size(), versioned)) { J.status = BBP_ERR_FORMAT; return; }
+    P.nc = (uint32_t)(J.commitments.size() / 32); P.nt = (uint32_t)(J.t_c.size() / 32);
+    // the reference indexes vars[0], vars[1], vars[3] and toggle[0], items[i] (panics otherwise: SURVEY.md §5)
+    if (P.nc < 4 || P.nt < 1 || J.pub_list.size() < P.nt) { J.status = BBP_ERR_FORMAT; return; }
+    P.m = P.nc + P.nt;
+    std::shared_ptr<const circuit_template> tpl = blindbid_template(P.nc, P.nt);
+    P.n1 = tpl->n1; P.n = next_pow2_u32(P.n1); P.lg = log2_u32(P.n);
+    const r1cs_proof_host &pf = P.pf;
+    merlin_transcript tr("BlindBidProofGadget");
+    tr.r1cs_domain_sep();
+    for (uint32_t i = 0; i < P.nc; i++) tr.append_point("V", &J.commitments[32 * (size_t)i]);
+    for (uint32_t i = 0; i < P.nt; i++) tr.append_point("V", &J.t_c[32 * (size_t)i]);
+    tr.append_u64("m", P.m);
+    if (!tr.validate_and_append_point("A_I1", pf.A_I1) || !tr.validate_and_append_point("A_O1", pf.A_O1) || !tr.validate_and_append_point("S1", pf.S1)) {
+        J.status = BBP_ERR_VERIFICATION; return;
+    }
+    tr.r1cs_1phase_domain_sep();
+    if (P.n > ctx->gens_capacity || ctx->party_capacity < 1) { J.status = BBP_ERR_INVALID_GENERATORS_LENGTH; return; }
+    tr.append_point("A_I2", pf.A_I2); tr.append_point("A_O2", pf.A_O2); tr.append_point("S2", pf.S2);
+    P.chal.assign(CH_N, sc_zero());
+    sc *c = P.chal.data();
+    sc y = tr.challenge_scalar("y"), z = tr.challenge_scalar("z");
+    if (!tr.validate_and_append_point("T_1", pf.T_1) || !tr.validate_and_append_point("T_3", pf.T_3) || !tr.validate_and_append_point("T_4", pf.T_4) ||
+        !tr.validate_and_append_point("T_5", pf.T_5) || !tr.validate_and_append_point("T_6", pf.T_6)) {
+        J.status = BBP_ERR_VERIFICATION; return;
+    }
+    sc u = tr.challenge_scalar("u"), x = tr.challenge_scalar("x");
+    tr.append_scalar("t_x", pf.t_x);
+    tr.append_scalar("t_x_blinding", pf.t_x_blinding);
+    tr.append_scalar("e_blinding", pf.e_blinding);
+    sc w = tr.challenge_scalar("w");
+    // InnerProductProof::verification_scalars
+    uint32_t lg_p = (uint32_t)(pf.LR.size() / 64);
+    if (lg_p >= 32 || P.n != (1u << lg_p)) { J.status = BBP_ERR_VERIFICATION; return; }
+    tr.innerproduct_domain_sep(P.n);
+    std::vector<sc> uj(lg_p);
+    for (uint32_t j = 0; j < lg_p; j++) {
+        if (!tr.validate_and_append_point("L", &pf.LR[64 * (size_t)j]) || !tr.validate_and_append_point("R", &pf.LR[64 * (size_t)j + 32])) {
+            J.status = BBP_ERR_VERIFICATION; return;
+        }
+        uj[j] = tr.challenge_scalar("u");
+    }
+    // batch inversion of y and the u_j (one exponentiation)
+    std::vector<sc> all(uj);
+    all.push_back(y);
+    std::vector<sc> pre(all.size());
+    sc acc = sc_one();
+    for (size_t i = 0; i < all.size(); i++) { pre[i] = acc; acc = sc_mul(acc, all[i]); }
+    sc inv = sc_invert(acc);
+    std::vector<sc> allinv(all.size());
+    for (size_t i = all.size(); i-- > 0;) { allinv[i] = sc_mul(inv, pre[i]); inv = sc_mul(inv, all[i]); }
+    merlin_rng rng = tr.build_rng().finalize(J.rng_seed);
+    sc r = rng.random_scalar();
+    c[CH_Y] = y; c[CH_YINV] = allinv[lg_p]; c[CH_Z] = z; c[CH_X] = x; c[CH_U] = u; c[CH_W] = w; c[CH_R] = r;
+    c[CH_A] = pf.a; c[CH_B] = pf.b; c[CH_TX] = pf.t_x; c[CH_TXBL] = pf.t_x_blinding; c[CH_EBL] = pf.e_blinding; c[CH_RHO] = sc_one();
+    for (uint32_t j = 0; j < lg_p; j++) { c[CH_UJ0 + j] = uj[j]; c[CH_UJ0 + lg_p + j] = allinv[j]; }
+    fill_public_values(P.pub, J.seed, J.score, J.z_img, J.pub_list.data(), P.nt);
+    // dynamic points / scalars: [V_0..V_{m-1} | A_I1 A_O1 S1 A_I2 A_O2 S2 | T_1 T_3 T_4 T_5 T_6 | L_j | R_j]
+    uint32_t ds = P.m + 11 + 2 * lg_p;
+    P.dyn_sc.assign(ds, sc_zero());
+    P.dyn_pts.resize((size_t)ds * 32);
+    memcpy(P.dyn_pts.data(), J.commitments.data(), (size_t)P.nc * 32);
+    memcpy(P.dyn_pts.data() + (size_t)P.nc * 32, J.t_c.data(), (size_t)P.nt * 32);
+    const uint8_t *fixed_pts[11] = {pf.A_I1, pf.A_O1, pf.S1, pf.A_I2, pf.A_O2, pf.S2, pf.T_1, pf.T_3, pf.T_4, pf.T_5, pf.T_6};
+    for (int k = 0; k < 11; k++) memcpy(P.dyn_pts.data() + (size_t)(P.m + k) * 32, fixed_pts[k], 32);
+    sc xx = sc_mul(x, x), xxx = sc_mul(xx, x), rxx = sc_mul(r, xx);
+    sc *d = P.dyn_sc.data() + P.m;
+    d[0] = x; d[1] = xx; d[2] = xxx; d[3] = sc_mul(u, x); d[4] = sc_mul(u, xx); d[5] = sc_mul(u, xxx);
+    d[6] = sc_mul(r, x); d[7] = sc_mul(rxx, x); d[8] = sc_mul(rxx, xx); d[9] = sc_mul(rxx, xxx); d[10] = sc_mul(sc_mul(rxx, xx), xx);
+    for (uint32_t j = 0; j < lg_p; j++) {
+        memcpy(P.dyn_pts.data() + (size_t)(P.m + 11 + j) * 32, &pf.LR[64 * (size_t)j], 32);
+        memcpy(P.dyn_pts.data() + (size_t)(P.m + 11 + lg_p + j) * 32, &pf.LR[64 * (size_t)j + 32], 32);
+        d[11 + j] = sc_mul(uj[j], uj[j]);
+        d[11 + lg_p + j] = sc_mul(allinv[j], allinv[j]);
+    }
+    P.live = true;
+}
+
+// GPU part for prepared requests idx[0..B) that share (nc, nt). combined = false: one verdict per request (rho = 1);
+// combined = true: one random linear combination (weights rho[bi]) -> a single verdict. Verdicts: 1 = mega-check is the identity.
+// Requests with a point that fails to decompress get status VERIFICATION and weight zero.
+inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector<verify_prepared> &prep, const std::vector<size_t> &idx, bool combined,
+                        const std::vector<sc> *rho, std::vector<uint8_t> &verdicts, uint8_t *d_partial_ext /* combined: 2 x 128 B, optional */) {
+    proto_state *ps = proto_get(ctx);
+    const uint32_t B = (uint32_t)idx.size();
+    const verify_prepared &P0 = prep[idx[0]];
+    int rc;
+    if ((rc = proto_tables(ctx))) return rc;
+    dev_template *dt;
+    if ((rc = proto_template(ctx, P0.nc, P0.nt, &dt))) return rc;
+    const circuit_template &T = *dt->tpl;
+    const uint32_t n1 = T.n1, m = T.m, n = P0.n, lg = P0.lg, slot_len = 2 + 2 * n, ds = m + 11 + 2 * lg;
+    const uint32_t n_groups = combined ? 1 : B;
+
+    // ---- dynamic points first: a failed decompression removes the request from the check
+    std::vector<uint8_t> dyn_pts((size_t)B * ds * 32);
+    for (uint32_t bi = 0; bi < B; bi++) memcpy(&dyn_pts[(size_t)bi * ds * 32], prep[idx[bi]].dyn_pts.data(), (size_t)ds * 32);
+    if ((rc = ps->dyn_pts.ensure(dyn_pts.size())) || (rc = ps->dyn_niels.ensure((size_t)B * ds * 96)) || (rc = ps->valid.ensure((size_t)B * ds + 4))) return rc;
+    if ((rc = h2d(ctx, ps->dyn_pts.p, dyn_pts.data(), dyn_pts.size()))) return rc;
+    int *d_all = (int *)(ps->valid.p + (((size_t)B * ds + 3) & ~(size_t)3));
+    if ((rc = ps->valid.ensure((((size_t)B * ds + 3) & ~(size_t)3) + 4))) return rc;
+    d_all = (int *)(ps->valid.p + (((size_t)B * ds + 3) & ~(size_t)3));
+    BBP_CUDA_OK(cudaMemsetAsync(d_all, 1, 4, ctx->stream));
+    k_decompress_to_niels<<<(B * ds + 127) / 128, 128, 0, ctx->stream>>>(ps->dyn_pts.as<uint32_t>(), ps->dyn_niels.p, B * ds, d_all, ps->valid.p);
+    ctx->launches++;
+    std::vector<uint8_t> valid((size_t)B * ds);
+    if ((rc = d2h_sync(ctx, valid.data(), ps->valid.p, valid.size()))) return rc;
+
+    std::vector<sc> chal((size_t)B * CH_N), pub((size_t)B * T.n_pub), dyn_sc((size_t)B * ds);
+    std::vector<uint8_t> alive(B, 1);
+    for (uint32_t bi = 0; bi < B; bi++) {
+        verify_prepared &P = prep[idx[bi]];
+        for (uint32_t k = 0; k < ds; k++)
+            if (!valid[(size_t)bi * ds + k]) alive[bi] = 0;
+        if (!alive[bi]) jobs[idx[bi]].status = BBP_ERR_VERIFICATION;   // optional_multiscalar_mul -> None -> VerificationError
+        sc w = alive[bi] ? (rho ? (*rho)[bi] : sc_one()) : sc_zero();
+        P.chal[CH_RHO] = w;
+        memcpy(&chal[(size_t)bi * CH_N], P.chal.data(), (size_t)CH_N * 32);
+        memcpy(&pub[(size_t)bi * T.n_pub], P.pub.data(), (size_t)T.n_pub * 32);
+        bool unit = sc_eq(w, sc_one());
+        for (uint32_t k = 0; k < ds; k++) dyn_sc[(size_t)bi * ds + k] = unit ? P.dyn_sc[k] : sc_mul(w, P.dyn_sc[k]);
+    }
+    if ((rc = ps->chal.ensure(chal.size() * 32)) || (rc = ps->pub.ensure(pub.size() * 32)) || (rc = ps->dyn_sc.ensure(dyn_sc.size() * 32)) ||
+        (rc = ps->zpow.ensure((size_t)B * T.q * 32)) || (rc = ps->ypow.ensure((size_t)B * n * 32)) || (rc = ps->yinvpow.ensure((size_t)B * n * 32)) ||
+        (rc = ps->stat.ensure((size_t)B * slot_len * 32)) || (rc = ps->stat_red.ensure((size_t)n_groups * slot_len * 32)) ||
+        (rc = ps->msm_ext.ensure((size_t)2 * n_groups * 128)) || (rc = ps->flags.ensure(n_groups)))
+        return rc;
+    if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32)) || (rc = h2d(ctx, ps->pub.p, pub.data(), pub.size() * 32)) ||
+        (rc = h2d(ctx, ps->dyn_sc.p, dyn_sc.data(), dyn_sc.size() * 32)))
+        return rc;
+
+    sc_batch SB;
+    memset(&SB, 0, sizeof SB);
+    SB.n_proofs = B; SB.n1 = n1; SB.q = T.q; SB.m = m; SB.n = n; SB.lg_n = lg; SB.n_pub = T.n_pub;
+    SB.row_ptr = dt->row_ptr; SB.entries = dt->entries; SB.const_j = dt->const_j; SB.const_idx = dt->const_idx; SB.n_const = (uint32_t)T.const_j.size();
+    SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>();
+    SB.pub = ps->pub.as<sc>(); SB.dyn_out = ps->dyn_sc.as<sc>(); SB.dyn_stride = ds; SB.stat = ps->stat.as<sc>();
+    k_powers<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+    k_verify_scalars<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+    k_stat_reduce<<<dim3((slot_len + BBP_SC_THREADS - 1) / BBP_SC_THREADS, n_groups), BBP_SC_THREADS, 0, ctx->stream>>>(SB.stat, combined ? B : 1, slot_len,
+                                                                                                                         ps->stat_red.as<sc>());
+    ctx->launches += 3;
+    // static bases: one fixed-table slot per group; dynamic bases: one variable-base slot per group
+    uint8_t *ext = ps->msm_ext.p;
+    if ((rc = msm_gens_device(ctx, ps->stat_red.as<sc>(), slot_len, n_groups, nullptr, ext))) return rc;
+    uint32_t dyn_total = B * ds, per_slot = combined ? dyn_total : ds;
+    msm_shape sh = msm_engine::make_shape(dyn_total, per_slot, dyn_total, false, 0, 0, 0);
+    if ((rc = ctx->msm.run(sh, ps->dyn_sc.p, ps->dyn_niels.p, ext + (size_t)n_groups * 128, nullptr))) return rc;
+    k_group_sum_identity<<<(n_groups + 63) / 64, 64, 0, ctx->stream>>>(ext, n_groups, 2, n_groups, ps->flags.p, nullptr);
+    ctx->launches++;
+    if (combined && d_partial_ext) BBP_CUDA_OK(cudaMemcpyAsync(d_partial_ext, ext, 256, cudaMemcpyDeviceToDevice, ctx->stream));
+    std::vector<uint8_t> fl(n_groups);
+    if ((rc = d2h_sync(ctx, fl.data(), ps->flags.p, n_groups))) return rc;
+    verdicts.assign(n_groups, 0);
+    for (uint32_t g = 0; g < n_groups; g++) verdicts[g] = fl[g];
+    if (!combined)
+        for (uint32_t bi = 0; bi < B; bi++)
+            if (alive[bi]) jobs[idx[bi]].status = fl[bi] ? 0 : BBP_ERR_VERIFICATION;
+    return 0;
+}
+
+// Verify::verify for every request independently (exactly the reference's per-request semantics)
+inline int verify_each(bbp_ctx *ctx, std::vector<verify_job> &jobs) {
+    proto_state *ps = proto_get(ctx);
+    std::vector<verify_prepared> prep(jobs.size());
+    bool versioned = ps->proof_versioned != 0;
+    parallel_for(jobs.size(), [&](size_t i) { verify_prepare(ctx, jobs[i], prep[i], versioned); });
+    std::map<uint64_t, std::vector<size_t>> groups;
+    for (size_t i = 0; i < jobs.size(); i++)
+        if (prep[i].live) groups[((uint64_t)prep[i].nc << 32) | prep[i].nt].push_back(i);
+    for (auto &g : groups) {
+        for (size_t off = 0; off < g.second.size(); off += 1024) {
+            std::vector<size_t> part(g.second.begin() + off, g.second.begin() + std::min(g.second.size(), off + 1024));
+            std::vector<uint8_t> verdicts;
+            int rc = verify_group(ctx, jobs, prep, part, false, nullptr, verdicts, nullptr);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+// Batch verification: one random linear combination of all mega-checks, weights drawn from a
+// Merlin transcript over every proof plus the caller's seed. If the combination is the identity every live request is
+// accepted; otherwise the requests are re-checked individually, so the verdicts always equal those of verify_each.
+// partial_only: stop after the combined pass and leave this GPU's partial sum (static | dynamic, 2 x 128 B extended) in
+// d_partial_ext for a cross-GPU reduction (proof-range sharding); *all_ok then reports the local verdict.
+inline int verify_batch(bbp_ctx *ctx, std::vector<verify_job> &jobs, const uint8_t batch_seed[32], int *all_ok, bool partial_only, uint8_t *d_partial_ext) {
+    proto_state *ps = proto_get(ctx);
+    std::vector<verify_prepared> prep(jobs.size());
+    bool versioned = ps->proof_versioned != 0;
+    parallel_for(jobs.size(), [&](size_t i) { verify_prepare(ctx, jobs[i], prep[i], versioned); });
+    merlin_transcript bt("bbp batch verification");
+    for (auto &J : jobs) bt.append_message("proof", J.proof.data(), J.proof.size());
+    merlin_rng brng = bt.build_rng().finalize(batch_seed);
+    std::map<uint64_t, std::vector<size_t>> groups;
+    std::vector<sc> rho_all(jobs.size());
+    for (size_t i = 0; i < jobs.size(); i++) {
+        rho_all[i] = brng.random_scalar();
+        if (prep[i].live) groups[((uint64_t)prep[i].nc << 32) | prep[i].nt].push_back(i);
+    }
+    bool ok = true;
+    if (partial_only && groups.size() > 1) return BBP_ERR_INPUT;   // sharded mode expects one circuit shape per call
+    for (auto &g : groups) {
+        std::vector<sc> rho;
+        for (size_t i : g.second) rho.push_back(rho_all[i]);
+        std::vector<uint8_t> verdicts;
+        int rc = verify_group(ctx, jobs, prep, g.second, true, &rho, verdicts, d_partial_ext);
+        if (rc) return rc;
+        bool any_dead = false;
+        for (size_t i : g.second) any_dead = any_dead || jobs[i].status != 0;
+        if (verdicts[0] && !partial_only) {
+            for (size_t i : g.second) if (jobs[i].status == 0) jobs[i].status = 0;
+        } else if (!partial_only) {
+            for (size_t i : g.second) jobs[i].status = 0;
+            for (size_t off = 0; off < g.second.size(); off += 1024) {
+                std::vector<size_t> part;
+                for (size_t k = off; k < std::min(g.second.size(), off + 1024); k++) part.push_back(g.second[k]);
+                std::vector<uint8_t> v2;
+                rc = verify_group(ctx, jobs, prep, part, false, nullptr, v2, nullptr);
+                if (rc) return rc;
+            }
+        }
+        ok = ok && verdicts[0];
+        (void)any_dead;
+    }
+    for (auto &J : jobs) ok = ok && (J.status == 0 || partial_only);
+    if (all_ok) *all_ok = ok ? 1 : 0;
+    return 0;
+}
+
+}  // namespace bbp

@@ -1,0 +1,339 @@
+// Scalar-vector (mod l) kernels of the R1CS prover / verifier and the inner-product argument:
+// z / y power tables, the flattened-constraint sparse product, the l(x) / r(x) polynomial build with the t_1..t_6 inner
+// products, the IPP round (fold + cross inner products + product-form L / R scalars) and the verifier's g / h / s
+// assembly. They restate on the device what bulletproofs 1.0.4 @ 4a05305 computes inside Prover::prove,
+// InnerProductProof::create and Verifier::verify (call sites src/blindbid/proof.rs:88, src/blindbid/verify.rs:88;
+// algorithm SURVEY.md §8 a-5 .. a-8). One CTA per proof; a batch of proofs is one launch.
+//
+// Number format: every vector that lives across kernels is kept in Montgomery form (x * 2^256 mod l) so that a product
+// is ONE CIOS multiplication; inputs are converted on first load, MSM scalars / proof scalars on the last store.
+//
+// The IPP never folds the generator vectors. Round j needs L_j = <a_lo, G_hi> + <b_hi, H_lo> + c_L Q over the folded
+// bases; writing the folded bases out in terms of the ORIGINAL generators gives L_j = sum_i (a[..] * sG[i]) G[i] + ...
+// with sG[i] the running product of u_k^(+-1) selected by the bits of i. L_j and R_j are therefore plain MSMs over the
+// resident generator table with scalars computed here — the same group elements as the reference's folded form, hence
+// the same compressed bytes — and the ~63 % of CPU time the reference spends folding G / H disappears.
+#pragma once
+#include "sc25519.cuh"
+
+namespace bbp {
+
+#define BBP_SC_THREADS 256
+
+// per-proof challenge block (normal form, 32 B each)
+enum chal_slot : uint32_t {
+    CH_Y = 0, CH_YINV, CH_Z, CH_X, CH_U, CH_W, CH_UJ, CH_UJINV,   // prover + verifier
+    CH_R, CH_A, CH_B, CH_TX, CH_TXBL, CH_EBL, CH_RHO,             // verifier only
+    CH_UJ0,                                                        // verifier: u_0 .. u_{lg n - 1}, then their inverses
+    CH_N = CH_UJ0 + 64
+};
+
+struct sc_batch {
+    uint32_t n_proofs, n1, q, m, n, lg_n, n_pub;
+    const uint32_t *row_ptr, *entries;         // circuit template CSR (shared by the batch)
+    const uint32_t *const_j, *const_idx;       // constant terms (verifier)
+    uint32_t n_const;
+    const sc *chal;                            // [n_proofs][CH_N]
+    sc *zpow, *ypow, *yinvpow;                 // [n_proofs][q], [n_proofs][n], [n_proofs][n]   (Montgomery)
+    // prover
+    const sc *aL, *aR, *aO, *sL, *sR;          // [n_proofs][n1] normal form
+    const sc *vbl;                             // [n_proofs][m]
+    const sc *blind3;                          // [n_proofs][3]: i_blinding, o_blinding, s_blinding
+    sc *poly;                                  // [n_proofs][6][n1]: l1, l2, l3, r0, r1, r3 (Montgomery)
+    sc *tout;                                  // [n_proofs][8]: t1..t6, t2_blinding, spare (normal form)
+    sc *a, *b, *sG, *sH;                       // [n_proofs][n] (Montgomery)
+    sc *slots;                                 // MSM scalar slots, 2 + 2n scalars each (normal form)
+    sc *ab_out;                                // [n_proofs][2] final a, b
+    // verifier
+    const sc *pub;                             // [n_proofs][n_pub] public value tables (normal form)
+    sc *dyn_out;                               // [n_proofs][dyn_stride]: first m entries = rho * wV[i] * r * x^2 (written here)
+    uint32_t dyn_stride;
+    sc *stat;                                  // [n_proofs][2 + 2n] rho-weighted static-base scalars (Montgomery)
+};
+
+__device__ __forceinline__ sc sc_mont_one() { return sc_to_mont(sc_one()); }
+__device__ __forceinline__ sc mm(const sc &a, const sc &b) { return sc_montmul(a.v, b.v); }
+
+// base^e in the Montgomery domain, e < 2^16
+__device__ inline sc sc_pow_small_mont(const sc &baseM, uint32_t e) {
+    sc r = sc_mont_one();
+    for (int bit = 15; bit >= 0; bit--) {
+        r = mm(r, r);
+        if ((e >> bit) & 1) r = mm(r, baseM);
+    }
+    return r;
+}
+
+// sum over the block; result valid in every thread. smem: BBP_SC_THREADS entries.
+__device__ inline sc block_sum_sc(sc v, sc *smem) {
+    const uint32_t t = threadIdx.x;
+    smem[t] = v;
+    __syncthreads();
+    for (uint32_t s = BBP_SC_THREADS / 2; s >= 1; s >>= 1) {
+        if (t < s) smem[t] = sc_add(smem[t], smem[t + s]);
+        __syncthreads();
+    }
+    sc r = smem[0];
+    __syncthreads();
+    return r;
+}
+
+// ---------------------------------------------------------------- power tables
+// zpow[j] = z^(j+1), j < q ; ypow[i] = y^i, yinvpow[i] = y^-i, i < n. Each thread raises to its chunk start, then walks.
+__global__ void __launch_bounds__(BBP_SC_THREADS) k_powers(sc_batch B) {
+    const uint32_t p = blockIdx.x, t = threadIdx.x;
+    const sc *ch = B.chal + (size_t)p * CH_N;
+    sc zM = sc_to_mont(ch[CH_Z]), yM = sc_to_mont(ch[CH_Y]), yiM = sc_to_mont(ch[CH_YINV]);
+    {
+        uint32_t chunk = (B.q + BBP_SC_THREADS - 1) / BBP_SC_THREADS, j0 = t * chunk, j1 = min(j0 + chunk, B.q);
+        if (j0 < j1) {
+            sc cur = sc_pow_small_mont(zM, j0 + 1);
+            sc *out = B.zpow + (size_t)p * B.q;
+            for (uint32_t j = j0; j < j1; j++) { out[j] = cur; cur = mm(cur, zM); }
+        }
+    }
+    {
+        uint32_t chunk = (B.n + BBP_SC_THREADS - 1) / BBP_SC_THREADS, i0 = t * chunk, i1 = min(i0 + chunk, B.n);
+        if (i0 < i1) {
+            sc cy = sc_pow_small_mont(yM, i0), ci = sc_pow_small_mont(yiM, i0);
+            sc *oy = B.ypow + (size_t)p * B.n, *oi = B.yinvpow + (size_t)p * B.n;
+            for (uint32_t i = i0; i < i1; i++) { oy[i] = cy; oi[i] = ci; cy = mm(cy, yM); ci = mm(ci, yiM); }
+        }
+    }
+}
+
+// signed sum of z powers over one CSR row (Montgomery form)
+__device__ __forceinline__ sc flatten_row(const sc_batch &B, const sc *zpow, uint32_t row) {
+    sc acc = sc_zero();
+    for (uint32_t e = B.row_ptr[row]; e < B.row_ptr[row + 1]; e++) {
+        uint32_t v = B.entries[e];
+        const sc &zp = zpow[v & 0x7fffffffu];
+        acc = (v >> 31) ? sc_sub(acc, zp) : sc_add(acc, zp);
+    }
+    return acc;
+}
+
+// ---------------------------------------------------------------- prover: commitment scalar slots
+// slot layout = generator table order: [B, B_blinding, G[0..n), H[0..n)]. Three slots per proof:
+//   A_I1 = i_bl B_bl + <a_L, G> + <a_R, H>;  A_O1 = o_bl B_bl + <a_O, G>;  S1 = s_bl B_bl + <s_L, G> + <s_R, H>
+__global__ void __launch_bounds__(BBP_SC_THREADS) k_commit_slots(sc_batch B) {
+    const uint32_t p = blockIdx.x / 3, which = blockIdx.x % 3;
+    const uint32_t slot_len = 2 + 2 * B.n;
+    sc *out = B.slots + (size_t)blockIdx.x * slot_len;
+    const sc *g = (which == 0 ? B.aL : which == 1 ? B.aO : B.sL) + (size_t)p * B.n1;
+    const sc *h = (which == 0 ? B.aR : which == 1 ? nullptr : B.sR);
+    if (h) h += (size_t)p * B.n1;
+    for (uint32_t i = threadIdx.x; i < slot_len; i += BBP_SC_THREADS) {
+        sc v = sc_zero();
+        if (i == 1) v = B.blind3[(size_t)p * 3 + which];
+        else if (i >= 2 && i < 2 + B.n) { if (i - 2 < B.n1) v = g[i - 2]; }
+        else if (i >= 2 + B.n) { if (h && i - 2 - B.n < B.n1) v = h[i - 2 - B.n]; }
+        out[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------- prover: l / r polynomials and t_1 .. t_6
+__global__ void __launch_bounds__(BBP_SC_THREADS) k_polys(sc_batch B) {
+    __shared__ sc smem[BBP_SC_THREADS];
+    const uint32_t p = blockIdx.x, t = threadIdx.x, n1 = B.n1;
+    const sc *zpow = B.zpow + (size_t)p * B.q, *ypow = B.ypow + (size_t)p * B.n, *yinv = B.yinvpow + (size_t)p * B.n;
+    sc *poly = B.poly + (size_t)p * 6 * n1;
+    sc t1 = sc_zero(), t2 = t1, t3 = t1, t4 = t1, t5 = t1, t6 = t1;
+    for (uint32_t i = t; i < n1; i += BBP_SC_THREADS) {
+        sc wL = flatten_row(B, zpow, i), wR = flatten_row(B, zpow, n1 + i), wO = flatten_row(B, zpow, 2 * n1 + i);
+        size_t k = (size_t)p * n1 + i;
+        sc aL = sc_to_mont(B.aL[k]), aR = sc_to_mont(B.aR[k]), aO = sc_to_mont(B.aO[k]), sL = sc_to_mont(B.sL[k]), sR = sc_to_mont(B.sR[k]);
+        sc l1 = sc_add(aL, mm(yinv[i], wR));
+        sc r0 = sc_sub(wO, ypow[i]);
+        sc r1 = sc_add(mm(ypow[i], aR), wL);
+        sc r3 = mm(ypow[i], sR);
+        poly[i] = l1; poly[n1 + i] = aO; poly[2 * n1 + i] = sL; poly[3 * n1 + i] = r0; poly[4 * n1 + i] = r1; poly[5 * n1 + i] = r3;
+        t1 = sc_add(t1, mm(l1, r0));
+        t2 = sc_add(t2, sc_add(mm(l1, r1), mm(aO, r0)));
+        t3 = sc_add(t3, sc_add(mm(aO, r1), mm(sL, r0)));
+        t4 = sc_add(t4, sc_add(mm(l1, r3), mm(sL, r1)));
+        t5 = sc_add(t5, mm(aO, r3));
+        t6 = sc_add(t6, mm(sL, r3));
+    }
+    // t2_blinding = <wV, v_blinding>
+    sc tb = sc_zero();
+    for (uint32_t i = t; i < B.m; i += BBP_SC_THREADS) {
+        sc wV = flatten_row(B, zpow, 3 * n1 + i);
+        tb = sc_add(tb, mm(wV, sc_to_mont(B.vbl[(size_t)p * B.m + i])));
+    }
+    sc r[7] = {t1, t2, t3, t4, t5, t6, tb};
+    for (int k = 0; k < 7; k++) {
+        sc s = block_sum_sc(r[k], smem);
+        if (t == 0) B.tout[(size_t)p * 8 + k] = sc_from_mont(s);
+    }
+}
+
+// ---------------------------------------------------------------- prover: IPP set-up
+// a = l(x), b = r(x) padded to n (l = 0, r = -y^i beyond n1); sG = G_factors (1 | u), sH = y^-i * G_factors
+__global__ void __launch_bounds__(BBP_SC_THREADS) k_ipp_init(sc_batch B) {
+    const uint32_t p = blockIdx.x, n1 = B.n1;
+    const sc *ch = B.chal + (size_t)p * CH_N;
+    const sc *poly = B.poly + (size_t)p * 6 * n1, *ypow = B.ypow + (size_t)p * B.n, *yinv = B.yinvpow + (size_t)p * B.n;
+    sc xM = sc_to_mont(ch[CH_X]), uM = sc_to_mont(ch[CH_U]);
+    sc x2 = mm(xM, xM), x3 = mm(x2, xM), one = sc_mont_one();
+    for (uint32_t i = threadIdx.x; i < B.n; i += BBP_SC_THREADS) {
+        sc l, r, gf;
+        if (i < n1) {
+            l = sc_add(sc_add(mm(poly[i], xM), mm(poly[n1 + i], x2)), mm(poly[2 * n1 + i], x3));
+            r = sc_add(sc_add(poly[3 * n1 + i], mm(poly[4 * n1 + i], xM)), mm(poly[5 * n1 + i], x3));
+            gf = one;
+        } else {
+            l = sc_zero();
+            r = sc_neg(ypow[i]);
+            gf = uM;
+        }
+        size_t k = (size_t)p * B.n + i;
+        B.a[k] = l; B.b[k] = r; B.sG[k] = gf; B.sH[k] = mm(yinv[i], gf);
+    }
+}
+
+// ---------------------------------------------------------------- IPP round j (0-based)
+// 1. for j > 0: fold a, b with the previous challenge (CH_UJ / CH_UJINV) and extend the product-form factors sG, sH
+// 2. c_L = <a_lo, b_hi>, c_R = <a_hi, b_lo>
+// 3. write the L slot (2p) and R slot (2p + 1): coefficient on B is c * w (Q = w B), B_blinding gets 0
+// With fold_only the kernel stops after step 1 on the final length-1 vectors and emits a, b.
+__global__ void __launch_bounds__(BBP_SC_THREADS) k_ipp_round(sc_batch B, uint32_t j, uint32_t fold_only) {
+    __shared__ sc smem[BBP_SC_THREADS];
+    const uint32_t p = blockIdx.x, t = threadIdx.x, n = B.n;
+    const sc *ch = B.chal + (size_t)p * CH_N;
+    sc *a = B.a + (size_t)p * n, *b = B.b + (size_t)p * n, *sG = B.sG + (size_t)p * n, *sH = B.sH + (size_t)p * n;
+    const uint32_t nj = n >> j;           // current vector length
+    if (j > 0) {
+        sc uM = sc_to_mont(ch[CH_UJ]), uiM = sc_to_mont(ch[CH_UJINV]);
+        for (uint32_t k = t; k < nj; k += BBP_SC_THREADS) {
+            a[k] = sc_add(mm(a[k], uM), mm(uiM, a[nj + k]));
+            b[k] = sc_add(mm(b[k], uiM), mm(uM, b[nj + k]));
+        }
+        if (!fold_only) {
+            const uint32_t n_old = nj << 1;
+            for (uint32_t i = t; i < n; i += BBP_SC_THREADS) {
+                bool lo = (i & (n_old - 1)) < nj;
+                sG[i] = mm(sG[i], lo ? uiM : uM);
+                sH[i] = mm(sH[i], lo ? uM : uiM);
+            }
+        }
+        __syncthreads();
+    }
+    if (fold_only) {
+        if (t == 0) { B.ab_out[(size_t)p * 2] = sc_from_mont(a[0]); B.ab_out[(size_t)p * 2 + 1] = sc_from_mont(b[0]); }
+        return;
+    }
+    const uint32_t nh = nj >> 1;
+    sc cl = sc_zero(), cr = sc_zero();
+    for (uint32_t k = t; k < nh; k += BBP_SC_THREADS) {
+        cl = sc_add(cl, mm(a[k], b[nh + k]));
+        cr = sc_add(cr, mm(a[nh + k], b[k]));
+    }
+    cl = block_sum_sc(cl, smem);
+    cr = block_sum_sc(cr, smem);
+    const uint32_t slot_len = 2 + 2 * n;
+    sc *sl = B.slots + (size_t)(2 * p) * slot_len, *sr = sl + slot_len;
+    if (t == 0) {
+        sc wM = sc_to_mont(ch[CH_W]);
+        sl[0] = sc_from_mont(mm(cl, wM)); sr[0] = sc_from_mont(mm(cr, wM));
+        sl[1] = sc_zero(); sr[1] = sc_zero();
+    }
+    for (uint32_t i = t; i < n; i += BBP_SC_THREADS) {
+        uint32_t k = i & (nj - 1);
+        sc zero = sc_zero();
+        if (k >= nh) {   // G[i] sits in the high half of its block: L takes a_lo * G_hi, R takes b_lo * H_hi
+            sl[2 + i] = sc_from_mont(mm(a[k - nh], sG[i]));
+            sr[2 + i] = zero;
+            sl[2 + n + i] = zero;
+            sr[2 + n + i] = sc_from_mont(mm(b[k - nh], sH[i]));
+        } else {          // low half: R takes a_hi * G_lo, L takes b_hi * H_lo
+            sl[2 + i] = zero;
+            sr[2 + i] = sc_from_mont(mm(a[k + nh], sG[i]));
+            sl[2 + n + i] = sc_from_mont(mm(b[k + nh], sH[i]));
+            sr[2 + n + i] = zero;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- verifier scalar assembly
+// Per proof (weight rho, 1 for a single verification):
+//   stat[0]   (B)          rho * ( w (t_x - a b) + r (x^2 (wc + delta) - t_x) )
+//   stat[1]   (B_blinding) rho * ( -e_blinding - r t_x_blinding )
+//   stat[2+i] (G[i])       rho * uf[i] (x y^-i wR[i] - a s[i])
+//   stat[2+n+i] (H[i])     rho * uf[i] (y^-i (x wL[i] + wO[i] - b s[n-1-i]) - 1)
+//   dyn_out[i] = rho * wV[i] r x^2   (coefficients of the V commitments)
+// with s[i] = prod_j u_j^(+-1) (bit (lg n - 1 - j) of i set -> u_j, else u_j^-1), uf = 1 (i < n1) | u, delta = <y^-n wR, wL>.
+// Results stay in Montgomery form; k_stat_reduce sums them over the batch and converts.
+__global__ void __launch_bounds__(BBP_SC_THREADS) k_verify_scalars(sc_batch B) {
+    __shared__ sc smem[BBP_SC_THREADS];
+    __shared__ sc uj[64];
+    const uint32_t p = blockIdx.x, t = threadIdx.x, n = B.n, n1 = B.n1, lg = B.lg_n;
+    const sc *ch = B.chal + (size_t)p * CH_N;
+    const sc *zpow = B.zpow + (size_t)p * B.q, *yinv = B.yinvpow + (size_t)p * n;
+    if (t < 2 * lg) uj[t] = sc_to_mont(ch[CH_UJ0 + t]);   // u_0..u_{lg-1}, then u_0^-1..u_{lg-1}^-1
+    __syncthreads();
+    sc xM = sc_to_mont(ch[CH_X]), uM = sc_to_mont(ch[CH_U]), aM = sc_to_mont(ch[CH_A]), bM = sc_to_mont(ch[CH_B]);
+    sc rhoM = sc_to_mont(ch[CH_RHO]), one = sc_mont_one();
+    sc *stat = B.stat + (size_t)p * (2 + 2 * n);
+    // wc = - sum sign * z^(j+1) * pub[idx]
+    sc wc = sc_zero();
+    const sc *pub = B.pub + (size_t)p * B.n_pub;
+    for (uint32_t e = t; e < B.n_const; e += BBP_SC_THREADS) {
+        uint32_t v = B.const_j[e];
+        sc term = mm(zpow[v & 0x7fffffffu], sc_to_mont(pub[B.const_idx[e]]));
+        wc = (v >> 31) ? sc_add(wc, term) : sc_sub(wc, term);
+    }
+    wc = block_sum_sc(wc, smem);
+    sc delta = sc_zero();
+    for (uint32_t i = t; i < n; i += BBP_SC_THREADS) {
+        // s[i] and s[n-1-i] (bitwise complement of i: the inverse product)
+        sc s = one, srev = one;
+        for (uint32_t j = 0; j < lg; j++) {
+            bool bit = (i >> (lg - 1 - j)) & 1;
+            s = mm(s, bit ? uj[j] : uj[lg + j]);
+            srev = mm(srev, bit ? uj[lg + j] : uj[j]);
+        }
+        sc g, h;
+        sc uf = (i < n1) ? one : uM;
+        if (i < n1) {
+            sc wL = flatten_row(B, zpow, i), wR = flatten_row(B, zpow, n1 + i), wO = flatten_row(B, zpow, 2 * n1 + i);
+            sc ywR = mm(yinv[i], wR);
+            delta = sc_add(delta, mm(ywR, wL));
+            g = sc_sub(mm(xM, ywR), mm(aM, s));
+            h = sc_sub(mm(yinv[i], sc_sub(sc_add(mm(xM, wL), wO), mm(bM, srev))), one);
+        } else {
+            g = sc_neg(mm(aM, s));
+            h = sc_sub(sc_neg(mm(yinv[i], mm(bM, srev))), one);
+        }
+        stat[2 + i] = mm(rhoM, mm(uf, g));
+        stat[2 + n + i] = mm(rhoM, mm(uf, h));
+    }
+    delta = block_sum_sc(delta, smem);
+    sc rM = sc_to_mont(ch[CH_R]);
+    sc x2 = mm(xM, xM), rx2 = mm(rM, x2);
+    for (uint32_t i = t; i < B.m; i += BBP_SC_THREADS) {
+        sc wV = flatten_row(B, zpow, 3 * n1 + i);
+        B.dyn_out[(size_t)p * B.dyn_stride + i] = sc_from_mont(mm(rhoM, mm(wV, rx2)));
+    }
+    if (t == 0) {
+        sc txM = sc_to_mont(ch[CH_TX]), wM = sc_to_mont(ch[CH_W]);
+        sc bs = sc_add(mm(wM, sc_sub(txM, mm(aM, bM))), mm(rM, sc_sub(mm(x2, sc_add(wc, delta)), txM)));
+        sc bbs = sc_sub(sc_neg(sc_to_mont(ch[CH_EBL])), mm(rM, sc_to_mont(ch[CH_TXBL])));
+        stat[0] = mm(rhoM, bs);
+        stat[1] = mm(rhoM, bbs);
+    }
+}
+
+// sums the per-proof static-base scalars over groups of `group_size` consecutive proofs -> one slot of slot_len scalars
+// per group (normal form). group_size = 1 converts each proof's slot for an individual check; group_size = n_proofs
+// builds the single combined slot of a batch verification.
+__global__ void __launch_bounds__(BBP_SC_THREADS) k_stat_reduce(const sc *__restrict__ stat, uint32_t group_size, uint32_t slot_len, sc *__restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
+    if (i >= slot_len) return;
+    sc acc = sc_zero();
+    const sc *base = stat + (size_t)g * group_size * slot_len;
+    for (uint32_t p = 0; p < group_size; p++) acc = sc_add(acc, base[(size_t)p * slot_len + i]);
+    out[(size_t)g * slot_len + i] = sc_from_mont(acc);
+}
+
+}  // namespace bbp

@@ -98,6 +98,68 @@ int bbp_decompress(bbp_ctx *ctx, const uint8_t *compressed, size_t n, uint8_t *o
 int bbp_compress(bbp_ctx *ctx, const uint8_t *points_ext, size_t n, uint8_t *out_compressed);
 int bbp_from_uniform_bytes(bbp_ctx *ctx, const uint8_t *bytes64, size_t n, uint8_t *out_compressed);
 
+/* ---- L3: blind-bid entry points (mirror Proof::prove, src/blindbid/proof.rs:36-91, and Verify::verify,
+ * src/blindbid/verify.rs:47-89; bulletproofs Prover / Verifier / InnerProductProof underneath) ----
+ * RNG contract replacing thread_rng (proof.rs:53,64 and the two finalize(&mut thread_rng()) sites inside bulletproofs):
+ * the caller supplies the 4+L commitment blindings and the 32 "external randomness" bytes keyed into the TranscriptRng.
+ * With those fixed every output byte is a deterministic function of the inputs.
+ * Scalars d .. seed: any 32 bytes, reduced mod l. pub_list items: Scalar::from_bits semantics (bid.rs:27, verify.rs:115). */
+typedef struct bbp_prove_req {
+    const uint8_t *d, *k, *y, *y_inv, *q, *z_img, *seed; /* 32 B each */
+    const uint8_t *pub_list;                             /* L x 32 B */
+    size_t L;                                            /* >= 1 (the reference panics on an empty list) */
+    uint64_t toggle;                                     /* index of the bidder's own item */
+    const uint8_t *blindings;                            /* (4 + L) x 32 B */
+    const uint8_t *rng_seed;                             /* 32 B */
+    uint8_t *proof_out;                                  /* R1CSProof::to_bytes() */
+    size_t proof_cap, proof_len;                         /* capacity in, length out (1121 B for every legal L) */
+    uint8_t *commitments_out;                            /* 4 x 32 B: V_d, V_k, V_y, V_y_inv */
+    uint8_t *t_c_out;                                    /* L x 32 B: toggle commitments */
+    int status;                                          /* out: BBP_OK or a bbp_status */
+} bbp_prove_req;
+typedef struct bbp_verify_req {
+    const uint8_t *proof; size_t proof_len;
+    const uint8_t *commitments; size_t n_commitments;    /* >= 4 */
+    const uint8_t *t_c; size_t n_t_c;                    /* >= 1 */
+    const uint8_t *score, *z_img, *seed;                 /* 32 B each */
+    const uint8_t *pub_list; size_t L;                   /* L >= n_t_c */
+    const uint8_t *rng_seed;                             /* 32 B */
+    int status;                                          /* out: BBP_OK = accept, BBP_ERR_FORMAT / _VERIFICATION / _INVALID_GENERATORS_LENGTH */
+} bbp_verify_req;
+/* R1CSProof byte layout (SURVEY.md §8c risk R1): 1 = develop-branch form with a leading phase byte (default), 0 = legacy */
+int bbp_set_proof_format(bbp_ctx *ctx, int versioned);
+int bbp_blindbid_prove(bbp_ctx *ctx, const uint8_t d[32], const uint8_t k[32], const uint8_t y[32], const uint8_t y_inv[32], const uint8_t q[32],
+                       const uint8_t z_img[32], const uint8_t seed[32], const uint8_t *pub_list, size_t L, uint64_t toggle, const uint8_t *blindings,
+                       const uint8_t rng_seed[32], uint8_t *proof_out, size_t *proof_len, uint8_t *commitments_out, uint8_t *t_c_out);
+/* n requests in one pass over the GPU (requests are grouped by L internally); per-request status in reqs[i].status */
+int bbp_blindbid_prove_batch(bbp_ctx *ctx, size_t n, bbp_prove_req *reqs);
+/* returns BBP_OK when the proof verifies, a negative bbp_status otherwise (the reference maps every Err to the byte 0x00) */
+int bbp_blindbid_verify(bbp_ctx *ctx, const uint8_t *proof, size_t proof_len, const uint8_t *commitments, size_t n_commitments, const uint8_t *t_c,
+                        size_t n_t_c, const uint8_t score[32], const uint8_t z_img[32], const uint8_t seed[32], const uint8_t *pub_list, size_t L,
+                        const uint8_t rng_seed[32]);
+/* n independent verifications in one pass (each with its own mega-check): reqs[i].status */
+int bbp_blindbid_verify_each(bbp_ctx *ctx, size_t n, bbp_verify_req *reqs);
+/* batch verification: ONE combined mega-check over all requests (random weights from a Merlin transcript over the proofs
+ * and batch_seed); falls back to per-request checks when the combination fails, so reqs[i].status always equals what
+ * bbp_blindbid_verify_each reports. *all_ok = 1 iff every request verifies. */
+int bbp_blindbid_verify_batch(bbp_ctx *ctx, size_t n, bbp_verify_req *reqs, const uint8_t batch_seed[32], int *all_ok);
+/* proof-range sharding across GPUs: runs only the combined pass over this GPU's requests and leaves its
+ * partial sums (2 x 128 B extended points: static-base part, dynamic part) in HBM at partial_ext_device for the all-gather;
+ * the whole batch verifies iff the sum of all GPUs' partials is the identity (bbp_sum_compress_device -> 32 zero bytes). */
+int bbp_blindbid_verify_batch_partial(bbp_ctx *ctx, size_t n, bbp_verify_req *reqs, const uint8_t batch_seed[32], void *partial_ext_device, int *local_ok);
+/* native MiMC-x^7 hash the circuit constrains (src/gadgets.rs:37-68) and its constants (src/blindbid/mod.rs:7-24): host helpers */
+int bbp_mimc_hash(const uint8_t left[32], const uint8_t right[32], uint8_t out[32]);
+int bbp_mimc_constants(uint8_t out[90 * 32]);
+/* out = {multipliers n1, constraints q, commitments m} of the circuit for the given commitment / toggle counts */
+int bbp_blindbid_circuit_shape(size_t n_commitments, size_t n_toggles, size_t out[3]);
+
+/* ---- L1 building blocks over the resident generators --------------------------------------------------------------- */
+/* PedersenGens::commit: v*B + r*B_blinding for n (value, blinding) pairs; out = n x 32 B compressed */
+int bbp_pedersen_commit(bbp_ctx *ctx, const uint8_t *values, const uint8_t *blindings, size_t n, uint8_t *out);
+/* n_slots MSMs over the generator table in the order [B, B_blinding, G[0..cap), H[0..cap)] (party 0 first); scalars =
+ * n_slots x slot_len x 32 B, column i multiplies generator i; out = n_slots x 32 B compressed */
+int bbp_msm_gens(bbp_ctx *ctx, const uint8_t *scalars, size_t slot_len, size_t n_slots, uint8_t *out);
+
 /* ---- unit-test hooks (field / group primitives evaluated on the GPU; tests/ compares them with the oracle) ---------- */
 /* op: 0 mul, 1 add, 2 sub, 3 invert(a), 4 square(a), 5 neg(a); inputs are raw 256-bit limbs, output canonical */
 int bbp_test_fe(bbp_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, int op, uint8_t *out);

@@ -1,0 +1,255 @@
+"""GPU parity, protocol layer: Pedersen commitments, generator-table MSMs, the blind-bid prover (proof bytes identical
+to the oracle's under the same blindings / rng seed — BASELINE config 3) and verifier (same verdicts as the oracle on
+honest, mutated and malformed proofs — configs 1, 4). Everything goes through the C ABI."""
+import ctypes
+import hashlib
+
+import pytest
+
+import orc
+from orc import L_ORDER, from_le, le
+
+pytestmark = pytest.mark.gpu
+ZERO32 = bytes(32)
+
+
+@pytest.fixture(scope="module")
+def be():
+    from gpu_util import backend
+    return backend()
+
+
+def seed32(tag):
+    return hashlib.sha256(tag.encode()).digest()
+
+
+def make_case(i, L, toggle=None):
+    toggle = (i % L) if toggle is None else toggle
+    bid = orc.make_bid(1000 + i, L, toggle)
+    bid["blindings"] = orc.bid_blindings(1000 + i, L)
+    bid["rng_seed"] = seed32(f"rng{i}")
+    return bid
+
+
+def verify_item(bid, proof, comm, tc, i=0):
+    return dict(proof=proof, commitments=comm, t_c=tc, score=bid["q"], z_img=bid["z_img"], seed=bid["seed"], pub_list=bid["pub_list"],
+                rng_seed=seed32(f"vrng{i}"))
+
+
+def oracle_verify(item):
+    return orc.blindbid_verify(item["proof"], item["commitments"], item["t_c"], item["score"], item["z_img"], item["seed"], item["pub_list"],
+                               item["rng_seed"], threads=4)
+
+
+def split_proof(p):
+    """versioned one-phase layout: 1 + 8 points + 3 scalars + ipp"""
+    names = ["A_I1", "A_O1", "S1", "T_1", "T_3", "T_4", "T_5", "T_6", "t_x", "t_x_blinding", "e_blinding"]
+    out = {"version": p[:1]}
+    pos = 1
+    for n in names:
+        out[n] = p[pos:pos + 32]
+        pos += 32
+    k = 0
+    while pos + 64 < len(p):
+        out[f"L{k}"] = p[pos:pos + 32]
+        out[f"R{k}"] = p[pos + 32:pos + 64]
+        pos += 64
+        k += 1
+    out["a"], out["b"] = p[pos:pos + 32], p[pos + 32:pos + 64]
+    return out
+
+
+def test_pedersen_commit(be):
+    B, Bb = be.pedersen_gens()
+    n = 40
+    vals = bytearray(orc.random_scalars(31, n))
+    bls = bytearray(orc.random_scalars(32, n))
+    vals[0:32] = le(0); bls[32:64] = le(0); vals[64:96] = le(1); bls[64:96] = le(0)
+    vals[96:128] = le(L_ORDER - 1); bls[96:128] = le(L_ORDER - 1); vals[128:160] = le(0); bls[128:160] = le(0)
+    got = be.pedersen_commit(bytes(vals), bytes(bls))
+    for i in range(n):
+        want = orc.msm(bytes(vals[32 * i:32 * i + 32]) + bytes(bls[32 * i:32 * i + 32]), B + Bb, algo=0)
+        assert got[32 * i:32 * i + 32] == want, i
+    assert got[64:96] == B and got[128:160] == ZERO32
+
+
+def test_msm_over_generator_table(be):
+    """fixed-base (window table) MSM slots over [B, B_blinding, G, H] against the oracle over the compressed generators."""
+    B, Bb = be.pedersen_gens()
+    gens = B + Bb + be.bulletproof_gens("G", 0, 0, 2048) + be.bulletproof_gens("H", 0, 0, 2048)
+    slot_len = 4098
+    slots = 3
+    scs = bytearray(orc.random_scalars(41, slot_len * slots))
+    # slot 1: sparse (like A_O1: only B_blinding and part of G), slot 2: a few special scalars
+    for i in range(slot_len):
+        if i == 0 or i > 1500:
+            scs[32 * (slot_len + i):32 * (slot_len + i + 1)] = ZERO32
+    for k, s in enumerate([0, 1, L_ORDER - 1, 2**252, 1 << 11, (1 << 11) - 1, 1 << 10, (1 << 10) + 1]):
+        scs[32 * (2 * slot_len + k):32 * (2 * slot_len + k + 1)] = le(s)
+    scs = bytes(scs)
+    got = be.msm_gens(scs, slot_len, slots)
+    for k in range(slots):
+        assert got[32 * k:32 * k + 32] == orc.msm(scs[32 * slot_len * k:32 * slot_len * (k + 1)], gens, algo=1, threads=4), k
+    # short slots (2 columns) = Pedersen commitments through the same engine
+    two = orc.random_scalars(42, 2 * 5)
+    got = be.msm_gens(two, 2, 5)
+    for k in range(5):
+        assert got[32 * k:32 * k + 32] == orc.msm(two[64 * k:64 * k + 64], B + Bb, algo=0)
+
+
+@pytest.mark.parametrize("L", [1, 2, 8])
+def test_prove_bytes_identical_to_oracle(be, L):
+    """BASELINE config 3: proof bytes, commitments and toggle commitments equal the oracle's under fixed blindings / rng."""
+    bid = make_case(L, L)
+    rc, proof, comm, tc = orc.blindbid_prove(bid, bid["blindings"], bid["rng_seed"])
+    assert rc == 0
+    st, gproof, gcomm, gtc = be.blindbid_prove(bid)
+    assert st == 0
+    assert gcomm == comm and gtc == tc
+    want, got = split_proof(proof), split_proof(gproof)
+    for k in want:
+        assert got.get(k) == want[k], f"proof field {k} differs"
+    assert gproof == proof and len(gproof) == 1121
+    # the oracle accepts the GPU proof, the GPU accepts the oracle's proof
+    item = verify_item(bid, gproof, gcomm, gtc)
+    assert oracle_verify(item) == 0
+    assert be.blindbid_verify(item) == 0
+
+
+def test_prove_batch_mixed_lengths(be):
+    """a batch mixing list lengths and toggles: every proof equals the single-proof oracle output"""
+    cases = [make_case(10 + i, L) for i, L in enumerate([8, 8, 3, 8, 1, 3, 8, 8])]
+    outs = be.blindbid_prove_batch(cases)
+    for bid, (st, proof, comm, tc) in zip(cases, outs):
+        rc, oproof, ocomm, otc = orc.blindbid_prove(bid, bid["blindings"], bid["rng_seed"])
+        assert st == 0 and rc == 0
+        assert (proof, comm, tc) == (oproof, ocomm, otc)
+
+
+def mutations(bid, proof, comm, tc):
+    """(name, item) pairs; each must be rejected. Mirrors SURVEY.md §4.4-3."""
+    out = []
+    base = verify_item(bid, proof, comm, tc)
+    f = split_proof(proof)
+
+    def with_proof(name, p):
+        it = dict(base); it["proof"] = p
+        out.append((name, it))
+
+    off = 1
+    for idx, name in enumerate(["A_I1", "A_O1", "S1", "T_1", "T_3", "T_4", "T_5", "T_6"]):
+        p = bytearray(proof)
+        p[off + 32 * idx:off + 32 * idx + 32] = f["A_O1"] if name != "A_O1" else f["A_I1"]   # a valid but wrong point
+        with_proof("swap " + name, bytes(p))
+    p = bytearray(proof); p[1:33] = ZERO32; with_proof("identity A_I1", bytes(p))
+    p = bytearray(proof); p[1 + 32 * 3:1 + 32 * 4] = ZERO32; with_proof("identity T_1", bytes(p))
+    p = bytearray(proof); p[1] |= 1; with_proof("invalid point encoding A_I1", bytes(p))
+    for idx, name in enumerate(["t_x", "t_x_blinding", "e_blinding"]):
+        p = bytearray(proof)
+        v = (from_le(f[name]) + 1) % L_ORDER
+        p[off + 32 * (8 + idx):off + 32 * (9 + idx)] = le(v)
+        with_proof("bump " + name, bytes(p))
+    p = bytearray(proof); p[off + 32 * 8:off + 32 * 9] = le(L_ORDER); with_proof("non-canonical t_x", bytes(p))
+    p = bytearray(proof); p[off + 32 * 11:off + 32 * 12] = f["R0"]; with_proof("swap L0", bytes(p))
+    p = bytearray(proof); p[off + 32 * 11:off + 32 * 12] = ZERO32; with_proof("identity L0", bytes(p))
+    p = bytearray(proof); p[-32:] = le((from_le(f["b"]) + 1) % L_ORDER); with_proof("bump b", bytes(p))
+    p = bytearray(proof); p[-64:-32] = le(2**255 - 1); with_proof("non-canonical a", bytes(p))
+    with_proof("truncated", proof[:-32])
+    with_proof("one byte short", proof[:-1])
+    with_proof("two rounds dropped", proof[:-64 - 128] + proof[-64:])
+    with_proof("bad version byte", b"\x02" + proof[1:])
+    with_proof("empty", b"")
+    it = dict(base); it["score"] = le((from_le(bid["q"]) + 1) % L_ORDER); out.append(("wrong score", it))
+    it = dict(base); it["z_img"] = le((from_le(bid["z_img"]) + 1) % L_ORDER); out.append(("wrong z_img", it))
+    it = dict(base); it["seed"] = le((from_le(bid["seed"]) + 1) % L_ORDER); out.append(("wrong seed", it))
+    L = bid["L"]
+    pl = bytearray(bid["pub_list"]); t = bid["toggle"]
+    pl[32 * t:32 * t + 32] = le((from_le(pl[32 * t:32 * t + 32]) + 1) % L_ORDER)
+    it = dict(base); it["pub_list"] = bytes(pl); out.append(("own item changed in the list", it))
+    c = bytearray(comm); c[0:32], c[32:64] = comm[32:64], comm[0:32]
+    it = dict(base); it["commitments"] = bytes(c); out.append(("commitments swapped", it))
+    c = bytearray(comm); c[0] |= 1
+    it = dict(base); it["commitments"] = bytes(c); out.append(("invalid commitment encoding", it))
+    it = dict(base); it["commitments"] = comm[:96]; out.append(("three commitments", it))
+    it = dict(base); it["t_c"] = b""; out.append(("no toggles", it))
+    if L > 1:
+        it = dict(base); it["t_c"] = tc[:-32]; out.append(("one toggle commitment missing", it))
+        it = dict(base); it["pub_list"] = bid["pub_list"][:-32]; out.append(("list shorter than toggles", it))
+    return out
+
+
+@pytest.mark.parametrize("L", [2, 8])
+def test_verify_verdicts_match_oracle(be, L):
+    """accept / reject parity with the oracle, including the error class, over honest and mutated inputs"""
+    bid = make_case(50 + L, L)
+    rc, proof, comm, tc = orc.blindbid_prove(bid, bid["blindings"], bid["rng_seed"])
+    assert rc == 0
+    good = verify_item(bid, proof, comm, tc)
+    assert oracle_verify(good) == 0 and be.blindbid_verify(good) == 0
+    muts = mutations(bid, proof, comm, tc)
+    items = [it for _, it in muts]
+    gpu = be.blindbid_verify_each([good] + items)
+    assert gpu[0] == 0
+    for (name, it), g in zip(muts, gpu[1:]):
+        o = oracle_verify(it)
+        assert o != 0, name
+        assert g == o, f"{name}: gpu {g} oracle {o}"
+        assert be.blindbid_verify(it) == o, name
+
+
+def test_non_member_bid_does_not_verify(be):
+    """the prover does not check the witness: a bid whose x is not in the list yields a proof that fails to verify
+    (SURVEY.md §8b), identically on both sides"""
+    bid = make_case(77, 4)
+    pl = bytearray(bid["pub_list"]); t = bid["toggle"]
+    pl[32 * t:32 * t + 32] = orc.random_scalars(999, 1)
+    bid["pub_list"] = bytes(pl)
+    rc, proof, comm, tc = orc.blindbid_prove(bid, bid["blindings"], bid["rng_seed"])
+    st, gproof, gcomm, gtc = be.blindbid_prove(bid)
+    assert rc == 0 and st == 0 and (gproof, gcomm, gtc) == (proof, comm, tc)
+    item = verify_item(bid, gproof, gcomm, gtc)
+    assert oracle_verify(item) != 0 and be.blindbid_verify(item) == oracle_verify(item)
+
+
+def test_generator_capacity_limits(be):
+    """L = 202 is the largest list that fits gens(2048, 1); L = 203 -> InvalidGeneratorsLength on both sides"""
+    bid = make_case(90, 203)
+    rc, _, _, _ = orc.blindbid_prove(bid, bid["blindings"], bid["rng_seed"])
+    st, _, _, _ = be.blindbid_prove(bid)
+    assert rc == -1 and st == -1
+    bid = make_case(91, 202)
+    rc, proof, comm, tc = orc.blindbid_prove(bid, bid["blindings"], bid["rng_seed"])
+    st, gproof, gcomm, gtc = be.blindbid_prove(bid)
+    assert rc == 0 and st == 0 and (gproof, gcomm, gtc) == (proof, comm, tc)
+    assert be.blindbid_verify(verify_item(bid, gproof, gcomm, gtc)) == 0
+
+
+def test_batch_verify_equals_and_of_singles(be):
+    """BASELINE config 4 at test size: combined check verdict == AND of single verdicts, with 0 / 1 / k bad proofs"""
+    n = 24
+    cases = [make_case(200 + i, 8) for i in range(n)]
+    outs = be.blindbid_prove_batch(cases)
+    items = [verify_item(b, p, c, t, i) for i, (b, (st, p, c, t)) in enumerate(zip(cases, outs))]
+    assert all(st == 0 for st, _, _, _ in outs)
+    ok, st = be.blindbid_verify_batch(items, seed32("batch0"))
+    assert ok and st == [0] * n
+    for bad in ([5], [0, 7, 23]):
+        its = [dict(x) for x in items]
+        for b in bad:
+            p = bytearray(its[b]["proof"])
+            p[-1] ^= 1 if b != 7 else 0
+            if b == 7:
+                p[1 + 32 * 8] ^= 1       # t_x
+            its[b]["proof"] = bytes(p)
+        ok, st = be.blindbid_verify_batch(its, seed32("batch1"))
+        singles = be.blindbid_verify_each(its)
+        assert not ok
+        assert st == singles
+        assert [i for i, s in enumerate(st) if s != 0] == bad
+        for b in bad:
+            assert oracle_verify(its[b]) == st[b]
+    # a request with a malformed proof is reported and does not poison the others
+    its = [dict(x) for x in items]
+    its[3]["proof"] = its[3]["proof"][:-1]
+    ok, st = be.blindbid_verify_batch(its, seed32("batch2"))
+    assert not ok and st[3] == -2 and all(s == 0 for i, s in enumerate(st) if i != 3)
