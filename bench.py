@@ -159,6 +159,144 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ blind-bid legs
+LO = 2**252 + 27742317777372353535851937790883648493
+
+
+def le32(x):
+    return int(x).to_bytes(32, "little")
+
+
+def synth_bid(capi, i, L):
+    """Synthetic bid built with the product's own host MiMC helper."""
+    st = shake(b"bbp-bid" + i.to_bytes(8, "little"), 64 * (3 + L) + 8)
+    k = le32(int.from_bytes(st[0:64], "little") % LO)
+    d = le32(int.from_bytes(st[64:72], "little"))
+    seed = le32(int.from_bytes(st[128:192], "little") % LO)
+    m = capi.mimc_hash(k, le32(0))
+    x = capi.mimc_hash(d, m)
+    y = capi.mimc_hash(seed, x)
+    z_img = capi.mimc_hash(seed, m)
+    yi = pow(int.from_bytes(y, "little"), LO - 2, LO)
+    q = le32(int.from_bytes(d, "little") * yi % LO)
+    pub = [le32(int.from_bytes(st[64 * (3 + j):64 * (4 + j)], "little") % LO) for j in range(L)]
+    t = i % L
+    pub[t] = x
+    bl = shake(b"bbp-blindings" + i.to_bytes(8, "little"), 64 * (4 + L))
+    bl = b"".join(le32(int.from_bytes(bl[64 * j:64 * j + 64], "little") % LO) for j in range(4 + L))
+    return dict(d=d, k=k, y=y, y_inv=le32(yi), q=q, z_img=z_img, seed=seed, pub_list=b"".join(pub), toggle=t, blindings=bl,
+                rng_seed=hashlib.sha256(b"rng%d" % i).digest())
+
+
+def run_blindbid(pkg, be, torch, dist, rank, world, n_prove=256, n_verify=1024, L=8, reps=3):
+    """prove: n_prove bids per GPU in one batched pass (replicas across GPUs). batch-verify: n_verify proofs per GPU, one
+    combined mega-check; at N > 1 the batch is N*n_verify proofs sharded by proof range, the GPUs exchange their 2 x 128 B
+    partial sums with one all-gather and every rank tests the total for the identity. Host buffers in, host buffers out."""
+    capi = pkg.capi
+    bids = [synth_bid(capi, rank * 100000 + i, L) for i in range(max(n_prove, n_verify))]
+    be.blindbid_prove_batch(bids[:4])                      # builds tables / templates
+    proofs = []
+    for off in range(0, n_verify, n_prove):
+        proofs += be.blindbid_prove_batch(bids[off:off + n_prove])
+    assert all(p[0] == 0 for p in proofs)
+    items = [dict(proof=p[1], commitments=p[2], t_c=p[3], score=b["q"], z_img=b["z_img"], seed=b["seed"], pub_list=b["pub_list"],
+                  rng_seed=hashlib.sha256(b"v%d" % i).digest()) for i, (b, p) in enumerate(zip(bids, proofs))]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def tmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    barrier()
+    l0 = be.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        outs = be.blindbid_prove_batch(bids[:n_prove])
+    torch.cuda.synchronize()
+    prove_s = tmax((time.perf_counter() - t0) / reps)
+    prove_launches = (be.launch_count() - l0) // reps
+    assert outs[0][1] == proofs[0][1], "prover is not deterministic under a fixed seed"
+
+    batch_seed = hashlib.sha256(b"batch").digest()
+    d_partial = torch.zeros(256, dtype=torch.uint8, device="cuda")
+    d_gather = torch.zeros(256 * world, dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros(32, dtype=torch.uint8, device="cuda")
+
+    def verify_step():
+        if world == 1:
+            ok, st = be.blindbid_verify_batch(items[:n_verify], batch_seed)
+            return ok
+        be.blindbid_verify_batch_partial(items[:n_verify], batch_seed, d_partial.data_ptr())
+        dist.all_gather_into_tensor(d_gather, d_partial)
+        be.sum_compress_device(d_gather.data_ptr(), 2 * world, d_out.data_ptr())
+        return bytes(d_out.cpu().numpy()) == bytes(32)
+
+    assert verify_step()
+    barrier()
+    l0 = be.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ok = verify_step()
+    torch.cuda.synchronize()
+    verify_s = tmax((time.perf_counter() - t0) / reps)
+    verify_launches = (be.launch_count() - l0) // reps
+    assert ok
+    # single-request latency through the one-shot entry points
+    t0 = time.perf_counter()
+    be.blindbid_prove(bids[0])
+    lat_p = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    assert be.blindbid_verify(items[0]) == 0
+    lat_v = time.perf_counter() - t0
+    proof_bytes = len(items[0]["proof"])
+    return {
+        "list_len": L,
+        "prove": {"value": world * n_prove / prove_s, "unit": "proofs/s", "batch_per_gpu": n_prove, "ms_per_batch": 1e3 * prove_s,
+                  "gpu_launches_per_batch": prove_launches, "parallelism": "replicas" if world > 1 else "1 GPU",
+                  "call": "bbp_blindbid_prove_batch (host requests in, proof bytes out)"},
+        "batch_verify": {"value": world * n_verify / verify_s, "unit": "proofs/s", "batch_per_gpu": n_verify, "ms_per_batch": 1e3 * verify_s,
+                         "gpu_launches_per_batch": verify_launches,
+                         "parallelism": f"proof-range shards x{world}, all-gather of 256 B partial sums" if world > 1 else "1 GPU",
+                         "call": "bbp_blindbid_verify_batch (host requests in, verdicts out)", "proof_bytes": proof_bytes},
+        "single_request_ms": {"prove": 1e3 * lat_p, "verify": 1e3 * lat_v},
+    }
+
+
+def cpu_blindbid_rates(cores, L=8):
+    """oracle prove / verify on `cores` threads, one request per thread (ctypes releases the GIL)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    bids = [orc.make_bid(5000 + i, L, i % L) for i in range(cores)]
+    bls = [orc.bid_blindings(5000 + i, L) for i in range(cores)]
+    orc.blindbid_prove(bids[0], bls[0], bytes(32))           # builds the oracle's generator cache
+    res = [None] * cores
+
+    def prove(i):
+        res[i] = orc.blindbid_prove(bids[i], bls[i], bytes(32))
+
+    def verify(i):
+        _, p, c, tc = res[i]
+        assert orc.blindbid_verify(p, c, tc, bids[i]["q"], bids[i]["z_img"], bids[i]["seed"], bids[i]["pub_list"], bytes(32)) == 0
+
+    out = {}
+    for name, fn in (("prove", prove), ("verify", verify)):
+        th = [threading.Thread(target=fn, args=(i,)) for i in range(cores)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        out[name] = cores / (time.perf_counter() - t0)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def run_b200(args, rank, world):
     import torch
@@ -171,7 +309,7 @@ def run_b200(args, rank, world):
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    be = pkg.Backend(device=local, gens_capacity=0)
+    be = pkg.Backend(device=local, gens_capacity=2048, party_capacity=1)
     stream = torch.cuda.ExternalStream(be.stream(), device=local)
     n = 1 << LOG2_N
     plan = pkg.Backend.msm_plan(n)
@@ -254,6 +392,8 @@ def run_b200(args, rank, world):
         e2e_s = time.perf_counter() - t0
         if world == 1:
             assert r == bytes(d_out.cpu().numpy())
+        table.free()
+        blindbid = None if args.no_blindbid else run_blindbid(pkg, be, torch, dist, rank, world)
 
     t_ms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -283,11 +423,17 @@ def run_b200(args, rank, world):
             "stage_ms": dict(zip(["recode", "scan", "scatter", "accumulate", "chunk_reduce", "window_reduce", "combine"], [round(x, 4) for x in stage])),
             "clocks": clocks,
         }
+        if blindbid is not None:
+            line["blindbid"] = blindbid
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             rate, secs = cpu_msm_rate(1 << 18, cores, 2)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"one 2^18-point Pippenger MSM (oracle/msm.h, {cores} threads over point ranges), best of 2, {secs:.2f} s"}
+            if blindbid is not None:
+                r = cpu_blindbid_rates(cores)
+                line["cpu_baseline"]["blindbid"] = {"prove_proofs_per_s": r["prove"], "verify_proofs_per_s": r["verify"], "list_len": 8,
+                                                    "sample": f"{cores} independent requests, one per thread, oracle prover / verifier (generators cached)"}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -301,6 +447,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-blindbid", action="store_true", help="skip the blind-bid prove / batch-verify legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -12,6 +12,8 @@
 // takes from thread_rng inside TranscriptRngBuilder::finalize; with those fixed every proof byte is deterministic.
 #pragma once
 #include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <thread>
@@ -34,6 +36,29 @@ inline void parallel_for(size_t n, F fn) {
         th.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < n;) fn(i); });
     for (auto &x : th) x.join();
 }
+
+// BBP_TRACE=1: per-phase wall-clock of the batched prover / verifier on stderr (each phase ends with a stream sync)
+struct phase_trace {
+    bool on;
+    const char *what;
+    std::chrono::steady_clock::time_point t0;
+    std::vector<std::pair<const char *, double>> marks;
+    explicit phase_trace(const char *w) : on(getenv("BBP_TRACE") != nullptr), what(w), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *name) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        marks.push_back({name, std::chrono::duration<double, std::milli>(t1 - t0).count()});
+        t0 = t1;
+    }
+    ~phase_trace() {
+        if (!on) return;
+        double tot = 0;
+        for (auto &m : marks) tot += m.second;
+        fprintf(stderr, "[bbp trace] %s total %.3f ms:", what, tot);
+        for (auto &m : marks) fprintf(stderr, " %s=%.3f", m.first, m.second);
+        fprintf(stderr, "\n");
+    }
+};
 
 struct dev_buf {
     uint8_t *p = nullptr;
@@ -261,6 +286,7 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
         sc i_bl, o_bl, s_bl, tbl[6];   // tbl[1] (t_2 blinding) comes from the device
     };
     std::vector<hstate> hs(B);
+    phase_trace trace("prove_group");
 
     // ---- phase 0: witness + V commitments
     std::vector<sc> commit_vals((size_t)B * m * 2);
@@ -276,8 +302,10 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
         std::vector<sc> toggles(H.v.begin() + 4, H.v.end()), items(J.pub_list.begin(), J.pub_list.end());
         proof_gadget(H.ev, H.v[0], H.v[1], H.v[3], J.q, J.z_img, J.seed, toggles, items);
     });
+    trace.mark("host_witness");
     std::vector<uint8_t> V((size_t)B * m * 32);
     if ((rc = pedersen_commit_host(ctx, commit_vals.data(), (size_t)B * m, V.data()))) return rc;
+    trace.mark("gpu_V_commit");
 
     // ---- phase 1: transcript up to the blinding draws; upload witness
     std::vector<sc> wit((size_t)B * 5 * n1), vbl((size_t)B * m), blind3((size_t)B * 3);
@@ -307,6 +335,7 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
         for (uint32_t i = 0; i < n1; i++) W(4)[i] = H.rng->random_scalar();   // s_R
     });
 
+    trace.mark("host_rng_draws");
     // device buffers
     if ((rc = ps->chal.ensure((size_t)B * CH_N * 32)) || (rc = ps->zpow.ensure((size_t)B * T.q * 32)) || (rc = ps->ypow.ensure((size_t)B * n * 32)) ||
         (rc = ps->yinvpow.ensure((size_t)B * n * 32)) || (rc = ps->wit.ensure((size_t)B * 5 * n1 * 32)) || (rc = ps->vbl.ensure((size_t)B * m * 32)) ||
@@ -336,6 +365,7 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     if ((rc = msm_gens_device(ctx, SB.slots, slot_len, 3 * B, ps->msm_out.p, nullptr))) return rc;
     std::vector<uint8_t> pts((size_t)B * 3 * 32);
     if ((rc = d2h_sync(ctx, pts.data(), ps->msm_out.p, pts.size()))) return rc;
+    trace.mark("gpu_A_S_msm");
 
     // ---- phase 3 (host): y, z
     std::vector<sc> chal((size_t)B * CH_N, sc_zero());
@@ -360,6 +390,7 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     ctx->launches += 2;
     std::vector<sc> tout((size_t)B * 8);
     if ((rc = d2h_sync(ctx, tout.data(), ps->tout.p, tout.size() * 32))) return rc;
+    trace.mark("yz+gpu_polys");
 
     // ---- phase 5: T_1, T_3, T_4, T_5, T_6
     std::vector<sc> tvals((size_t)B * 5 * 2);
@@ -375,6 +406,7 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     });
     std::vector<uint8_t> Tp((size_t)B * 5 * 32);
     if ((rc = pedersen_commit_host(ctx, tvals.data(), (size_t)B * 5, Tp.data()))) return rc;
+    trace.mark("gpu_T_commit");
 
     // ---- phase 6 (host): u, x, t(x), blindings, w
     parallel_for(B, [&](size_t bi) {
@@ -408,12 +440,15 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     // ---- phase 7: inner-product argument, lg n rounds
     k_ipp_init<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
     ctx->launches++;
+    trace.mark("host_ux");
     std::vector<uint8_t> lr((size_t)B * 64);
+    double t_gpu_round = 0, t_host_round = 0;
     for (uint32_t j = 0; j < lg; j++) {
         k_ipp_round<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB, j, 0);
         ctx->launches++;
         if ((rc = msm_gens_device(ctx, SB.slots, slot_len, 2 * B, ps->msm_out.p, nullptr))) return rc;
         if ((rc = d2h_sync(ctx, lr.data(), ps->msm_out.p, lr.size()))) return rc;
+        trace.mark("gpu_ipp_round");
         parallel_for(B, [&](size_t bi) {
             hstate &H = hs[bi];
             memcpy(&H.pf.LR[(size_t)64 * j], &lr[bi * 64], 64);
@@ -424,7 +459,9 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
             c[CH_UJINV] = sc_invert(c[CH_UJ]);
         });
         if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32))) return rc;
+        trace.mark("host_ipp_round");
     }
+    (void)t_gpu_round; (void)t_host_round;
     k_ipp_round<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB, lg, 1);
     ctx->launches++;
     std::vector<sc> ab((size_t)B * 2);
@@ -574,6 +611,7 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     const circuit_template &T = *dt->tpl;
     const uint32_t n1 = T.n1, m = T.m, n = P0.n, lg = P0.lg, slot_len = 2 + 2 * n, ds = m + 11 + 2 * lg;
     const uint32_t n_groups = combined ? 1 : B;
+    phase_trace trace(combined ? "verify_group(combined)" : "verify_group(each)");
 
     // ---- dynamic points first: a failed decompression removes the request from the check
     std::vector<uint8_t> dyn_pts((size_t)B * ds * 32);
@@ -588,6 +626,7 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     ctx->launches++;
     std::vector<uint8_t> valid((size_t)B * ds);
     if ((rc = d2h_sync(ctx, valid.data(), ps->valid.p, valid.size()))) return rc;
+    trace.mark("decompress");
 
     std::vector<sc> chal((size_t)B * CH_N), pub((size_t)B * T.n_pub), dyn_sc((size_t)B * ds);
     std::vector<uint8_t> alive(B, 1);
@@ -612,6 +651,7 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
         (rc = h2d(ctx, ps->dyn_sc.p, dyn_sc.data(), dyn_sc.size() * 32)))
         return rc;
 
+    trace.mark("host_pack+h2d");
     sc_batch SB;
     memset(&SB, 0, sizeof SB);
     SB.n_proofs = B; SB.n1 = n1; SB.q = T.q; SB.m = m; SB.n = n; SB.lg_n = lg; SB.n_pub = T.n_pub;
@@ -634,6 +674,7 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     if (combined && d_partial_ext) BBP_CUDA_OK(cudaMemcpyAsync(d_partial_ext, ext, 256, cudaMemcpyDeviceToDevice, ctx->stream));
     std::vector<uint8_t> fl(n_groups);
     if ((rc = d2h_sync(ctx, fl.data(), ps->flags.p, n_groups))) return rc;
+    trace.mark("gpu_scalars+msm");
     verdicts.assign(n_groups, 0);
     for (uint32_t g = 0; g < n_groups; g++) verdicts[g] = fl[g];
     if (!combined)
@@ -671,7 +712,11 @@ inline int verify_batch(bbp_ctx *ctx, std::vector<verify_job> &jobs, const uint8
     proto_state *ps = proto_get(ctx);
     std::vector<verify_prepared> prep(jobs.size());
     bool versioned = ps->proof_versioned != 0;
-    parallel_for(jobs.size(), [&](size_t i) { verify_prepare(ctx, jobs[i], prep[i], versioned); });
+    {
+        phase_trace tp("verify_prepare(host)");
+        parallel_for(jobs.size(), [&](size_t i) { verify_prepare(ctx, jobs[i], prep[i], versioned); });
+        tp.mark("transcripts");
+    }
     merlin_transcript bt("bbp batch verification");
     for (auto &J : jobs) bt.append_message("proof", J.proof.data(), J.proof.size());
     merlin_rng brng = bt.build_rng().finalize(batch_seed);
