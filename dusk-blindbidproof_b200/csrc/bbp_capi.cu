@@ -198,24 +198,46 @@ int bbp_msm_points(bbp_ctx *ctx, const uint8_t *scalars, size_t n, const bbp_poi
     return bbp_msm_points_batched(ctx, scalars, n, 1, points, out);
 }
 
+// one-shot forms: temporary base table and staging live in grow-only context scratch (no allocation per call)
+static int msm_oneshot(bbp_ctx *ctx, const uint8_t *scalars, const uint8_t *points, size_t n, bool compressed, uint8_t out[32]) {
+    if (!ctx || !scalars || !points || !out || n == 0 || n > 0x7fffffffu) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    phase_trace trace("msm_oneshot");
+    const size_t pt_bytes = compressed ? 32 : 128;
+    int rc;
+    if ((rc = ctx->reserve_scratch(n * 96 + n * pt_bytes + 16))) return rc;
+    uint8_t *d_table = ctx->d_scratch, *d_pts = ctx->d_scratch + n * 96;
+    int *d_valid = (int *)(d_pts + n * pt_bytes);
+    int h_valid = 1;
+    BBP_CUDA_OK(cudaMemcpyAsync(d_pts, points, n * pt_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (compressed) {
+        BBP_CUDA_OK(cudaMemsetAsync(d_valid, 1, 4, ctx->stream));
+        k_decompress_to_niels<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const uint32_t *)d_pts, d_table, (uint32_t)n, d_valid, nullptr);
+    } else {
+        size_t threads = (n + BBP_NIELS_BATCH - 1) / BBP_NIELS_BATCH;
+        k_ext_to_niels<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(d_pts, d_table, (uint32_t)n);
+    }
+    ctx->launches++;
+    if ((rc = ctx->stage_in(scalars, n * 32))) return rc;
+    if ((rc = ctx->reserve_out(32))) return rc;
+    msm_shape sh = msm_engine::make_shape((uint32_t)n, (uint32_t)n, (uint32_t)n, false, 0, 0, 0);
+    if ((rc = ctx->msm.run(sh, ctx->d_in, d_table, nullptr, ctx->d_out))) return rc;
+    uint8_t res[32];
+    BBP_CUDA_OK(cudaMemcpyAsync(res, ctx->d_out, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    if (compressed) BBP_CUDA_OK(cudaMemcpyAsync(&h_valid, d_valid, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    trace.mark("h2d+table+msm+d2h");
+    if (!h_valid) return BBP_ERR_DECOMPRESS;   // optional_multiscalar_mul -> None; out untouched
+    memcpy(out, res, 32);
+    return BBP_OK;
+}
+
 int bbp_msm_vartime(bbp_ctx *ctx, const uint8_t *scalars, const uint8_t *points_ext, size_t n, uint8_t out[32]) {
-    bbp_points *p = nullptr;
-    int rc = bbp_points_from_extended(ctx, points_ext, n, &p);
-    if (rc) return rc;
-    rc = bbp_msm_points(ctx, scalars, n, p, out);
-    bbp_points_free(p);
-    return rc;
+    return msm_oneshot(ctx, scalars, points_ext, n, false, out);
 }
 
 int bbp_msm_optional(bbp_ctx *ctx, const uint8_t *scalars, const uint8_t *points_compressed, size_t n, uint8_t out[32]) {
-    bbp_points *p = nullptr;
-    int valid = 1;
-    int rc = bbp_points_from_compressed(ctx, points_compressed, n, &p, &valid);
-    if (rc) return rc;
-    if (!valid) { bbp_points_free(p); return BBP_ERR_DECOMPRESS; }
-    rc = bbp_msm_points(ctx, scalars, n, p, out);
-    bbp_points_free(p);
-    return rc;
+    return msm_oneshot(ctx, scalars, points_compressed, n, true, out);
 }
 
 // ---------------------------------------------------------------- codecs

@@ -33,8 +33,8 @@ struct bbp_ctx {
     // protocol layer state (templates, tables, scratch): protocol.cuh
     bbp::proto_state *proto = nullptr;
     // staging
-    uint8_t *d_in = nullptr, *d_out = nullptr;
-    size_t cap_in = 0, cap_out = 0;
+    uint8_t *d_in = nullptr, *d_out = nullptr, *d_scratch = nullptr;
+    size_t cap_in = 0, cap_out = 0, cap_scratch = 0;
 
     size_t gen_index(int which, uint32_t party, uint32_t i) const {
         return 2 + ((size_t)party * 2 + (which == 'H' ? 1 : 0)) * gens_capacity + i;
@@ -48,6 +48,15 @@ struct bbp_ctx {
             cap_in = bytes;
         }
         BBP_CUDA_OK(cudaMemcpyAsync(d_in, host, bytes, cudaMemcpyHostToDevice, stream));
+        return 0;
+    }
+    int reserve_scratch(size_t bytes) {
+        if (bytes > cap_scratch) {
+            cudaFree(d_scratch);
+            d_scratch = nullptr; cap_scratch = 0;
+            BBP_CUDA_OK(cudaMalloc(&d_scratch, bytes));
+            cap_scratch = bytes;
+        }
         return 0;
     }
     int reserve_out(size_t bytes) {
@@ -110,7 +119,7 @@ struct bbp_ctx {
         msm.release();
         bbp::proto_release(proto);
         proto = nullptr;
-        cudaFree(d_gens_ext); cudaFree(d_gens_niels); cudaFree(d_gens_wtable); cudaFree(d_in); cudaFree(d_out);
+        cudaFree(d_gens_ext); cudaFree(d_gens_niels); cudaFree(d_gens_wtable); cudaFree(d_in); cudaFree(d_out); cudaFree(d_scratch);
         if (stream) cudaStreamDestroy(stream);
         stream = nullptr;
     }
