@@ -230,13 +230,7 @@ def run_blindbid(pkg, be, torch, dist, rank, world, n_prove=256, n_verify=1024, 
     d_out = torch.zeros(32, dtype=torch.uint8, device="cuda")
 
     def verify_step():
-        if world == 1:
-            ok, st = be.blindbid_verify_batch(items[:n_verify], batch_seed)
-            return ok
-        be.blindbid_verify_batch_partial(items[:n_verify], batch_seed, d_partial.data_ptr())
-        dist.all_gather_into_tensor(d_gather, d_partial)
-        be.sum_compress_device(d_gather.data_ptr(), 2 * world, d_out.data_ptr())
-        return bytes(d_out.cpu().numpy()) == bytes(32)
+        return pkg.sharding.sharded_batch_verify(be, dist, items[:n_verify], batch_seed, d_partial, d_gather, d_out)
 
     assert verify_step()
     barrier()
@@ -337,12 +331,7 @@ def run_b200(args, rank, world):
         h_ext = torch.frombuffer(bytearray(ext), dtype=torch.uint8).pin_memory()
 
         def step():
-            if world == 1:
-                be.msm_points_device(d_scalars.data_ptr(), n, table, d_out.data_ptr(), None)
-            else:
-                be.msm_points_device(d_scalars.data_ptr(), n, table, None, d_ext.data_ptr())
-                dist.all_gather_into_tensor(d_gather, d_ext)
-                be.sum_compress_device(d_gather.data_ptr(), world, d_out.data_ptr())
+            pkg.sharding.sharded_msm(be, dist, d_scalars, n, table, d_ext, d_gather, d_out)
 
         def barrier():
             if dist is not None:

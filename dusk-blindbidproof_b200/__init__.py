@@ -7,5 +7,5 @@ fallback: importing ``capi`` without the built library, or creating a context wi
 The directory name contains a dash (it follows the reference's name), so import it with ``load()`` from
 ``bbp_loader.py`` at the repo root, which registers it as ``dusk_blindbidproof_b200``.
 """
-from . import capi  # noqa: F401
+from . import capi, sharding  # noqa: F401
 from .capi import Backend, BbpError, LIB_PATH  # noqa: F401

@@ -1,0 +1,54 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed for the only exchange the path has.
+
+Both sharded operations reduce to the same pattern: every rank leaves a few extended partial sums (128 B each) in its
+own memory, one all-gather makes all of them visible everywhere, and each rank adds them up locally (point addition is
+not an NCCL reduction). The traffic is 128-256 bytes per GPU, so the collective is latency-bound by construction.
+"""
+import torch
+
+
+def shard_range(n, rank, world):
+    """Contiguous, balanced partition of n units (points or proofs): returns (start, stop) of this rank's slice."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank / world size")
+    base, extra = divmod(n, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def gather_partials(dist, partial, out=None):
+    """all-gather of this rank's partial sums (uint8 tensor, k x 128 B) -> rank-major tensor of world * k x 128 B.
+    `dist` is torch.distributed (or None for a single process)."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return partial
+    world = dist.get_world_size()
+    if out is None:
+        out = torch.empty(partial.numel() * world, dtype=partial.dtype, device=partial.device)
+    dist.all_gather_into_tensor(out, partial.contiguous())
+    return out
+
+
+def sharded_msm(be, dist, d_scalars, n_local, table, d_ext, d_gather, d_out):
+    """This rank's slice of a point-range sharded MSM: local Pippenger -> 128 B extended partial -> all-gather -> local
+    sum + compression. All tensors are preallocated uint8 CUDA tensors; everything is enqueued on the backend's stream
+    (the caller makes it torch's current stream)."""
+    world = 1 if dist is None else dist.get_world_size()
+    if world == 1:
+        be.msm_points_device(d_scalars.data_ptr(), n_local, table, d_out.data_ptr(), None)
+        return
+    be.msm_points_device(d_scalars.data_ptr(), n_local, table, None, d_ext.data_ptr())
+    gather_partials(dist, d_ext, d_gather)
+    be.sum_compress_device(d_gather.data_ptr(), world, d_out.data_ptr())
+
+
+def sharded_batch_verify(be, dist, items, batch_seed, d_partial, d_gather, d_out):
+    """Proof-range sharded batch verification: items = this rank's requests. Returns True iff the combined mega-check
+    over ALL ranks' requests is the identity (every rank returns the same verdict)."""
+    world = 1 if dist is None else dist.get_world_size()
+    if world == 1:
+        ok, _ = be.blindbid_verify_batch(items, batch_seed)
+        return ok
+    be.blindbid_verify_batch_partial(items, batch_seed, d_partial.data_ptr())
+    gather_partials(dist, d_partial, d_gather)
+    be.sum_compress_device(d_gather.data_ptr(), 2 * world, d_out.data_ptr())
+    return bytes(d_out.cpu().numpy()) == bytes(32)
