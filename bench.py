@@ -50,48 +50,64 @@ def accumulate_imads(n, c, W):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons sampled every ~5 ms through NVML in a background thread while the timed regions
+    run (nvidia-smi's own loop is too coarse for a 30-70 ms region); falls back to one nvidia-smi query."""
+    BITS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
     def __init__(self, index):
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.samples, self.reasons, self.stop_flag, self.thr, self.max_mhz = index, [], set(), False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thr = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            except Exception:
+                pass
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
+                            else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for nm, bit in self.BITS.items():
+                            if r & bit:
+                                self.reasons.add(nm)
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+
+            self.thr = threading.Thread(target=loop, daemon=True)
             self.thr.start()
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.thr = None
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        mhz, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            f = [x.strip() for x in s.split(",")]
-            if len(f) < 6:
-                continue
+        if self.thr is None:
             try:
-                mhz.append(float(f[0])); mx = float(f[1])
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        mhz.sort()
-        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(mhz)}
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": [], "samples": 1, "how": "single nvidia-smi query after the run"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
+        self.stop_flag = True
+        self.thr.join(timeout=1)
+        mhz = sorted(self.samples)
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_min_mhz": mhz[0] if mhz else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(mhz), "how": "NVML every 5 ms during the timed MSM steps, stage profiling and e2e leg"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU port (oracle)
@@ -367,7 +383,6 @@ def run_b200(args, rank, world):
             stage = [a + b for a, b in zip(stage, s)]
         be.set_profiling(0)
         stage = [x / args.steps for x in stage]
-        clocks = sampler.stop()
 
         # end-to-end leg: host buffers in, 32 bytes out, through the trait-shaped entry point
         for _ in range(2):
@@ -381,6 +396,7 @@ def run_b200(args, rank, world):
         e2e_s = time.perf_counter() - t0
         if world == 1:
             assert r == bytes(d_out.cpu().numpy())
+        clocks = sampler.stop()
         table.free()
         blindbid = None if args.no_blindbid else run_blindbid(pkg, be, torch, dist, rank, world)
 

@@ -346,3 +346,42 @@ def circuit_shape(n_commitments, n_toggles):
     out = (ctypes.c_size_t * 3)()
     _chk(lib().bbp_blindbid_circuit_shape(_sz(n_commitments), _sz(n_toggles), out), "bbp_blindbid_circuit_shape")
     return out[0], out[1], out[2]
+
+
+def _rangeproof_methods():
+    def rangeproof_prove_batch(self, values, blindings, m, nbits, rng_seeds):
+        """values: list of n_proofs lists of m ints; blindings: n_proofs*m*32 bytes; rng_seeds: n_proofs*32 bytes.
+        Returns (statuses, [proof bytes], [commitment bytes])."""
+        n = len(values)
+        flat = (ctypes.c_uint64 * (n * m))(*[v for row in values for v in row])
+        stride = 32 * (9 + 2 * 16)
+        proofs, plen, comm = _out(stride * n), ctypes.c_size_t(0), _out(32 * m * n)
+        st = (ctypes.c_int * n)()
+        _chk(lib().bbp_rangeproof_prove_batch(self.ctx, _sz(n), flat, blindings, _sz(m), _sz(nbits), rng_seeds, proofs, _sz(stride), ctypes.byref(plen), comm, st),
+             "bbp_rangeproof_prove_batch")
+        L = plen.value
+        return list(st), [proofs.raw[i * stride:i * stride + L] for i in range(n)], [comm.raw[32 * m * i:32 * m * (i + 1)] for i in range(n)]
+
+    def rangeproof_verify_batch(self, proofs, commitments, m, nbits, rng_seeds):
+        n = len(proofs)
+        L = len(proofs[0])
+        st = (ctypes.c_int * n)()
+        _chk(lib().bbp_rangeproof_verify_batch(self.ctx, _sz(n), b"".join(proofs), _sz(L), _sz(L), b"".join(commitments), _sz(m), _sz(nbits), rng_seeds, st),
+             "bbp_rangeproof_verify_batch")
+        return list(st)
+
+    def rangeproof_prove(self, values, blindings, nbits, rng_seed):
+        m = len(values)
+        flat = (ctypes.c_uint64 * m)(*values)
+        proof, plen, comm = _out(2048), ctypes.c_size_t(2048), _out(32 * m)
+        rc = lib().bbp_rangeproof_prove_multiple(self.ctx, flat, blindings, _sz(m), _sz(nbits), rng_seed, proof, ctypes.byref(plen), comm)
+        return rc, proof.raw[:plen.value] if rc == 0 else b"", comm.raw
+
+    def rangeproof_verify(self, proof, commitments, nbits, rng_seed):
+        return lib().bbp_rangeproof_verify_multiple(self.ctx, proof, _sz(len(proof)), commitments, _sz(len(commitments) // 32), _sz(nbits), rng_seed)
+
+    for f in (rangeproof_prove_batch, rangeproof_verify_batch, rangeproof_prove, rangeproof_verify):
+        setattr(Backend, f.__name__, f)
+
+
+_rangeproof_methods()

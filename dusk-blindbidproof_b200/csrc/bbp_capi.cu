@@ -6,6 +6,7 @@
 #include "ctx.cuh"
 #include "msm.cuh"
 #include "protocol.cuh"
+#include "rangeproof.cuh"
 
 using namespace bbp;
 
@@ -518,6 +519,69 @@ int bbp_msm_gens(bbp_ctx *ctx, const uint8_t *scalars, size_t slot_len, size_t n
     BBP_CUDA_OK(cudaMemcpyAsync(out, ctx->d_out, n_slots * 32, cudaMemcpyDeviceToHost, ctx->stream));
     BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     return BBP_OK;
+}
+
+// ---------------------------------------------------------------- aggregated range proofs (BASELINE config 5)
+int bbp_rangeproof_prove_batch(bbp_ctx *ctx, size_t n_proofs, const uint64_t *values, const uint8_t *blindings, size_t m, size_t nbits,
+                               const uint8_t *rng_seeds, uint8_t *proofs_out, size_t proof_stride, size_t *proof_len, uint8_t *commitments_out,
+                               int *statuses) {
+    if (!ctx || !values || !blindings || !rng_seeds || !proofs_out || !proof_len || !commitments_out || n_proofs == 0) return BBP_ERR_INPUT;
+    if (!rp_params_ok(nbits, m)) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    std::vector<rp_prove_job> jobs(n_proofs);
+    for (size_t i = 0; i < n_proofs; i++) {
+        jobs[i].values.assign(values + i * m, values + (i + 1) * m);
+        // a value that does not fit nbits is NOT rejected here (as upstream): the proof is produced and fails to verify
+        jobs[i].blindings.resize(m);
+        for (size_t j = 0; j < m; j++) jobs[i].blindings[j] = load_scalar(blindings + 32 * (i * m + j));
+        memcpy(jobs[i].rng_seed, rng_seeds + 32 * i, 32);
+    }
+    int rc = rp_prove_group(ctx, jobs, (uint32_t)nbits);
+    if (rc) return rc;
+    size_t len = 0;
+    for (size_t i = 0; i < n_proofs; i++) {
+        if (statuses) statuses[i] = jobs[i].status;
+        if (jobs[i].status) continue;
+        len = jobs[i].proof.size();
+        if (len > proof_stride) return BBP_ERR_INPUT;
+        memcpy(proofs_out + i * proof_stride, jobs[i].proof.data(), len);
+        memcpy(commitments_out + 32 * i * m, jobs[i].commitments.data(), 32 * m);
+    }
+    *proof_len = len;
+    return BBP_OK;
+}
+
+int bbp_rangeproof_prove_multiple(bbp_ctx *ctx, const uint64_t *values, const uint8_t *blindings, size_t m, size_t nbits, const uint8_t rng_seed[32],
+                                  uint8_t *proof_out, size_t *proof_len, uint8_t *commitments_out) {
+    if (!proof_len) return BBP_ERR_INPUT;
+    int st = 0;
+    size_t cap = *proof_len;
+    int rc = bbp_rangeproof_prove_batch(ctx, 1, values, blindings, m, nbits, rng_seed, proof_out, cap, proof_len, commitments_out, &st);
+    return rc ? rc : st;
+}
+
+int bbp_rangeproof_verify_batch(bbp_ctx *ctx, size_t n_proofs, const uint8_t *proofs, size_t proof_stride, size_t proof_len, const uint8_t *commitments,
+                                size_t m, size_t nbits, const uint8_t *rng_seeds, int *statuses) {
+    if (!ctx || !proofs || !commitments || !rng_seeds || !statuses || n_proofs == 0 || proof_len > proof_stride) return BBP_ERR_INPUT;
+    if (!rp_params_ok(nbits, m)) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    std::vector<rp_verify_job> jobs(n_proofs);
+    for (size_t i = 0; i < n_proofs; i++) {
+        jobs[i].proof.assign(proofs + i * proof_stride, proofs + i * proof_stride + proof_len);
+        jobs[i].commitments.assign(commitments + 32 * i * m, commitments + 32 * (i + 1) * m);
+        memcpy(jobs[i].rng_seed, rng_seeds + 32 * i, 32);
+    }
+    int rc = rp_verify_group(ctx, jobs, (uint32_t)nbits, (uint32_t)m);
+    if (rc) return rc;
+    for (size_t i = 0; i < n_proofs; i++) statuses[i] = jobs[i].status;
+    return BBP_OK;
+}
+
+int bbp_rangeproof_verify_multiple(bbp_ctx *ctx, const uint8_t *proof, size_t proof_len, const uint8_t *commitments, size_t m, size_t nbits,
+                                   const uint8_t rng_seed[32]) {
+    int st = 0;
+    int rc = bbp_rangeproof_verify_batch(ctx, 1, proof, proof_len, proof_len, commitments, m, nbits, rng_seed, &st);
+    return rc ? rc : st;
 }
 
 }  // extern "C"

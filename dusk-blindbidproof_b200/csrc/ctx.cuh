@@ -21,7 +21,8 @@ struct bbp_ctx {
     cudaStream_t stream = nullptr;
     bbp::msm_engine msm;
     uint64_t launches = 0;
-    // generators: index 0 = B, 1 = B_blinding, then per party j: G[j][0..cap), H[j][0..cap)
+    // generators: index 0 = B, 1 = B_blinding, then G[party 0][0..cap), G[party 1][..), ..., then all H the same way, so
+    // that the aggregated vectors bulletproofs iterates (party-major) are contiguous column ranges
     uint32_t gens_capacity = 0, party_capacity = 0;
     size_t n_gens = 0;
     uint8_t *d_gens_ext = nullptr;     // n_gens x 128 B
@@ -37,7 +38,7 @@ struct bbp_ctx {
     size_t cap_in = 0, cap_out = 0, cap_scratch = 0;
 
     size_t gen_index(int which, uint32_t party, uint32_t i) const {
-        return 2 + ((size_t)party * 2 + (which == 'H' ? 1 : 0)) * gens_capacity + i;
+        return 2 + (which == 'H' ? (size_t)gens_capacity * party_capacity : 0) + (size_t)party * gens_capacity + i;
     }
 
     int stage_in(const void *host, size_t bytes) {

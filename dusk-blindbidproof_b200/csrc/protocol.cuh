@@ -271,7 +271,8 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     dev_template *dt;
     if ((rc = proto_template(ctx, 4, L, &dt))) return rc;
     const circuit_template &T = *dt->tpl;
-    const uint32_t n1 = T.n1, m = T.m, n = next_pow2_u32(n1), lg = log2_u32(n), slot_len = 2 + 2 * n;
+    const uint32_t n1 = T.n1, m = T.m, n = next_pow2_u32(n1), lg = log2_u32(n);
+    const uint32_t gcols = ctx->gens_capacity * ctx->party_capacity, slot_len = 2 + 2 * gcols;
     if (n > ctx->gens_capacity || ctx->party_capacity < 1) {   // bp_gens.gens_capacity < padded_n -> InvalidGeneratorsLength
         for (size_t i : idx) jobs[i].status = BBP_ERR_INVALID_GENERATORS_LENGTH;
         return 0;
@@ -350,7 +351,7 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
 
     sc_batch SB;
     memset(&SB, 0, sizeof SB);
-    SB.n_proofs = B; SB.n1 = n1; SB.q = T.q; SB.m = m; SB.n = n; SB.lg_n = lg; SB.n_pub = T.n_pub;
+    SB.n_proofs = B; SB.n1 = n1; SB.q = T.q; SB.m = m; SB.n = n; SB.lg_n = lg; SB.n_pub = T.n_pub; SB.gcols = gcols;
     SB.row_ptr = dt->row_ptr; SB.entries = dt->entries; SB.const_j = dt->const_j; SB.const_idx = dt->const_idx; SB.n_const = (uint32_t)T.const_j.size();
     SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>();
     const sc *dw = ps->wit.as<sc>();
@@ -609,7 +610,7 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     dev_template *dt;
     if ((rc = proto_template(ctx, P0.nc, P0.nt, &dt))) return rc;
     const circuit_template &T = *dt->tpl;
-    const uint32_t n1 = T.n1, m = T.m, n = P0.n, lg = P0.lg, slot_len = 2 + 2 * n, ds = m + 11 + 2 * lg;
+    const uint32_t n1 = T.n1, m = T.m, n = P0.n, lg = P0.lg, gcols = ctx->gens_capacity * ctx->party_capacity, slot_len = 2 + 2 * gcols, ds = m + 11 + 2 * lg;
     const uint32_t n_groups = combined ? 1 : B;
     phase_trace trace(combined ? "verify_group(combined)" : "verify_group(each)");
 
@@ -654,7 +655,7 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     trace.mark("host_pack+h2d");
     sc_batch SB;
     memset(&SB, 0, sizeof SB);
-    SB.n_proofs = B; SB.n1 = n1; SB.q = T.q; SB.m = m; SB.n = n; SB.lg_n = lg; SB.n_pub = T.n_pub;
+    SB.n_proofs = B; SB.n1 = n1; SB.q = T.q; SB.m = m; SB.n = n; SB.lg_n = lg; SB.n_pub = T.n_pub; SB.gcols = gcols;
     SB.row_ptr = dt->row_ptr; SB.entries = dt->entries; SB.const_j = dt->const_j; SB.const_idx = dt->const_idx; SB.n_const = (uint32_t)T.const_j.size();
     SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>();
     SB.pub = ps->pub.as<sc>(); SB.dyn_out = ps->dyn_sc.as<sc>(); SB.dyn_stride = ds; SB.stat = ps->stat.as<sc>();

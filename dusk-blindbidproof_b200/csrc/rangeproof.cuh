@@ -1,0 +1,357 @@
+// Aggregated range proofs on the GPU: bulletproofs 1.0.4 RangeProof::{prove_multiple, verify_multiple} with the
+// dealer / party protocol collapsed into one prover. The reference has no call site;
+// BASELINE.json configs[4] names the workload (m = 64 parties x n = 64 bits => a 4096-element inner-product argument).
+// Because every party message the dealer adds up is a Pedersen / vector commitment, the sums A = sum A_j, S = sum S_j,
+// T_k = sum T_{k,j} are single MSMs over the concatenated generators — the same group elements, hence the same bytes.
+//
+// Generator requirement: the context must hold BulletproofGens::new(n_bits, >= m), i.e. bbp_init(device, n_bits, parties),
+// so that the aggregated G / H vectors are contiguous column ranges of the resident table.
+// RNG contract: upstream draws from the caller's rng (not a TranscriptRng); here the rng is the SHAKE256 stream of the
+// caller's 32-byte seed, 64 bytes per Scalar::random in upstream's draw order (per party: a_blinding, s_blinding,
+// s_L[0..n), s_R[0..n); then per party: t_1 blinding, t_2 blinding). The verifier's batching scalar c is the first
+// draw of SHAKE256(rng32). Transcript label: "bbp-rangeproof" (caller-chosen in upstream).
+#pragma once
+#include "protocol.cuh"
+
+namespace bbp {
+
+struct shake_scalar_rng {
+    keccak_sponge s;
+    explicit shake_scalar_rng(const uint8_t seed[32]) : s(shake256_new()) { s.absorb(seed, 32); }
+    sc random_scalar() {
+        uint8_t b[64];
+        s.squeeze(b, 64);
+        return sc_from_wide(b);
+    }
+};
+
+struct rp_prove_job {
+    std::vector<uint64_t> values;
+    std::vector<sc> blindings;
+    uint8_t rng_seed[32];
+    int status = 0;
+    std::vector<uint8_t> proof, commitments;
+};
+
+inline bool rp_params_ok(size_t nbits, size_t m) {
+    return (nbits == 8 || nbits == 16 || nbits == 32 || nbits == 64) && m != 0 && (m & (m - 1)) == 0;
+}
+
+inline sc sc_pow_u64(const sc &x, uint64_t e) {
+    sc r = sc_one(), b = x;
+    while (e) {
+        if (e & 1) r = sc_mul(r, b);
+        b = sc_mul(b, b);
+        e >>= 1;
+    }
+    return r;
+}
+
+// all jobs share (nbits, m)
+inline int rp_prove_group(bbp_ctx *ctx, std::vector<rp_prove_job> &jobs, uint32_t nbits) {
+    proto_state *ps = proto_get(ctx);
+    const uint32_t P = (uint32_t)jobs.size(), m = (uint32_t)jobs[0].values.size(), nm = nbits * m, lg = log2_u32(nm);
+    const uint32_t gcols = ctx->gens_capacity * ctx->party_capacity, slot_len = 2 + 2 * gcols;
+    int rc;
+    if (ctx->gens_capacity != nbits || ctx->party_capacity < m) {
+        for (auto &J : jobs) J.status = BBP_ERR_INVALID_GENERATORS_LENGTH;
+        return 0;
+    }
+    if ((rc = proto_tables(ctx))) return rc;
+    struct hstate {
+        std::unique_ptr<merlin_transcript> tr;
+        std::unique_ptr<shake_scalar_rng> rng;
+        sc sum_a, sum_s, sum_t1, sum_t2, y, z, x;
+        uint8_t A[32], S[32], T1[32], T2[32];
+        sc t_x, t_x_bl, e_bl;
+        std::vector<uint8_t> LR;
+    };
+    std::vector<hstate> hs(P);
+    // ---- party draws, V commitments
+    std::vector<sc> sLR((size_t)2 * P * nm), blind3((size_t)P * 3, sc_zero()), cv((size_t)P * m * 2);
+    std::vector<uint64_t> vals((size_t)P * m);
+    parallel_for(P, [&](size_t pi) {
+        rp_prove_job &J = jobs[pi];
+        hstate &H = hs[pi];
+        H.rng.reset(new shake_scalar_rng(J.rng_seed));
+        H.sum_a = sc_zero(); H.sum_s = sc_zero();
+        for (uint32_t j = 0; j < m; j++) {
+            vals[pi * m + j] = J.values[j];
+            cv[(pi * m + j) * 2] = sc_from_u64(J.values[j]);
+            cv[(pi * m + j) * 2 + 1] = J.blindings[j];
+            H.sum_a = sc_add(H.sum_a, H.rng->random_scalar());
+            H.sum_s = sc_add(H.sum_s, H.rng->random_scalar());
+            for (uint32_t i = 0; i < nbits; i++) sLR[(size_t)pi * nm + j * nbits + i] = H.rng->random_scalar();
+            for (uint32_t i = 0; i < nbits; i++) sLR[(size_t)(P + pi) * nm + j * nbits + i] = H.rng->random_scalar();
+        }
+        blind3[pi * 3] = H.sum_a; blind3[pi * 3 + 1] = H.sum_s;
+    });
+    std::vector<uint8_t> V((size_t)P * m * 32);
+    if ((rc = pedersen_commit_host(ctx, cv.data(), (size_t)P * m, V.data()))) return rc;
+
+    if ((rc = ps->chal.ensure((size_t)P * CH_N * 32)) || (rc = ps->zpow.ensure(32)) || (rc = ps->ypow.ensure((size_t)P * nm * 32)) ||
+        (rc = ps->yinvpow.ensure((size_t)P * nm * 32)) || (rc = ps->wit.ensure((size_t)2 * P * nm * 32)) || (rc = ps->blind3.ensure((size_t)P * 96)) ||
+        (rc = ps->poly.ensure((size_t)P * 4 * nm * 32)) || (rc = ps->tout.ensure((size_t)P * 8 * 32)) || (rc = ps->a.ensure((size_t)P * nm * 32)) ||
+        (rc = ps->b.ensure((size_t)P * nm * 32)) || (rc = ps->sG.ensure((size_t)P * nm * 32)) || (rc = ps->sH.ensure((size_t)P * nm * 32)) ||
+        (rc = ps->slots.ensure((size_t)P * 2 * slot_len * 32)) || (rc = ps->ab.ensure((size_t)P * 64)) || (rc = ps->msm_out.ensure((size_t)P * 2 * 32)) ||
+        (rc = ps->pub.ensure((size_t)P * m * 8)))
+        return rc;
+    if ((rc = h2d(ctx, ps->wit.p, sLR.data(), sLR.size() * 32)) || (rc = h2d(ctx, ps->blind3.p, blind3.data(), blind3.size() * 32)) ||
+        (rc = h2d(ctx, ps->pub.p, vals.data(), vals.size() * 8)))
+        return rc;
+    sc_batch SB;
+    memset(&SB, 0, sizeof SB);
+    SB.n_proofs = P; SB.n = nm; SB.lg_n = lg; SB.gcols = gcols; SB.rp_bits = nbits; SB.rp_m = m; SB.q = 0;
+    SB.rp_values = ps->pub.as<uint64_t>();
+    SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>();
+    SB.sL = ps->wit.as<sc>(); SB.sR = ps->wit.as<sc>() + (size_t)P * nm; SB.blind3 = ps->blind3.as<sc>();
+    SB.poly = ps->poly.as<sc>(); SB.tout = ps->tout.as<sc>(); SB.a = ps->a.as<sc>(); SB.b = ps->b.as<sc>(); SB.sG = ps->sG.as<sc>(); SB.sH = ps->sH.as<sc>();
+    SB.slots = ps->slots.as<sc>(); SB.ab_out = ps->ab.as<sc>();
+
+    // ---- A, S
+    k_rp_commit_slots<<<2 * P, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+    ctx->launches++;
+    if ((rc = msm_gens_device(ctx, SB.slots, slot_len, 2 * P, ps->msm_out.p, nullptr))) return rc;
+    std::vector<uint8_t> as((size_t)P * 64);
+    if ((rc = d2h_sync(ctx, as.data(), ps->msm_out.p, as.size()))) return rc;
+    std::vector<sc> chal((size_t)P * CH_N, sc_zero());
+    parallel_for(P, [&](size_t pi) {
+        rp_prove_job &J = jobs[pi];
+        hstate &H = hs[pi];
+        J.commitments.assign(&V[pi * m * 32], &V[pi * m * 32] + (size_t)m * 32);
+        H.tr.reset(new merlin_transcript("bbp-rangeproof"));
+        H.tr->rangeproof_domain_sep(nbits, m);
+        for (uint32_t j = 0; j < m; j++) H.tr->append_point("V", &V[(pi * m + j) * 32]);
+        memcpy(H.A, &as[pi * 64], 32); memcpy(H.S, &as[pi * 64 + 32], 32);
+        H.tr->append_point("A", H.A);
+        H.tr->append_point("S", H.S);
+        H.y = H.tr->challenge_scalar("y");
+        H.z = H.tr->challenge_scalar("z");
+        sc *c = &chal[pi * CH_N];
+        c[CH_Y] = H.y; c[CH_Z] = H.z; c[CH_YINV] = sc_invert(H.y);
+        H.sum_t1 = sc_zero(); H.sum_t2 = sc_zero();
+        for (uint32_t j = 0; j < m; j++) {
+            H.sum_t1 = sc_add(H.sum_t1, H.rng->random_scalar());
+            H.sum_t2 = sc_add(H.sum_t2, H.rng->random_scalar());
+        }
+    });
+    if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32))) return rc;
+    k_powers<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+    k_rp_polys<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+    ctx->launches += 2;
+    std::vector<sc> tout((size_t)P * 8);
+    if ((rc = d2h_sync(ctx, tout.data(), ps->tout.p, tout.size() * 32))) return rc;
+    // ---- T_1, T_2
+    std::vector<sc> tv((size_t)P * 4);
+    for (uint32_t pi = 0; pi < P; pi++) {
+        tv[pi * 4] = tout[pi * 8 + 1]; tv[pi * 4 + 1] = hs[pi].sum_t1;
+        tv[pi * 4 + 2] = tout[pi * 8 + 2]; tv[pi * 4 + 3] = hs[pi].sum_t2;
+    }
+    std::vector<uint8_t> Tp((size_t)P * 64);
+    if ((rc = pedersen_commit_host(ctx, tv.data(), (size_t)P * 2, Tp.data()))) return rc;
+    parallel_for(P, [&](size_t pi) {
+        rp_prove_job &J = jobs[pi];
+        hstate &H = hs[pi];
+        memcpy(H.T1, &Tp[pi * 64], 32); memcpy(H.T2, &Tp[pi * 64 + 32], 32);
+        H.tr->append_point("T_1", H.T1);
+        H.tr->append_point("T_2", H.T2);
+        sc x = H.tr->challenge_scalar("x");
+        H.x = x;
+        if (sc_iszero(x)) { J.status = BBP_ERR_VERIFICATION; }   // MaliciousDealer in upstream; probability 2^-252
+        const sc *t = &tout[pi * 8];
+        H.t_x = sc_add(t[0], sc_mul(x, sc_add(t[1], sc_mul(x, t[2]))));
+        sc zz = sc_mul(H.z, H.z), acc = sc_zero(), ez = zz;
+        for (uint32_t j = 0; j < m; j++) { acc = sc_add(acc, sc_mul(ez, J.blindings[j])); ez = sc_mul(ez, H.z); }
+        H.t_x_bl = sc_add(acc, sc_mul(x, sc_add(H.sum_t1, sc_mul(x, H.sum_t2))));
+        H.e_bl = sc_add(H.sum_a, sc_mul(H.sum_s, x));
+        H.tr->append_scalar("t_x", H.t_x);
+        H.tr->append_scalar("t_x_blinding", H.t_x_bl);
+        H.tr->append_scalar("e_blinding", H.e_bl);
+        sc *c = &chal[pi * CH_N];
+        c[CH_X] = x;
+        c[CH_W] = H.tr->challenge_scalar("w");
+        H.tr->innerproduct_domain_sep(nm);
+        H.LR.resize((size_t)64 * lg);
+    });
+    if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32))) return rc;
+    k_rp_ipp_init<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+    ctx->launches++;
+    std::vector<uint8_t> lr((size_t)P * 64);
+    for (uint32_t j = 0; j < lg; j++) {
+        k_ipp_round<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB, j, 0);
+        ctx->launches++;
+        if ((rc = msm_gens_device(ctx, SB.slots, slot_len, 2 * P, ps->msm_out.p, nullptr))) return rc;
+        if ((rc = d2h_sync(ctx, lr.data(), ps->msm_out.p, lr.size()))) return rc;
+        parallel_for(P, [&](size_t pi) {
+            hstate &H = hs[pi];
+            memcpy(&H.LR[(size_t)64 * j], &lr[pi * 64], 64);
+            H.tr->append_point("L", &lr[pi * 64]);
+            H.tr->append_point("R", &lr[pi * 64 + 32]);
+            sc *c = &chal[pi * CH_N];
+            c[CH_UJ] = H.tr->challenge_scalar("u");
+            c[CH_UJINV] = sc_invert(c[CH_UJ]);
+        });
+        if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32))) return rc;
+    }
+    k_ipp_round<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB, lg, 1);
+    ctx->launches++;
+    std::vector<sc> ab((size_t)P * 2);
+    if ((rc = d2h_sync(ctx, ab.data(), ps->ab.p, ab.size() * 32))) return rc;
+    for (uint32_t pi = 0; pi < P; pi++) {
+        rp_prove_job &J = jobs[pi];
+        hstate &H = hs[pi];
+        if (J.status) continue;
+        std::vector<uint8_t> &o = J.proof;
+        o.clear();
+        auto put = [&](const uint8_t *b) { o.insert(o.end(), b, b + 32); };
+        auto puts = [&](const sc &s) { uint8_t t[32]; sc_tobytes(t, s); put(t); };
+        put(H.A); put(H.S); put(H.T1); put(H.T2); puts(H.t_x); puts(H.t_x_bl); puts(H.e_bl);
+        o.insert(o.end(), H.LR.begin(), H.LR.end());
+        puts(ab[pi * 2]); puts(ab[pi * 2 + 1]);
+    }
+    return 0;
+}
+
+struct rp_verify_job {
+    std::vector<uint8_t> proof, commitments;   // m x 32
+    uint8_t rng_seed[32];
+    int status = 0;
+};
+
+// every job independently (one mega-check each); all jobs share (nbits, m)
+inline int rp_verify_group(bbp_ctx *ctx, std::vector<rp_verify_job> &jobs, uint32_t nbits, uint32_t m) {
+    proto_state *ps = proto_get(ctx);
+    const uint32_t nm = nbits * m, lg = log2_u32(nm);
+    const uint32_t gcols = ctx->gens_capacity * ctx->party_capacity, slot_len = 2 + 2 * gcols, ds = 4 + 2 * lg + m;
+    int rc;
+    if (ctx->gens_capacity != nbits || ctx->party_capacity < m) {
+        for (auto &J : jobs) J.status = BBP_ERR_INVALID_GENERATORS_LENGTH;
+        return 0;
+    }
+    if ((rc = proto_tables(ctx))) return rc;
+    std::vector<size_t> live;
+    std::vector<std::vector<sc>> chal_all(jobs.size()), dyn_all(jobs.size());
+    std::vector<std::vector<uint8_t>> pts_all(jobs.size());
+    parallel_for(jobs.size(), [&](size_t i) {
+        rp_verify_job &J = jobs[i];
+        const uint8_t *pf = J.proof.data();
+        size_t len = J.proof.size();
+        J.status = BBP_ERR_FORMAT;
+        if (len % 32 != 0 || len < 7 * 32) return;
+        sc t_x, t_x_bl, e_bl, a, b;
+        if (!sc_from_canonical(t_x, pf + 128) || !sc_from_canonical(t_x_bl, pf + 160) || !sc_from_canonical(e_bl, pf + 192)) return;
+        size_t ne = (len - 224) / 32;
+        if (ne < 2 || (ne - 2) % 2 != 0) return;
+        size_t lg_p = (ne - 2) / 2;
+        if (lg_p >= 32) return;
+        const uint8_t *LR = pf + 224;
+        if (!sc_from_canonical(a, LR + 64 * lg_p) || !sc_from_canonical(b, LR + 64 * lg_p + 32)) return;
+        J.status = BBP_ERR_VERIFICATION;
+        merlin_transcript tr("bbp-rangeproof");
+        tr.rangeproof_domain_sep(nbits, m);
+        for (uint32_t j = 0; j < m; j++) tr.append_point("V", &J.commitments[32 * (size_t)j]);
+        if (!tr.validate_and_append_point("A", pf) || !tr.validate_and_append_point("S", pf + 32)) return;
+        sc y = tr.challenge_scalar("y"), z = tr.challenge_scalar("z");
+        if (!tr.validate_and_append_point("T_1", pf + 64) || !tr.validate_and_append_point("T_2", pf + 96)) return;
+        sc x = tr.challenge_scalar("x");
+        tr.append_scalar("t_x", t_x);
+        tr.append_scalar("t_x_blinding", t_x_bl);
+        tr.append_scalar("e_blinding", e_bl);
+        sc w = tr.challenge_scalar("w");
+        shake_scalar_rng crng(J.rng_seed);
+        sc c = crng.random_scalar();
+        if (nm != ((size_t)1 << lg_p)) return;
+        tr.innerproduct_domain_sep(nm);
+        std::vector<sc> uj(lg_p);
+        for (size_t j = 0; j < lg_p; j++) {
+            if (!tr.validate_and_append_point("L", LR + 64 * j) || !tr.validate_and_append_point("R", LR + 64 * j + 32)) return;
+            uj[j] = tr.challenge_scalar("u");
+        }
+        std::vector<sc> all(uj);
+        all.push_back(y);
+        std::vector<sc> pre(all.size()), allinv(all.size());
+        sc acc = sc_one();
+        for (size_t k = 0; k < all.size(); k++) { pre[k] = acc; acc = sc_mul(acc, all[k]); }
+        sc inv = sc_invert(acc);
+        for (size_t k = all.size(); k-- > 0;) { allinv[k] = sc_mul(inv, pre[k]); inv = sc_mul(inv, all[k]); }
+        std::vector<sc> &ch = chal_all[i];
+        ch.assign(CH_N, sc_zero());
+        ch[CH_Y] = y; ch[CH_YINV] = allinv[lg_p]; ch[CH_Z] = z; ch[CH_X] = x; ch[CH_W] = w; ch[CH_A] = a; ch[CH_B] = b; ch[CH_RHO] = sc_one();
+        for (size_t j = 0; j < lg_p; j++) { ch[CH_UJ0 + j] = uj[j]; ch[CH_UJ0 + lg_p + j] = allinv[j]; }
+        // B and B_blinding coefficients
+        sc zz = sc_mul(z, z);
+        auto sum_pow = [&](const sc &base, size_t cnt) { sc s = sc_zero(), e = sc_one(); for (size_t k = 0; k < cnt; k++) { s = sc_add(s, e); e = sc_mul(e, base); } return s; };
+        sc sum_y = sum_pow(y, nm), sum_2 = sum_pow(sc_from_u64(2), nbits), sum_z = sum_pow(z, m);
+        sc delta = sc_sub(sc_mul(sc_sub(z, zz), sum_y), sc_mul(sc_mul(sc_mul(zz, z), sum_2), sum_z));
+        ch[CH_TX] = sc_add(sc_mul(w, sc_sub(t_x, sc_mul(a, b))), sc_mul(c, sc_sub(delta, t_x)));
+        ch[CH_TXBL] = sc_sub(sc_neg(e_bl), sc_mul(c, t_x_bl));
+        // dynamic: A, S, T_1, T_2, L_j, R_j, V_j
+        std::vector<sc> &d = dyn_all[i];
+        std::vector<uint8_t> &pp = pts_all[i];
+        d.assign(ds, sc_zero());
+        pp.resize((size_t)ds * 32);
+        memcpy(pp.data(), pf, 128);
+        d[0] = sc_one(); d[1] = x; d[2] = sc_mul(c, x); d[3] = sc_mul(c, sc_mul(x, x));
+        for (size_t j = 0; j < lg_p; j++) {
+            memcpy(&pp[(4 + j) * 32], LR + 64 * j, 32);
+            memcpy(&pp[(4 + lg_p + j) * 32], LR + 64 * j + 32, 32);
+            d[4 + j] = sc_mul(uj[j], uj[j]);
+            d[4 + lg_p + j] = sc_mul(allinv[j], allinv[j]);
+        }
+        sc ez = sc_mul(c, zz);
+        for (uint32_t j = 0; j < m; j++) {
+            memcpy(&pp[(4 + 2 * lg_p + j) * 32], &J.commitments[32 * (size_t)j], 32);
+            d[4 + 2 * lg_p + j] = ez;
+            ez = sc_mul(ez, z);
+        }
+        J.status = 1;   // live
+    });
+    for (size_t i = 0; i < jobs.size(); i++) if (jobs[i].status == 1) live.push_back(i);
+    const uint32_t P = (uint32_t)live.size();
+    if (!P) return 0;
+    std::vector<uint8_t> pts((size_t)P * ds * 32);
+    for (uint32_t k = 0; k < P; k++) memcpy(&pts[(size_t)k * ds * 32], pts_all[live[k]].data(), (size_t)ds * 32);
+    size_t voff = ((size_t)P * ds + 3) & ~(size_t)3;
+    if ((rc = ps->dyn_pts.ensure(pts.size())) || (rc = ps->dyn_niels.ensure((size_t)P * ds * 96)) || (rc = ps->valid.ensure(voff + 4))) return rc;
+    if ((rc = h2d(ctx, ps->dyn_pts.p, pts.data(), pts.size()))) return rc;
+    int *d_all = (int *)(ps->valid.p + voff);
+    BBP_CUDA_OK(cudaMemsetAsync(d_all, 1, 4, ctx->stream));
+    k_decompress_to_niels<<<(P * ds + 127) / 128, 128, 0, ctx->stream>>>(ps->dyn_pts.as<uint32_t>(), ps->dyn_niels.p, P * ds, d_all, ps->valid.p);
+    ctx->launches++;
+    std::vector<uint8_t> valid((size_t)P * ds);
+    if ((rc = d2h_sync(ctx, valid.data(), ps->valid.p, valid.size()))) return rc;
+    std::vector<sc> chal((size_t)P * CH_N), dyn((size_t)P * ds);
+    std::vector<uint8_t> alive(P, 1);
+    for (uint32_t k = 0; k < P; k++) {
+        for (uint32_t t = 0; t < ds; t++) if (!valid[(size_t)k * ds + t]) alive[k] = 0;
+        std::vector<sc> &ch = chal_all[live[k]];
+        if (!alive[k]) { ch[CH_RHO] = sc_zero(); ch[CH_TX] = sc_zero(); ch[CH_TXBL] = sc_zero(); }
+        memcpy(&chal[(size_t)k * CH_N], ch.data(), (size_t)CH_N * 32);
+        for (uint32_t t = 0; t < ds; t++) dyn[(size_t)k * ds + t] = alive[k] ? dyn_all[live[k]][t] : sc_zero();
+    }
+    if ((rc = ps->chal.ensure(chal.size() * 32)) || (rc = ps->dyn_sc.ensure(dyn.size() * 32)) || (rc = ps->zpow.ensure(32)) ||
+        (rc = ps->ypow.ensure((size_t)P * nm * 32)) || (rc = ps->yinvpow.ensure((size_t)P * nm * 32)) || (rc = ps->stat.ensure((size_t)P * slot_len * 32)) ||
+        (rc = ps->stat_red.ensure((size_t)P * slot_len * 32)) || (rc = ps->msm_ext.ensure((size_t)2 * P * 128)) || (rc = ps->flags.ensure(P)))
+        return rc;
+    if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32)) || (rc = h2d(ctx, ps->dyn_sc.p, dyn.data(), dyn.size() * 32))) return rc;
+    sc_batch SB;
+    memset(&SB, 0, sizeof SB);
+    SB.n_proofs = P; SB.n = nm; SB.lg_n = lg; SB.gcols = gcols; SB.rp_bits = nbits; SB.rp_m = m; SB.q = 0;
+    SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>(); SB.stat = ps->stat.as<sc>();
+    k_powers<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+    k_rp_verify_scalars<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+    k_stat_reduce<<<dim3((slot_len + BBP_SC_THREADS - 1) / BBP_SC_THREADS, P), BBP_SC_THREADS, 0, ctx->stream>>>(SB.stat, 1, slot_len, ps->stat_red.as<sc>());
+    ctx->launches += 3;
+    uint8_t *ext = ps->msm_ext.p;
+    if ((rc = msm_gens_device(ctx, ps->stat_red.as<sc>(), slot_len, P, nullptr, ext))) return rc;
+    msm_shape sh = msm_engine::make_shape(P * ds, ds, P * ds, false, 0, 0, 0);
+    if ((rc = ctx->msm.run(sh, ps->dyn_sc.p, ps->dyn_niels.p, ext + (size_t)P * 128, nullptr))) return rc;
+    k_group_sum_identity<<<(P + 63) / 64, 64, 0, ctx->stream>>>(ext, P, 2, P, ps->flags.p, nullptr);
+    ctx->launches++;
+    std::vector<uint8_t> fl(P);
+    if ((rc = d2h_sync(ctx, fl.data(), ps->flags.p, P))) return rc;
+    for (uint32_t k = 0; k < P; k++) jobs[live[k]].status = (alive[k] && fl[k]) ? 0 : BBP_ERR_VERIFICATION;
+    return 0;
+}
+
+}  // namespace bbp

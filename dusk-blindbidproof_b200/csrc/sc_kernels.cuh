@@ -30,6 +30,8 @@ enum chal_slot : uint32_t {
 
 struct sc_batch {
     uint32_t n_proofs, n1, q, m, n, lg_n, n_pub;
+    uint32_t gcols;                            // generator columns per family in the table (capacity x parties >= n): slot
+                                               // layout [B, B_blinding, G[0..gcols), H[0..gcols)], slot length 2 + 2 gcols
     const uint32_t *row_ptr, *entries;         // circuit template CSR (shared by the batch)
     const uint32_t *const_j, *const_idx;       // constant terms (verifier)
     uint32_t n_const;
@@ -48,7 +50,10 @@ struct sc_batch {
     const sc *pub;                             // [n_proofs][n_pub] public value tables (normal form)
     sc *dyn_out;                               // [n_proofs][dyn_stride]: first m entries = rho * wV[i] * r * x^2 (written here)
     uint32_t dyn_stride;
-    sc *stat;                                  // [n_proofs][2 + 2n] rho-weighted static-base scalars (Montgomery)
+    sc *stat;                                  // [n_proofs][2 + 2 gcols] rho-weighted static-base scalars (Montgomery)
+    // aggregated range proofs (bulletproofs RangeProof::prove_multiple / verify_multiple)
+    const uint64_t *rp_values;                 // [n_proofs][rp_m]
+    uint32_t rp_bits, rp_m;                    // n = rp_bits * rp_m
 };
 
 __device__ __forceinline__ sc sc_mont_one() { return sc_to_mont(sc_one()); }
@@ -118,7 +123,7 @@ __device__ __forceinline__ sc flatten_row(const sc_batch &B, const sc *zpow, uin
 //   A_I1 = i_bl B_bl + <a_L, G> + <a_R, H>;  A_O1 = o_bl B_bl + <a_O, G>;  S1 = s_bl B_bl + <s_L, G> + <s_R, H>
 __global__ void __launch_bounds__(BBP_SC_THREADS) k_commit_slots(sc_batch B) {
     const uint32_t p = blockIdx.x / 3, which = blockIdx.x % 3;
-    const uint32_t slot_len = 2 + 2 * B.n;
+    const uint32_t slot_len = 2 + 2 * B.gcols;
     sc *out = B.slots + (size_t)blockIdx.x * slot_len;
     const sc *g = (which == 0 ? B.aL : which == 1 ? B.aO : B.sL) + (size_t)p * B.n1;
     const sc *h = (which == 0 ? B.aR : which == 1 ? nullptr : B.sR);
@@ -126,8 +131,8 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_commit_slots(sc_batch B) {
     for (uint32_t i = threadIdx.x; i < slot_len; i += BBP_SC_THREADS) {
         sc v = sc_zero();
         if (i == 1) v = B.blind3[(size_t)p * 3 + which];
-        else if (i >= 2 && i < 2 + B.n) { if (i - 2 < B.n1) v = g[i - 2]; }
-        else if (i >= 2 + B.n) { if (h && i - 2 - B.n < B.n1) v = h[i - 2 - B.n]; }
+        else if (i >= 2 && i < 2 + B.gcols) { if (i - 2 < B.n1) v = g[i - 2]; }
+        else if (i >= 2 + B.gcols) { if (h && i - 2 - B.gcols < B.n1) v = h[i - 2 - B.gcols]; }
         out[i] = v;
     }
 }
@@ -231,26 +236,30 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_ipp_round(sc_batch B, uint32
     }
     cl = block_sum_sc(cl, smem);
     cr = block_sum_sc(cr, smem);
-    const uint32_t slot_len = 2 + 2 * n;
+    const uint32_t gc = B.gcols, slot_len = 2 + 2 * gc;
     sc *sl = B.slots + (size_t)(2 * p) * slot_len, *sr = sl + slot_len;
     if (t == 0) {
         sc wM = sc_to_mont(ch[CH_W]);
         sl[0] = sc_from_mont(mm(cl, wM)); sr[0] = sc_from_mont(mm(cr, wM));
         sl[1] = sc_zero(); sr[1] = sc_zero();
     }
-    for (uint32_t i = t; i < n; i += BBP_SC_THREADS) {
-        uint32_t k = i & (nj - 1);
+    for (uint32_t i = t; i < gc; i += BBP_SC_THREADS) {
         sc zero = sc_zero();
+        if (i >= n) {     // generator columns beyond the vector length are unused
+            sl[2 + i] = zero; sr[2 + i] = zero; sl[2 + gc + i] = zero; sr[2 + gc + i] = zero;
+            continue;
+        }
+        uint32_t k = i & (nj - 1);
         if (k >= nh) {   // G[i] sits in the high half of its block: L takes a_lo * G_hi, R takes b_lo * H_hi
             sl[2 + i] = sc_from_mont(mm(a[k - nh], sG[i]));
             sr[2 + i] = zero;
-            sl[2 + n + i] = zero;
-            sr[2 + n + i] = sc_from_mont(mm(b[k - nh], sH[i]));
+            sl[2 + gc + i] = zero;
+            sr[2 + gc + i] = sc_from_mont(mm(b[k - nh], sH[i]));
         } else {          // low half: R takes a_hi * G_lo, L takes b_hi * H_lo
             sl[2 + i] = zero;
             sr[2 + i] = sc_from_mont(mm(a[k + nh], sG[i]));
-            sl[2 + n + i] = sc_from_mont(mm(b[k + nh], sH[i]));
-            sr[2 + n + i] = zero;
+            sl[2 + gc + i] = sc_from_mont(mm(b[k + nh], sH[i]));
+            sr[2 + gc + i] = zero;
         }
     }
 }
@@ -274,7 +283,9 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_verify_scalars(sc_batch B) {
     __syncthreads();
     sc xM = sc_to_mont(ch[CH_X]), uM = sc_to_mont(ch[CH_U]), aM = sc_to_mont(ch[CH_A]), bM = sc_to_mont(ch[CH_B]);
     sc rhoM = sc_to_mont(ch[CH_RHO]), one = sc_mont_one();
-    sc *stat = B.stat + (size_t)p * (2 + 2 * n);
+    const uint32_t gc = B.gcols;
+    sc *stat = B.stat + (size_t)p * (2 + 2 * gc);
+    for (uint32_t i = n + t; i < gc; i += BBP_SC_THREADS) { stat[2 + i] = sc_zero(); stat[2 + gc + i] = sc_zero(); }
     // wc = - sum sign * z^(j+1) * pub[idx]
     sc wc = sc_zero();
     const sc *pub = B.pub + (size_t)p * B.n_pub;
@@ -306,7 +317,7 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_verify_scalars(sc_batch B) {
             h = sc_sub(sc_neg(mm(yinv[i], mm(bM, srev))), one);
         }
         stat[2 + i] = mm(rhoM, mm(uf, g));
-        stat[2 + n + i] = mm(rhoM, mm(uf, h));
+        stat[2 + gc + i] = mm(rhoM, mm(uf, h));
     }
     delta = block_sum_sc(delta, smem);
     sc rM = sc_to_mont(ch[CH_R]);
@@ -322,6 +333,109 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_verify_scalars(sc_batch B) {
         stat[0] = mm(rhoM, bs);
         stat[1] = mm(rhoM, bbs);
     }
+}
+
+// ================================================================ aggregated range proofs
+// vectors are indexed k = j * bits + i (party j, bit i), the order bulletproofs' aggregated generators iterate in.
+__device__ __forceinline__ uint32_t rp_bit(const sc_batch &B, uint32_t p, uint32_t k) {
+    return (uint32_t)((B.rp_values[(size_t)p * B.rp_m + k / B.rp_bits] >> (k % B.rp_bits)) & 1ull);
+}
+
+// slot 2p: A = (sum a_blinding) B_bl + sum_k (bit ? G_k : -H_k);  slot 2p+1: S = (sum s_blinding) B_bl + <s_L, G> + <s_R, H>
+__global__ void __launch_bounds__(BBP_SC_THREADS) k_rp_commit_slots(sc_batch B) {
+    const uint32_t p = blockIdx.x / 2, which = blockIdx.x % 2, gc = B.gcols, slot_len = 2 + 2 * gc;
+    sc *out = B.slots + (size_t)blockIdx.x * slot_len;
+    sc minus_one = sc_neg(sc_one());
+    for (uint32_t i = threadIdx.x; i < slot_len; i += BBP_SC_THREADS) {
+        sc v = sc_zero();
+        if (i == 1) v = B.blind3[(size_t)p * 3 + which];
+        else if (i >= 2) {
+            uint32_t k = (i - 2) % gc;
+            bool is_h = (i - 2) >= gc;
+            if (k < B.n) {
+                if (which == 0) {
+                    uint32_t bit = rp_bit(B, p, k);
+                    if (!is_h && bit) v = sc_one();
+                    if (is_h && !bit) v = minus_one;
+                } else {
+                    v = (is_h ? B.sR : B.sL)[(size_t)p * B.n + k];
+                }
+            }
+        }
+        out[i] = v;
+    }
+}
+
+// l0 = a_L - z, l1 = s_L, r0 = y^k (a_R + z) + z^(2+j) 2^i, r1 = y^k s_R; t0 = <l0,r0>, t1 = <l0,r1> + <l1,r0>, t2 = <l1,r1>
+__global__ void __launch_bounds__(BBP_SC_THREADS) k_rp_polys(sc_batch B) {
+    __shared__ sc smem[BBP_SC_THREADS];
+    const uint32_t p = blockIdx.x, t = threadIdx.x, n = B.n;
+    const sc *ch = B.chal + (size_t)p * CH_N, *ypow = B.ypow + (size_t)p * n;
+    sc *poly = B.poly + (size_t)p * 4 * n;
+    sc zM = sc_to_mont(ch[CH_Z]), one = sc_mont_one();
+    sc t0 = sc_zero(), t1 = t0, t2 = t0;
+    for (uint32_t k = t; k < n; k += BBP_SC_THREADS) {
+        uint32_t j = k / B.rp_bits, i = k % B.rp_bits, bit = rp_bit(B, p, k);
+        sc aL = bit ? one : sc_zero(), aR = bit ? sc_zero() : sc_neg(one);
+        sc sL = sc_to_mont(B.sL[(size_t)p * n + k]), sR = sc_to_mont(B.sR[(size_t)p * n + k]);
+        sc zz_j = sc_pow_small_mont(zM, 2 + j);
+        sc two_i = sc_to_mont(sc_from_u64(1ull << i));
+        sc l0 = sc_sub(aL, zM);
+        sc r0 = sc_add(mm(ypow[k], sc_add(aR, zM)), mm(zz_j, two_i));
+        sc r1 = mm(ypow[k], sR);
+        poly[k] = l0; poly[n + k] = sL; poly[2 * n + k] = r0; poly[3 * n + k] = r1;
+        t0 = sc_add(t0, mm(l0, r0));
+        t1 = sc_add(t1, sc_add(mm(l0, r1), mm(sL, r0)));
+        t2 = sc_add(t2, mm(sL, r1));
+    }
+    sc r[3] = {t0, t1, t2};
+    for (int k = 0; k < 3; k++) {
+        sc s = block_sum_sc(r[k], smem);
+        if (t == 0) B.tout[(size_t)p * 8 + k] = sc_from_mont(s);
+    }
+}
+
+// a = l0 + l1 x, b = r0 + r1 x, G factors 1, H factors y^-k
+__global__ void __launch_bounds__(BBP_SC_THREADS) k_rp_ipp_init(sc_batch B) {
+    const uint32_t p = blockIdx.x, n = B.n;
+    const sc *ch = B.chal + (size_t)p * CH_N, *poly = B.poly + (size_t)p * 4 * n, *yinv = B.yinvpow + (size_t)p * n;
+    sc xM = sc_to_mont(ch[CH_X]), one = sc_mont_one();
+    for (uint32_t k = threadIdx.x; k < n; k += BBP_SC_THREADS) {
+        size_t o = (size_t)p * n + k;
+        B.a[o] = sc_add(poly[k], mm(poly[n + k], xM));
+        B.b[o] = sc_add(poly[2 * n + k], mm(poly[3 * n + k], xM));
+        B.sG[o] = one;
+        B.sH[o] = yinv[k];
+    }
+}
+
+// verifier: G_k gets rho (-z - a s[k]), H_k gets rho (z + y^-k (z^2 z^j 2^i - b s[n-1-k])); the B / B_blinding coefficients
+// are computed on the host (they need only O(m + n) scalar work) and arrive, already weighted, in CH_TX / CH_TXBL.
+__global__ void __launch_bounds__(BBP_SC_THREADS) k_rp_verify_scalars(sc_batch B) {
+    __shared__ sc uj[64];
+    const uint32_t p = blockIdx.x, t = threadIdx.x, n = B.n, lg = B.lg_n, gc = B.gcols;
+    const sc *ch = B.chal + (size_t)p * CH_N, *yinv = B.yinvpow + (size_t)p * n;
+    if (t < 2 * lg) uj[t] = sc_to_mont(ch[CH_UJ0 + t]);
+    __syncthreads();
+    sc zM = sc_to_mont(ch[CH_Z]), aM = sc_to_mont(ch[CH_A]), bM = sc_to_mont(ch[CH_B]), rhoM = sc_to_mont(ch[CH_RHO]), one = sc_mont_one();
+    sc *stat = B.stat + (size_t)p * (2 + 2 * gc);
+    for (uint32_t i = n + t; i < gc; i += BBP_SC_THREADS) { stat[2 + i] = sc_zero(); stat[2 + gc + i] = sc_zero(); }
+    for (uint32_t k = t; k < n; k += BBP_SC_THREADS) {
+        sc s = one, srev = one;
+        for (uint32_t j = 0; j < lg; j++) {
+            bool bit = (k >> (lg - 1 - j)) & 1;
+            s = mm(s, bit ? uj[j] : uj[lg + j]);
+            srev = mm(srev, bit ? uj[lg + j] : uj[j]);
+        }
+        uint32_t j = k / B.rp_bits, i = k % B.rp_bits;
+        sc zz_j = sc_pow_small_mont(zM, 2 + j);
+        sc two_i = sc_to_mont(sc_from_u64(1ull << i));
+        sc g = sc_sub(sc_neg(zM), mm(aM, s));
+        sc h = sc_add(zM, mm(yinv[k], sc_sub(mm(zz_j, two_i), mm(bM, srev))));
+        stat[2 + k] = mm(rhoM, g);
+        stat[2 + gc + k] = mm(rhoM, h);
+    }
+    if (t == 0) { stat[0] = sc_to_mont(ch[CH_TX]); stat[1] = sc_to_mont(ch[CH_TXBL]); }
 }
 
 // sums the per-proof static-base scalars over groups of `group_size` consecutive proofs -> one slot of slot_len scalars

@@ -153,6 +153,23 @@ int bbp_mimc_constants(uint8_t out[90 * 32]);
 /* out = {multipliers n1, constraints q, commitments m} of the circuit for the given commitment / toggle counts */
 int bbp_blindbid_circuit_shape(size_t n_commitments, size_t n_toggles, size_t out[3]);
 
+/* ---- aggregated range proofs: bulletproofs RangeProof::prove_multiple / verify_multiple (BASELINE.json configs[4]; the
+ * reference itself has no call site). m values of nbits bits each (nbits in {8,16,32,64}, m a power of two);
+ * the context must have been created with bbp_init(device, nbits, parties >= m). Proof = 32 * (9 + 2 lg(nbits m)) bytes.
+ * RNG contract: rng_seed keys a SHAKE256 stream that replaces the caller's rng of upstream (draw order as upstream).
+ * Transcript label "bbp-rangeproof". */
+int bbp_rangeproof_prove_multiple(bbp_ctx *ctx, const uint64_t *values, const uint8_t *blindings, size_t m, size_t nbits, const uint8_t rng_seed[32],
+                                  uint8_t *proof_out, size_t *proof_len, uint8_t *commitments_out /* m x 32 */);
+/* BBP_OK = accept */
+int bbp_rangeproof_verify_multiple(bbp_ctx *ctx, const uint8_t *proof, size_t proof_len, const uint8_t *commitments, size_t m, size_t nbits,
+                                   const uint8_t rng_seed[32]);
+/* n_proofs aggregated proofs in one pass (inputs concatenated proof-major; proofs_out rows of proof_stride bytes) */
+int bbp_rangeproof_prove_batch(bbp_ctx *ctx, size_t n_proofs, const uint64_t *values, const uint8_t *blindings, size_t m, size_t nbits,
+                               const uint8_t *rng_seeds, uint8_t *proofs_out, size_t proof_stride, size_t *proof_len, uint8_t *commitments_out,
+                               int *statuses);
+int bbp_rangeproof_verify_batch(bbp_ctx *ctx, size_t n_proofs, const uint8_t *proofs, size_t proof_stride, size_t proof_len, const uint8_t *commitments,
+                                size_t m, size_t nbits, const uint8_t *rng_seeds, int *statuses);
+
 /* ---- L1 building blocks over the resident generators --------------------------------------------------------------- */
 /* PedersenGens::commit: v*B + r*B_blinding for n (value, blinding) pairs; out = n x 32 B compressed */
 int bbp_pedersen_commit(bbp_ctx *ctx, const uint8_t *values, const uint8_t *blindings, size_t n, uint8_t *out);
