@@ -425,7 +425,7 @@ def run_b200(args, rank, world):
                          "kernel_ms": acc_ms, "peak_source": "bbp_int_peak measured in this run (IMAD.WIDE.U32 x2, 8 chains/thread, all SMs)",
                          "whole_msm_frac": msm_imads(n, plan["c"], plan["W"]) / (ms / args.steps * 1e-3) / peak_imad,
                          "hbm_gather_gbs": plan["W"] * n * 96 / (acc_ms * 1e-3) / 1e9},
-            "stage_ms": dict(zip(["recode", "scan", "scatter", "accumulate", "chunk_reduce", "window_reduce", "combine"], [round(x, 4) for x in stage])),
+            "stage_ms": dict(zip(["recode", "scan", "scatter", "accumulate", "reduce_level1", "reduce_merge", "combine"], [round(x, 4) for x in stage])),
             "clocks": clocks,
         }
         if blindbid is not None:

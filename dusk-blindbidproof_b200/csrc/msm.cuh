@@ -16,6 +16,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include "ge25519.cuh"
 #include "sc25519.cuh"
@@ -186,7 +187,8 @@ __global__ void k_task_fill(const uint32_t *__restrict__ toffs, uint32_t *__rest
 }
 
 // ---------------------------------------------------------------- bucket accumulation: one thread per task
-__global__ void __launch_bounds__(128) k_accumulate(const uint8_t *__restrict__ table, const uint32_t *__restrict__ entries,
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_accumulate(const uint8_t *__restrict__ table, const uint32_t *__restrict__ entries,
                                                     const uint32_t *__restrict__ offs, const uint32_t *__restrict__ toffs,
                                                     const uint32_t *__restrict__ task_key, uint8_t *__restrict__ partial, msm_shape sh) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -205,19 +207,26 @@ __global__ void __launch_bounds__(128) k_accumulate(const uint8_t *__restrict__ 
     ge_store(partial + 128 * (size_t)t, acc);
 }
 
-// ---------------------------------------------------------------- chunk reduce: CH buckets -> (acc, run)
-//   run = sum_b bucket_b, acc = sum_b (b - b0 + 1) * bucket_b   over the chunk's buckets b0 .. b0+CH-1
-__global__ void __launch_bounds__(128) k_chunk_reduce(const uint8_t *__restrict__ partial, const uint32_t *__restrict__ toffs,
-                                                      uint8_t *__restrict__ chunk_acc, uint8_t *__restrict__ chunk_run, msm_shape sh) {
+// ---------------------------------------------------------------- bucket reduction: sum_b b * bucket_b per bucket set
+// Multi-level, every level one thread per group of <= 8 elements. An element stands for a block of `len` consecutive
+// buckets and carries R = sum of the block's buckets and A = sum (local index, 1-based) * bucket. Merging g elements:
+//   R' = sum_i R_i,   A' = sum_i A_i + len * sum_i i * R_i   (i = 0 .. g-1),   sum_i i R_i by running suffix sums.
+// Level 1 reads the task partials of 8 buckets (len = 1, A_i = R_i = bucket_i); the last level leaves one element per
+// bucket set whose A is the set total. Depth: log_8(buckets) levels of ~3*8 additions instead of one long chain.
+#define BBP_RED_G 8
+__global__ void __launch_bounds__(128) k_reduce_level1(const uint8_t *__restrict__ partial, const uint32_t *__restrict__ toffs,
+                                                       uint8_t *__restrict__ outA, uint8_t *__restrict__ outR, uint32_t n_groups, uint32_t g) {
     uint32_t ck = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t n_chunks = sh.nkeys / sh.CH;
-    if (ck >= n_chunks) return;
-    uint32_t k0 = ck * sh.CH;
+    if (ck >= n_groups) return;
+    uint32_t k0 = ck * g;
+    uint32_t to[BBP_RED_G + 1];
+#pragma unroll
+    for (uint32_t i = 0; i <= BBP_RED_G; i++) to[i] = (i <= g) ? toffs[k0 + i] : 0u;
     ge run = ge_identity(), acc = ge_identity();
     bool run_nz = false, acc_nz = false;
-    for (uint32_t k = k0 + sh.CH; k-- > k0;) {
-        uint32_t t0 = toffs[k], t1 = toffs[k + 1];
-        for (uint32_t t = t0; t < t1; t++) {
+#pragma unroll 1
+    for (uint32_t i = g; i-- > 0;) {
+        for (uint32_t t = to[i]; t < to[i + 1]; t++) {
             ge p = ge_load(partial + 128 * (size_t)t);
             if (run_nz) run = ge_add(run, p);
             else { run = p; run_nz = true; }
@@ -227,86 +236,97 @@ __global__ void __launch_bounds__(128) k_chunk_reduce(const uint8_t *__restrict_
             else { acc = run; acc_nz = true; }
         }
     }
-    ge_store(chunk_acc + 128 * (size_t)ck, acc);
-    ge_store(chunk_run + 128 * (size_t)ck, run);
+    ge_store(outA + 128 * (size_t)ck, acc);
+    ge_store(outR + 128 * (size_t)ck, run);
+}
+// merges g consecutive elements of block length `len` (a power of two)
+__global__ void __launch_bounds__(128) k_reduce_merge(const uint8_t *__restrict__ inA, const uint8_t *__restrict__ inR, uint8_t *__restrict__ outA,
+                                                      uint8_t *__restrict__ outR, uint32_t n_groups, uint32_t g, uint32_t len) {
+    uint32_t ck = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ck >= n_groups) return;
+    size_t e0 = (size_t)ck * g;
+    // suffix running sums: run = R_{g-1} + ... + R_i ; w = sum_{i>=1} run_i = sum_i i * R_i
+    ge run = ge_load(inR + 128 * (e0 + g - 1));
+    ge w = run;
+    ge A = ge_load(inA + 128 * (e0 + g - 1));
+#pragma unroll 1
+    for (uint32_t i = g - 1; i-- > 0;) {
+        run = ge_add(run, ge_load(inR + 128 * (e0 + i)));
+        if (i >= 1) w = ge_add(w, run);
+        A = ge_add(A, ge_load(inA + 128 * (e0 + i)));
+    }
+    if (g > 1) {
+        for (uint32_t m = len; m > 1; m >>= 1) w = ge_dbl(w);
+        A = ge_add(A, w);
+    }
+    ge_store(outA + 128 * (size_t)ck, A);
+    ge_store(outR + 128 * (size_t)ck, run);
 }
 
-// ---------------------------------------------------------------- window reduce: one block per bucket set
-//   total = sum_k acc_k + CH * sum_k k * run_k over the set's n_ch chunks. 256 threads; thread j owns the r = n_ch/256
-//   (>= 1) consecutive chunks [j*r, j*r + r):  A_j = sum acc_k, R_j = sum run_k, W_j = sum (k - j*r) * run_k, so that
-//   sum_k k*run_k = sum_j W_j + r * sum_j j*R_j, and sum_j j*R_j = sum_{j>=1} Sfx_j with Sfx the suffix sums of R
-//   (Hillis-Steele scan in shared memory), followed by a tree sum.
-#define BBP_WR_THREADS 256
-__global__ void __launch_bounds__(BBP_WR_THREADS) k_window_reduce(const uint8_t *__restrict__ chunk_acc, const uint8_t *__restrict__ chunk_run,
-                                                                  uint8_t *__restrict__ set_total, msm_shape sh) {
-    __shared__ uint4 smem_u4[BBP_WR_THREADS * 8];
-    uint8_t *sm = (uint8_t *)smem_u4;
-    const uint32_t j = threadIdx.x;
-    const uint32_t r = sh.n_ch > BBP_WR_THREADS ? sh.n_ch / BBP_WR_THREADS : 1;
-    const uint32_t nthr = sh.n_ch / r;           // active threads (power of two <= 256)
-    const size_t base = (size_t)blockIdx.x * sh.n_ch + (size_t)j * r;
-    ge A = ge_identity(), R = ge_identity(), Wt = ge_identity();
-    if (j < nthr) {
-        // high chunk to low: Wt accumulates the running sum before the current chunk is added (weights r-1 .. 0)
-        for (uint32_t k = r; k-- > 0;) {
-            if (k != r - 1) Wt = ge_add(Wt, R);
-            R = (k == r - 1) ? ge_load(chunk_run + 128 * (base + k)) : ge_add(R, ge_load(chunk_run + 128 * (base + k)));
-            A = (k == r - 1) ? ge_load(chunk_acc + 128 * (base + k)) : ge_add(A, ge_load(chunk_acc + 128 * (base + k)));
-        }
-        ge_store(sm + 128 * j, R);
-    }
-    __syncthreads();
-    ge s = R;
-    for (uint32_t off = 1; off < nthr; off <<= 1) {
-        ge t;
-        bool has = j + off < nthr;
-        if (has) t = ge_load(sm + 128 * (j + off));
-        __syncthreads();
-        if (has) { s = ge_add(s, t); ge_store(sm + 128 * j, s); }
-        __syncthreads();
-    }
-    // y_j = A_j + CH * (W_j + r * [j >= 1] Sfx_j)
-    if (j < nthr) {
-        ge w = Wt;
-        if (j >= 1) {
-            for (uint32_t m = r; m > 1; m >>= 1) s = ge_dbl(s);
-            w = (r > 1) ? ge_add(w, s) : s;
-        }
-        if (r > 1 || j >= 1) {
-            for (uint32_t m = sh.CH; m > 1; m >>= 1) w = ge_dbl(w);
-            A = ge_add(A, w);
-        }
-        ge_store(sm + 128 * j, A);
-    }
-    __syncthreads();
-    for (uint32_t stride = nthr >> 1; stride >= 1; stride >>= 1) {
-        if (j < stride) {
-            ge a = ge_load(sm + 128 * j), b = ge_load(sm + 128 * (j + stride));
-            ge_store(sm + 128 * j, ge_add(a, b));
-        }
-        __syncthreads();
-    }
-    if (j == 0) ge_store(set_total + 128 * (size_t)blockIdx.x, ge_load(sm));
+// ---------------------------------------------------------------- final combine: four lanes per slot
+// variable bases: Horner over the W window totals (c doublings per step); fixed bases: the single set total. The
+// doublings are the only long dependency chain of the whole MSM ((W-1)*c of them), so each one is spread over four
+// lanes: lane l owns coordinate l of the accumulator, the four squarings and the four products of dbl-2008-hwcd run
+// side by side, operands travel by warp shuffles. Writes compressed (32 B) and / or extended (128 B) results.
+struct ge4 {   // coordinate `lane & 3` of an extended point
+    fe c;
+};
+BBP_DEV fe fe_shfl4(const fe &v, int src) {
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, v.v[i], src, 4);
+    return r;
 }
-
-// ---------------------------------------------------------------- final combine: one thread per slot
-// variable bases: Horner over the W window totals; fixed bases: the single set total. Optionally adds a carried-in
-// point (extended, 128 B per slot) before compressing; writes compressed (32 B) and extended (128 B) results.
+BBP_DEV fe ge4_finish(const fe &E, const fe &F, const fe &G, const fe &H, int l) {
+    // lane 0: E*F (X), lane 1: G*H (Y), lane 2: F*G (Z), lane 3: E*H (T)
+    fe m1 = (l == 0 || l == 3) ? E : (l == 1 ? G : F);
+    fe m2 = (l == 0) ? F : ((l == 1 || l == 3) ? H : G);
+    return fe_mul(m1, m2);
+}
+BBP_DEV fe ge4_dbl(const fe &c, int l) {
+    fe X = fe_shfl4(c, 0), Y = fe_shfl4(c, 1);
+    fe op = (l == 3) ? fe_add(X, Y) : c;
+    fe sq = fe_sq(op);
+    fe A = fe_shfl4(sq, 0), B = fe_shfl4(sq, 1), Zq = fe_shfl4(sq, 2), Sq = fe_shfl4(sq, 3);
+    fe C = fe_dbl(Zq), D = fe_neg(A);
+    fe E = fe_sub(fe_sub(Sq, A), B), G = fe_add(D, B), F = fe_sub(G, C), H = fe_sub(D, B);
+    return ge4_finish(E, F, G, H, l);
+}
+// acc + q, q given in full on every lane
+BBP_DEV fe ge4_add(const fe &c, const ge &q, int l) {
+    fe X = fe_shfl4(c, 0), Y = fe_shfl4(c, 1), Z = fe_shfl4(c, 2), T = fe_shfl4(c, 3);
+    fe a, b;
+    if (l == 0) { a = fe_sub(Y, X); b = fe_sub(q.Y, q.X); }
+    else if (l == 1) { a = fe_add(Y, X); b = fe_add(q.Y, q.X); }
+    else if (l == 2) { a = T; b = fe_mul(q.T, fe_d2()); }
+    else { a = fe_dbl(Z); b = q.Z; }
+    fe pr = fe_mul(a, b);
+    fe A = fe_shfl4(pr, 0), B = fe_shfl4(pr, 1), C = fe_shfl4(pr, 2), D = fe_shfl4(pr, 3);
+    fe E = fe_sub(B, A), F = fe_sub(D, C), G = fe_add(D, C), H = fe_add(B, A);
+    return ge4_finish(E, F, G, H, l);
+}
 __global__ void __launch_bounds__(32) k_combine(const uint8_t *__restrict__ set_total, uint8_t *__restrict__ out_ext,
                                                 uint32_t *__restrict__ out_compressed, msm_shape sh) {
-    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= sh.n_slots) return;
-    ge acc;
+    const int l = threadIdx.x & 3;
+    uint32_t slot = blockIdx.x * 8 + (threadIdx.x >> 2);
+    bool live = slot < sh.n_slots;
+    uint32_t sl = live ? slot : 0;   // idle lane groups shadow slot 0 so that the shuffles stay convergent
+    fe c;
     if (sh.fixed) {
-        acc = ge_load(set_total + 128 * (size_t)slot);
+        c = fe_load(set_total + 128 * (size_t)sl + 32 * l);
     } else {
-        const uint8_t *st = set_total + 128 * (size_t)slot * sh.W;
-        acc = ge_load(st + 128 * (size_t)(sh.W - 1));
+        const uint8_t *st = set_total + 128 * (size_t)sl * sh.W;
+        c = fe_load(st + 128 * (size_t)(sh.W - 1) + 32 * l);
+#pragma unroll 1
         for (uint32_t w = sh.W - 1; w-- > 0;) {
-            for (uint32_t j = 0; j < sh.c; j++) acc = ge_dbl(acc);
-            acc = ge_add(acc, ge_load(st + 128 * (size_t)w));
+#pragma unroll 1
+            for (uint32_t j = 0; j < sh.c; j++) c = ge4_dbl(c, l);
+            c = ge4_add(c, ge_load(st + 128 * (size_t)w), l);
         }
     }
+    ge acc;
+    acc.X = fe_shfl4(c, 0); acc.Y = fe_shfl4(c, 1); acc.Z = fe_shfl4(c, 2); acc.T = fe_shfl4(c, 3);
+    if (!live || l != 0) return;
     if (out_ext) ge_store(out_ext + 128 * (size_t)slot, acc);
     if (out_compressed) ge_compress_words(out_compressed + 8 * (size_t)slot, acc);
 }
@@ -319,7 +339,7 @@ struct msm_engine {
     int32_t *digits = nullptr;
     uint32_t *hist = nullptr, *offs = nullptr, *cursor = nullptr, *toffs = nullptr, *entries = nullptr, *task_key = nullptr;
     uint32_t *tile_sums = nullptr, *total = nullptr;
-    uint8_t *partial = nullptr, *chunk_acc = nullptr, *chunk_run = nullptr, *set_total = nullptr;
+    uint8_t *partial = nullptr, *lvl[4] = {nullptr, nullptr, nullptr, nullptr};   // lvl: ping-pong (A, R) arrays of the bucket reduction
     uint64_t launches = 0;
     // optional per-stage timing (bbp_set_profiling): events around recode / scans / scatter+fill / accumulate /
     // chunk reduce / window reduce / combine on the launching stream
@@ -350,15 +370,16 @@ struct msm_engine {
 
     void release() {
         cudaFree(digits); cudaFree(hist); cudaFree(offs); cudaFree(cursor); cudaFree(toffs); cudaFree(entries); cudaFree(task_key);
-        cudaFree(tile_sums); cudaFree(total); cudaFree(partial); cudaFree(chunk_acc); cudaFree(chunk_run); cudaFree(set_total);
+        cudaFree(tile_sums); cudaFree(total); cudaFree(partial);
+        for (int i = 0; i < 4; i++) { cudaFree(lvl[i]); lvl[i] = nullptr; }
         digits = nullptr; hist = offs = cursor = toffs = entries = task_key = tile_sums = total = nullptr;
-        partial = chunk_acc = chunk_run = set_total = nullptr;
+        partial = nullptr;
         cap_pairs = cap_keys = cap_tasks = cap_chunks = cap_sets = 0;
         for (int i = 0; i <= N_STAGES; i++) if (ev[i]) { cudaEventDestroy(ev[i]); ev[i] = nullptr; }
     }
 
     int reserve(const msm_shape &sh) {
-        size_t pairs = (size_t)sh.n * sh.W, keys = sh.nkeys, tasks = max_tasks(sh), chunks = keys / sh.CH, sets = (size_t)sh.n_slots * sh.sets_per_slot;
+        size_t pairs = (size_t)sh.n * sh.W, keys = sh.nkeys, tasks = max_tasks(sh), chunks = keys / 2 + 1, sets = (size_t)sh.n_slots * sh.sets_per_slot;
         if (pairs > cap_pairs) {
             cudaFree(digits); cudaFree(entries);
             BBP_CUDA_OK(cudaMalloc(&digits, pairs * 4));
@@ -382,16 +403,14 @@ struct msm_engine {
             cap_tasks = tasks;
         }
         if (chunks > cap_chunks) {
-            cudaFree(chunk_acc); cudaFree(chunk_run);
-            BBP_CUDA_OK(cudaMalloc(&chunk_acc, chunks * 128));
-            BBP_CUDA_OK(cudaMalloc(&chunk_run, chunks * 128));
+            for (int i = 0; i < 4; i++) {
+                cudaFree(lvl[i]);
+                lvl[i] = nullptr;
+                BBP_CUDA_OK(cudaMalloc(&lvl[i], chunks * 128));
+            }
             cap_chunks = chunks;
         }
-        if (sets > cap_sets) {
-            cudaFree(set_total);
-            BBP_CUDA_OK(cudaMalloc(&set_total, sets * 128));
-            cap_sets = sets;
-        }
+        cap_sets = sets;
         return 0;
     }
 
@@ -443,18 +462,40 @@ struct msm_engine {
         k_task_fill<<<(sh.nkeys + 255) / 256, 256, 0, stream>>>(toffs, task_key, sh.nkeys);
         if (mark(3)) return -100;
         size_t mt = max_tasks(sh);
-        k_accumulate<<<(unsigned)((mt + 127) / 128), 128, 0, stream>>>(d_table, entries, offs, toffs, task_key, partial, sh);
+        {
+            // resident CTAs per SM for the accumulation kernel (register budget 65536 / (128 * MINB)); BBP_ACC_MINB overrides
+            static const int minb = [] { const char *e = getenv("BBP_ACC_MINB"); return e ? atoi(e) : 4; }();
+            unsigned grid = (unsigned)((mt + 127) / 128);
+            if (minb <= 3) k_accumulate<3><<<grid, 128, 0, stream>>>(d_table, entries, offs, toffs, task_key, partial, sh);
+            else if (minb == 4) k_accumulate<4><<<grid, 128, 0, stream>>>(d_table, entries, offs, toffs, task_key, partial, sh);
+            else if (minb == 5) k_accumulate<5><<<grid, 128, 0, stream>>>(d_table, entries, offs, toffs, task_key, partial, sh);
+            else k_accumulate<6><<<grid, 128, 0, stream>>>(d_table, entries, offs, toffs, task_key, partial, sh);
+        }
         if (mark(4)) return -100;
-        uint32_t n_chunks = sh.nkeys / sh.CH;
-        k_chunk_reduce<<<(n_chunks + 127) / 128, 128, 0, stream>>>(partial, toffs, chunk_acc, chunk_run, sh);
-        if (mark(5)) return -100;
+        // bucket reduction: B buckets per set -> 1 element per set, groups of <= 8 per level
+        uint32_t per_set = sh.B, g = std::min<uint32_t>(BBP_RED_G, per_set);
         uint32_t sets = sh.n_slots * sh.sets_per_slot;
-        k_window_reduce<<<sets, BBP_WR_THREADS, 0, stream>>>(chunk_acc, chunk_run, set_total, sh);
+        uint32_t n_groups = sets * (per_set / g);
+        k_reduce_level1<<<(n_groups + 127) / 128, 128, 0, stream>>>(partial, toffs, lvl[0], lvl[1], n_groups, g);
+        launches++;
+        if (mark(5)) return -100;
+        per_set /= g;
+        uint32_t len = g;
+        int cur = 0;
+        while (per_set > 1) {
+            g = std::min<uint32_t>(BBP_RED_G, per_set);
+            n_groups = sets * (per_set / g);
+            k_reduce_merge<<<(n_groups + 127) / 128, 128, 0, stream>>>(lvl[cur], lvl[cur + 1], lvl[cur ^ 2], lvl[(cur ^ 2) + 1], n_groups, g, len);
+            launches++;
+            per_set /= g;
+            len *= g;
+            cur ^= 2;
+        }
         if (mark(6)) return -100;
-        k_combine<<<(sh.n_slots + 31) / 32, 32, 0, stream>>>(set_total, d_out_ext, (uint32_t *)d_out_compressed, sh);
+        k_combine<<<(sh.n_slots + 7) / 8, 32, 0, stream>>>(lvl[cur], d_out_ext, (uint32_t *)d_out_compressed, sh);
         if (mark(7)) return -100;
         if (profile) stage_pending = true;
-        launches += 6;
+        launches += 5;
         BBP_CUDA_OK(cudaGetLastError());
         return 0;
     }

@@ -52,7 +52,7 @@ int bbp_sync(bbp_ctx *ctx);
 /* ---- measurement hooks (bench.py): per-stage MSM timing with CUDA events on the context stream, the MSM plan for a
  * size, and the measured integer-multiply ceiling of the device (no reference counterpart) */
 int bbp_set_profiling(bbp_ctx *ctx, int on);
-/* ms[0..7): recode, scans, scatter+task table, bucket accumulation, chunk reduce, window reduce, combine+compress */
+/* ms[0..7): recode, scans, scatter+task table, bucket accumulation, bucket reduction level 1, merge levels, combine+compress */
 int bbp_msm_stage_ms(bbp_ctx *ctx, float *ms, size_t n_stages);
 /* out = {window bits c, windows W, max entries per task S, buckets per chunk CH} chosen for an n-point MSM */
 int bbp_msm_plan(size_t n, uint32_t out[4]);
