@@ -12,34 +12,46 @@
 
 namespace bbp {
 
+// Keccak-f[1600], lane-wise and unrolled per round (the transcript RNG draws ~3 k permutations per proof, so this is the
+// host-side hot loop of the prover)
+inline uint64_t keccak_rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
 inline void keccak_f1600(uint64_t s[25]) {
     static const uint64_t RC[24] = {
         0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL, 0x0000000080000001ULL,
         0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
         0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL,
         0x000000000000800aULL, 0x800000008000000aULL, 0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
-    static const int ROT[24] = {1, 3, 6, 10, 15, 21, 28, 36, 45, 55, 2, 14, 27, 41, 56, 8, 25, 43, 62, 18, 39, 61, 20, 44};
-    static const int PIL[24] = {10, 7, 11, 17, 18, 3, 5, 16, 8, 21, 24, 4, 15, 23, 19, 13, 12, 2, 20, 14, 22, 9, 6, 1};
+    uint64_t a00 = s[0], a01 = s[1], a02 = s[2], a03 = s[3], a04 = s[4], a05 = s[5], a06 = s[6], a07 = s[7], a08 = s[8], a09 = s[9], a10 = s[10],
+             a11 = s[11], a12 = s[12], a13 = s[13], a14 = s[14], a15 = s[15], a16 = s[16], a17 = s[17], a18 = s[18], a19 = s[19], a20 = s[20],
+             a21 = s[21], a22 = s[22], a23 = s[23], a24 = s[24];
     for (int r = 0; r < 24; r++) {
-        uint64_t bc[5];
-        for (int i = 0; i < 5; i++) bc[i] = s[i] ^ s[i + 5] ^ s[i + 10] ^ s[i + 15] ^ s[i + 20];
-        for (int i = 0; i < 5; i++) {
-            uint64_t t = bc[(i + 4) % 5] ^ ((bc[(i + 1) % 5] << 1) | (bc[(i + 1) % 5] >> 63));
-            for (int j = 0; j < 25; j += 5) s[j + i] ^= t;
-        }
-        uint64_t t = s[1];
-        for (int i = 0; i < 24; i++) {
-            int j = PIL[i];
-            uint64_t b = s[j];
-            s[j] = (t << ROT[i]) | (t >> (64 - ROT[i]));
-            t = b;
-        }
-        for (int j = 0; j < 25; j += 5) {
-            for (int i = 0; i < 5; i++) bc[i] = s[j + i];
-            for (int i = 0; i < 5; i++) s[j + i] ^= (~bc[(i + 1) % 5]) & bc[(i + 2) % 5];
-        }
-        s[0] ^= RC[r];
+        // theta
+        uint64_t c0 = a00 ^ a05 ^ a10 ^ a15 ^ a20, c1 = a01 ^ a06 ^ a11 ^ a16 ^ a21, c2 = a02 ^ a07 ^ a12 ^ a17 ^ a22,
+                 c3 = a03 ^ a08 ^ a13 ^ a18 ^ a23, c4 = a04 ^ a09 ^ a14 ^ a19 ^ a24;
+        uint64_t d0 = c4 ^ keccak_rotl(c1, 1), d1 = c0 ^ keccak_rotl(c2, 1), d2 = c1 ^ keccak_rotl(c3, 1), d3 = c2 ^ keccak_rotl(c4, 1),
+                 d4 = c3 ^ keccak_rotl(c0, 1);
+        a00 ^= d0; a05 ^= d0; a10 ^= d0; a15 ^= d0; a20 ^= d0;
+        a01 ^= d1; a06 ^= d1; a11 ^= d1; a16 ^= d1; a21 ^= d1;
+        a02 ^= d2; a07 ^= d2; a12 ^= d2; a17 ^= d2; a22 ^= d2;
+        a03 ^= d3; a08 ^= d3; a13 ^= d3; a18 ^= d3; a23 ^= d3;
+        a04 ^= d4; a09 ^= d4; a14 ^= d4; a19 ^= d4; a24 ^= d4;
+        // rho + pi: b[y][2x+3y] = rotl(a[x][y]) with lanes indexed a[x + 5y]
+        uint64_t b00 = a00, b10 = keccak_rotl(a01, 1), b20 = keccak_rotl(a02, 62), b05 = keccak_rotl(a03, 28), b15 = keccak_rotl(a04, 27),
+                 b16 = keccak_rotl(a05, 36), b01 = keccak_rotl(a06, 44), b11 = keccak_rotl(a07, 6), b21 = keccak_rotl(a08, 55), b06 = keccak_rotl(a09, 20),
+                 b07 = keccak_rotl(a10, 3), b17 = keccak_rotl(a11, 10), b02 = keccak_rotl(a12, 43), b12 = keccak_rotl(a13, 25), b22 = keccak_rotl(a14, 39),
+                 b23 = keccak_rotl(a15, 41), b08 = keccak_rotl(a16, 45), b18 = keccak_rotl(a17, 15), b03 = keccak_rotl(a18, 21), b13 = keccak_rotl(a19, 8),
+                 b14 = keccak_rotl(a20, 18), b24 = keccak_rotl(a21, 2), b09 = keccak_rotl(a22, 61), b19 = keccak_rotl(a23, 56), b04 = keccak_rotl(a24, 14);
+        // chi
+        a00 = b00 ^ (~b01 & b02); a01 = b01 ^ (~b02 & b03); a02 = b02 ^ (~b03 & b04); a03 = b03 ^ (~b04 & b00); a04 = b04 ^ (~b00 & b01);
+        a05 = b05 ^ (~b06 & b07); a06 = b06 ^ (~b07 & b08); a07 = b07 ^ (~b08 & b09); a08 = b08 ^ (~b09 & b05); a09 = b09 ^ (~b05 & b06);
+        a10 = b10 ^ (~b11 & b12); a11 = b11 ^ (~b12 & b13); a12 = b12 ^ (~b13 & b14); a13 = b13 ^ (~b14 & b10); a14 = b14 ^ (~b10 & b11);
+        a15 = b15 ^ (~b16 & b17); a16 = b16 ^ (~b17 & b18); a17 = b17 ^ (~b18 & b19); a18 = b18 ^ (~b19 & b15); a19 = b19 ^ (~b15 & b16);
+        a20 = b20 ^ (~b21 & b22); a21 = b21 ^ (~b22 & b23); a22 = b22 ^ (~b23 & b24); a23 = b23 ^ (~b24 & b20); a24 = b24 ^ (~b20 & b21);
+        a00 ^= RC[r];
     }
+    s[0] = a00; s[1] = a01; s[2] = a02; s[3] = a03; s[4] = a04; s[5] = a05; s[6] = a06; s[7] = a07; s[8] = a08; s[9] = a09; s[10] = a10; s[11] = a11;
+    s[12] = a12; s[13] = a13; s[14] = a14; s[15] = a15; s[16] = a16; s[17] = a17; s[18] = a18; s[19] = a19; s[20] = a20; s[21] = a21; s[22] = a22;
+    s[23] = a23; s[24] = a24;
 }
 
 struct keccak_sponge {
@@ -190,6 +202,16 @@ class strobe128 {
     void ad(const void *d, size_t n, bool more) { begin_op(FLAG_A, more); absorb((const uint8_t *)d, n); }
     void prf(void *d, size_t n, bool more) { begin_op(FLAG_I | FLAG_A | FLAG_C, more); squeeze((uint8_t *)d, n); }
     void key(const void *d, size_t n, bool more) { begin_op(FLAG_A | FLAG_C, more); overwrite((const uint8_t *)d, n); }
+    // hand-off to / from the device-side continuation (rng_kernels.cuh): 200 B state, pos, pos_begin, cur_flags
+    void export_state(uint8_t out[208]) const {
+        memcpy(out, st_, 200);
+        out[200] = pos_; out[201] = pos_begin_; out[202] = cur_flags_;
+        memset(out + 203, 0, 5);
+    }
+    void import_state(const uint8_t in[208]) {
+        memcpy(st_, in, 200);
+        pos_ = in[200]; pos_begin_ = in[201]; cur_flags_ = in[202];
+    }
 
   private:
     static const int R = 166;
@@ -245,6 +267,8 @@ class merlin_rng {
         fill_bytes(b, 64);
         return sc_from_wide(b);
     }
+    void export_state(uint8_t out[208]) const { s_.export_state(out); }
+    void import_state(const uint8_t in[208]) { s_.import_state(in); }
   private:
     strobe128 s_;
 };

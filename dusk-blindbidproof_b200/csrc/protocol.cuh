@@ -20,6 +20,7 @@
 #include "circuit.h"
 #include "ctx.cuh"
 #include "fixedbase.cuh"
+#include "rng_kernels.cuh"
 #include "sc_kernels.cuh"
 
 namespace bbp {
@@ -88,7 +89,7 @@ struct proto_state {
     uint8_t *comb = nullptr;       // Pedersen comb table
     uint8_t *wtable = nullptr;     // generator window table, WT_W rows of n_gens niels entries
     dev_buf chal, zpow, ypow, yinvpow, wit, vbl, blind3, poly, tout, a, b, sG, sH, slots, ab, pub, dyn_sc, dyn_pts, dyn_niels, stat, stat_red,
-        msm_out, msm_ext, flags, valid, commit_in, commit_out;
+        msm_out, msm_ext, flags, valid, commit_in, commit_out, rng_states;
     int proof_versioned = 1;       // R1CSProof::to_bytes layout (SURVEY.md §8c risk R1): 1 = leading phase byte, 0 = legacy 14-point form
 };
 
@@ -103,7 +104,7 @@ void proto_release(proto_state *ps) {
     cudaFree(ps->comb); cudaFree(ps->wtable);
     dev_buf *all[] = {&ps->chal, &ps->zpow, &ps->ypow, &ps->yinvpow, &ps->wit, &ps->vbl, &ps->blind3, &ps->poly, &ps->tout, &ps->a, &ps->b, &ps->sG, &ps->sH,
                       &ps->slots, &ps->ab, &ps->pub, &ps->dyn_sc, &ps->dyn_pts, &ps->dyn_niels, &ps->stat, &ps->stat_red, &ps->msm_out, &ps->msm_ext,
-                      &ps->flags, &ps->valid, &ps->commit_in, &ps->commit_out};
+                      &ps->flags, &ps->valid, &ps->commit_in, &ps->commit_out, &ps->rng_states};
     for (dev_buf *b : all) b->release();
     delete ps;
 }
@@ -309,7 +310,11 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     trace.mark("gpu_V_commit");
 
     // ---- phase 1: transcript up to the blinding draws; upload witness
-    std::vector<sc> wit((size_t)B * 5 * n1), vbl((size_t)B * m), blind3((size_t)B * 3);
+    // the 2 n1 blinding-vector draws run on the device for batches (one thread per proof continues the transcript RNG)
+    static const int rng_threshold = [] { const char *e = getenv("BBP_DEVICE_RNG_MIN_BATCH"); return e ? atoi(e) : 8; }();
+    const bool device_rng = (int)B >= rng_threshold;
+    std::vector<uint8_t> rng_states(device_rng ? (size_t)B * BBP_STROBE_STATE_BYTES : 0);
+    std::vector<sc> wit((size_t)B * (device_rng ? 3 : 5) * n1), vbl((size_t)B * m), blind3((size_t)B * 3);
     parallel_for(B, [&](size_t bi) {
         prove_job &J = jobs[idx[bi]];
         hstate &H = hs[bi];
@@ -332,8 +337,12 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
         // witness layout: vector-major [a_L | a_R | a_O | s_L | s_R], each B x n1
         auto W = [&](uint32_t k) { return &wit[((size_t)k * B + bi) * n1]; };
         for (uint32_t i = 0; i < n1; i++) { W(0)[i] = H.ev.a_L[i]; W(1)[i] = H.ev.a_R[i]; W(2)[i] = H.ev.a_O[i]; }
-        for (uint32_t i = 0; i < n1; i++) W(3)[i] = H.rng->random_scalar();   // s_L
-        for (uint32_t i = 0; i < n1; i++) W(4)[i] = H.rng->random_scalar();   // s_R
+        if (device_rng) {
+            H.rng->export_state(&rng_states[bi * BBP_STROBE_STATE_BYTES]);
+        } else {
+            for (uint32_t i = 0; i < n1; i++) W(3)[i] = H.rng->random_scalar();   // s_L
+            for (uint32_t i = 0; i < n1; i++) W(4)[i] = H.rng->random_scalar();   // s_R
+        }
     });
 
     trace.mark("host_rng_draws");
@@ -348,6 +357,13 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     if ((rc = h2d(ctx, ps->wit.p, wit.data(), wit.size() * 32)) || (rc = h2d(ctx, ps->vbl.p, vbl.data(), vbl.size() * 32)) ||
         (rc = h2d(ctx, ps->blind3.p, blind3.data(), blind3.size() * 32)))
         return rc;
+    if (device_rng) {
+        if ((rc = ps->rng_states.ensure(rng_states.size())) || (rc = h2d(ctx, ps->rng_states.p, rng_states.data(), rng_states.size()))) return rc;
+        k_rng_draws<<<(B + 31) / 32, 32, 0, ctx->stream>>>(ps->rng_states.p, B, 2 * n1, n1, (size_t)B * n1, ps->wit.as<sc>() + (size_t)3 * B * n1);
+        ctx->launches++;
+        BBP_CUDA_OK(cudaMemcpyAsync(rng_states.data(), ps->rng_states.p, rng_states.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        // the states come back with the A / S commitments below (same stream, one synchronisation)
+    }
 
     sc_batch SB;
     memset(&SB, 0, sizeof SB);
@@ -373,6 +389,7 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     parallel_for(B, [&](size_t bi) {
         hstate &H = hs[bi];
         r1cs_proof_host &P = H.pf;
+        if (device_rng) H.rng->import_state(&rng_states[bi * BBP_STROBE_STATE_BYTES]);
         memcpy(P.A_I1, &pts[(bi * 3) * 32], 32); memcpy(P.A_O1, &pts[(bi * 3 + 1) * 32], 32); memcpy(P.S1, &pts[(bi * 3 + 2) * 32], 32);
         H.tr->append_point("A_I1", P.A_I1); H.tr->append_point("A_O1", P.A_O1); H.tr->append_point("S1", P.S1);
         H.tr->r1cs_1phase_domain_sep();     // the circuit has no randomised (second phase) constraints

@@ -1,0 +1,115 @@
+// merlin::TranscriptRng on the device: the prover draws 2 n1 + 8 scalars per proof from a STROBE-128 PRF (one
+// Keccak-f[1600] per draw, inherently sequential per proof), which is the host-side hot loop of Prover::prove
+// (SURVEY.md §3.4 "scalar side", §7 "TranscriptRng is inherently serial"). For batches the chain runs here instead: one
+// thread per proof continues the transcript RNG from the exported STROBE state, writes s_L and s_R straight into the
+// witness arrays in HBM (no H2D of 2 n1 scalars per proof) and hands the state back for the later T-blinding draws.
+// Bit-exact with keccak.h's strobe128 / merlin_rng (the host path used for small batches).
+#pragma once
+#include <cstdint>
+#include "sc25519.cuh"
+
+namespace bbp {
+
+#define BBP_STROBE_R 166
+#define BBP_STROBE_STATE_BYTES 208   // 200 B Keccak state, pos, pos_begin, cur_flags, 5 B padding
+
+__constant__ uint64_t KECCAK_RC_DEV[24] = {
+    0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL, 0x0000000080000001ULL,
+    0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+    0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL,
+    0x000000000000800aULL, 0x800000008000000aULL, 0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+
+__device__ inline void keccak_f1600_dev(uint64_t *s) {
+    uint64_t a00 = s[0], a01 = s[1], a02 = s[2], a03 = s[3], a04 = s[4], a05 = s[5], a06 = s[6], a07 = s[7], a08 = s[8], a09 = s[9], a10 = s[10],
+             a11 = s[11], a12 = s[12], a13 = s[13], a14 = s[14], a15 = s[15], a16 = s[16], a17 = s[17], a18 = s[18], a19 = s[19], a20 = s[20],
+             a21 = s[21], a22 = s[22], a23 = s[23], a24 = s[24];
+#pragma unroll 1
+    for (int r = 0; r < 24; r++) {
+        uint64_t c0 = a00 ^ a05 ^ a10 ^ a15 ^ a20, c1 = a01 ^ a06 ^ a11 ^ a16 ^ a21, c2 = a02 ^ a07 ^ a12 ^ a17 ^ a22,
+                 c3 = a03 ^ a08 ^ a13 ^ a18 ^ a23, c4 = a04 ^ a09 ^ a14 ^ a19 ^ a24;
+        uint64_t d0 = c4 ^ rotl64(c1, 1), d1 = c0 ^ rotl64(c2, 1), d2 = c1 ^ rotl64(c3, 1), d3 = c2 ^ rotl64(c4, 1), d4 = c3 ^ rotl64(c0, 1);
+        a00 ^= d0; a05 ^= d0; a10 ^= d0; a15 ^= d0; a20 ^= d0;
+        a01 ^= d1; a06 ^= d1; a11 ^= d1; a16 ^= d1; a21 ^= d1;
+        a02 ^= d2; a07 ^= d2; a12 ^= d2; a17 ^= d2; a22 ^= d2;
+        a03 ^= d3; a08 ^= d3; a13 ^= d3; a18 ^= d3; a23 ^= d3;
+        a04 ^= d4; a09 ^= d4; a14 ^= d4; a19 ^= d4; a24 ^= d4;
+        uint64_t b00 = a00, b10 = rotl64(a01, 1), b20 = rotl64(a02, 62), b05 = rotl64(a03, 28), b15 = rotl64(a04, 27), b16 = rotl64(a05, 36),
+                 b01 = rotl64(a06, 44), b11 = rotl64(a07, 6), b21 = rotl64(a08, 55), b06 = rotl64(a09, 20), b07 = rotl64(a10, 3), b17 = rotl64(a11, 10),
+                 b02 = rotl64(a12, 43), b12 = rotl64(a13, 25), b22 = rotl64(a14, 39), b23 = rotl64(a15, 41), b08 = rotl64(a16, 45), b18 = rotl64(a17, 15),
+                 b03 = rotl64(a18, 21), b13 = rotl64(a19, 8), b14 = rotl64(a20, 18), b24 = rotl64(a21, 2), b09 = rotl64(a22, 61), b19 = rotl64(a23, 56),
+                 b04 = rotl64(a24, 14);
+        a00 = b00 ^ (~b01 & b02); a01 = b01 ^ (~b02 & b03); a02 = b02 ^ (~b03 & b04); a03 = b03 ^ (~b04 & b00); a04 = b04 ^ (~b00 & b01);
+        a05 = b05 ^ (~b06 & b07); a06 = b06 ^ (~b07 & b08); a07 = b07 ^ (~b08 & b09); a08 = b08 ^ (~b09 & b05); a09 = b09 ^ (~b05 & b06);
+        a10 = b10 ^ (~b11 & b12); a11 = b11 ^ (~b12 & b13); a12 = b12 ^ (~b13 & b14); a13 = b13 ^ (~b14 & b10); a14 = b14 ^ (~b10 & b11);
+        a15 = b15 ^ (~b16 & b17); a16 = b16 ^ (~b17 & b18); a17 = b17 ^ (~b18 & b19); a18 = b18 ^ (~b19 & b15); a19 = b19 ^ (~b15 & b16);
+        a20 = b20 ^ (~b21 & b22); a21 = b21 ^ (~b22 & b23); a22 = b22 ^ (~b23 & b24); a23 = b23 ^ (~b24 & b20); a24 = b24 ^ (~b20 & b21);
+        a00 ^= KECCAK_RC_DEV[r];
+    }
+    s[0] = a00; s[1] = a01; s[2] = a02; s[3] = a03; s[4] = a04; s[5] = a05; s[6] = a06; s[7] = a07; s[8] = a08; s[9] = a09; s[10] = a10; s[11] = a11;
+    s[12] = a12; s[13] = a13; s[14] = a14; s[15] = a15; s[16] = a16; s[17] = a17; s[18] = a18; s[19] = a19; s[20] = a20; s[21] = a21; s[22] = a22;
+    s[23] = a23; s[24] = a24;
+}
+
+struct strobe_dev {
+    uint64_t st[25];
+    uint32_t pos, pos_begin;
+    __device__ uint8_t *bytes() { return (uint8_t *)st; }
+    __device__ void run_f() {
+        uint8_t *s = bytes();
+        s[pos] ^= (uint8_t)pos_begin;
+        s[pos + 1] ^= 0x04;
+        s[BBP_STROBE_R + 1] ^= 0x80;
+        keccak_f1600_dev(st);
+        pos = 0; pos_begin = 0;
+    }
+    __device__ void absorb_byte(uint8_t b) {
+        bytes()[pos++] ^= b;
+        if (pos == BBP_STROBE_R) run_f();
+    }
+    // begin_op for a fresh (more = false) operation with the given flags
+    __device__ void begin_op(uint8_t flags) {
+        uint8_t old_begin = (uint8_t)pos_begin;
+        pos_begin = pos + 1;
+        absorb_byte(old_begin);
+        absorb_byte(flags);
+        if ((flags & (4 | 32)) && pos != 0) run_f();   // FLAG_C | FLAG_K
+    }
+    // TranscriptRng::fill_bytes(64): meta_ad(LE32(64)) ; prf(64)
+    __device__ void fill64(uint8_t *out) {
+        begin_op(16 | 2);                   // FLAG_M | FLAG_A
+        absorb_byte(64); absorb_byte(0); absorb_byte(0); absorb_byte(0);
+        begin_op(1 | 2 | 4);                // FLAG_I | FLAG_A | FLAG_C
+        uint8_t *s = bytes();
+        for (int i = 0; i < 64; i++) {
+            out[i] = s[pos];
+            s[pos++] = 0;
+            if (pos == BBP_STROBE_R) run_f();
+        }
+    }
+};
+
+// states: [n_proofs][208] (in / out). Draw d of proof p goes to out[(d / per_vec) * vec_stride + p * per_vec + d % per_vec]:
+// with per_vec = n1, vec_stride = n_proofs * n1 the first n1 draws fill s_L and the next n1 fill s_R.
+__global__ void __launch_bounds__(32) k_rng_draws(uint8_t *__restrict__ states, uint32_t n_proofs, uint32_t n_draws, uint32_t per_vec, size_t vec_stride,
+                                                  sc *__restrict__ out) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_proofs) return;
+    strobe_dev S;
+    const uint64_t *in = (const uint64_t *)(states + (size_t)p * BBP_STROBE_STATE_BYTES);
+    for (int i = 0; i < 25; i++) S.st[i] = in[i];
+    const uint8_t *tail = states + (size_t)p * BBP_STROBE_STATE_BYTES + 200;
+    S.pos = tail[0]; S.pos_begin = tail[1];
+    for (uint32_t d = 0; d < n_draws; d++) {
+        uint8_t buf[64];
+        S.fill64(buf);
+        out[(size_t)(d / per_vec) * vec_stride + (size_t)p * per_vec + d % per_vec] = sc_from_wide(buf);
+    }
+    uint64_t *o = (uint64_t *)(states + (size_t)p * BBP_STROBE_STATE_BYTES);
+    for (int i = 0; i < 25; i++) o[i] = S.st[i];
+    uint8_t *ot = states + (size_t)p * BBP_STROBE_STATE_BYTES + 200;
+    ot[0] = (uint8_t)S.pos; ot[1] = (uint8_t)S.pos_begin; ot[2] = 1 | 2 | 4;   // cur_flags after a prf
+}
+
+}  // namespace bbp

@@ -77,7 +77,51 @@ BBP_HD sc sc_neg(const sc &a) {
 BBP_HD sc sc_sub(const sc &a, const sc &b) { return sc_add(a, sc_neg(b)); }
 
 // Montgomery product a*b/2^256 mod l; inputs < 2^256 with a*b < l*2^256; output < l
+#if !defined(__CUDA_ARCH__)
+// host build: the same CIOS recurrence on 4 x 64-bit limbs (unsigned __int128 products)
+inline sc sc_montmul_host64(const uint32_t *a32, const uint32_t *b32) {
+    typedef unsigned __int128 u128;
+    uint64_t a[4], b[4], L[4], t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        a[i] = (uint64_t)a32[2 * i] | ((uint64_t)a32[2 * i + 1] << 32);
+        b[i] = (uint64_t)b32[2 * i] | ((uint64_t)b32[2 * i + 1] << 32);
+        L[i] = (uint64_t)sc_l_limb(2 * i) | ((uint64_t)sc_l_limb(2 * i + 1) << 32);
+    }
+    // -l^-1 mod 2^64 from the 32-bit constant by one Newton step
+    uint64_t n0 = (uint64_t)SC_N0INV;          // n0 * l == -1 mod 2^32
+    n0 = n0 * (2 + L[0] * n0);                 // x' = x (2 + l x) keeps x l == -1 and doubles the precision
+    for (int i = 0; i < 4; i++) {
+        u128 c = 0;
+        for (int j = 0; j < 4; j++) {
+            c += (u128)a[j] * b[i] + t[j];
+            t[j] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[4] = (uint64_t)c;
+        t[5] = (uint64_t)(c >> 64);
+        uint64_t m = t[0] * n0;
+        c = (u128)m * L[0] + t[0];
+        c >>= 64;
+        for (int j = 1; j < 4; j++) {
+            c += (u128)m * L[j] + t[j];
+            t[j - 1] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[3] = (uint64_t)c;
+        t[4] = t[5] + (uint64_t)(c >> 64);
+    }
+    sc r;
+    for (int i = 0; i < 4; i++) { r.v[2 * i] = (uint32_t)t[i]; r.v[2 * i + 1] = (uint32_t)(t[i] >> 32); }
+    if (t[4] || sc_geq_l(r.v)) sc_sub_l(r.v);
+    return r;
+}
+#endif
 BBP_HD sc sc_montmul(const uint32_t *a, const uint32_t *b) {
+#if !defined(__CUDA_ARCH__)
+    return sc_montmul_host64(a, b);
+#else
     uint32_t t[10];
 #pragma unroll
     for (int i = 0; i < 10; i++) t[i] = 0;
@@ -110,6 +154,7 @@ BBP_HD sc sc_montmul(const uint32_t *a, const uint32_t *b) {
     for (int i = 0; i < 8; i++) r.v[i] = t[i];
     if (t[8] || sc_geq_l(r.v)) sc_sub_l(r.v);
     return r;
+#endif
 }
 BBP_HD sc sc_r2() { sc r; for (int i = 0; i < 8; i++) r.v[i] = sc_r2_limb(i); return r; }
 BBP_HD sc sc_mul(const sc &a, const sc &b) {

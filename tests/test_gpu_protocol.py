@@ -126,6 +126,20 @@ def test_prove_batch_mixed_lengths(be):
         assert (proof, comm, tc) == (oproof, ocomm, otc)
 
 
+def test_prove_batch_device_rng_matches_oracle(be):
+    """batches of >= 8 equal-length bids continue the TranscriptRng on the device (rng_kernels.cuh): bytes must still equal
+    the oracle's, and equal what the host-RNG path (single request) produces"""
+    cases = [make_case(300 + i, 3) for i in range(12)]
+    outs = be.blindbid_prove_batch(cases)
+    for i, (bid, (st, proof, comm, tc)) in enumerate(zip(cases, outs)):
+        assert st == 0
+        if i % 4 == 0:
+            rc, oproof, ocomm, otc = orc.blindbid_prove(bid, bid["blindings"], bid["rng_seed"])
+            assert rc == 0 and (proof, comm, tc) == (oproof, ocomm, otc), i
+        if i % 4 == 1:
+            assert be.blindbid_prove(bid) == (st, proof, comm, tc)
+
+
 def mutations(bid, proof, comm, tc):
     """(name, item) pairs; each must be rejected. Mirrors SURVEY.md §4.4-3."""
     out = []
