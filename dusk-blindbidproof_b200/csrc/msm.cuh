@@ -58,6 +58,10 @@ __global__ void k_recode(const uint32_t *__restrict__ scalars, int32_t *__restri
     const uint4 *q = (const uint4 *)(scalars + 8 * (size_t)i);
     uint4 a = __ldg(q), b = __ldg(q + 1);
     w8[0] = a.x; w8[1] = a.y; w8[2] = a.z; w8[3] = a.w; w8[4] = b.x; w8[5] = b.y; w8[6] = b.z; w8[7] = b.w;
+    if ((w8[0] | w8[1] | w8[2] | w8[3] | w8[4] | w8[5] | w8[6] | w8[7]) == 0) {   // protocol slots are padded with zeros
+        for (uint32_t w = 0; w < sh.W; w++) digits[(size_t)w * sh.n + i] = 0;
+        return;
+    }
     sc s = sc_reduce_words(w8);
     uint32_t slot = i / sh.n_per_slot;
     uint32_t carry = 0;

@@ -77,6 +77,23 @@ struct dev_buf {
     template <class T> T *as() const { return (T *)p; }
 };
 
+// grow-only pinned host staging (fresh pageable vectors of tens of MB cost more in page faults than the copy itself)
+struct host_buf {
+    uint8_t *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4;
+        if (cudaHostAlloc((void **)&p, want, cudaHostAllocDefault) != cudaSuccess) { fprintf(stderr, "bbp: cudaHostAlloc(%zu) failed\n", want); return BBP_ERR_CUDA; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
 struct dev_template {
     std::shared_ptr<const circuit_template> tpl;
     uint32_t *row_ptr = nullptr, *entries = nullptr, *const_j = nullptr, *const_idx = nullptr;
@@ -90,6 +107,7 @@ struct proto_state {
     uint8_t *wtable = nullptr;     // generator window table, WT_W rows of n_gens niels entries
     dev_buf chal, zpow, ypow, yinvpow, wit, vbl, blind3, poly, tout, a, b, sG, sH, slots, ab, pub, dyn_sc, dyn_pts, dyn_niels, stat, stat_red,
         msm_out, msm_ext, flags, valid, commit_in, commit_out, rng_states;
+    host_buf h_wit;
     int proof_versioned = 1;       // R1CSProof::to_bytes layout (SURVEY.md §8c risk R1): 1 = leading phase byte, 0 = legacy 14-point form
 };
 
@@ -106,6 +124,7 @@ void proto_release(proto_state *ps) {
                       &ps->slots, &ps->ab, &ps->pub, &ps->dyn_sc, &ps->dyn_pts, &ps->dyn_niels, &ps->stat, &ps->stat_red, &ps->msm_out, &ps->msm_ext,
                       &ps->flags, &ps->valid, &ps->commit_in, &ps->commit_out, &ps->rng_states};
     for (dev_buf *b : all) b->release();
+    ps->h_wit.release();
     delete ps;
 }
 
@@ -314,7 +333,10 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     static const int rng_threshold = [] { const char *e = getenv("BBP_DEVICE_RNG_MIN_BATCH"); return e ? atoi(e) : 8; }();
     const bool device_rng = (int)B >= rng_threshold;
     std::vector<uint8_t> rng_states(device_rng ? (size_t)B * BBP_STROBE_STATE_BYTES : 0);
-    std::vector<sc> wit((size_t)B * (device_rng ? 3 : 5) * n1), vbl((size_t)B * m), blind3((size_t)B * 3);
+    const size_t wit_count = (size_t)B * (device_rng ? 3 : 5) * n1;
+    if ((rc = ps->h_wit.ensure(wit_count * 32))) return rc;
+    sc *wit = ps->h_wit.as<sc>();
+    std::vector<sc> vbl((size_t)B * m), blind3((size_t)B * 3);
     parallel_for(B, [&](size_t bi) {
         prove_job &J = jobs[idx[bi]];
         hstate &H = hs[bi];
@@ -354,7 +376,7 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
         (rc = ps->sH.ensure((size_t)B * n * 32)) || (rc = ps->slots.ensure((size_t)B * 3 * slot_len * 32)) || (rc = ps->ab.ensure((size_t)B * 64)) ||
         (rc = ps->msm_out.ensure((size_t)B * 3 * 32)))
         return rc;
-    if ((rc = h2d(ctx, ps->wit.p, wit.data(), wit.size() * 32)) || (rc = h2d(ctx, ps->vbl.p, vbl.data(), vbl.size() * 32)) ||
+    if ((rc = h2d(ctx, ps->wit.p, wit, wit_count * 32)) || (rc = h2d(ctx, ps->vbl.p, vbl.data(), vbl.size() * 32)) ||
         (rc = h2d(ctx, ps->blind3.p, blind3.data(), blind3.size() * 32)))
         return rc;
     if (device_rng) {
@@ -363,6 +385,7 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
         ctx->launches++;
         BBP_CUDA_OK(cudaMemcpyAsync(rng_states.data(), ps->rng_states.p, rng_states.size(), cudaMemcpyDeviceToHost, ctx->stream));
         // the states come back with the A / S commitments below (same stream, one synchronisation)
+        if (trace.on) { cudaStreamSynchronize(ctx->stream); trace.mark("h2d_witness+gpu_rng_draws"); }
     }
 
     sc_batch SB;

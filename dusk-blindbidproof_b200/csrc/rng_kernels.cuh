@@ -90,6 +90,15 @@ struct strobe_dev {
     }
 };
 
+// Steady state of consecutive 64-byte draws: every draw starts at pos = 64, pos_begin = 0 (the previous prf squeezed lanes
+// 0..7 after a permutation), so the STROBE framing of one draw is a fixed pattern of byte XORs:
+//   bytes 64..71 (lane 8):  old_begin = 0, flags M|A = 0x12, LE32(64), old_begin = 65, flags I|A|C = 0x07
+//   run_f at pos = 72:      byte 72 ^= pos_begin (71), byte 73 ^= 0x04 (lane 9), byte 167 ^= 0x80 (lane 20, top byte)
+// then Keccak-f, output = lanes 0..7, which are zeroed. The whole draw runs on registers.
+#define BBP_STROBE_DRAW_LANE8 0x0741000000401200ULL
+#define BBP_STROBE_DRAW_LANE9 0x0000000000000447ULL
+#define BBP_STROBE_DRAW_LANE20 0x8000000000000000ULL
+
 // states: [n_proofs][208] (in / out). Draw d of proof p goes to out[(d / per_vec) * vec_stride + p * per_vec + d % per_vec]:
 // with per_vec = n1, vec_stride = n_proofs * n1 the first n1 draws fill s_L and the next n1 fill s_R.
 __global__ void __launch_bounds__(32) k_rng_draws(uint8_t *__restrict__ states, uint32_t n_proofs, uint32_t n_draws, uint32_t per_vec, size_t vec_stride,
@@ -102,9 +111,24 @@ __global__ void __launch_bounds__(32) k_rng_draws(uint8_t *__restrict__ states, 
     const uint8_t *tail = states + (size_t)p * BBP_STROBE_STATE_BYTES + 200;
     S.pos = tail[0]; S.pos_begin = tail[1];
     for (uint32_t d = 0; d < n_draws; d++) {
-        uint8_t buf[64];
-        S.fill64(buf);
-        out[(size_t)(d / per_vec) * vec_stride + (size_t)p * per_vec + d % per_vec] = sc_from_wide(buf);
+        uint32_t w[16];
+        if (S.pos == 64 && S.pos_begin == 0) {
+            S.st[8] ^= BBP_STROBE_DRAW_LANE8;
+            S.st[9] ^= BBP_STROBE_DRAW_LANE9;
+            S.st[20] ^= BBP_STROBE_DRAW_LANE20;
+            keccak_f1600_dev(S.st);
+#pragma unroll
+            for (int i = 0; i < 8; i++) { w[2 * i] = (uint32_t)S.st[i]; w[2 * i + 1] = (uint32_t)(S.st[i] >> 32); S.st[i] = 0; }
+        } else {
+            uint8_t buf[64];
+            S.fill64(buf);
+            for (int i = 0; i < 16; i++) w[i] = (uint32_t)buf[4 * i] | ((uint32_t)buf[4 * i + 1] << 8) | ((uint32_t)buf[4 * i + 2] << 16) | ((uint32_t)buf[4 * i + 3] << 24);
+        }
+        // Scalar::from_bytes_mod_order_wide: lo + hi * 2^256
+        sc lo = sc_reduce_words(w);
+        sc r2 = sc_r2();
+        sc hi = sc_montmul(w + 8, r2.v);
+        out[(size_t)(d / per_vec) * vec_stride + (size_t)p * per_vec + d % per_vec] = sc_add(lo, hi);
     }
     uint64_t *o = (uint64_t *)(states + (size_t)p * BBP_STROBE_STATE_BYTES);
     for (int i = 0; i < 25; i++) o[i] = S.st[i];
