@@ -204,7 +204,7 @@ def synth_bid(capi, i, L):
                 rng_seed=hashlib.sha256(b"rng%d" % i).digest())
 
 
-def run_blindbid(pkg, be, torch, dist, rank, world, n_prove=256, n_verify=1024, L=8, reps=3):
+def run_blindbid(pkg, be, torch, dist, rank, world, n_prove=1024, n_verify=1024, L=8, reps=3):
     """prove: n_prove bids per GPU in one batched pass (replicas across GPUs). batch-verify: n_verify proofs per GPU, one
     combined mega-check; at N > 1 the batch is N*n_verify proofs sharded by proof range, the GPUs exchange their 2 x 128 B
     partial sums with one all-gather and every rank tests the total for the identity. Host buffers in, host buffers out."""

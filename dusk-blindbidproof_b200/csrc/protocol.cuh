@@ -671,7 +671,7 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
 
     std::vector<sc> chal((size_t)B * CH_N), pub((size_t)B * T.n_pub), dyn_sc((size_t)B * ds);
     std::vector<uint8_t> alive(B, 1);
-    for (uint32_t bi = 0; bi < B; bi++) {
+    parallel_for(B, [&](size_t bi) {
         verify_prepared &P = prep[idx[bi]];
         for (uint32_t k = 0; k < ds; k++)
             if (!valid[(size_t)bi * ds + k]) alive[bi] = 0;
@@ -682,7 +682,7 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
         memcpy(&pub[(size_t)bi * T.n_pub], P.pub.data(), (size_t)T.n_pub * 32);
         bool unit = sc_eq(w, sc_one());
         for (uint32_t k = 0; k < ds; k++) dyn_sc[(size_t)bi * ds + k] = unit ? P.dyn_sc[k] : sc_mul(w, P.dyn_sc[k]);
-    }
+    });
     if ((rc = ps->chal.ensure(chal.size() * 32)) || (rc = ps->pub.ensure(pub.size() * 32)) || (rc = ps->dyn_sc.ensure(dyn_sc.size() * 32)) ||
         (rc = ps->zpow.ensure((size_t)B * T.q * 32)) || (rc = ps->ypow.ensure((size_t)B * n * 32)) || (rc = ps->yinvpow.ensure((size_t)B * n * 32)) ||
         (rc = ps->stat.ensure((size_t)B * slot_len * 32)) || (rc = ps->stat_red.ensure((size_t)n_groups * slot_len * 32)) ||
@@ -758,8 +758,16 @@ inline int verify_batch(bbp_ctx *ctx, std::vector<verify_job> &jobs, const uint8
         parallel_for(jobs.size(), [&](size_t i) { verify_prepare(ctx, jobs[i], prep[i], versioned); });
         tp.mark("transcripts");
     }
+    // batch weights: a Merlin transcript over one 32-byte digest per request — the verifier scalar r that request's own
+    // transcript produced after absorbing the whole proof (so it binds every proof byte) — keyed with the caller's seed
     merlin_transcript bt("bbp batch verification");
-    for (auto &J : jobs) bt.append_message("proof", J.proof.data(), J.proof.size());
+    bt.append_u64("n", jobs.size());
+    for (size_t i = 0; i < jobs.size(); i++) {
+        uint8_t dg[32];
+        memset(dg, 0, 32);
+        if (prep[i].live) sc_tobytes(dg, prep[i].chal[CH_R]);
+        bt.append_message("proof", dg, 32);
+    }
     merlin_rng brng = bt.build_rng().finalize(batch_seed);
     std::map<uint64_t, std::vector<size_t>> groups;
     std::vector<sc> rho_all(jobs.size());
