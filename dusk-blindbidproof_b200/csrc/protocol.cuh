@@ -699,6 +699,8 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     SB.row_ptr = dt->row_ptr; SB.entries = dt->entries; SB.const_j = dt->const_j; SB.const_idx = dt->const_idx; SB.n_const = (uint32_t)T.const_j.size();
     SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>();
     SB.pub = ps->pub.as<sc>(); SB.dyn_out = ps->dyn_sc.as<sc>(); SB.dyn_stride = ds; SB.stat = ps->stat.as<sc>();
+    if ((rc = ps->sG.ensure((size_t)B * n * 32))) return rc;
+    SB.stab = ps->sG.as<sc>();
     k_powers<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
     k_verify_scalars<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
     k_stat_reduce<<<dim3((slot_len + BBP_SC_THREADS - 1) / BBP_SC_THREADS, n_groups), BBP_SC_THREADS, 0, ctx->stream>>>(SB.stat, combined ? B : 1, slot_len,

@@ -51,6 +51,7 @@ struct sc_batch {
     sc *dyn_out;                               // [n_proofs][dyn_stride]: first m entries = rho * wV[i] * r * x^2 (written here)
     uint32_t dyn_stride;
     sc *stat;                                  // [n_proofs][2 + 2 gcols] rho-weighted static-base scalars (Montgomery)
+    sc *stab;                                  // [n_proofs][n] scratch: the IPP verification vector s (Montgomery)
     // aggregated range proofs (bulletproofs RangeProof::prove_multiple / verify_multiple)
     const uint64_t *rp_values;                 // [n_proofs][rp_m]
     uint32_t rp_bits, rp_m;                    // n = rp_bits * rp_m
@@ -264,6 +265,24 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_ipp_round(sc_batch B, uint32
     }
 }
 
+// InnerProductProof::verification_scalars: s[0] = prod u_j^-1, s[i] = s[i - 2^b] * u_{lg-1-b}^2 for 2^b <= i < 2^(b+1):
+// one multiplication per element, lg n block-wide steps (the whole CTA works on one proof). uj: u_0.., then inverses.
+__device__ inline void build_s_table(sc *stab, const sc *uj, uint32_t lg, uint32_t n) {
+    const uint32_t t = threadIdx.x;
+    if (t == 0) {
+        sc acc = sc_mont_one();
+        for (uint32_t j = 0; j < lg; j++) acc = mm(acc, uj[lg + j]);
+        stab[0] = acc;
+    }
+    __syncthreads();
+    for (uint32_t b = 0; b < lg; b++) {
+        const uint32_t half = 1u << b;
+        sc usq = mm(uj[lg - 1 - b], uj[lg - 1 - b]);
+        for (uint32_t i = half + t; i < 2 * half && i < n; i += BBP_SC_THREADS) stab[i] = mm(stab[i - half], usq);
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------- verifier scalar assembly
 // Per proof (weight rho, 1 for a single verification):
 //   stat[0]   (B)          rho * ( w (t_x - a b) + r (x^2 (wc + delta) - t_x) )
@@ -296,14 +315,10 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_verify_scalars(sc_batch B) {
     }
     wc = block_sum_sc(wc, smem);
     sc delta = sc_zero();
+    sc *stab = B.stab + (size_t)p * n;
+    build_s_table(stab, uj, lg, n);
     for (uint32_t i = t; i < n; i += BBP_SC_THREADS) {
-        // s[i] and s[n-1-i] (bitwise complement of i: the inverse product)
-        sc s = one, srev = one;
-        for (uint32_t j = 0; j < lg; j++) {
-            bool bit = (i >> (lg - 1 - j)) & 1;
-            s = mm(s, bit ? uj[j] : uj[lg + j]);
-            srev = mm(srev, bit ? uj[lg + j] : uj[j]);
-        }
+        sc s = stab[i], srev = stab[n - 1 - i];
         sc g, h;
         sc uf = (i < n1) ? one : uM;
         if (i < n1) {
@@ -420,13 +435,10 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_rp_verify_scalars(sc_batch B
     sc zM = sc_to_mont(ch[CH_Z]), aM = sc_to_mont(ch[CH_A]), bM = sc_to_mont(ch[CH_B]), rhoM = sc_to_mont(ch[CH_RHO]), one = sc_mont_one();
     sc *stat = B.stat + (size_t)p * (2 + 2 * gc);
     for (uint32_t i = n + t; i < gc; i += BBP_SC_THREADS) { stat[2 + i] = sc_zero(); stat[2 + gc + i] = sc_zero(); }
+    sc *stab = B.stab + (size_t)p * n;
+    build_s_table(stab, uj, lg, n);
     for (uint32_t k = t; k < n; k += BBP_SC_THREADS) {
-        sc s = one, srev = one;
-        for (uint32_t j = 0; j < lg; j++) {
-            bool bit = (k >> (lg - 1 - j)) & 1;
-            s = mm(s, bit ? uj[j] : uj[lg + j]);
-            srev = mm(srev, bit ? uj[lg + j] : uj[j]);
-        }
+        sc s = stab[k], srev = stab[n - 1 - k];
         uint32_t j = k / B.rp_bits, i = k % B.rp_bits;
         sc zz_j = sc_pow_small_mont(zM, 2 + j);
         sc two_i = sc_to_mont(sc_from_u64(1ull << i));
