@@ -203,9 +203,16 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate(const uint8_t *__restr
     uint32_t end = min(start + sh.S, offs[key + 1]);
     uint32_t e = entries[start];
     ge acc = ge_from_niels(niels_load_ro(table + 96 * (size_t)(e & 0x7fffffffu)), (e >> 31) != 0);
-    for (uint32_t j = start + 1; j < end; j++) {
-        e = entries[j];
+    if (start + 1 < end) {
+        // software pipeline: the gather of entry j+1 is in flight while entry j is being added
+        e = entries[start + 1];
         niels q = niels_load_ro(table + 96 * (size_t)(e & 0x7fffffffu));
+        for (uint32_t j = start + 2; j < end; j++) {
+            uint32_t en = entries[j];
+            niels qn = niels_load_ro(table + 96 * (size_t)(en & 0x7fffffffu));
+            acc = ge_madd(acc, q, (e >> 31) != 0);
+            q = qn; e = en;
+        }
         acc = ge_madd(acc, q, (e >> 31) != 0);
     }
     ge_store(partial + 128 * (size_t)t, acc);
