@@ -47,7 +47,21 @@ struct msm_shape {
     uint32_t S;            // max entries per task
     uint32_t CH;           // buckets per chunk (power of two)
     uint32_t n_ch;         // chunks per bucket set = B / CH
+    // point reference of scalar i. mode 0: i % base_mod. mode 1: colmap[i % colmap_len] (compact slots over scattered
+    // columns of a fixed table). mode 2: per-group tables — element e = i % n_per_slot of a slot refers to entry
+    // (i / grp_div) * grp_stride + e, except the last element of every slot, which refers to the shared entry tail_ref.
+    uint32_t ref_mode;
+    const uint32_t *colmap;
+    uint32_t colmap_len, grp_div, grp_stride, tail_ref;
 };
+__device__ __forceinline__ uint32_t msm_ref(const msm_shape &sh, uint32_t i) {
+    if (sh.ref_mode == 1) return sh.colmap[i % sh.colmap_len];
+    if (sh.ref_mode == 2) {
+        uint32_t e = i % sh.n_per_slot;
+        return (e + 1 == sh.n_per_slot) ? sh.tail_ref : (i / sh.grp_div) * sh.grp_stride + e;
+    }
+    return i % sh.base_mod;
+}
 
 // ---------------------------------------------------------------- recode + histogram
 // digits are stored window-major: digits[w * n + i]
@@ -171,7 +185,7 @@ __global__ void k_scatter(const int32_t *__restrict__ digits, const uint32_t *__
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= sh.n) return;
     uint32_t slot = i / sh.n_per_slot;
-    uint32_t ref = i % sh.base_mod;
+    uint32_t ref = msm_ref(sh, i);
     for (uint32_t w = 0; w < sh.W; w++) {
         int32_t d = digits[(size_t)w * sh.n + i];
         if (d == 0) continue;
@@ -439,6 +453,7 @@ struct msm_engine {
         msm_shape sh;
         sh.n = n; sh.n_per_slot = n_per_slot; sh.n_slots = (n + n_per_slot - 1) / n_per_slot; sh.base_mod = base_mod;
         sh.fixed = fixed ? 1 : 0;
+        sh.ref_mode = 0; sh.colmap = nullptr; sh.colmap_len = 0; sh.grp_div = 1; sh.grp_stride = 0; sh.tail_ref = 0;
         if (fixed) {
             sh.c = table_c; sh.W = table_W; sh.table_stride = table_stride; sh.sets_per_slot = 1;
         } else {

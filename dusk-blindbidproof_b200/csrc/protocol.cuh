@@ -100,11 +100,18 @@ struct dev_template {
 };
 
 static const uint32_t WT_C = 11, WT_W = 24;   // window table over the generators: 24 windows of 11 bits (264 >= 254 bits)
+static const uint32_t WT2_C = 6, WT2_W = 43;   // second table, small windows: 32 buckets per slot, for the many tiny slots of the
+                                               // IPP materialisation MSM (16 scalars each)
+static const uint32_t IPP_NF = 128;            // hybrid IPP: folded bases are materialised when the vectors reach this length
 
 struct proto_state {
     std::map<uint64_t, dev_template> templates;
     uint8_t *comb = nullptr;       // Pedersen comb table
     uint8_t *wtable = nullptr;     // generator window table, WT_W rows of n_gens niels entries
+    uint8_t *wtable2 = nullptr;    // same with WT2_C-bit windows
+    uint32_t *colmap = nullptr;    // compact slot -> generator column map of the materialisation MSM
+    uint32_t colmap_n = 0, colmap_gcols = 0;
+    dev_buf fext, ftab;            // materialised folded bases: extended, then niels (+ B at the tail)
     dev_buf chal, zpow, ypow, yinvpow, wit, vbl, blind3, poly, tout, a, b, sG, sH, slots, ab, pub, dyn_sc, dyn_pts, dyn_niels, stat, stat_red,
         msm_out, msm_ext, flags, valid, commit_in, commit_out, rng_states;
     host_buf h_wit;
@@ -119,7 +126,8 @@ inline proto_state *proto_get(bbp_ctx *ctx) {
 void proto_release(proto_state *ps) {
     if (!ps) return;
     for (auto &kv : ps->templates) { cudaFree(kv.second.row_ptr); cudaFree(kv.second.entries); cudaFree(kv.second.const_j); cudaFree(kv.second.const_idx); }
-    cudaFree(ps->comb); cudaFree(ps->wtable);
+    cudaFree(ps->comb); cudaFree(ps->wtable); cudaFree(ps->wtable2); cudaFree(ps->colmap);
+    ps->fext.release(); ps->ftab.release();
     dev_buf *all[] = {&ps->chal, &ps->zpow, &ps->ypow, &ps->yinvpow, &ps->wit, &ps->vbl, &ps->blind3, &ps->poly, &ps->tout, &ps->a, &ps->b, &ps->sG, &ps->sH,
                       &ps->slots, &ps->ab, &ps->pub, &ps->dyn_sc, &ps->dyn_pts, &ps->dyn_niels, &ps->stat, &ps->stat_red, &ps->msm_out, &ps->msm_ext,
                       &ps->flags, &ps->valid, &ps->commit_in, &ps->commit_out, &ps->rng_states};
@@ -140,6 +148,12 @@ inline int proto_tables(bbp_ctx *ctx) {
     if (!ps->wtable && ctx->n_gens > 2) {
         BBP_CUDA_OK(cudaMalloc(&ps->wtable, (size_t)WT_W * ctx->n_gens * 96));
         k_build_window_table<<<(unsigned)((ctx->n_gens + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_gens_ext, ps->wtable, (uint32_t)ctx->n_gens, WT_C, WT_W,
+                                                                                              (uint32_t)ctx->n_gens);
+        ctx->launches++;
+    }
+    if (!ps->wtable2 && ctx->n_gens > 2) {
+        BBP_CUDA_OK(cudaMalloc(&ps->wtable2, (size_t)WT2_W * ctx->n_gens * 96));
+        k_build_window_table<<<(unsigned)((ctx->n_gens + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_gens_ext, ps->wtable2, (uint32_t)ctx->n_gens, WT2_C, WT2_W,
                                                                                               (uint32_t)ctx->n_gens);
         ctx->launches++;
     }
@@ -202,6 +216,77 @@ inline int msm_gens_device(bbp_ctx *ctx, const sc *d_scalars, uint32_t slot_len,
     if (slot_len > ctx->n_gens || !ps->wtable) return BBP_ERR_INVALID_GENERATORS_LENGTH;
     msm_shape sh = msm_engine::make_shape(n_slots * slot_len, slot_len, slot_len, true, WT_C, WT_W, (uint32_t)ctx->n_gens);
     return ctx->msm.run(sh, (const uint8_t *)d_scalars, ps->wtable, d_out_ext, d_out_compressed);
+}
+
+// Inner-product argument for a batch of P proofs whose a, b, sG, sH live in SB (set up by k_ipp_init / k_rp_ipp_init).
+// Early rounds: L_j, R_j as MSMs over the ORIGINAL generators with product-form scalars (no folding, see sc_kernels.cuh).
+// Once the vectors have shrunk to IPP_NF the folded bases are materialised ONCE (one MSM with 2*IPP_NF tiny slots per
+// proof over the small-window table), and the remaining rounds are 2*IPP_NF+1-point MSMs over those per-proof bases.
+// on_round(j, lr) receives the compressed L_j, R_j (64 B per proof) and must fill CH_UJ / CH_UJINV of every proof in chal.
+template <class F>
+inline int ipp_rounds(bbp_ctx *ctx, sc_batch &SB, uint32_t P, std::vector<sc> &chal, F on_round, phase_trace &trace) {
+    proto_state *ps = proto_get(ctx);
+    const uint32_t n = SB.n, lg = SB.lg_n, gcols = SB.gcols, slot_len = 2 + 2 * gcols;
+    static const int hybrid_env = [] { const char *e = getenv("BBP_IPP_HYBRID"); return e ? atoi(e) : 1; }();
+    const bool hybrid = hybrid_env && n >= 4 * IPP_NF;
+    const uint32_t j0 = hybrid ? lg - log2_u32(IPP_NF) : lg, nf = IPP_NF;
+    int rc;
+    std::vector<uint8_t> lr((size_t)P * 64);
+    SB.fac_n = n; SB.late = 0;
+    if ((rc = ps->msm_out.ensure((size_t)P * 64))) return rc;
+    for (uint32_t j = 0; j < lg; j++) {
+        uint32_t mode = 0;
+        if (hybrid && j == j0) {
+            // ---- materialise F_G, F_H: compact scalars -> MSM over the generator table -> per-proof niels tables (+ B)
+            if (ps->colmap_n != n || ps->colmap_gcols != gcols) {
+                std::vector<uint32_t> cm((size_t)2 * n);
+                const uint32_t E = n / nf;
+                for (uint32_t idx = 0; idx < 2 * n; idx++) {
+                    uint32_t fam = idx / n, r = idx % n, k = r / E, e = r % E;
+                    cm[idx] = 2 + fam * gcols + k + nf * e;
+                }
+                cudaFree(ps->colmap);
+                ps->colmap = nullptr;
+                BBP_CUDA_OK(cudaMalloc(&ps->colmap, cm.size() * 4));
+                BBP_CUDA_OK(cudaMemcpyAsync(ps->colmap, cm.data(), cm.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+                ps->colmap_n = n; ps->colmap_gcols = gcols;
+            }
+            const size_t n_f_pts = (size_t)P * 2 * nf;
+            if ((rc = ps->fext.ensure(n_f_pts * 128)) || (rc = ps->ftab.ensure((n_f_pts + 1) * 96))) return rc;
+            SB.mat = SB.slots;   // the slot buffer is free between rounds and large enough (2 slots of 2 + 2 gcols >= 2 n)
+            k_ipp_materialize<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB, j0);
+            ctx->launches++;
+            msm_shape sh = msm_engine::make_shape(P * 2 * n, n / nf, n / nf, true, WT2_C, WT2_W, (uint32_t)ctx->n_gens);
+            sh.ref_mode = 1; sh.colmap = ps->colmap; sh.colmap_len = 2 * n;
+            if ((rc = ctx->msm.run(sh, (const uint8_t *)SB.mat, ps->wtable2, ps->fext.p, nullptr))) return rc;
+            size_t thr = (n_f_pts + BBP_NIELS_BATCH - 1) / BBP_NIELS_BATCH;
+            k_ext_to_niels<<<(unsigned)((thr + 127) / 128), 128, 0, ctx->stream>>>(ps->fext.p, ps->ftab.p, (uint32_t)n_f_pts);
+            ctx->launches++;
+            BBP_CUDA_OK(cudaMemcpyAsync(ps->ftab.p + n_f_pts * 96, ctx->d_gens_niels, 96, cudaMemcpyDeviceToDevice, ctx->stream));
+            SB.fac_n = nf; SB.late = 1;
+            mode = 2;   // the fold of this round was applied by k_ipp_materialize
+            if (trace.on) { cudaStreamSynchronize(ctx->stream); trace.mark("gpu_ipp_materialize"); }
+        }
+        k_ipp_round<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB, j, mode);
+        ctx->launches++;
+        if (!SB.late) {
+            if ((rc = msm_gens_device(ctx, SB.slots, slot_len, 2 * P, ps->msm_out.p, nullptr))) return rc;
+        } else {
+            const uint32_t sl = 2 * nf + 1;
+            msm_shape sh = msm_engine::make_shape(P * 2 * sl, sl, sl, false, 0, 0, 0);
+            sh.ref_mode = 2; sh.grp_div = 2 * sl; sh.grp_stride = 2 * nf; sh.tail_ref = P * 2 * nf;
+            if ((rc = ctx->msm.run(sh, (const uint8_t *)SB.slots, ps->ftab.p, nullptr, ps->msm_out.p))) return rc;
+        }
+        if ((rc = d2h_sync(ctx, lr.data(), ps->msm_out.p, lr.size()))) return rc;
+        trace.mark(SB.late ? "gpu_ipp_round_late" : "gpu_ipp_round");
+        on_round(j, lr);
+        if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32))) return rc;
+        trace.mark("host_ipp_round");
+    }
+    k_ipp_round<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB, lg, 1);
+    ctx->launches++;
+    return 0;
 }
 
 // ================================================================ R1CSProof (de)serialisation
@@ -482,14 +567,7 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     k_ipp_init<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
     ctx->launches++;
     trace.mark("host_ux");
-    std::vector<uint8_t> lr((size_t)B * 64);
-    double t_gpu_round = 0, t_host_round = 0;
-    for (uint32_t j = 0; j < lg; j++) {
-        k_ipp_round<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB, j, 0);
-        ctx->launches++;
-        if ((rc = msm_gens_device(ctx, SB.slots, slot_len, 2 * B, ps->msm_out.p, nullptr))) return rc;
-        if ((rc = d2h_sync(ctx, lr.data(), ps->msm_out.p, lr.size()))) return rc;
-        trace.mark("gpu_ipp_round");
+    rc = ipp_rounds(ctx, SB, B, chal, [&](uint32_t j, const std::vector<uint8_t> &lr) {
         parallel_for(B, [&](size_t bi) {
             hstate &H = hs[bi];
             memcpy(&H.pf.LR[(size_t)64 * j], &lr[bi * 64], 64);
@@ -499,12 +577,8 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
             c[CH_UJ] = H.tr->challenge_scalar("u");
             c[CH_UJINV] = sc_invert(c[CH_UJ]);
         });
-        if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32))) return rc;
-        trace.mark("host_ipp_round");
-    }
-    (void)t_gpu_round; (void)t_host_round;
-    k_ipp_round<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB, lg, 1);
-    ctx->launches++;
+    }, trace);
+    if (rc) return rc;
     std::vector<sc> ab((size_t)B * 2);
     if ((rc = d2h_sync(ctx, ab.data(), ps->ab.p, ab.size() * 32))) return rc;
     for (uint32_t bi = 0; bi < B; bi++) {

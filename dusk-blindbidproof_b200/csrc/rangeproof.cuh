@@ -176,12 +176,8 @@ inline int rp_prove_group(bbp_ctx *ctx, std::vector<rp_prove_job> &jobs, uint32_
     if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32))) return rc;
     k_rp_ipp_init<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
     ctx->launches++;
-    std::vector<uint8_t> lr((size_t)P * 64);
-    for (uint32_t j = 0; j < lg; j++) {
-        k_ipp_round<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB, j, 0);
-        ctx->launches++;
-        if ((rc = msm_gens_device(ctx, SB.slots, slot_len, 2 * P, ps->msm_out.p, nullptr))) return rc;
-        if ((rc = d2h_sync(ctx, lr.data(), ps->msm_out.p, lr.size()))) return rc;
+    phase_trace trace("rp_prove_group");
+    rc = ipp_rounds(ctx, SB, P, chal, [&](uint32_t j, const std::vector<uint8_t> &lr) {
         parallel_for(P, [&](size_t pi) {
             hstate &H = hs[pi];
             memcpy(&H.LR[(size_t)64 * j], &lr[pi * 64], 64);
@@ -191,10 +187,8 @@ inline int rp_prove_group(bbp_ctx *ctx, std::vector<rp_prove_job> &jobs, uint32_
             c[CH_UJ] = H.tr->challenge_scalar("u");
             c[CH_UJINV] = sc_invert(c[CH_UJ]);
         });
-        if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32))) return rc;
-    }
-    k_ipp_round<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB, lg, 1);
-    ctx->launches++;
+    }, trace);
+    if (rc) return rc;
     std::vector<sc> ab((size_t)P * 2);
     if ((rc = d2h_sync(ctx, ab.data(), ps->ab.p, ab.size() * 32))) return rc;
     for (uint32_t pi = 0; pi < P; pi++) {

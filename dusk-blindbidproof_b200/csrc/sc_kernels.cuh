@@ -52,6 +52,10 @@ struct sc_batch {
     uint32_t dyn_stride;
     sc *stat;                                  // [n_proofs][2 + 2 gcols] rho-weighted static-base scalars (Montgomery)
     sc *stab;                                  // [n_proofs][n] scratch: the IPP verification vector s (Montgomery)
+    // hybrid IPP: after the first rounds the folded bases ARE materialised once (n_f per family), later rounds work on them
+    uint32_t fac_n;                            // length of the live part of sG / sH (n, or n_f after materialisation)
+    uint32_t late;                             // 0: slots over [B, B_bl, G, H] of the generator table; 1: [F_G, F_H, B]
+    sc *mat;                                   // [n_proofs][2 n] compact scalars of the materialisation MSM
     // aggregated range proofs (bulletproofs RangeProof::prove_multiple / verify_multiple)
     const uint64_t *rp_values;                 // [n_proofs][rp_m]
     uint32_t rp_bits, rp_m;                    // n = rp_bits * rp_m
@@ -203,13 +207,14 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_ipp_init(sc_batch B) {
 // 2. c_L = <a_lo, b_hi>, c_R = <a_hi, b_lo>
 // 3. write the L slot (2p) and R slot (2p + 1): coefficient on B is c * w (Q = w B), B_blinding gets 0
 // With fold_only the kernel stops after step 1 on the final length-1 vectors and emits a, b.
-__global__ void __launch_bounds__(BBP_SC_THREADS) k_ipp_round(sc_batch B, uint32_t j, uint32_t fold_only) {
+__global__ void __launch_bounds__(BBP_SC_THREADS) k_ipp_round(sc_batch B, uint32_t j, uint32_t mode) {
     __shared__ sc smem[BBP_SC_THREADS];
-    const uint32_t p = blockIdx.x, t = threadIdx.x, n = B.n;
+    const uint32_t p = blockIdx.x, t = threadIdx.x, n = B.n, fn = B.fac_n;
+    const bool fold_only = mode & 1, skip_fold = mode & 2;
     const sc *ch = B.chal + (size_t)p * CH_N;
     sc *a = B.a + (size_t)p * n, *b = B.b + (size_t)p * n, *sG = B.sG + (size_t)p * n, *sH = B.sH + (size_t)p * n;
     const uint32_t nj = n >> j;           // current vector length
-    if (j > 0) {
+    if (j > 0 && !skip_fold) {
         sc uM = sc_to_mont(ch[CH_UJ]), uiM = sc_to_mont(ch[CH_UJINV]);
         for (uint32_t k = t; k < nj; k += BBP_SC_THREADS) {
             a[k] = sc_add(mm(a[k], uM), mm(uiM, a[nj + k]));
@@ -217,7 +222,7 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_ipp_round(sc_batch B, uint32
         }
         if (!fold_only) {
             const uint32_t n_old = nj << 1;
-            for (uint32_t i = t; i < n; i += BBP_SC_THREADS) {
+            for (uint32_t i = t; i < fn; i += BBP_SC_THREADS) {
                 bool lo = (i & (n_old - 1)) < nj;
                 sG[i] = mm(sG[i], lo ? uiM : uM);
                 sH[i] = mm(sH[i], lo ? uM : uiM);
@@ -237,32 +242,59 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_ipp_round(sc_batch B, uint32
     }
     cl = block_sum_sc(cl, smem);
     cr = block_sum_sc(cr, smem);
-    const uint32_t gc = B.gcols, slot_len = 2 + 2 * gc;
+    // slot layout: early rounds [B, B_bl, G[0..gc), H[0..gc)]; late rounds [F_G[0..fn), F_H[0..fn), B]
+    const uint32_t gc = B.late ? fn : B.gcols, hdr = B.late ? 0 : 2, slot_len = B.late ? 2 * fn + 1 : 2 + 2 * gc;
     sc *sl = B.slots + (size_t)(2 * p) * slot_len, *sr = sl + slot_len;
     if (t == 0) {
         sc wM = sc_to_mont(ch[CH_W]);
-        sl[0] = sc_from_mont(mm(cl, wM)); sr[0] = sc_from_mont(mm(cr, wM));
-        sl[1] = sc_zero(); sr[1] = sc_zero();
+        uint32_t bpos = B.late ? 2 * fn : 0;
+        sl[bpos] = sc_from_mont(mm(cl, wM)); sr[bpos] = sc_from_mont(mm(cr, wM));
+        if (!B.late) { sl[1] = sc_zero(); sr[1] = sc_zero(); }
     }
     for (uint32_t i = t; i < gc; i += BBP_SC_THREADS) {
         sc zero = sc_zero();
-        if (i >= n) {     // generator columns beyond the vector length are unused
-            sl[2 + i] = zero; sr[2 + i] = zero; sl[2 + gc + i] = zero; sr[2 + gc + i] = zero;
+        if (i >= fn) {    // generator columns beyond the vector length are unused
+            sl[hdr + i] = zero; sr[hdr + i] = zero; sl[hdr + gc + i] = zero; sr[hdr + gc + i] = zero;
             continue;
         }
         uint32_t k = i & (nj - 1);
-        if (k >= nh) {   // G[i] sits in the high half of its block: L takes a_lo * G_hi, R takes b_lo * H_hi
-            sl[2 + i] = sc_from_mont(mm(a[k - nh], sG[i]));
-            sr[2 + i] = zero;
-            sl[2 + gc + i] = zero;
-            sr[2 + gc + i] = sc_from_mont(mm(b[k - nh], sH[i]));
+        if (k >= nh) {   // base i sits in the high half of its block: L takes a_lo * G_hi, R takes b_lo * H_hi
+            sl[hdr + i] = sc_from_mont(mm(a[k - nh], sG[i]));
+            sr[hdr + i] = zero;
+            sl[hdr + gc + i] = zero;
+            sr[hdr + gc + i] = sc_from_mont(mm(b[k - nh], sH[i]));
         } else {          // low half: R takes a_hi * G_lo, L takes b_hi * H_lo
-            sl[2 + i] = zero;
-            sr[2 + i] = sc_from_mont(mm(a[k + nh], sG[i]));
-            sl[2 + gc + i] = sc_from_mont(mm(b[k + nh], sH[i]));
-            sr[2 + gc + i] = zero;
+            sl[hdr + i] = zero;
+            sr[hdr + i] = sc_from_mont(mm(a[k + nh], sG[i]));
+            sl[hdr + gc + i] = sc_from_mont(mm(b[k + nh], sH[i]));
+            sr[hdr + gc + i] = zero;
         }
     }
+}
+
+// Materialisation step of the hybrid IPP, run once when the vectors have shrunk to n_f = n >> j0: applies the pending
+// fold (challenge of round j0 - 1), then emits the compact scalars of F_G[k] = sum_e sG[k + n_f e] G[k + n_f e] (and F_H):
+// mat[fam][k][e], k < n_f, e < n / n_f — one MSM slot of n / n_f scalars per folded base — and resets the factors to 1.
+__global__ void __launch_bounds__(BBP_SC_THREADS) k_ipp_materialize(sc_batch B, uint32_t j0) {
+    const uint32_t p = blockIdx.x, t = threadIdx.x, n = B.n;
+    const sc *ch = B.chal + (size_t)p * CH_N;
+    sc *a = B.a + (size_t)p * n, *b = B.b + (size_t)p * n, *sG = B.sG + (size_t)p * n, *sH = B.sH + (size_t)p * n;
+    const uint32_t nf = n >> j0, n_old = nf << 1, E = n / nf;
+    sc uM = sc_to_mont(ch[CH_UJ]), uiM = sc_to_mont(ch[CH_UJINV]);
+    for (uint32_t k = t; k < nf; k += BBP_SC_THREADS) {
+        a[k] = sc_add(mm(a[k], uM), mm(uiM, a[nf + k]));
+        b[k] = sc_add(mm(b[k], uiM), mm(uM, b[nf + k]));
+    }
+    sc *mat = B.mat + (size_t)p * 2 * n;
+    for (uint32_t idx = t; idx < 2 * n; idx += BBP_SC_THREADS) {
+        uint32_t fam = idx / n, r = idx % n, k = r / E, e = r % E, src = k + nf * e;
+        bool lo = (src & (n_old - 1)) < nf;
+        sc f = fam ? mm(sH[src], lo ? uM : uiM) : mm(sG[src], lo ? uiM : uM);
+        mat[idx] = sc_from_mont(f);
+    }
+    __syncthreads();
+    sc one = sc_mont_one();
+    for (uint32_t k = t; k < nf; k += BBP_SC_THREADS) { sG[k] = one; sH[k] = one; }
 }
 
 // InnerProductProof::verification_scalars: s[0] = prod u_j^-1, s[i] = s[i - 2^b] * u_{lg-1-b}^2 for 2^b <= i < 2^(b+1):
