@@ -457,8 +457,8 @@ struct msm_engine {
         if (fixed) {
             sh.c = table_c; sh.W = table_W; sh.table_stride = table_stride; sh.sets_per_slot = 1;
         } else {
-            uint32_t c = 5;
-            while (c < 16 && ((size_t)n_per_slot >> (c + 3)) >= 1) c++;   // ~16+ points per bucket
+            uint32_t c = 4;
+            while (c < 16 && ((size_t)n_per_slot >> (c + 4)) >= 1) c++;   // >= 16 points per bucket on average
             sh.c = c; sh.W = 253 / c + 1; sh.table_stride = 0; sh.sets_per_slot = sh.W;
         }
         sh.B = 1u << (sh.c - 1);

@@ -114,7 +114,9 @@ struct proto_state {
     dev_buf fext, ftab;            // materialised folded bases: extended, then niels (+ B at the tail)
     dev_buf chal, zpow, ypow, yinvpow, wit, vbl, blind3, poly, tout, a, b, sG, sH, slots, ab, pub, dyn_sc, dyn_pts, dyn_niels, stat, stat_red,
         msm_out, msm_ext, flags, valid, commit_in, commit_out, rng_states;
-    host_buf h_wit;
+    host_buf h_wit, h_states;
+    cudaStream_t rng_stream = nullptr;   // the device TranscriptRng chain runs beside the A_I1 / A_O1 commitments
+    cudaEvent_t ev_up = nullptr, ev_rng = nullptr;
     int proof_versioned = 1;       // R1CSProof::to_bytes layout (SURVEY.md §8c risk R1): 1 = leading phase byte, 0 = legacy 14-point form
 };
 
@@ -132,7 +134,10 @@ void proto_release(proto_state *ps) {
                       &ps->slots, &ps->ab, &ps->pub, &ps->dyn_sc, &ps->dyn_pts, &ps->dyn_niels, &ps->stat, &ps->stat_red, &ps->msm_out, &ps->msm_ext,
                       &ps->flags, &ps->valid, &ps->commit_in, &ps->commit_out, &ps->rng_states};
     for (dev_buf *b : all) b->release();
-    ps->h_wit.release();
+    ps->h_wit.release(); ps->h_states.release();
+    if (ps->rng_stream) cudaStreamDestroy(ps->rng_stream);
+    if (ps->ev_up) cudaEventDestroy(ps->ev_up);
+    if (ps->ev_rng) cudaEventDestroy(ps->ev_rng);
     delete ps;
 }
 
@@ -417,7 +422,15 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     // the 2 n1 blinding-vector draws run on the device for batches (one thread per proof continues the transcript RNG)
     static const int rng_threshold = [] { const char *e = getenv("BBP_DEVICE_RNG_MIN_BATCH"); return e ? atoi(e) : 8; }();
     const bool device_rng = (int)B >= rng_threshold;
-    std::vector<uint8_t> rng_states(device_rng ? (size_t)B * BBP_STROBE_STATE_BYTES : 0);
+    if (device_rng) {
+        if ((rc = ps->h_states.ensure((size_t)B * BBP_STROBE_STATE_BYTES))) return rc;
+        if (!ps->rng_stream) {
+            BBP_CUDA_OK(cudaStreamCreateWithFlags(&ps->rng_stream, cudaStreamNonBlocking));
+            BBP_CUDA_OK(cudaEventCreateWithFlags(&ps->ev_up, cudaEventDisableTiming));
+            BBP_CUDA_OK(cudaEventCreateWithFlags(&ps->ev_rng, cudaEventDisableTiming));
+        }
+    }
+    uint8_t *rng_states = ps->h_states.p;
     const size_t wit_count = (size_t)B * (device_rng ? 3 : 5) * n1;
     if ((rc = ps->h_wit.ensure(wit_count * 32))) return rc;
     sc *wit = ps->h_wit.as<sc>();
@@ -465,14 +478,16 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
         (rc = h2d(ctx, ps->blind3.p, blind3.data(), blind3.size() * 32)))
         return rc;
     if (device_rng) {
-        if ((rc = ps->rng_states.ensure(rng_states.size())) || (rc = h2d(ctx, ps->rng_states.p, rng_states.data(), rng_states.size()))) return rc;
-        k_rng_draws<<<(B + 31) / 32, 32, 0, ctx->stream>>>(ps->rng_states.p, B, 2 * n1, n1, (size_t)B * n1, ps->wit.as<sc>() + (size_t)3 * B * n1);
+        const size_t sb = (size_t)B * BBP_STROBE_STATE_BYTES;
+        if ((rc = ps->rng_states.ensure(sb)) || (rc = h2d(ctx, ps->rng_states.p, rng_states, sb))) return rc;
+        // the draw chain (one thread per proof, latency bound) runs on its own stream next to the A_I1 / A_O1 MSMs
+        BBP_CUDA_OK(cudaEventRecord(ps->ev_up, ctx->stream));
+        BBP_CUDA_OK(cudaStreamWaitEvent(ps->rng_stream, ps->ev_up, 0));
+        k_rng_draws<<<(B + 31) / 32, 32, 0, ps->rng_stream>>>(ps->rng_states.p, B, 2 * n1, n1, (size_t)B * n1, ps->wit.as<sc>() + (size_t)3 * B * n1);
         ctx->launches++;
-        BBP_CUDA_OK(cudaMemcpyAsync(rng_states.data(), ps->rng_states.p, rng_states.size(), cudaMemcpyDeviceToHost, ctx->stream));
-        // the states come back with the A / S commitments below (same stream, one synchronisation)
-        if (trace.on) { cudaStreamSynchronize(ctx->stream); trace.mark("h2d_witness+gpu_rng_draws"); }
+        BBP_CUDA_OK(cudaMemcpyAsync(rng_states, ps->rng_states.p, sb, cudaMemcpyDeviceToHost, ps->rng_stream));
+        BBP_CUDA_OK(cudaEventRecord(ps->ev_rng, ps->rng_stream));
     }
-
     sc_batch SB;
     memset(&SB, 0, sizeof SB);
     SB.n_proofs = B; SB.n1 = n1; SB.q = T.q; SB.m = m; SB.n = n; SB.lg_n = lg; SB.n_pub = T.n_pub; SB.gcols = gcols;
@@ -485,9 +500,13 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     SB.a = ps->a.as<sc>(); SB.b = ps->b.as<sc>(); SB.sG = ps->sG.as<sc>(); SB.sH = ps->sH.as<sc>(); SB.slots = ps->slots.as<sc>(); SB.ab_out = ps->ab.as<sc>();
 
     // ---- phase 2 (GPU): A_I1, A_O1, S1
-    k_commit_slots<<<3 * B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+    k_commit_slots<<<2 * B, BBP_SC_THREADS, 0, ctx->stream>>>(SB, 0, 2, 0);
     ctx->launches++;
-    if ((rc = msm_gens_device(ctx, SB.slots, slot_len, 3 * B, ps->msm_out.p, nullptr))) return rc;
+    if ((rc = msm_gens_device(ctx, SB.slots, slot_len, 2 * B, ps->msm_out.p, nullptr))) return rc;
+    if (device_rng) BBP_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ps->ev_rng, 0));
+    k_commit_slots<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB, 2, 1, 2 * B);
+    ctx->launches++;
+    if ((rc = msm_gens_device(ctx, SB.slots + (size_t)2 * B * slot_len, slot_len, B, ps->msm_out.p + (size_t)2 * B * 32, nullptr))) return rc;
     std::vector<uint8_t> pts((size_t)B * 3 * 32);
     if ((rc = d2h_sync(ctx, pts.data(), ps->msm_out.p, pts.size()))) return rc;
     trace.mark("gpu_A_S_msm");
@@ -498,7 +517,7 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
         hstate &H = hs[bi];
         r1cs_proof_host &P = H.pf;
         if (device_rng) H.rng->import_state(&rng_states[bi * BBP_STROBE_STATE_BYTES]);
-        memcpy(P.A_I1, &pts[(bi * 3) * 32], 32); memcpy(P.A_O1, &pts[(bi * 3 + 1) * 32], 32); memcpy(P.S1, &pts[(bi * 3 + 2) * 32], 32);
+        memcpy(P.A_I1, &pts[(bi * 2) * 32], 32); memcpy(P.A_O1, &pts[(bi * 2 + 1) * 32], 32); memcpy(P.S1, &pts[((size_t)2 * B + bi) * 32], 32);
         H.tr->append_point("A_I1", P.A_I1); H.tr->append_point("A_O1", P.A_O1); H.tr->append_point("S1", P.S1);
         H.tr->r1cs_1phase_domain_sep();     // the circuit has no randomised (second phase) constraints
         memset(P.A_I2, 0, 32); memset(P.A_O2, 0, 32); memset(P.S2, 0, 32);

@@ -126,10 +126,12 @@ __device__ __forceinline__ sc flatten_row(const sc_batch &B, const sc *zpow, uin
 // ---------------------------------------------------------------- prover: commitment scalar slots
 // slot layout = generator table order: [B, B_blinding, G[0..n), H[0..n)]. Three slots per proof:
 //   A_I1 = i_bl B_bl + <a_L, G> + <a_R, H>;  A_O1 = o_bl B_bl + <a_O, G>;  S1 = s_bl B_bl + <s_L, G> + <s_R, H>
-__global__ void __launch_bounds__(BBP_SC_THREADS) k_commit_slots(sc_batch B) {
-    const uint32_t p = blockIdx.x / 3, which = blockIdx.x % 3;
+// launch 1 (which0 = 0, n_which = 2): A_I1, A_O1 interleaved per proof into slots [0, 2P); launch 2 (which0 = 2, n_which = 1):
+// S1 into slots [2P, 3P) — S1 needs the s_L / s_R draws, which may still be running on the RNG stream during launch 1.
+__global__ void __launch_bounds__(BBP_SC_THREADS) k_commit_slots(sc_batch B, uint32_t which0, uint32_t n_which, uint32_t slot0) {
+    const uint32_t p = blockIdx.x / n_which, which = which0 + blockIdx.x % n_which;
     const uint32_t slot_len = 2 + 2 * B.gcols;
-    sc *out = B.slots + (size_t)blockIdx.x * slot_len;
+    sc *out = B.slots + (size_t)(slot0 + blockIdx.x) * slot_len;
     const sc *g = (which == 0 ? B.aL : which == 1 ? B.aO : B.sL) + (size_t)p * B.n1;
     const sc *h = (which == 0 ? B.aR : which == 1 ? nullptr : B.sR);
     if (h) h += (size_t)p * B.n1;
