@@ -113,7 +113,7 @@ struct proto_state {
     uint32_t colmap_n = 0, colmap_gcols = 0;
     dev_buf fext, ftab;            // materialised folded bases: extended, then niels (+ B at the tail)
     dev_buf chal, zpow, ypow, yinvpow, wit, vbl, blind3, poly, tout, a, b, sG, sH, slots, ab, pub, dyn_sc, dyn_pts, dyn_niels, stat, stat_red,
-        msm_out, msm_ext, flags, valid, commit_in, commit_out, rng_states;
+        msm_out, msm_ext, flags, valid, commit_in, commit_out, rng_states, rng_raw;
     host_buf h_wit, h_states;
     cudaStream_t rng_stream = nullptr;   // the device TranscriptRng chain runs beside the A_I1 / A_O1 commitments
     cudaEvent_t ev_up = nullptr, ev_rng = nullptr;
@@ -132,7 +132,7 @@ void proto_release(proto_state *ps) {
     ps->fext.release(); ps->ftab.release();
     dev_buf *all[] = {&ps->chal, &ps->zpow, &ps->ypow, &ps->yinvpow, &ps->wit, &ps->vbl, &ps->blind3, &ps->poly, &ps->tout, &ps->a, &ps->b, &ps->sG, &ps->sH,
                       &ps->slots, &ps->ab, &ps->pub, &ps->dyn_sc, &ps->dyn_pts, &ps->dyn_niels, &ps->stat, &ps->stat_red, &ps->msm_out, &ps->msm_ext,
-                      &ps->flags, &ps->valid, &ps->commit_in, &ps->commit_out, &ps->rng_states};
+                      &ps->flags, &ps->valid, &ps->commit_in, &ps->commit_out, &ps->rng_states, &ps->rng_raw};
     for (dev_buf *b : all) b->release();
     ps->h_wit.release(); ps->h_states.release();
     if (ps->rng_stream) cudaStreamDestroy(ps->rng_stream);
@@ -483,8 +483,11 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
         // the draw chain (one thread per proof, latency bound) runs on its own stream next to the A_I1 / A_O1 MSMs
         BBP_CUDA_OK(cudaEventRecord(ps->ev_up, ctx->stream));
         BBP_CUDA_OK(cudaStreamWaitEvent(ps->rng_stream, ps->ev_up, 0));
-        k_rng_draws<<<(B + 31) / 32, 32, 0, ps->rng_stream>>>(ps->rng_states.p, B, 2 * n1, n1, (size_t)B * n1, ps->wit.as<sc>() + (size_t)3 * B * n1);
-        ctx->launches++;
+        if ((rc = ps->rng_raw.ensure((size_t)B * 2 * n1 * 64))) return rc;
+        k_rng_draws<<<(B + 31) / 32, 32, 0, ps->rng_stream>>>(ps->rng_states.p, B, 2 * n1, ps->rng_raw.as<uint32_t>());
+        k_wide_reduce<<<(unsigned)(((size_t)B * 2 * n1 + 127) / 128), 128, 0, ps->rng_stream>>>(ps->rng_raw.as<uint32_t>(), B, 2 * n1, n1, (size_t)B * n1,
+                                                                                                 ps->wit.as<sc>() + (size_t)3 * B * n1);
+        ctx->launches += 2;
         BBP_CUDA_OK(cudaMemcpyAsync(rng_states, ps->rng_states.p, sb, cudaMemcpyDeviceToHost, ps->rng_stream));
         BBP_CUDA_OK(cudaEventRecord(ps->ev_rng, ps->rng_stream));
     }

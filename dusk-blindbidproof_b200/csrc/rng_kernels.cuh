@@ -99,10 +99,11 @@ struct strobe_dev {
 #define BBP_STROBE_DRAW_LANE9 0x0000000000000447ULL
 #define BBP_STROBE_DRAW_LANE20 0x8000000000000000ULL
 
-// states: [n_proofs][208] (in / out). Draw d of proof p goes to out[(d / per_vec) * vec_stride + p * per_vec + d % per_vec]:
-// with per_vec = n1, vec_stride = n_proofs * n1 the first n1 draws fill s_L and the next n1 fill s_R.
-__global__ void __launch_bounds__(32) k_rng_draws(uint8_t *__restrict__ states, uint32_t n_proofs, uint32_t n_draws, uint32_t per_vec, size_t vec_stride,
-                                                  sc *__restrict__ out) {
+// states: [n_proofs][208] (in / out). Draw d of proof p is written RAW (64 B, 16 words) to raw[(p * n_draws + d) * 16];
+// k_wide_reduce turns the raw draws into scalars in parallel, so that the sequential chain carries nothing but Keccak.
+// The generic (byte-wise) path runs only until the steady state pos = 64, pos_begin = 0 is reached — normally one
+// draw — after which the state lives in registers.
+__global__ void __launch_bounds__(32) k_rng_draws(uint8_t *__restrict__ states, uint32_t n_proofs, uint32_t n_draws, uint32_t *__restrict__ raw) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_proofs) return;
     strobe_dev S;
@@ -110,30 +111,56 @@ __global__ void __launch_bounds__(32) k_rng_draws(uint8_t *__restrict__ states, 
     for (int i = 0; i < 25; i++) S.st[i] = in[i];
     const uint8_t *tail = states + (size_t)p * BBP_STROBE_STATE_BYTES + 200;
     S.pos = tail[0]; S.pos_begin = tail[1];
-    for (uint32_t d = 0; d < n_draws; d++) {
-        uint32_t w[16];
-        if (S.pos == 64 && S.pos_begin == 0) {
-            S.st[8] ^= BBP_STROBE_DRAW_LANE8;
-            S.st[9] ^= BBP_STROBE_DRAW_LANE9;
-            S.st[20] ^= BBP_STROBE_DRAW_LANE20;
-            keccak_f1600_dev(S.st);
+    uint32_t *out = raw + (size_t)p * n_draws * 16;
+    uint32_t d = 0;
+    for (; d < n_draws && !(S.pos == 64 && S.pos_begin == 0); d++) {
+        uint8_t buf[64];
+        S.fill64(buf);
+        for (int i = 0; i < 16; i++)
+            out[(size_t)d * 16 + i] = (uint32_t)buf[4 * i] | ((uint32_t)buf[4 * i + 1] << 8) | ((uint32_t)buf[4 * i + 2] << 16) | ((uint32_t)buf[4 * i + 3] << 24);
+    }
+    if (d < n_draws) {
+        uint64_t r[25];
 #pragma unroll
-            for (int i = 0; i < 8; i++) { w[2 * i] = (uint32_t)S.st[i]; w[2 * i + 1] = (uint32_t)(S.st[i] >> 32); S.st[i] = 0; }
-        } else {
-            uint8_t buf[64];
-            S.fill64(buf);
-            for (int i = 0; i < 16; i++) w[i] = (uint32_t)buf[4 * i] | ((uint32_t)buf[4 * i + 1] << 8) | ((uint32_t)buf[4 * i + 2] << 16) | ((uint32_t)buf[4 * i + 3] << 24);
+        for (int i = 0; i < 25; i++) r[i] = S.st[i];
+#pragma unroll 1
+        for (; d < n_draws; d++) {
+            r[8] ^= BBP_STROBE_DRAW_LANE8;
+            r[9] ^= BBP_STROBE_DRAW_LANE9;
+            r[20] ^= BBP_STROBE_DRAW_LANE20;
+            keccak_f1600_dev(r);
+            uint4 *o = (uint4 *)(out + (size_t)d * 16);
+            o[0] = make_uint4((uint32_t)r[0], (uint32_t)(r[0] >> 32), (uint32_t)r[1], (uint32_t)(r[1] >> 32));
+            o[1] = make_uint4((uint32_t)r[2], (uint32_t)(r[2] >> 32), (uint32_t)r[3], (uint32_t)(r[3] >> 32));
+            o[2] = make_uint4((uint32_t)r[4], (uint32_t)(r[4] >> 32), (uint32_t)r[5], (uint32_t)(r[5] >> 32));
+            o[3] = make_uint4((uint32_t)r[6], (uint32_t)(r[6] >> 32), (uint32_t)r[7], (uint32_t)(r[7] >> 32));
+#pragma unroll
+            for (int i = 0; i < 8; i++) r[i] = 0;
         }
-        // Scalar::from_bytes_mod_order_wide: lo + hi * 2^256
-        sc lo = sc_reduce_words(w);
-        sc r2 = sc_r2();
-        sc hi = sc_montmul(w + 8, r2.v);
-        out[(size_t)(d / per_vec) * vec_stride + (size_t)p * per_vec + d % per_vec] = sc_add(lo, hi);
+#pragma unroll
+        for (int i = 0; i < 25; i++) S.st[i] = r[i];
     }
     uint64_t *o = (uint64_t *)(states + (size_t)p * BBP_STROBE_STATE_BYTES);
     for (int i = 0; i < 25; i++) o[i] = S.st[i];
     uint8_t *ot = states + (size_t)p * BBP_STROBE_STATE_BYTES + 200;
     ot[0] = (uint8_t)S.pos; ot[1] = (uint8_t)S.pos_begin; ot[2] = 1 | 2 | 4;   // cur_flags after a prf
+}
+
+// Scalar::from_bytes_mod_order_wide over the raw draws: draw d of proof p -> out[(d / per_vec) * vec_stride + p * per_vec + d % per_vec]
+// (per_vec = n1, vec_stride = n_proofs * n1: the first n1 draws fill s_L, the next n1 fill s_R)
+__global__ void __launch_bounds__(128) k_wide_reduce(const uint32_t *__restrict__ raw, uint32_t n_proofs, uint32_t n_draws, uint32_t per_vec, size_t vec_stride,
+                                                     sc *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n_proofs * n_draws) return;
+    uint32_t p = (uint32_t)(i / n_draws), d = (uint32_t)(i % n_draws);
+    uint32_t w[16];
+    const uint4 *q = (const uint4 *)(raw + i * 16);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { uint4 v = q[k]; w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
+    sc lo = sc_reduce_words(w);
+    sc r2 = sc_r2();
+    sc hi = sc_montmul(w + 8, r2.v);
+    out[(size_t)(d / per_vec) * vec_stride + (size_t)p * per_vec + d % per_vec] = sc_add(lo, hi);
 }
 
 }  // namespace bbp
