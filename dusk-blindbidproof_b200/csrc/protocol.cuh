@@ -232,8 +232,9 @@ template <class F>
 inline int ipp_rounds(bbp_ctx *ctx, sc_batch &SB, uint32_t P, std::vector<sc> &chal, F on_round, phase_trace &trace) {
     proto_state *ps = proto_get(ctx);
     const uint32_t n = SB.n, lg = SB.lg_n, gcols = SB.gcols, slot_len = 2 + 2 * gcols;
-    static const int hybrid_env = [] { const char *e = getenv("BBP_IPP_HYBRID"); return e ? atoi(e) : 1; }();
-    const bool hybrid = hybrid_env && n >= 4 * IPP_NF;
+    const char *hyb_env = getenv("BBP_IPP_HYBRID");   // 0 = never, 2 = always (tests), default: batches of >= 32
+    const int hyb = hyb_env ? atoi(hyb_env) : 1;
+    const bool hybrid = hyb && n >= 4 * IPP_NF && (P >= 32 || hyb == 2);   // small batches are launch bound: fewer, larger rounds win
     const uint32_t j0 = hybrid ? lg - log2_u32(IPP_NF) : lg, nf = IPP_NF;
     int rc;
     std::vector<uint8_t> lr((size_t)P * 64);
@@ -420,7 +421,10 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
 
     // ---- phase 1: transcript up to the blinding draws; upload witness
     // the 2 n1 blinding-vector draws run on the device for batches (one thread per proof continues the transcript RNG)
-    static const int rng_threshold = [] { const char *e = getenv("BBP_DEVICE_RNG_MIN_BATCH"); return e ? atoi(e) : 8; }();
+    // (the chain costs ~19 ms of latency whatever the batch; host threads draw ~2.4 ms per proof each, so the device wins
+    // once the batch exceeds about six proofs per host thread)
+    const char *rng_env = getenv("BBP_DEVICE_RNG_MIN_BATCH");   // read per call so that tests can force either path
+    const int rng_threshold = rng_env ? atoi(rng_env) : (int)(6 * std::max(1u, std::thread::hardware_concurrency()));
     const bool device_rng = (int)B >= rng_threshold;
     if (device_rng) {
         if ((rc = ps->h_states.ensure((size_t)B * BBP_STROBE_STATE_BYTES))) return rc;

@@ -126,11 +126,16 @@ def test_prove_batch_mixed_lengths(be):
         assert (proof, comm, tc) == (oproof, ocomm, otc)
 
 
-def test_prove_batch_device_rng_matches_oracle(be):
-    """batches of >= 8 equal-length bids continue the TranscriptRng on the device (rng_kernels.cuh): bytes must still equal
-    the oracle's, and equal what the host-RNG path (single request) produces"""
+def test_prove_batch_device_rng_matches_oracle(be, monkeypatch):
+    """large batches continue the TranscriptRng on the device (rng_kernels.cuh) and switch the inner-product argument to
+    its hybrid form (materialised folded bases): bytes must still equal the oracle's, and equal what the host-RNG /
+    plain path (single request) produces"""
     cases = [make_case(300 + i, 3) for i in range(12)]
+    monkeypatch.setenv("BBP_DEVICE_RNG_MIN_BATCH", "8")
+    monkeypatch.setenv("BBP_IPP_HYBRID", "2")
     outs = be.blindbid_prove_batch(cases)
+    monkeypatch.delenv("BBP_DEVICE_RNG_MIN_BATCH")
+    monkeypatch.delenv("BBP_IPP_HYBRID")
     for i, (bid, (st, proof, comm, tc)) in enumerate(zip(cases, outs)):
         assert st == 0
         if i % 4 == 0:

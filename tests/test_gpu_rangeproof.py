@@ -68,8 +68,11 @@ def test_rangeproof_small_matches_oracle():
     be.close()
 
 
-def test_rangeproof_config5_shape():
-    """m = 64, n = 64: 4096-element IPP, 12 rounds, 1056-byte proof, byte-identical to the oracle; batch of 3"""
+@pytest.mark.parametrize("hybrid", ["0", "2"])
+def test_rangeproof_config5_shape(hybrid, monkeypatch):
+    """m = 64, n = 64: 4096-element IPP, 12 rounds, 1056-byte proof, byte-identical to the oracle; batch of 3; with the
+    plain and the hybrid (materialised bases) inner-product argument"""
+    monkeypatch.setenv("BBP_IPP_HYBRID", hybrid)
     be = backend(64, 64)
     seeds = [hashlib.sha256(b"rp%d" % i).digest() for i in range(3)]
     vals = [[from_le(hashlib.shake_256(b"rp-v" + bytes([i, k])).digest(8)) for i in range(64)] for k in range(3)]
