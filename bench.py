@@ -410,6 +410,12 @@ def run_b200(args, rank, world):
         acc_ms = stage[3]
         peak_imad = 2.0 * peak_wide              # §8d counts mad.lo and mad.hi separately; one IMAD.WIDE does both
         achieved = accumulate_imads(n, plan["c"], plan["W"]) / (acc_ms * 1e-3)
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "k_accumulate_traffic.json")) as f:
+                traffic = json.load(f)["dram_bytes_per_launch"]   # from the committed ncu --set full capture of this kernel
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -421,7 +427,7 @@ def run_b200(args, rank, world):
                     "call": "bbp_msm_vartime(host scalars, host extended points) incl. niels table build"},
             "gpu_launches": launches,
             "roofline": {"bound": "int32-multiply", "kernel": "k_accumulate", "achieved": achieved / 1e12, "peak": peak_imad / 1e12,
-                         "unit": "T IMAD-eq/s", "frac": achieved / peak_imad, "traffic": None,
+                         "unit": "T IMAD-eq/s", "frac": achieved / peak_imad, "traffic": traffic,
                          "kernel_ms": acc_ms, "peak_source": "bbp_int_peak measured in this run (IMAD.WIDE.U32 x2, 8 chains/thread, all SMs)",
                          "whole_msm_frac": msm_imads(n, plan["c"], plan["W"]) / (ms / args.steps * 1e-3) / peak_imad,
                          "hbm_gather_gbs": plan["W"] * n * 96 / (acc_ms * 1e-3) / 1e9},
