@@ -201,7 +201,8 @@ int bbp_msm_points(bbp_ctx *ctx, const uint8_t *scalars, size_t n, const bbp_poi
 
 // one-shot forms: temporary base table and staging live in grow-only context scratch (no allocation per call)
 static int msm_oneshot(bbp_ctx *ctx, const uint8_t *scalars, const uint8_t *points, size_t n, bool compressed, uint8_t out[32]) {
-    if (!ctx || !scalars || !points || !out || n == 0 || n > 0x7fffffffu) return BBP_ERR_INPUT;
+    if (ctx && out && n == 0) { memset(out, 0, 32); return BBP_OK; }   // the empty sum is the identity, as in dalek
+    if (!ctx || !scalars || !points || !out || n > 0x7fffffffu) return BBP_ERR_INPUT;
     cudaSetDevice(ctx->device);
     phase_trace trace("msm_oneshot");
     const size_t pt_bytes = compressed ? 32 : 128;

@@ -81,6 +81,28 @@ def test_msm_scalar_edge_cases(be):
     assert be.msm_optional(le(1) + le(L_ORDER - 1), one + one) == ZERO32
 
 
+def test_msm_empty_and_bad_arguments(be):
+    """the empty sum is the identity (dalek semantics); malformed calls return BBP_ERR_INPUT instead of crashing"""
+    import ctypes
+    import bbp_loader
+    capi = bbp_loader.load().capi
+    L = capi.lib()
+    out = ctypes.create_string_buffer(b"\xff" * 32, 32)
+    assert L.bbp_msm_optional(be.ctx, None, None, ctypes.c_size_t(0), out) == 0 and out.raw == ZERO32
+    out = ctypes.create_string_buffer(b"\xff" * 32, 32)
+    assert L.bbp_msm_vartime(be.ctx, None, None, ctypes.c_size_t(0), out) == 0 and out.raw == ZERO32
+    assert L.bbp_msm_vartime(be.ctx, None, None, ctypes.c_size_t(3), out) == capi.BBP_ERR_INPUT
+    assert L.bbp_msm_optional(None, b"", b"", ctypes.c_size_t(1), out) == capi.BBP_ERR_INPUT
+    assert L.bbp_decompress(be.ctx, None, ctypes.c_size_t(1), out, None) == capi.BBP_ERR_INPUT
+    h = ctypes.c_void_p()
+    assert L.bbp_points_from_compressed(be.ctx, b"", ctypes.c_size_t(0), ctypes.byref(h), None) == capi.BBP_ERR_INPUT
+    # scalars / points length mismatch with a resident table
+    from gpu_util import gpu_random_points
+    tab, ok = be.points_from_compressed(gpu_random_points(1, 8))
+    assert L.bbp_msm_points(be.ctx, orc.random_scalars(1, 7), ctypes.c_size_t(7), tab.handle, out) == capi.BBP_ERR_INPUT
+    tab.free()
+
+
 def test_msm_optional_none_on_invalid_point(be):
     """optional_multiscalar_mul returns None when any point fails to decompress."""
     from gpu_util import gpu_random_points
