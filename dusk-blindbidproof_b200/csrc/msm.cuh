@@ -239,6 +239,44 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate(const uint8_t *__restr
 // Level 1 reads the task partials of 8 buckets (len = 1, A_i = R_i = bucket_i); the last level leaves one element per
 // bucket set whose A is the set total. Depth: log_8(buckets) levels of ~3*8 additions instead of one long chain.
 #define BBP_RED_G 8
+#define BBP_FOLD_MIN 8
+// Buckets whose entries were split over MANY tasks (skewed digits: equal scalars, or a top window that only ever holds
+// the recoding carry) are folded first by a whole warp: lanes sum a strided share of the task partials, then a 5-step
+// tree through shared memory; the bucket sum replaces the first task's partial. Buckets with <= BBP_FOLD_MIN tasks (the
+// common case) are left to level 1, which adds their few partials itself.
+__global__ void __launch_bounds__(256) k_heavy_list(const uint32_t *__restrict__ toffs, uint32_t nkeys, uint32_t *__restrict__ list, uint32_t *__restrict__ count) {
+    uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= nkeys) return;
+    if (toffs[key + 1] - toffs[key] > BBP_FOLD_MIN) list[atomicAdd(count, 1u)] = key;
+}
+#define BBP_FOLD_BLOCKS 1024
+__global__ void __launch_bounds__(128) k_bucket_fold(uint8_t *__restrict__ partial, const uint32_t *__restrict__ toffs, const uint32_t *__restrict__ list,
+                                                     const uint32_t *__restrict__ count) {
+    __shared__ uint4 sm_u4[4 * 32 * 8];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *sm = (uint8_t *)sm_u4 + (size_t)warp * 32 * 128;
+    const uint32_t n_heavy = *count;
+    for (uint32_t h = blockIdx.x * 4 + warp; h < n_heavy; h += gridDim.x * 4) {
+        uint32_t key = list[h];
+        uint32_t t0 = toffs[key], t1 = toffs[key + 1];
+        ge acc = ge_identity();
+        bool nz = false;
+        for (uint32_t t = t0 + lane; t < t1; t += 32) {
+            ge p = ge_load(partial + 128 * (size_t)t);
+            if (nz) acc = ge_add(acc, p);
+            else { acc = p; nz = true; }
+        }
+        ge_store(sm + 128 * lane, acc);
+        __syncwarp();
+        for (uint32_t stride = 16; stride >= 1; stride >>= 1) {
+            if (lane < stride) ge_store(sm + 128 * lane, ge_add(ge_load(sm + 128 * lane), ge_load(sm + 128 * (lane + stride))));
+            __syncwarp();
+        }
+        if (lane == 0) ge_store(partial + 128 * (size_t)t0, ge_load(sm));
+        __syncwarp();
+    }
+}
+// level 1: groups of g buckets (task partials at toffs[bucket] ..; heavy buckets already folded into the first) -> (A, R)
 __global__ void __launch_bounds__(128) k_reduce_level1(const uint8_t *__restrict__ partial, const uint32_t *__restrict__ toffs,
                                                        uint8_t *__restrict__ outA, uint8_t *__restrict__ outR, uint32_t n_groups, uint32_t g) {
     uint32_t ck = blockIdx.x * blockDim.x + threadIdx.x;
@@ -251,7 +289,9 @@ __global__ void __launch_bounds__(128) k_reduce_level1(const uint8_t *__restrict
     bool run_nz = false, acc_nz = false;
 #pragma unroll 1
     for (uint32_t i = g; i-- > 0;) {
-        for (uint32_t t = to[i]; t < to[i + 1]; t++) {
+        uint32_t cnt = to[i + 1] - to[i];
+        if (cnt > BBP_FOLD_MIN) cnt = 1;   // folded by k_bucket_fold into its first partial
+        for (uint32_t t = to[i]; t < to[i] + cnt; t++) {
             ge p = ge_load(partial + 128 * (size_t)t);
             if (run_nz) run = ge_add(run, p);
             else { run = p; run_nz = true; }
@@ -502,8 +542,12 @@ struct msm_engine {
         uint32_t per_set = sh.B, g = std::min<uint32_t>(BBP_RED_G, per_set);
         uint32_t sets = sh.n_slots * sh.sets_per_slot;
         uint32_t n_groups = sets * (per_set / g);
-        k_reduce_level1<<<(n_groups + 127) / 128, 128, 0, stream>>>(partial, toffs, lvl[0], lvl[1], n_groups, g);
+        // cursor[] is free after the scatter: [0, nkeys) becomes the list of heavy buckets, cursor[nkeys] (zeroed above) its length
+        k_heavy_list<<<(sh.nkeys + 255) / 256, 256, 0, stream>>>(toffs, sh.nkeys, cursor, cursor + sh.nkeys);
+        k_bucket_fold<<<BBP_FOLD_BLOCKS, 128, 0, stream>>>(partial, toffs, cursor, cursor + sh.nkeys);
         launches++;
+        k_reduce_level1<<<(n_groups + 127) / 128, 128, 0, stream>>>(partial, toffs, lvl[0], lvl[1], n_groups, g);
+        launches += 2;
         if (mark(5)) return -100;
         per_set /= g;
         uint32_t len = g;

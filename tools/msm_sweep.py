@@ -15,7 +15,7 @@ raw = bytearray(hashlib.shake_256(b"bbp-bench-scalars" + (0).to_bytes(8, "little
 for i in range(31, 32 * nmax, 32):
     raw[i] &= 0x0f
 with torch.cuda.stream(stream):
-    for lg in range(10, 21):
+    for lg in range(int(sys.argv[1]) if len(sys.argv) > 1 else 10, (int(sys.argv[2]) if len(sys.argv) > 2 else 20) + 1):
         n = 1 << lg
         tab, ok = be.points_from_compressed(pts[:32 * n])
         d_sc = torch.frombuffer(bytearray(raw[:32 * n]), dtype=torch.uint8).cuda()
@@ -31,7 +31,11 @@ with torch.cuda.stream(stream):
             e1.synchronize()
             ts.append(e0.elapsed_time(e1))
         ts.sort()
+        be.set_profiling(1)
+        be.msm_points_device(d_sc.data_ptr(), n, tab, d_out.data_ptr(), None)
+        stage = [round(x, 4) for x in be.msm_stage_ms()]
+        be.set_profiling(0)
         plan = pkg.Backend.msm_plan(n)
         print(json.dumps({"log2_n": lg, "n": n, "ms_median": ts[10], "ms_min": ts[0], "points_per_s": n / (ts[10] * 1e-3), "window_bits": plan["c"],
-                          "windows": plan["W"], "result": bytes(d_out.cpu().numpy()).hex()}), flush=True)
+                          "windows": plan["W"], "S": plan["S"], "stage_ms": stage, "result": bytes(d_out.cpu().numpy()).hex()}), flush=True)
         tab.free()
