@@ -272,3 +272,34 @@ def test_batch_verify_equals_and_of_singles(be):
     its[3]["proof"] = its[3]["proof"][:-1]
     ok, st = be.blindbid_verify_batch(its, seed32("batch2"))
     assert not ok and st[3] == -2 and all(s == 0 for i, s in enumerate(st) if i != 3)
+
+
+def test_batch_verify_config4_full_size(be):
+    """BASELINE config 4 at full size: 1024 proofs in ONE combined mega-check; with 1 and with 16 corrupted proofs the
+    verdicts must single out exactly the corrupted requests (re-check pass), and equal the per-request verdicts.
+    Size-independent properties only (the oracle needs ~50 ms per verification): single-request verification on the
+    GPU is pinned against the oracle by the tests above."""
+    n = 1024
+    cases = [make_case(5000 + i, 8) for i in range(n)]
+    outs = be.blindbid_prove_batch(cases)
+    assert all(st == 0 and len(p) == 1121 for st, p, _, _ in outs)
+    items = [verify_item(b, p, c, t, i) for i, (b, (st, p, c, t)) in enumerate(zip(cases, outs))]
+    ok, st = be.blindbid_verify_batch(items, seed32("full"))
+    assert ok and st == [0] * n
+    # determinism: a second proving pass yields identical bytes
+    again = be.blindbid_prove_batch(cases[:64])
+    assert [o[1] for o in again] == [o[1] for o in outs[:64]]
+    # spot-check three of them against the oracle
+    for i in (0, 511, 1023):
+        assert oracle_verify(items[i]) == 0
+    for bad in ([777], list(range(5, 1024, 64))):
+        its = [dict(x) for x in items]
+        for k, b in enumerate(bad):
+            p = bytearray(its[b]["proof"])
+            pos = [-1, 1 + 32 * 8, 40, -70, 1 + 32 * 9 + 3][k % 5]      # b, t_x, A_O1, a, t_x_blinding
+            p[pos] ^= 4
+            its[b]["proof"] = bytes(p)
+        ok, st = be.blindbid_verify_batch(its, seed32("full-bad"))
+        assert not ok
+        assert [i for i, s in enumerate(st) if s != 0] == bad
+        assert st == be.blindbid_verify_each(its)
