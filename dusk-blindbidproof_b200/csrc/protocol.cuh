@@ -28,8 +28,15 @@ namespace bbp {
 // ---------------------------------------------------------------- small host utilities
 template <class F>
 inline void parallel_for(size_t n, F fn) {
-    size_t hw = std::thread::hardware_concurrency();
-    size_t nt = std::min<size_t>(std::max<size_t>(hw, 1), std::min<size_t>(n, 64));
+    // host threads for the per-proof phases: BBP_HOST_THREADS, else the hardware threads divided among the processes that
+    // share this host (torchrun exports LOCAL_WORLD_SIZE: one process per GPU)
+    static const size_t hw = [] {
+        if (const char *e = getenv("BBP_HOST_THREADS")) return (size_t)std::max(1, atoi(e));
+        size_t h = std::max<size_t>(std::thread::hardware_concurrency(), 1);
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) h = std::max<size_t>(h / (size_t)std::max(1, atoi(e)), 1);
+        return h;
+    }();
+    size_t nt = std::min<size_t>(hw, std::min<size_t>(n, 64));
     if (nt <= 1) { for (size_t i = 0; i < n; i++) fn(i); return; }
     std::atomic<size_t> next(0);
     std::vector<std::thread> th;
