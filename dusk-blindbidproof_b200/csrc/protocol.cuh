@@ -26,17 +26,20 @@
 namespace bbp {
 
 // ---------------------------------------------------------------- small host utilities
-template <class F>
-inline void parallel_for(size_t n, F fn) {
-    // host threads for the per-proof phases: BBP_HOST_THREADS, else the hardware threads divided among the processes that
-    // share this host (torchrun exports LOCAL_WORLD_SIZE: one process per GPU)
+// host threads for the per-proof phases: BBP_HOST_THREADS, else the hardware threads divided among the processes that
+// share this host (torchrun exports LOCAL_WORLD_SIZE: one process per GPU)
+inline size_t host_threads() {
     static const size_t hw = [] {
         if (const char *e = getenv("BBP_HOST_THREADS")) return (size_t)std::max(1, atoi(e));
         size_t h = std::max<size_t>(std::thread::hardware_concurrency(), 1);
         if (const char *e = getenv("LOCAL_WORLD_SIZE")) h = std::max<size_t>(h / (size_t)std::max(1, atoi(e)), 1);
         return h;
     }();
-    size_t nt = std::min<size_t>(hw, std::min<size_t>(n, 64));
+    return hw;
+}
+template <class F>
+inline void parallel_for(size_t n, F fn) {
+    size_t nt = std::min<size_t>(host_threads(), std::min<size_t>(n, 64));
     if (nt <= 1) { for (size_t i = 0; i < n; i++) fn(i); return; }
     std::atomic<size_t> next(0);
     std::vector<std::thread> th;
@@ -431,7 +434,7 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     // (the chain costs ~19 ms of latency whatever the batch; host threads draw ~2.4 ms per proof each, so the device wins
     // once the batch exceeds about six proofs per host thread)
     const char *rng_env = getenv("BBP_DEVICE_RNG_MIN_BATCH");   // read per call so that tests can force either path
-    const int rng_threshold = rng_env ? atoi(rng_env) : (int)(6 * std::max(1u, std::thread::hardware_concurrency()));
+    const int rng_threshold = rng_env ? atoi(rng_env) : (int)(6 * host_threads());
     const bool device_rng = (int)B >= rng_threshold;
     if (device_rng) {
         if ((rc = ps->h_states.ensure((size_t)B * BBP_STROBE_STATE_BYTES))) return rc;

@@ -10,11 +10,11 @@ from bench import synth_bid
 L = 8
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 bids = [synth_bid(pkg.capi, i, L) for i in range(N)]
-for lanes in (1, 2, 3, 4):
+for lanes in (1, 2, 3):
     ctxs = [pkg.Backend(device=0, gens_capacity=2048, party_capacity=1) for _ in range(lanes)]
     for c in ctxs:
         c.blindbid_prove_batch(bids[:N // lanes])    # warm (allocations)
-    for chunk in (N // lanes, max(1, N // (2 * lanes))):
+    for chunk in (N // lanes,):
         res = [None] * lanes
 
         def work(k):
