@@ -164,7 +164,7 @@ class Backend:
     def msm_plan(n):
         out = (ctypes.c_uint32 * 4)()
         _chk(lib().bbp_msm_plan(_sz(n), out), "bbp_msm_plan")
-        return dict(c=out[0], W=out[1], S=out[2], CH=out[3])
+        return dict(c=out[0], W=out[1], S=out[2], B=out[3])
 
     def int_peak(self):
         v = ctypes.c_double()

@@ -79,7 +79,7 @@ int bbp_msm_stage_ms(bbp_ctx *ctx, float *ms, size_t n_stages) {
 int bbp_msm_plan(size_t n, uint32_t out[4]) {
     if (!out || n == 0 || n > 0x7fffffffu) return BBP_ERR_INPUT;
     msm_shape sh = msm_engine::make_shape((uint32_t)n, (uint32_t)n, (uint32_t)n, false, 0, 0, 0);
-    out[0] = sh.c; out[1] = sh.W; out[2] = sh.S; out[3] = sh.CH;
+    out[0] = sh.c; out[1] = sh.W; out[2] = sh.S; out[3] = sh.B;
     return BBP_OK;
 }
 int bbp_int_peak(bbp_ctx *ctx, double *wide_mads_per_s) {

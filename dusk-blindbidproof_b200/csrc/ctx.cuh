@@ -28,9 +28,6 @@ struct bbp_ctx {
     uint8_t *d_gens_ext = nullptr;     // n_gens x 128 B
     uint8_t *d_gens_niels = nullptr;   // n_gens x 96 B
     uint8_t pc_compressed[64];
-    // fixed-base window table over the generator set (built on demand)
-    uint8_t *d_gens_wtable = nullptr;
-    uint32_t wtable_c = 0, wtable_W = 0;
     // protocol layer state (templates, tables, scratch): protocol.cuh
     bbp::proto_state *proto = nullptr;
     // staging
@@ -120,7 +117,7 @@ struct bbp_ctx {
         msm.release();
         bbp::proto_release(proto);
         proto = nullptr;
-        cudaFree(d_gens_ext); cudaFree(d_gens_niels); cudaFree(d_gens_wtable); cudaFree(d_in); cudaFree(d_out); cudaFree(d_scratch);
+        cudaFree(d_gens_ext); cudaFree(d_gens_niels); cudaFree(d_in); cudaFree(d_out); cudaFree(d_scratch);
         if (stream) cudaStreamDestroy(stream);
         stream = nullptr;
     }

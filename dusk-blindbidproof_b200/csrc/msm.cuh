@@ -8,9 +8,8 @@
 //   2 scan       exclusive scan of the histogram (bucket offsets) and of ceil(count / S) (task offsets)
 //   3 scatter    counting sort of (point ref | sign) entries by key
 //   4 accumulate one thread per task (<= S entries of one bucket): 7M mixed additions from the niels table
-//   5 chunk      one thread per CH consecutive buckets: merge task partials, running sums (acc_k, run_k)
-//   6 window     one block per (slot, window): suffix scan + tree reduction in shared memory
-//   7 combine    Horner over windows (c doublings each), Ristretto compression
+//   5 reduce     heavy buckets folded by a warp each; then levels of 8-way merges of (sum, index-weighted sum) pairs
+//   6 combine    Horner over windows (c doublings each, four lanes per slot), Ristretto compression
 // Two base layouts share the kernels: "variable" bases (one niels entry per point, W bucket sets per slot) and
 // "fixed" bases (a precomputed table of 2^(c*w) * P_i, all windows of a slot share ONE bucket set, no doublings).
 #pragma once
@@ -45,8 +44,6 @@ struct msm_shape {
     uint32_t sets_per_slot;// W (variable) or 1 (fixed)
     uint32_t nkeys;        // n_slots * sets_per_slot * B
     uint32_t S;            // max entries per task
-    uint32_t CH;           // buckets per chunk (power of two)
-    uint32_t n_ch;         // chunks per bucket set = B / CH
     // point reference of scalar i. mode 0: i % base_mod. mode 1: colmap[i % colmap_len] (compact slots over scattered
     // columns of a fixed table). mode 2: per-group tables — element e = i % n_per_slot of a slot refers to entry
     // (i / grp_div) * grp_stride + e, except the last element of every slot, which refers to the shared entry tail_ref.
@@ -506,8 +503,6 @@ struct msm_engine {
         size_t pairs_per_set = fixed ? (size_t)n_per_slot * sh.W : n_per_slot;
         size_t avg = pairs_per_set / sh.B + 1;
         sh.S = (uint32_t)std::min<size_t>(std::max<size_t>(2 * avg, 16), 64);
-        sh.CH = std::max(1u, std::min(32u, sh.B / 256));   // power of two; n_ch = B / CH is a power of two as well
-        sh.n_ch = sh.B / sh.CH;
         return sh;
     }
 

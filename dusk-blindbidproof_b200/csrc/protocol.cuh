@@ -245,7 +245,9 @@ inline int ipp_rounds(bbp_ctx *ctx, sc_batch &SB, uint32_t P, std::vector<sc> &c
     const char *hyb_env = getenv("BBP_IPP_HYBRID");   // 0 = never, 2 = always (tests), default: batches of >= 32
     const int hyb = hyb_env ? atoi(hyb_env) : 1;
     const bool hybrid = hyb && n >= 4 * IPP_NF && (P >= 32 || hyb == 2);   // small batches are launch bound: fewer, larger rounds win
-    const uint32_t j0 = hybrid ? lg - log2_u32(IPP_NF) : lg, nf = IPP_NF;
+    const char *nf_env = getenv("BBP_IPP_NF");   // tuning knob (power of two, 16 .. n / 4)
+    const uint32_t nf = nf_env ? (uint32_t)atoi(nf_env) : IPP_NF;
+    const uint32_t j0 = hybrid ? lg - log2_u32(nf) : lg;
     int rc;
     std::vector<uint8_t> lr((size_t)P * 64);
     SB.fac_n = n; SB.late = 0;
@@ -895,11 +897,7 @@ inline int verify_batch(bbp_ctx *ctx, std::vector<verify_job> &jobs, const uint8
         std::vector<uint8_t> verdicts;
         int rc = verify_group(ctx, jobs, prep, g.second, true, &rho, verdicts, d_partial_ext);
         if (rc) return rc;
-        bool any_dead = false;
-        for (size_t i : g.second) any_dead = any_dead || jobs[i].status != 0;
-        if (verdicts[0] && !partial_only) {
-            for (size_t i : g.second) if (jobs[i].status == 0) jobs[i].status = 0;
-        } else if (!partial_only) {
+        if (!verdicts[0] && !partial_only) {   // the combination failed: find the culprits with one per-request pass
             for (size_t i : g.second) jobs[i].status = 0;
             for (size_t off = 0; off < g.second.size(); off += 1024) {
                 std::vector<size_t> part;
@@ -910,7 +908,6 @@ inline int verify_batch(bbp_ctx *ctx, std::vector<verify_job> &jobs, const uint8
             }
         }
         ok = ok && verdicts[0];
-        (void)any_dead;
     }
     for (auto &J : jobs) ok = ok && (J.status == 0 || partial_only);
     if (all_ok) *all_ok = ok ? 1 : 0;

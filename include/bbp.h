@@ -54,7 +54,7 @@ int bbp_sync(bbp_ctx *ctx);
 int bbp_set_profiling(bbp_ctx *ctx, int on);
 /* ms[0..7): recode, scans, scatter+task table, bucket accumulation, bucket reduction level 1, merge levels, combine+compress */
 int bbp_msm_stage_ms(bbp_ctx *ctx, float *ms, size_t n_stages);
-/* out = {window bits c, windows W, max entries per task S, buckets per chunk CH} chosen for an n-point MSM */
+/* out = {window bits c, windows W, max entries per task S, buckets per window B} chosen for an n-point MSM */
 int bbp_msm_plan(size_t n, uint32_t out[4]);
 /* sustained 32x32->64 multiply-accumulates per second (IMAD.WIDE.U32), all SMs, 8 independent chains per thread */
 int bbp_int_peak(bbp_ctx *ctx, double *wide_mads_per_s);
