@@ -51,3 +51,15 @@ def test_product_does_not_link_or_reference_the_oracle():
             if f.endswith((".cu", ".cuh", ".h", ".py", ".inc", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "liboracle" not in text and "oracle/" not in text and "import orc" not in text, os.path.join(dirpath, f)
+
+
+def test_rust_sys_crate_matches_header():
+    """rust/bbp-sys is source only (no Rust toolchain here): at least keep its extern block in lock-step with include/bbp.h"""
+    src = open(os.path.join(ROOT, "rust", "bbp-sys", "src", "lib.rs")).read()
+    rust = set(re.findall(r"pub fn (bbp_[a-z0-9_]+)\s*\(", src))
+    hdr = set(declared_symbols())
+    assert rust and rust <= hdr, sorted(rust - hdr)
+    # every entry point of the blind-bid path is bound
+    for must in ("bbp_init", "bbp_free", "bbp_blindbid_prove_batch", "bbp_blindbid_verify_each", "bbp_blindbid_verify_batch",
+                 "bbp_msm_vartime", "bbp_msm_optional", "bbp_rangeproof_prove_multiple", "bbp_rangeproof_verify_multiple"):
+        assert must in rust, must
