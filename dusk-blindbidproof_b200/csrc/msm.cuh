@@ -201,14 +201,59 @@ __global__ void k_task_fill(const uint32_t *__restrict__ toffs, uint32_t *__rest
     for (uint32_t t = t0; t < t1; t++) task_key[t] = key;
 }
 
+// ---------------------------------------------------------------- task order: longest first, equal lengths together
+// Bucket sizes are Poisson distributed, so the tasks of 32 neighbouring buckets differ in length by +-30 % and a warp
+// would wait for its longest task. A counting sort of the task ids by length (<= 64, block-aggregated atomics) makes
+// every warp run tasks of (almost) one length; the partial of task t still goes to slot t, so nothing downstream changes.
+#define BBP_MAX_S 64
+__device__ __forceinline__ uint32_t task_len(const uint32_t *offs, const uint32_t *toffs, const uint32_t *task_key, uint32_t t, uint32_t S) {
+    uint32_t key = task_key[t];
+    uint32_t start = offs[key] + (t - toffs[key]) * S;
+    return min(start + S, offs[key + 1]) - start;
+}
+// bins[0..65): number of tasks per length
+__global__ void __launch_bounds__(256) k_task_hist(const uint32_t *__restrict__ offs, const uint32_t *__restrict__ toffs, const uint32_t *__restrict__ task_key,
+                                                   uint32_t *__restrict__ bins, uint32_t nkeys, uint32_t S) {
+    __shared__ uint32_t s_cnt[BBP_MAX_S + 1];
+    if (threadIdx.x <= BBP_MAX_S) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < toffs[nkeys]) atomicAdd(&s_cnt[task_len(offs, toffs, task_key, t, S)], 1u);
+    __syncthreads();
+    if (threadIdx.x <= BBP_MAX_S && s_cnt[threadIdx.x]) atomicAdd(&bins[threadIdx.x], s_cnt[threadIdx.x]);
+}
+// bins[128 + len] = first position of length len in the permutation (descending length)
+__global__ void k_task_bin_scan(uint32_t *__restrict__ bins) {
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int len = BBP_MAX_S; len >= 0; len--) { bins[128 + len] = acc; acc += bins[len]; }
+    }
+}
+__global__ void __launch_bounds__(256) k_task_perm(const uint32_t *__restrict__ offs, const uint32_t *__restrict__ toffs, const uint32_t *__restrict__ task_key,
+                                                   uint32_t *__restrict__ bins, uint32_t *__restrict__ perm, uint32_t nkeys, uint32_t S) {
+    __shared__ uint32_t s_cnt[BBP_MAX_S + 1], s_base[BBP_MAX_S + 1];
+    if (threadIdx.x <= BBP_MAX_S) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = t < toffs[nkeys];
+    uint32_t len = 0, rank = 0;
+    if (live) { len = task_len(offs, toffs, task_key, t, S); rank = atomicAdd(&s_cnt[len], 1u); }
+    __syncthreads();
+    if (threadIdx.x <= BBP_MAX_S && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&bins[128 + threadIdx.x], s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (live) perm[s_base[len] + rank] = t;
+}
+
 // ---------------------------------------------------------------- bucket accumulation: one thread per task
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_accumulate(const uint8_t *__restrict__ table, const uint32_t *__restrict__ entries,
                                                     const uint32_t *__restrict__ offs, const uint32_t *__restrict__ toffs,
-                                                    const uint32_t *__restrict__ task_key, uint8_t *__restrict__ partial, msm_shape sh) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+                                                    const uint32_t *__restrict__ task_key, const uint32_t *__restrict__ perm,
+                                                    uint8_t *__restrict__ partial, msm_shape sh) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n_tasks = toffs[sh.nkeys];
-    if (t >= n_tasks) return;
+    if (i >= n_tasks) return;
+    uint32_t t = perm[i];
     uint32_t key = task_key[t];
     uint32_t start = offs[key] + (t - toffs[key]) * sh.S;
     uint32_t end = min(start + sh.S, offs[key + 1]);
@@ -400,7 +445,7 @@ struct msm_engine {
     size_t cap_pairs = 0, cap_keys = 0, cap_tasks = 0, cap_chunks = 0, cap_sets = 0;
     int32_t *digits = nullptr;
     uint32_t *hist = nullptr, *offs = nullptr, *cursor = nullptr, *toffs = nullptr, *entries = nullptr, *task_key = nullptr;
-    uint32_t *tile_sums = nullptr, *total = nullptr;
+    uint32_t *tile_sums = nullptr, *total = nullptr, *task_perm = nullptr, *len_bins = nullptr;
     uint8_t *partial = nullptr, *lvl[4] = {nullptr, nullptr, nullptr, nullptr};   // lvl: ping-pong (A, R) arrays of the bucket reduction
     uint64_t launches = 0;
     // optional per-stage timing (bbp_set_profiling): events around recode / scans / scatter+fill / accumulate /
@@ -432,7 +477,8 @@ struct msm_engine {
 
     void release() {
         cudaFree(digits); cudaFree(hist); cudaFree(offs); cudaFree(cursor); cudaFree(toffs); cudaFree(entries); cudaFree(task_key);
-        cudaFree(tile_sums); cudaFree(total); cudaFree(partial);
+        cudaFree(tile_sums); cudaFree(total); cudaFree(partial); cudaFree(task_perm); cudaFree(len_bins);
+        task_perm = len_bins = nullptr;
         for (int i = 0; i < 4; i++) { cudaFree(lvl[i]); lvl[i] = nullptr; }
         digits = nullptr; hist = offs = cursor = toffs = entries = task_key = tile_sums = total = nullptr;
         partial = nullptr;
@@ -459,8 +505,10 @@ struct msm_engine {
             cap_keys = keys;
         }
         if (tasks > cap_tasks) {
-            cudaFree(task_key); cudaFree(partial);
+            cudaFree(task_key); cudaFree(partial); cudaFree(task_perm);
             BBP_CUDA_OK(cudaMalloc(&task_key, tasks * 4));
+            BBP_CUDA_OK(cudaMalloc(&task_perm, tasks * 4));
+            if (!len_bins) BBP_CUDA_OK(cudaMalloc(&len_bins, 256 * 4));
             BBP_CUDA_OK(cudaMalloc(&partial, tasks * 128));
             cap_tasks = tasks;
         }
@@ -496,6 +544,7 @@ struct msm_engine {
         } else {
             uint32_t c = 4;
             while (c < 16 && ((size_t)n_per_slot >> (c + 4)) >= 1) c++;   // >= 16 points per bucket on average
+            if (const char *e = getenv("BBP_MSM_C")) { int v = atoi(e); if (v >= 4 && v <= 16) c = (uint32_t)v; }   // tuning knob
             sh.c = c; sh.W = 253 / c + 1; sh.table_stride = 0; sh.sets_per_slot = sh.W;
         }
         sh.B = 1u << (sh.c - 1);
@@ -513,6 +562,7 @@ struct msm_engine {
         if (rc) return rc;
         BBP_CUDA_OK(cudaMemsetAsync(hist, 0, ((size_t)sh.nkeys + 1) * 4, stream));
         BBP_CUDA_OK(cudaMemsetAsync(cursor, 0, ((size_t)sh.nkeys + 1) * 4, stream));
+        BBP_CUDA_OK(cudaMemsetAsync(len_bins, 0, 256 * 4, stream));
         if (mark(0)) return -100;
         k_recode<<<(sh.n + 127) / 128, 128, 0, stream>>>((const uint32_t *)d_scalars, digits, hist, sh);
         if (mark(1)) return -100;
@@ -521,16 +571,20 @@ struct msm_engine {
         if (mark(2)) return -100;
         k_scatter<<<(sh.n + 127) / 128, 128, 0, stream>>>(digits, offs, cursor, entries, sh);
         k_task_fill<<<(sh.nkeys + 255) / 256, 256, 0, stream>>>(toffs, task_key, sh.nkeys);
-        if (mark(3)) return -100;
         size_t mt = max_tasks(sh);
+        k_task_hist<<<(unsigned)((mt + 255) / 256), 256, 0, stream>>>(offs, toffs, task_key, len_bins, sh.nkeys, sh.S);
+        k_task_bin_scan<<<1, 32, 0, stream>>>(len_bins);
+        k_task_perm<<<(unsigned)((mt + 255) / 256), 256, 0, stream>>>(offs, toffs, task_key, len_bins, task_perm, sh.nkeys, sh.S);
+        launches += 3;
+        if (mark(3)) return -100;
         {
             // resident CTAs per SM for the accumulation kernel (register budget 65536 / (128 * MINB)); BBP_ACC_MINB overrides
             static const int minb = [] { const char *e = getenv("BBP_ACC_MINB"); return e ? atoi(e) : 4; }();
             unsigned grid = (unsigned)((mt + 127) / 128);
-            if (minb <= 3) k_accumulate<3><<<grid, 128, 0, stream>>>(d_table, entries, offs, toffs, task_key, partial, sh);
-            else if (minb == 4) k_accumulate<4><<<grid, 128, 0, stream>>>(d_table, entries, offs, toffs, task_key, partial, sh);
-            else if (minb == 5) k_accumulate<5><<<grid, 128, 0, stream>>>(d_table, entries, offs, toffs, task_key, partial, sh);
-            else k_accumulate<6><<<grid, 128, 0, stream>>>(d_table, entries, offs, toffs, task_key, partial, sh);
+            if (minb <= 3) k_accumulate<3><<<grid, 128, 0, stream>>>(d_table, entries, offs, toffs, task_key, task_perm, partial, sh);
+            else if (minb == 4) k_accumulate<4><<<grid, 128, 0, stream>>>(d_table, entries, offs, toffs, task_key, task_perm, partial, sh);
+            else if (minb == 5) k_accumulate<5><<<grid, 128, 0, stream>>>(d_table, entries, offs, toffs, task_key, task_perm, partial, sh);
+            else k_accumulate<6><<<grid, 128, 0, stream>>>(d_table, entries, offs, toffs, task_key, task_perm, partial, sh);
         }
         if (mark(4)) return -100;
         // bucket reduction: B buckets per set -> 1 element per set, groups of <= 8 per level
