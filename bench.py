@@ -386,7 +386,8 @@ def run_b200(args, rank, world):
         if world == 1:
             assert bytes(d_out.cpu().numpy()) == be.msm_points(scalars, table), "device and host MSM entry points disagree"
 
-        peak_wide = be.int_peak()                # IMAD.WIDE.U32 per second, measured now on this GPU
+        peak_wide, peak_per_clk = be.int_peak()  # IMAD.WIDE.U32: per second (power-capped loop) and per SM clock, measured now
+        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
         sampler = ClockSampler(local)
         sampler.start()
         l0 = be.launch_count()
@@ -433,7 +434,11 @@ def run_b200(args, rank, world):
         value = n * world * args.steps / (ms * 1e-3)
         e2e_value = n * world * e2e_steps / (e2e_ms * 1e-3)
         acc_ms = stage[3]
-        peak_imad = 2.0 * peak_wide              # §8d counts mad.lo and mad.hi separately; one IMAD.WIDE does both
+        # §8d counts mad.lo and mad.hi separately; one IMAD.WIDE does both. Ceiling = measured issue rate per SM clock x SMs
+        # x the SM clock sampled while the MSM steps ran (the multiplier loop itself is power-capped to a lower clock, so
+        # its per-second figure is below what a mixed kernel can reach and is reported separately as peak_sustained).
+        sm_hz = 1e6 * (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0)
+        peak_imad = 2.0 * peak_per_clk * n_sm * sm_hz
         achieved = accumulate_imads(n, plan["c"], plan["W"]) / (acc_ms * 1e-3)
         traffic = None
         try:
@@ -453,7 +458,9 @@ def run_b200(args, rank, world):
             "gpu_launches": launches,
             "roofline": {"bound": "int32-multiply", "kernel": "k_accumulate", "achieved": achieved / 1e12, "peak": peak_imad / 1e12,
                          "unit": "T IMAD-eq/s", "frac": achieved / peak_imad, "traffic": traffic,
-                         "kernel_ms": acc_ms, "peak_source": "bbp_int_peak measured in this run (IMAD.WIDE.U32 x2, 8 chains/thread, all SMs)",
+                         "kernel_ms": acc_ms, "peak_source": "bbp_int_peak measured in this run: IMAD.WIDE.U32 issue rate per SM clock (clock64) x 2 IMAD-eq x SMs x SM clock sampled during the MSM steps",
+                         "peak_per_clk_per_sm_wide": peak_per_clk, "peak_sustained": 2.0 * peak_wide / 1e12,
+                         "peak_sustained_note": "same loop in IMAD-eq per wall-clock second: a pure multiplier loop is power-capped to ~1.45 GHz",
                          "whole_msm_frac": msm_imads(n, plan["c"], plan["W"]) / (ms / args.steps * 1e-3) / peak_imad,
                          "hbm_gather_gbs": plan["W"] * n * 96 / (acc_ms * 1e-3) / 1e9},
             "stage_ms": dict(zip(["recode", "scan", "scatter", "accumulate", "reduce_level1", "reduce_merge", "combine"], [round(x, 4) for x in stage])),

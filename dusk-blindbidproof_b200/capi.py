@@ -167,9 +167,10 @@ class Backend:
         return dict(c=out[0], W=out[1], S=out[2], B=out[3])
 
     def int_peak(self):
-        v = ctypes.c_double()
-        _chk(lib().bbp_int_peak(self.ctx, ctypes.byref(v)), "bbp_int_peak")
-        return v.value
+        """(IMAD.WIDE per second sustained, IMAD.WIDE per SM clock per SM)"""
+        v, c = ctypes.c_double(), ctypes.c_double()
+        _chk(lib().bbp_int_peak(self.ctx, ctypes.byref(v), ctypes.byref(c)), "bbp_int_peak")
+        return v.value, c.value
 
     def msm_vartime(self, scalars, points_ext):
         out = _out(32)

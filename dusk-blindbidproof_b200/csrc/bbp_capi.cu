@@ -83,34 +83,41 @@ int bbp_msm_plan(size_t n, uint32_t out[4]) {
     out[0] = sh.c; out[1] = sh.W; out[2] = sh.S; out[3] = sh.B;
     return BBP_OK;
 }
-int bbp_int_peak(bbp_ctx *ctx, double *wide_mads_per_s) {
+int bbp_int_peak(bbp_ctx *ctx, double *wide_mads_per_s, double *wide_mads_per_clk_per_sm) {
     if (!ctx || !wide_mads_per_s) return BBP_ERR_INPUT;
     cudaSetDevice(ctx->device);
     cudaDeviceProp prop;
     BBP_CUDA_OK(cudaGetDeviceProperties(&prop, ctx->device));
     int blocks = prop.multiProcessorCount * 2, threads = 1024;
     uint32_t *d = nullptr;
+    unsigned long long *d_cyc = nullptr;
     BBP_CUDA_OK(cudaMalloc(&d, (size_t)blocks * threads * 4));
+    BBP_CUDA_OK(cudaMalloc(&d_cyc, (size_t)blocks * 8));
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    // burst measurement: one ~1.5 ms launch at a time with idle gaps in between, so that the figure is taken at the clocks a
-    // short kernel sees (back-to-back launches of a pure multiplier loop pull the chip down to ~1.45 GHz under the power cap)
     float best = 1e30f;
+    std::vector<unsigned long long> cyc(blocks);
+    double best_per_clk = 0;
     for (int rep = 0; rep < 6; rep++) {
-        cudaStreamSynchronize(ctx->stream);
-        struct timespec ts = {0, 30 * 1000 * 1000};
-        nanosleep(&ts, nullptr);
         cudaEventRecord(e0, ctx->stream);
-        k_int_peak<<<blocks, threads, 0, ctx->stream>>>(d, rep + 1);
+        k_int_peak<<<blocks, threads, 0, ctx->stream>>>(d, rep + 1, d_cyc);
         cudaEventRecord(e1, ctx->stream);
-        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return BBP_ERR_CUDA; }
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); cudaFree(d_cyc); return BBP_ERR_CUDA; }
         float ms;
         cudaEventElapsedTime(&ms, e0, e1);
         if (rep && ms < best) best = ms;
+        cudaMemcpy(cyc.data(), d_cyc, (size_t)blocks * 8, cudaMemcpyDeviceToHost);
+        double avg = 0;
+        for (int i = 0; i < blocks; i++) avg += (double)cyc[i];
+        avg /= blocks;
+        // two resident CTAs per SM share the multiplier for `avg` SM clocks
+        double per_clk = 2.0 * threads * (double)BBP_PEAK_ITERS * BBP_PEAK_ILP / avg;
+        if (rep && per_clk > best_per_clk) best_per_clk = per_clk;
     }
     ctx->launches += 6;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d); cudaFree(d_cyc);
     *wide_mads_per_s = (double)blocks * threads * (double)BBP_PEAK_ITERS * BBP_PEAK_ILP / (best * 1e-3);
+    if (wide_mads_per_clk_per_sm) *wide_mads_per_clk_per_sm = best_per_clk;
     return BBP_OK;
 }
 

@@ -108,11 +108,13 @@ __global__ void __launch_bounds__(128) k_build_window_table(const uint8_t *__res
 // from (ptxas fuses each mad.lo.cc / madc.hi pair into one), at full occupancy. The roofline denominator of the MSM.
 #define BBP_PEAK_ILP 8
 #define BBP_PEAK_ITERS 4096
-__global__ void __launch_bounds__(1024, 2) k_int_peak(uint32_t *out, uint32_t seed) {
+__global__ void __launch_bounds__(1024, 2) k_int_peak(uint32_t *out, uint32_t seed, unsigned long long *cycles) {
     uint64_t acc[BBP_PEAK_ILP];
     uint32_t x = seed + threadIdx.x;
 #pragma unroll
     for (int i = 0; i < BBP_PEAK_ILP; i++) acc[i] = ((uint64_t)(seed * 3 + blockIdx.x + 7 * i) << 32) | (x + i);
+    __syncthreads();
+    long long c0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < BBP_PEAK_ITERS; it += 4) {
 #pragma unroll
@@ -121,10 +123,12 @@ __global__ void __launch_bounds__(1024, 2) k_int_peak(uint32_t *out, uint32_t se
             for (int i = 0; i < BBP_PEAK_ILP; i++) acc[i] += (uint64_t)(uint32_t)acc[i] * x;   // IMAD.WIDE.U32 Rd, Ra.lo, x, Rd
         }
     }
+    long long c1 = clock64();
     uint32_t r = 0;
 #pragma unroll
     for (int i = 0; i < BBP_PEAK_ILP; i++) r ^= (uint32_t)acc[i] ^ (uint32_t)(acc[i] >> 32);
     out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = (unsigned long long)(c1 - c0);
 }
 
 // sum of n (<= 1024) extended points, compressed: the local tail of a sharded MSM after the all-gather of the

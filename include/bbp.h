@@ -56,8 +56,10 @@ int bbp_set_profiling(bbp_ctx *ctx, int on);
 int bbp_msm_stage_ms(bbp_ctx *ctx, float *ms, size_t n_stages);
 /* out = {window bits c, windows W, max entries per task S, buckets per window B} chosen for an n-point MSM */
 int bbp_msm_plan(size_t n, uint32_t out[4]);
-/* sustained 32x32->64 multiply-accumulates per second (IMAD.WIDE.U32), all SMs, 8 independent chains per thread */
-int bbp_int_peak(bbp_ctx *ctx, double *wide_mads_per_s);
+/* 32x32+64 multiply-accumulates (IMAD.WIDE.U32), all SMs, 8 independent chains per thread, full occupancy: sustained rate
+ * per second (a pure multiplier loop runs power-capped at ~1.45 GHz) and the rate per SM clock (from clock64), which is the
+ * architectural issue rate and does not depend on the clock the chip happened to hold */
+int bbp_int_peak(bbp_ctx *ctx, double *wide_mads_per_s, double *wide_mads_per_clk_per_sm);
 
 /* ---- generators (bulletproofs PedersenGens / BulletproofGens, used at src/blindbid/mod.rs:35-36) ------------------- */
 /* compressed B, B_blinding */
