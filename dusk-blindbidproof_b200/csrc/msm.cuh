@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(128) k_bucket_fold(uint8_t *__restrict__ parti
     }
 }
 // level 1: groups of g buckets (task partials at toffs[bucket] ..; heavy buckets already folded into the first) -> (A, R)
-__global__ void __launch_bounds__(128, 4) k_reduce_level1(const uint8_t *__restrict__ partial, const uint32_t *__restrict__ toffs,
+__global__ void __launch_bounds__(128) k_reduce_level1(const uint8_t *__restrict__ partial, const uint32_t *__restrict__ toffs,
                                                        uint8_t *__restrict__ outA, uint8_t *__restrict__ outR, uint32_t n_groups, uint32_t g) {
     uint32_t ck = blockIdx.x * blockDim.x + threadIdx.x;
     if (ck >= n_groups) return;
