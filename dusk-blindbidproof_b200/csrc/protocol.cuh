@@ -12,6 +12,9 @@
 // takes from thread_rng inside TranscriptRngBuilder::finalize; with those fixed every proof byte is deterministic.
 #pragma once
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <chrono>
 #include <cstdlib>
 #include <map>
@@ -37,15 +40,106 @@ inline size_t host_threads() {
     }();
     return hw;
 }
+// Persistent host worker pool (one per process): the per-proof phases are short (tens of microseconds per proof), so
+// spawning threads per phase would cost as much as the phase. Workers sleep on a condition variable between phases.
+class host_pool {
+  public:
+    static host_pool &get() {
+        static host_pool p;
+        return p;
+    }
+    // runs fn(lo, hi) over a partition of [0, n) into contiguous chunks, at most one chunk per worker; blocks until done.
+    // Calls from different threads (several contexts) are serialised.
+    template <class F>
+    void run_chunks(size_t n, F fn) {
+        if (n == 0) return;
+        size_t nt = std::min<size_t>(workers_.size() + 1, n);
+        if (nt <= 1) { fn((size_t)0, n); return; }
+        std::lock_guard<std::mutex> call_lock(call_mu_);
+        std::function<void(size_t)> job = [&](size_t t) {
+            size_t lo = n * t / nt, hi = n * (t + 1) / nt;
+            if (lo < hi) fn(lo, hi);
+        };
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            job_ = &job; n_chunks_ = nt; next_ = 1; pending_ = nt - 1; generation_++;
+        }
+        cv_.notify_all();
+        job(0);   // the caller takes chunk 0
+        // help with leftover chunks, then wait for the workers
+        for (;;) {
+            size_t t;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (next_ >= n_chunks_) break;
+                t = next_++;
+            }
+            job(t);
+            std::lock_guard<std::mutex> lk(mu_);
+            pending_--;
+        }
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+  private:
+    host_pool() {
+        size_t n = host_threads();
+        for (size_t i = 1; i < n; i++) workers_.emplace_back([this] { loop(); });
+    }
+    ~host_pool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return stop_ || (generation_ != seen && job_ && next_ < n_chunks_); });
+            if (stop_) return;
+            seen = generation_;
+            while (job_ && next_ < n_chunks_) {
+                size_t t = next_++;
+                std::function<void(size_t)> *job = job_;
+                lk.unlock();
+                (*job)(t);
+                lk.lock();
+                if (--pending_ == 0) done_cv_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_, call_mu_;
+    std::condition_variable cv_, done_cv_;
+    std::function<void(size_t)> *job_ = nullptr;
+    size_t n_chunks_ = 0, next_ = 0, pending_ = 0;
+    uint64_t generation_ = 0;
+    bool stop_ = false;
+};
+
+template <class F>
+inline void parallel_chunks(size_t n, F fn) { host_pool::get().run_chunks(n, fn); }
 template <class F>
 inline void parallel_for(size_t n, F fn) {
-    size_t nt = std::min<size_t>(host_threads(), std::min<size_t>(n, 64));
-    if (nt <= 1) { for (size_t i = 0; i < n; i++) fn(i); return; }
-    std::atomic<size_t> next(0);
-    std::vector<std::thread> th;
-    for (size_t t = 0; t < nt; t++)
-        th.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < n;) fn(i); });
-    for (auto &x : th) x.join();
+    parallel_chunks(n, [&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; i++) fn(i); });
+}
+
+// Montgomery's trick: xs[i] <- xs[i]^-1 for all i with ONE exponentiation (inputs must be non-zero, which a Fiat-Shamir
+// challenge is except with probability 2^-252; a zero would poison the chunk, so it falls back to single inversions)
+inline void sc_batch_invert(sc *xs, size_t n) {
+    if (n == 0) return;
+    std::vector<sc> pre(n);
+    sc acc = sc_one();
+    bool has_zero = false;
+    for (size_t i = 0; i < n; i++) { has_zero = has_zero || sc_iszero(xs[i]); pre[i] = acc; acc = sc_mul(acc, xs[i]); }
+    if (has_zero) { for (size_t i = 0; i < n; i++) xs[i] = sc_invert(xs[i]); return; }
+    sc inv = sc_invert(acc);
+    for (size_t i = n; i-- > 0;) { sc t = sc_mul(inv, pre[i]); inv = sc_mul(inv, xs[i]); xs[i] = t; }
 }
 
 // BBP_TRACE=1: per-phase wall-clock of the batched prover / verifier on stderr (each phase ends with a stream sync)
@@ -606,14 +700,17 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     ctx->launches++;
     trace.mark("host_ux");
     rc = ipp_rounds(ctx, SB, B, chal, [&](uint32_t j, const std::vector<uint8_t> &lr) {
-        parallel_for(B, [&](size_t bi) {
-            hstate &H = hs[bi];
-            memcpy(&H.pf.LR[(size_t)64 * j], &lr[bi * 64], 64);
-            H.tr->append_point("L", &lr[bi * 64]);
-            H.tr->append_point("R", &lr[bi * 64 + 32]);
-            sc *c = &chal[bi * CH_N];
-            c[CH_UJ] = H.tr->challenge_scalar("u");
-            c[CH_UJINV] = sc_invert(c[CH_UJ]);
+        parallel_chunks(B, [&](size_t lo, size_t hi) {
+            std::vector<sc> inv(hi - lo);
+            for (size_t bi = lo; bi < hi; bi++) {
+                hstate &H = hs[bi];
+                memcpy(&H.pf.LR[(size_t)64 * j], &lr[bi * 64], 64);
+                H.tr->append_point("L", &lr[bi * 64]);
+                H.tr->append_point("R", &lr[bi * 64 + 32]);
+                inv[bi - lo] = chal[bi * CH_N + CH_UJ] = H.tr->challenge_scalar("u");
+            }
+            sc_batch_invert(inv.data(), inv.size());   // one exponentiation per chunk instead of one per proof
+            for (size_t bi = lo; bi < hi; bi++) chal[bi * CH_N + CH_UJINV] = inv[bi - lo];
         });
     }, trace);
     if (rc) return rc;

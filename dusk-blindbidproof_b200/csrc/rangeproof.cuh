@@ -178,14 +178,17 @@ inline int rp_prove_group(bbp_ctx *ctx, std::vector<rp_prove_job> &jobs, uint32_
     ctx->launches++;
     phase_trace trace("rp_prove_group");
     rc = ipp_rounds(ctx, SB, P, chal, [&](uint32_t j, const std::vector<uint8_t> &lr) {
-        parallel_for(P, [&](size_t pi) {
-            hstate &H = hs[pi];
-            memcpy(&H.LR[(size_t)64 * j], &lr[pi * 64], 64);
-            H.tr->append_point("L", &lr[pi * 64]);
-            H.tr->append_point("R", &lr[pi * 64 + 32]);
-            sc *c = &chal[pi * CH_N];
-            c[CH_UJ] = H.tr->challenge_scalar("u");
-            c[CH_UJINV] = sc_invert(c[CH_UJ]);
+        parallel_chunks(P, [&](size_t lo, size_t hi) {
+            std::vector<sc> inv(hi - lo);
+            for (size_t pi = lo; pi < hi; pi++) {
+                hstate &H = hs[pi];
+                memcpy(&H.LR[(size_t)64 * j], &lr[pi * 64], 64);
+                H.tr->append_point("L", &lr[pi * 64]);
+                H.tr->append_point("R", &lr[pi * 64 + 32]);
+                inv[pi - lo] = chal[pi * CH_N + CH_UJ] = H.tr->challenge_scalar("u");
+            }
+            sc_batch_invert(inv.data(), inv.size());
+            for (size_t pi = lo; pi < hi; pi++) chal[pi * CH_N + CH_UJINV] = inv[pi - lo];
         });
     }, trace);
     if (rc) return rc;
