@@ -22,6 +22,22 @@ __global__ void __launch_bounds__(128) k_decompress_to_niels(const uint32_t *__r
     niels_store(out + 96 * (size_t)i, ge_affine_to_niels(p.X, p.Y, p.T));
 }
 
+// same, reading point i from a strided layout: groups of `per_group` consecutive 32-byte encodings, one group every
+// `group_stride` bytes (the verifier's request blobs)
+__global__ void __launch_bounds__(128) k_decompress_to_niels_strided(const uint8_t *__restrict__ in, uint32_t per_group, uint32_t group_stride,
+                                                                     uint8_t *__restrict__ out, uint32_t n, uint8_t *__restrict__ valid_flags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 *q = (const uint4 *)(in + (size_t)(i / per_group) * group_stride + 32 * (size_t)(i % per_group));
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    ge p;
+    bool ok = ge_decompress_words(p, w);
+    if (!ok) p = ge_identity();
+    valid_flags[i] = ok ? 1 : 0;
+    niels_store(out + 96 * (size_t)i, ge_affine_to_niels(p.X, p.Y, p.T));
+}
+
 // compressed -> extended (n x 128 B)
 __global__ void __launch_bounds__(128) k_decompress_to_ext(const uint32_t *__restrict__ in, uint8_t *__restrict__ out, uint32_t n,
                                                            int *__restrict__ all_valid, uint8_t *__restrict__ valid_flags) {

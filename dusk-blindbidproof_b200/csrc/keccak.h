@@ -317,6 +317,7 @@ class merlin_transcript {
         s_.prf(dest, n, false);
     }
     merlin_rng_builder build_rng() const { return merlin_rng_builder(s_); }
+    void export_state(uint8_t out[208]) const { s_.export_state(out); }   // hand-off to the device-side replay
 
     void domain_sep(const char *name) { append_message("dom-sep", name, strlen(name)); }
     void r1cs_domain_sep() { domain_sep("r1cs v1"); }

@@ -757,100 +757,53 @@ struct verify_job {
 
 struct verify_prepared {
     bool live = false;              // passed every host-side check; takes part in the GPU check
-    r1cs_proof_host pf;
     uint32_t nc = 0, nt = 0, m = 0, n1 = 0, n = 0, lg = 0;
-    std::vector<sc> chal;           // CH_N
+    // [V_0..V_{m-1} | A_I1 A_O1 S1 A_I2 A_O2 S2 | T_1 T_3 T_4 T_5 T_6 | L_0 R_0 .. | t_x t_x_blinding e_blinding | a b], 32 B each:
+    // the first m + 11 + 2 lg entries are the dynamic points of the mega-check, the whole blob is what the transcript absorbs
+    std::vector<uint8_t> blob;
     std::vector<sc> pub;
-    std::vector<sc> dyn_sc;         // dyn_stride host-side dynamic scalars (entries [0, m) are filled on the device)
-    std::vector<uint8_t> dyn_pts;   // dyn_stride x 32 compressed
 };
 
-// host part of Verifier::verify for one request: parse, replay the transcript, derive every challenge
+// Host part of Verifier::verify for one request: parse (FormatError), the structural checks the reference would panic
+// on, the identity checks of validate_and_append_point (VerificationError) and the generator capacity check, in the
+// order the reference reports them. The Fiat-Shamir replay itself runs on the device (k_verify_transcript).
 inline void verify_prepare(bbp_ctx *ctx, verify_job &J, verify_prepared &P, bool versioned) {
     P.live = false;
-    if (!r1cs_from_bytes(P.pf, J.proof.data(), J.proof.size(), versioned)) { J.status = BBP_ERR_FORMAT; return; }
+    r1cs_proof_host pf;
+    if (!r1cs_from_bytes(pf, J.proof.data(), J.proof.size(), versioned)) { J.status = BBP_ERR_FORMAT; return; }
     P.nc = (uint32_t)(J.commitments.size() / 32); P.nt = (uint32_t)(J.t_c.size() / 32);
     // the reference indexes vars[0], vars[1], vars[3] and toggle[0], items[i] (panics otherwise: SURVEY.md §5)
     if (P.nc < 4 || P.nt < 1 || J.pub_list.size() < P.nt) { J.status = BBP_ERR_FORMAT; return; }
     P.m = P.nc + P.nt;
     std::shared_ptr<const circuit_template> tpl = blindbid_template(P.nc, P.nt);
     P.n1 = tpl->n1; P.n = next_pow2_u32(P.n1); P.lg = log2_u32(P.n);
-    const r1cs_proof_host &pf = P.pf;
-    merlin_transcript tr("BlindBidProofGadget");
-    tr.r1cs_domain_sep();
-    for (uint32_t i = 0; i < P.nc; i++) tr.append_point("V", &J.commitments[32 * (size_t)i]);
-    for (uint32_t i = 0; i < P.nt; i++) tr.append_point("V", &J.t_c[32 * (size_t)i]);
-    tr.append_u64("m", P.m);
-    if (!tr.validate_and_append_point("A_I1", pf.A_I1) || !tr.validate_and_append_point("A_O1", pf.A_O1) || !tr.validate_and_append_point("S1", pf.S1)) {
-        J.status = BBP_ERR_VERIFICATION; return;
-    }
-    tr.r1cs_1phase_domain_sep();
+    if (all_zero32(pf.A_I1) || all_zero32(pf.A_O1) || all_zero32(pf.S1)) { J.status = BBP_ERR_VERIFICATION; return; }
     if (P.n > ctx->gens_capacity || ctx->party_capacity < 1) { J.status = BBP_ERR_INVALID_GENERATORS_LENGTH; return; }
-    tr.append_point("A_I2", pf.A_I2); tr.append_point("A_O2", pf.A_O2); tr.append_point("S2", pf.S2);
-    P.chal.assign(CH_N, sc_zero());
-    sc *c = P.chal.data();
-    sc y = tr.challenge_scalar("y"), z = tr.challenge_scalar("z");
-    if (!tr.validate_and_append_point("T_1", pf.T_1) || !tr.validate_and_append_point("T_3", pf.T_3) || !tr.validate_and_append_point("T_4", pf.T_4) ||
-        !tr.validate_and_append_point("T_5", pf.T_5) || !tr.validate_and_append_point("T_6", pf.T_6)) {
-        J.status = BBP_ERR_VERIFICATION; return;
-    }
-    sc u = tr.challenge_scalar("u"), x = tr.challenge_scalar("x");
-    tr.append_scalar("t_x", pf.t_x);
-    tr.append_scalar("t_x_blinding", pf.t_x_blinding);
-    tr.append_scalar("e_blinding", pf.e_blinding);
-    sc w = tr.challenge_scalar("w");
+    if (all_zero32(pf.T_1) || all_zero32(pf.T_3) || all_zero32(pf.T_4) || all_zero32(pf.T_5) || all_zero32(pf.T_6)) { J.status = BBP_ERR_VERIFICATION; return; }
     // InnerProductProof::verification_scalars
     uint32_t lg_p = (uint32_t)(pf.LR.size() / 64);
     if (lg_p >= 32 || P.n != (1u << lg_p)) { J.status = BBP_ERR_VERIFICATION; return; }
-    tr.innerproduct_domain_sep(P.n);
-    std::vector<sc> uj(lg_p);
-    for (uint32_t j = 0; j < lg_p; j++) {
-        if (!tr.validate_and_append_point("L", &pf.LR[64 * (size_t)j]) || !tr.validate_and_append_point("R", &pf.LR[64 * (size_t)j + 32])) {
-            J.status = BBP_ERR_VERIFICATION; return;
-        }
-        uj[j] = tr.challenge_scalar("u");
-    }
-    // batch inversion of y and the u_j (one exponentiation)
-    std::vector<sc> all(uj);
-    all.push_back(y);
-    std::vector<sc> pre(all.size());
-    sc acc = sc_one();
-    for (size_t i = 0; i < all.size(); i++) { pre[i] = acc; acc = sc_mul(acc, all[i]); }
-    sc inv = sc_invert(acc);
-    std::vector<sc> allinv(all.size());
-    for (size_t i = all.size(); i-- > 0;) { allinv[i] = sc_mul(inv, pre[i]); inv = sc_mul(inv, all[i]); }
-    merlin_rng rng = tr.build_rng().finalize(J.rng_seed);
-    sc r = rng.random_scalar();
-    c[CH_Y] = y; c[CH_YINV] = allinv[lg_p]; c[CH_Z] = z; c[CH_X] = x; c[CH_U] = u; c[CH_W] = w; c[CH_R] = r;
-    c[CH_A] = pf.a; c[CH_B] = pf.b; c[CH_TX] = pf.t_x; c[CH_TXBL] = pf.t_x_blinding; c[CH_EBL] = pf.e_blinding; c[CH_RHO] = sc_one();
-    for (uint32_t j = 0; j < lg_p; j++) { c[CH_UJ0 + j] = uj[j]; c[CH_UJ0 + lg_p + j] = allinv[j]; }
-    fill_public_values(P.pub, J.seed, J.score, J.z_img, J.pub_list.data(), P.nt);
-    // dynamic points / scalars: [V_0..V_{m-1} | A_I1 A_O1 S1 A_I2 A_O2 S2 | T_1 T_3 T_4 T_5 T_6 | L_j | R_j]
-    uint32_t ds = P.m + 11 + 2 * lg_p;
-    P.dyn_sc.assign(ds, sc_zero());
-    P.dyn_pts.resize((size_t)ds * 32);
-    memcpy(P.dyn_pts.data(), J.commitments.data(), (size_t)P.nc * 32);
-    memcpy(P.dyn_pts.data() + (size_t)P.nc * 32, J.t_c.data(), (size_t)P.nt * 32);
+    for (uint32_t j = 0; j < 2 * lg_p; j++)
+        if (all_zero32(&pf.LR[32 * (size_t)j])) { J.status = BBP_ERR_VERIFICATION; return; }
+    P.blob.resize((size_t)32 * (P.m + 11 + 2 * lg_p + 5));
+    uint8_t *o = P.blob.data();
+    memcpy(o, J.commitments.data(), (size_t)P.nc * 32); o += (size_t)P.nc * 32;
+    memcpy(o, J.t_c.data(), (size_t)P.nt * 32); o += (size_t)P.nt * 32;
     const uint8_t *fixed_pts[11] = {pf.A_I1, pf.A_O1, pf.S1, pf.A_I2, pf.A_O2, pf.S2, pf.T_1, pf.T_3, pf.T_4, pf.T_5, pf.T_6};
-    for (int k = 0; k < 11; k++) memcpy(P.dyn_pts.data() + (size_t)(P.m + k) * 32, fixed_pts[k], 32);
-    sc xx = sc_mul(x, x), xxx = sc_mul(xx, x), rxx = sc_mul(r, xx);
-    sc *d = P.dyn_sc.data() + P.m;
-    d[0] = x; d[1] = xx; d[2] = xxx; d[3] = sc_mul(u, x); d[4] = sc_mul(u, xx); d[5] = sc_mul(u, xxx);
-    d[6] = sc_mul(r, x); d[7] = sc_mul(rxx, x); d[8] = sc_mul(rxx, xx); d[9] = sc_mul(rxx, xxx); d[10] = sc_mul(sc_mul(rxx, xx), xx);
-    for (uint32_t j = 0; j < lg_p; j++) {
-        memcpy(P.dyn_pts.data() + (size_t)(P.m + 11 + j) * 32, &pf.LR[64 * (size_t)j], 32);
-        memcpy(P.dyn_pts.data() + (size_t)(P.m + 11 + lg_p + j) * 32, &pf.LR[64 * (size_t)j + 32], 32);
-        d[11 + j] = sc_mul(uj[j], uj[j]);
-        d[11 + lg_p + j] = sc_mul(allinv[j], allinv[j]);
-    }
+    for (int k = 0; k < 11; k++) { memcpy(o, fixed_pts[k], 32); o += 32; }
+    memcpy(o, pf.LR.data(), pf.LR.size()); o += pf.LR.size();
+    sc_tobytes(o, pf.t_x); sc_tobytes(o + 32, pf.t_x_blinding); sc_tobytes(o + 64, pf.e_blinding); sc_tobytes(o + 96, pf.a); sc_tobytes(o + 128, pf.b);
+    fill_public_values(P.pub, J.seed, J.score, J.z_img, J.pub_list.data(), P.nt);
     P.live = true;
 }
 
-// GPU part for prepared requests idx[0..B) that share (nc, nt). combined = false: one verdict per request (rho = 1);
-// combined = true: one random linear combination (weights rho[bi]) -> a single verdict. Verdicts: 1 = mega-check is the identity.
+// GPU part for prepared requests idx[0..B) that share (nc, nt). combined = false: one verdict per request (weight 1);
+// combined = true: ONE random linear combination -> a single verdict; the weights come from a Merlin transcript over one
+// digest per request — the verifier scalar r that request's own transcript yields after absorbing the whole proof, so it
+// binds every proof byte — keyed with batch_seed. Verdicts: 1 = mega-check is the identity.
 // Requests with a point that fails to decompress get status VERIFICATION and weight zero.
 inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector<verify_prepared> &prep, const std::vector<size_t> &idx, bool combined,
-                        const std::vector<sc> *rho, std::vector<uint8_t> &verdicts, uint8_t *d_partial_ext /* combined: 2 x 128 B, optional */) {
+                        const uint8_t *batch_seed, std::vector<uint8_t> &verdicts, uint8_t *d_partial_ext /* combined: 2 x 128 B, optional */) {
     proto_state *ps = proto_get(ctx);
     const uint32_t B = (uint32_t)idx.size();
     const verify_prepared &P0 = prep[idx[0]];
@@ -859,56 +812,79 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     dev_template *dt;
     if ((rc = proto_template(ctx, P0.nc, P0.nt, &dt))) return rc;
     const circuit_template &T = *dt->tpl;
-    const uint32_t n1 = T.n1, m = T.m, n = P0.n, lg = P0.lg, gcols = ctx->gens_capacity * ctx->party_capacity, slot_len = 2 + 2 * gcols, ds = m + 11 + 2 * lg;
+    const uint32_t n1 = T.n1, m = T.m, n = P0.n, lg = P0.lg, gcols = ctx->gens_capacity * ctx->party_capacity, slot_len = 2 + 2 * gcols;
+    const uint32_t ds = m + 11 + 2 * lg, blob_stride = 32 * (ds + 5);
     const uint32_t n_groups = combined ? 1 : B;
     phase_trace trace(combined ? "verify_group(combined)" : "verify_group(each)");
 
-    // ---- dynamic points first: a failed decompression removes the request from the check
-    std::vector<uint8_t> dyn_pts((size_t)B * ds * 32);
-    for (uint32_t bi = 0; bi < B; bi++) memcpy(&dyn_pts[(size_t)bi * ds * 32], prep[idx[bi]].dyn_pts.data(), (size_t)ds * 32);
-    if ((rc = ps->dyn_pts.ensure(dyn_pts.size())) || (rc = ps->dyn_niels.ensure((size_t)B * ds * 96)) || (rc = ps->valid.ensure((size_t)B * ds + 4))) return rc;
-    if ((rc = h2d(ctx, ps->dyn_pts.p, dyn_pts.data(), dyn_pts.size()))) return rc;
-    int *d_all = (int *)(ps->valid.p + (((size_t)B * ds + 3) & ~(size_t)3));
-    if ((rc = ps->valid.ensure((((size_t)B * ds + 3) & ~(size_t)3) + 4))) return rc;
-    d_all = (int *)(ps->valid.p + (((size_t)B * ds + 3) & ~(size_t)3));
-    BBP_CUDA_OK(cudaMemsetAsync(d_all, 1, 4, ctx->stream));
-    k_decompress_to_niels<<<(B * ds + 127) / 128, 128, 0, ctx->stream>>>(ps->dyn_pts.as<uint32_t>(), ps->dyn_niels.p, B * ds, d_all, ps->valid.p);
-    ctx->launches++;
-    std::vector<uint8_t> valid((size_t)B * ds);
-    if ((rc = d2h_sync(ctx, valid.data(), ps->valid.p, valid.size()))) return rc;
-    trace.mark("decompress");
-
-    std::vector<sc> chal((size_t)B * CH_N), pub((size_t)B * T.n_pub), dyn_sc((size_t)B * ds);
-    std::vector<uint8_t> alive(B, 1);
+    // ---- upload blobs, seeds, public values; decompress the dynamic points; replay the transcripts
+    if ((rc = ps->h_wit.ensure((size_t)B * (blob_stride + 32 + (size_t)T.n_pub * 32)))) return rc;
+    uint8_t *h_blobs = ps->h_wit.p, *h_seeds = h_blobs + (size_t)B * blob_stride;
+    sc *h_pub = (sc *)(h_seeds + (size_t)B * 32);
     parallel_for(B, [&](size_t bi) {
-        verify_prepared &P = prep[idx[bi]];
+        const verify_prepared &P = prep[idx[bi]];
+        memcpy(h_blobs + bi * blob_stride, P.blob.data(), blob_stride);
+        memcpy(h_seeds + bi * 32, jobs[idx[bi]].rng_seed, 32);
+        memcpy(h_pub + bi * T.n_pub, P.pub.data(), (size_t)T.n_pub * 32);
+    });
+    if ((rc = ps->dyn_pts.ensure((size_t)B * blob_stride)) || (rc = ps->rng_states.ensure((size_t)B * 32)) || (rc = ps->pub.ensure((size_t)B * T.n_pub * 32)) ||
+        (rc = ps->dyn_niels.ensure((size_t)B * ds * 96)) || (rc = ps->valid.ensure((size_t)B * ds)) || (rc = ps->chal.ensure((size_t)B * CH_N * 32)) ||
+        (rc = ps->dyn_sc.ensure((size_t)B * ds * 32)) || (rc = ps->zpow.ensure((size_t)B * T.q * 32)) || (rc = ps->ypow.ensure((size_t)B * n * 32)) ||
+        (rc = ps->yinvpow.ensure((size_t)B * n * 32)) || (rc = ps->stat.ensure((size_t)B * slot_len * 32)) || (rc = ps->sG.ensure((size_t)B * n * 32)) ||
+        (rc = ps->stat_red.ensure((size_t)n_groups * slot_len * 32)) || (rc = ps->msm_ext.ensure((size_t)2 * n_groups * 128)) || (rc = ps->flags.ensure(n_groups)))
+        return rc;
+    if ((rc = h2d(ctx, ps->dyn_pts.p, h_blobs, (size_t)B * blob_stride)) || (rc = h2d(ctx, ps->rng_states.p, h_seeds, (size_t)B * 32)) ||
+        (rc = h2d(ctx, ps->pub.p, h_pub, (size_t)B * T.n_pub * 32)))
+        return rc;
+    k_decompress_to_niels_strided<<<(B * ds + 127) / 128, 128, 0, ctx->stream>>>(ps->dyn_pts.p, ds, blob_stride, ps->dyn_niels.p, B * ds, ps->valid.p);
+    transcript_init init;
+    {
+        merlin_transcript tr("BlindBidProofGadget");   // src/blindbid/mod.rs:37
+        tr.r1cs_domain_sep();                            // Verifier::new
+        tr.export_state(init.state);
+    }
+    k_verify_transcript<<<(B + 31) / 32, 32, 0, ctx->stream>>>(init, ps->dyn_pts.p, blob_stride, ps->rng_states.p, B, m, lg, (uint64_t)n, ps->chal.as<sc>(),
+                                                               ps->dyn_sc.as<sc>(), ds);
+    ctx->launches += 2;
+    std::vector<uint8_t> valid((size_t)B * ds);
+    std::vector<sc> rvals(combined ? B : 0);
+    if (combined)
+        BBP_CUDA_OK(cudaMemcpy2DAsync(rvals.data(), 32, ps->chal.as<sc>() + CH_R, (size_t)CH_N * 32, 32, B, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = d2h_sync(ctx, valid.data(), ps->valid.p, valid.size()))) return rc;
+    trace.mark("h2d+decompress+transcripts");
+
+    // ---- weights
+    std::vector<uint8_t> alive(B, 1);
+    std::vector<sc> rho(B, sc_one());
+    bool any_dead = false;
+    for (uint32_t bi = 0; bi < B; bi++) {
         for (uint32_t k = 0; k < ds; k++)
             if (!valid[(size_t)bi * ds + k]) alive[bi] = 0;
-        if (!alive[bi]) jobs[idx[bi]].status = BBP_ERR_VERIFICATION;   // optional_multiscalar_mul -> None -> VerificationError
-        sc w = alive[bi] ? (rho ? (*rho)[bi] : sc_one()) : sc_zero();
-        P.chal[CH_RHO] = w;
-        memcpy(&chal[(size_t)bi * CH_N], P.chal.data(), (size_t)CH_N * 32);
-        memcpy(&pub[(size_t)bi * T.n_pub], P.pub.data(), (size_t)T.n_pub * 32);
-        bool unit = sc_eq(w, sc_one());
-        for (uint32_t k = 0; k < ds; k++) dyn_sc[(size_t)bi * ds + k] = unit ? P.dyn_sc[k] : sc_mul(w, P.dyn_sc[k]);
-    });
-    if ((rc = ps->chal.ensure(chal.size() * 32)) || (rc = ps->pub.ensure(pub.size() * 32)) || (rc = ps->dyn_sc.ensure(dyn_sc.size() * 32)) ||
-        (rc = ps->zpow.ensure((size_t)B * T.q * 32)) || (rc = ps->ypow.ensure((size_t)B * n * 32)) || (rc = ps->yinvpow.ensure((size_t)B * n * 32)) ||
-        (rc = ps->stat.ensure((size_t)B * slot_len * 32)) || (rc = ps->stat_red.ensure((size_t)n_groups * slot_len * 32)) ||
-        (rc = ps->msm_ext.ensure((size_t)2 * n_groups * 128)) || (rc = ps->flags.ensure(n_groups)))
-        return rc;
-    if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32)) || (rc = h2d(ctx, ps->pub.p, pub.data(), pub.size() * 32)) ||
-        (rc = h2d(ctx, ps->dyn_sc.p, dyn_sc.data(), dyn_sc.size() * 32)))
-        return rc;
+        if (!alive[bi]) { jobs[idx[bi]].status = BBP_ERR_VERIFICATION; rho[bi] = sc_zero(); any_dead = true; }   // optional_multiscalar_mul -> None
+    }
+    if (combined) {
+        merlin_transcript bt("bbp batch verification");
+        bt.append_u64("n", B);
+        for (uint32_t bi = 0; bi < B; bi++) {
+            uint8_t dg[32];
+            sc_tobytes(dg, rvals[bi]);
+            bt.append_message("proof", dg, 32);
+        }
+        merlin_rng brng = bt.build_rng().finalize(batch_seed);
+        for (uint32_t bi = 0; bi < B; bi++) {
+            sc w = brng.random_scalar();
+            if (alive[bi]) rho[bi] = w;
+        }
+    }
+    if (combined || any_dead)
+        BBP_CUDA_OK(cudaMemcpy2DAsync(ps->chal.as<sc>() + CH_RHO, (size_t)CH_N * 32, rho.data(), 32, 32, B, cudaMemcpyHostToDevice, ctx->stream));
 
-    trace.mark("host_pack+h2d");
     sc_batch SB;
     memset(&SB, 0, sizeof SB);
     SB.n_proofs = B; SB.n1 = n1; SB.q = T.q; SB.m = m; SB.n = n; SB.lg_n = lg; SB.n_pub = T.n_pub; SB.gcols = gcols;
     SB.row_ptr = dt->row_ptr; SB.entries = dt->entries; SB.const_j = dt->const_j; SB.const_idx = dt->const_idx; SB.n_const = (uint32_t)T.const_j.size();
     SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>();
     SB.pub = ps->pub.as<sc>(); SB.dyn_out = ps->dyn_sc.as<sc>(); SB.dyn_stride = ds; SB.stat = ps->stat.as<sc>();
-    if ((rc = ps->sG.ensure((size_t)B * n * 32))) return rc;
     SB.stab = ps->sG.as<sc>();
     k_powers<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
     k_verify_scalars<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
@@ -935,15 +911,23 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     return 0;
 }
 
-// Verify::verify for every request independently (exactly the reference's per-request semantics)
-inline int verify_each(bbp_ctx *ctx, std::vector<verify_job> &jobs) {
+inline void verify_prepare_all(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector<verify_prepared> &prep, std::map<uint64_t, std::vector<size_t>> &groups) {
     proto_state *ps = proto_get(ctx);
-    std::vector<verify_prepared> prep(jobs.size());
     bool versioned = ps->proof_versioned != 0;
-    parallel_for(jobs.size(), [&](size_t i) { verify_prepare(ctx, jobs[i], prep[i], versioned); });
-    std::map<uint64_t, std::vector<size_t>> groups;
+    {
+        phase_trace tp("verify_prepare(host)");
+        parallel_for(jobs.size(), [&](size_t i) { verify_prepare(ctx, jobs[i], prep[i], versioned); });
+        tp.mark("parse");
+    }
     for (size_t i = 0; i < jobs.size(); i++)
         if (prep[i].live) groups[((uint64_t)prep[i].nc << 32) | prep[i].nt].push_back(i);
+}
+
+// Verify::verify for every request independently (exactly the reference's per-request semantics)
+inline int verify_each(bbp_ctx *ctx, std::vector<verify_job> &jobs) {
+    std::vector<verify_prepared> prep(jobs.size());
+    std::map<uint64_t, std::vector<size_t>> groups;
+    verify_prepare_all(ctx, jobs, prep, groups);
     for (auto &g : groups) {
         for (size_t off = 0; off < g.second.size(); off += 1024) {
             std::vector<size_t> part(g.second.begin() + off, g.second.begin() + std::min(g.second.size(), off + 1024));
@@ -955,44 +939,20 @@ inline int verify_each(bbp_ctx *ctx, std::vector<verify_job> &jobs) {
     return 0;
 }
 
-// Batch verification: one random linear combination of all mega-checks, weights drawn from a
-// Merlin transcript over every proof plus the caller's seed. If the combination is the identity every live request is
-// accepted; otherwise the requests are re-checked individually, so the verdicts always equal those of verify_each.
+// Batch verification: one random linear combination of the mega-checks of all requests of a
+// circuit shape. If the combination is the identity every live request is accepted; otherwise the requests are
+// re-checked individually, so the verdicts always equal those of verify_each.
 // partial_only: stop after the combined pass and leave this GPU's partial sum (static | dynamic, 2 x 128 B extended) in
 // d_partial_ext for a cross-GPU reduction (proof-range sharding); *all_ok then reports the local verdict.
 inline int verify_batch(bbp_ctx *ctx, std::vector<verify_job> &jobs, const uint8_t batch_seed[32], int *all_ok, bool partial_only, uint8_t *d_partial_ext) {
-    proto_state *ps = proto_get(ctx);
     std::vector<verify_prepared> prep(jobs.size());
-    bool versioned = ps->proof_versioned != 0;
-    {
-        phase_trace tp("verify_prepare(host)");
-        parallel_for(jobs.size(), [&](size_t i) { verify_prepare(ctx, jobs[i], prep[i], versioned); });
-        tp.mark("transcripts");
-    }
-    // batch weights: a Merlin transcript over one 32-byte digest per request — the verifier scalar r that request's own
-    // transcript produced after absorbing the whole proof (so it binds every proof byte) — keyed with the caller's seed
-    merlin_transcript bt("bbp batch verification");
-    bt.append_u64("n", jobs.size());
-    for (size_t i = 0; i < jobs.size(); i++) {
-        uint8_t dg[32];
-        memset(dg, 0, 32);
-        if (prep[i].live) sc_tobytes(dg, prep[i].chal[CH_R]);
-        bt.append_message("proof", dg, 32);
-    }
-    merlin_rng brng = bt.build_rng().finalize(batch_seed);
     std::map<uint64_t, std::vector<size_t>> groups;
-    std::vector<sc> rho_all(jobs.size());
-    for (size_t i = 0; i < jobs.size(); i++) {
-        rho_all[i] = brng.random_scalar();
-        if (prep[i].live) groups[((uint64_t)prep[i].nc << 32) | prep[i].nt].push_back(i);
-    }
+    verify_prepare_all(ctx, jobs, prep, groups);
     bool ok = true;
     if (partial_only && groups.size() > 1) return BBP_ERR_INPUT;   // sharded mode expects one circuit shape per call
     for (auto &g : groups) {
-        std::vector<sc> rho;
-        for (size_t i : g.second) rho.push_back(rho_all[i]);
         std::vector<uint8_t> verdicts;
-        int rc = verify_group(ctx, jobs, prep, g.second, true, &rho, verdicts, d_partial_ext);
+        int rc = verify_group(ctx, jobs, prep, g.second, true, batch_seed, verdicts, d_partial_ext);
         if (rc) return rc;
         if (!verdicts[0] && !partial_only) {   // the combination failed: find the culprits with one per-request pass
             for (size_t i : g.second) jobs[i].status = 0;

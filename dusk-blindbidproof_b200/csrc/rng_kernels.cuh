@@ -7,6 +7,7 @@
 #pragma once
 #include <cstdint>
 #include "sc25519.cuh"
+#include "sc_kernels.cuh"
 
 namespace bbp {
 
@@ -75,6 +76,48 @@ struct strobe_dev {
         absorb_byte(old_begin);
         absorb_byte(flags);
         if ((flags & (4 | 32)) && pos != 0) run_f();   // FLAG_C | FLAG_K
+    }
+    // ---- the Merlin subset of STROBE operations (bit-exact twins of keccak.h's strobe128 / merlin_transcript)
+    __device__ void absorb(const uint8_t *d, uint32_t n) { for (uint32_t i = 0; i < n; i++) absorb_byte(d[i]); }
+    __device__ void meta_ad_label(const char *label, uint32_t n) { begin_op(16 | 2); for (uint32_t i = 0; i < n; i++) absorb_byte((uint8_t)label[i]); }
+    __device__ void meta_ad_len(uint32_t len) {   // meta_ad(LE32(len), more = true): continues the running meta_ad
+        absorb_byte((uint8_t)len); absorb_byte((uint8_t)(len >> 8)); absorb_byte((uint8_t)(len >> 16)); absorb_byte((uint8_t)(len >> 24));
+    }
+    __device__ void append_message(const char *label, uint32_t llen, const uint8_t *msg, uint32_t n) {
+        meta_ad_label(label, llen);
+        meta_ad_len(n);
+        begin_op(2);                        // ad
+        absorb(msg, n);
+    }
+    __device__ void append_u64(const char *label, uint32_t llen, uint64_t x) {
+        uint8_t b[8];
+        for (int i = 0; i < 8; i++) b[i] = (uint8_t)(x >> (8 * i));
+        append_message(label, llen, b, 8);
+    }
+    __device__ void prf(uint8_t *out, uint32_t n) {
+        begin_op(1 | 2 | 4);
+        uint8_t *s = bytes();
+        for (uint32_t i = 0; i < n; i++) {
+            out[i] = s[pos];
+            s[pos++] = 0;
+            if (pos == BBP_STROBE_R) run_f();
+        }
+    }
+    __device__ void key(const uint8_t *d, uint32_t n) {
+        begin_op(2 | 4);                    // FLAG_A | FLAG_C
+        uint8_t *s = bytes();
+        for (uint32_t i = 0; i < n; i++) {
+            s[pos++] = d[i];
+            if (pos == BBP_STROBE_R) run_f();
+        }
+    }
+    // TranscriptProtocol::challenge_scalar: 64 challenge bytes, wide-reduced
+    __device__ sc challenge_scalar(const char *label, uint32_t llen) {
+        meta_ad_label(label, llen);
+        meta_ad_len(64);
+        uint8_t b[64];
+        prf(b, 64);
+        return sc_from_wide(b);
     }
     // TranscriptRng::fill_bytes(64): meta_ad(LE32(64)) ; prf(64)
     __device__ void fill64(uint8_t *out) {
@@ -161,6 +204,112 @@ __global__ void __launch_bounds__(128) k_wide_reduce(const uint32_t *__restrict_
     sc r2 = sc_r2();
     sc hi = sc_montmul(w + 8, r2.v);
     out[(size_t)(d / per_vec) * vec_stride + (size_t)p * per_vec + d % per_vec] = sc_add(lo, hi);
+}
+
+// ---------------------------------------------------------------- the verifier's transcript replay on the device
+// One thread per request replays Verifier::verify's Fiat-Shamir transcript from the request's blob
+//   [V_0..V_{m-1} | A_I1 A_O1 S1 A_I2 A_O2 S2 | T_1 T_3 T_4 T_5 T_6 | L_0 R_0 .. | t_x t_x_blinding e_blinding | a b]   (32 B each)
+// starting from the exported state after Transcript::new(label) + "r1cs v1" (identical for every request), derives
+// y, z, u, x, w, the u_j, the verifier's random scalar r (TranscriptRng keyed with the request's rng seed), inverts y and
+// the u_j with one exponentiation, and writes the request's challenge block and the transcript-dependent dynamic scalars.
+// The identity / canonical checks of validate_and_append_point and from_bytes are done on the host while parsing.
+#define BBP_LBL(s) s, (uint32_t)(sizeof(s) - 1)
+struct transcript_init { uint8_t state[BBP_STROBE_STATE_BYTES]; };
+
+__global__ void __launch_bounds__(32) k_verify_transcript(transcript_init init, const uint8_t *__restrict__ blobs, uint32_t blob_stride, const uint8_t *__restrict__ seeds,
+                                                          uint32_t n_req, uint32_t m, uint32_t lg, uint64_t n_ipp, sc *__restrict__ chal, sc *__restrict__ dyn,
+                                                          uint32_t dyn_stride) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_req) return;
+    strobe_dev S;
+    {
+        const uint64_t *in = (const uint64_t *)init.state;
+        for (int i = 0; i < 25; i++) S.st[i] = in[i];
+        S.pos = init.state[200]; S.pos_begin = init.state[201];
+    }
+    const uint8_t *blob = blobs + (size_t)p * blob_stride;
+    const uint8_t *pts = blob + 32 * (size_t)m;                   // A_I1 ...
+    const uint8_t *lr = pts + 32 * 11;
+    const uint8_t *scal = lr + 64 * (size_t)lg;                   // t_x, t_x_blinding, e_blinding, a, b
+    sc *c = chal + (size_t)p * CH_N;
+    for (uint32_t i = 0; i < m; i++) S.append_message(BBP_LBL("V"), blob + 32 * (size_t)i, 32);
+    S.append_u64(BBP_LBL("m"), m);
+    S.append_message(BBP_LBL("A_I1"), pts, 32);
+    S.append_message(BBP_LBL("A_O1"), pts + 32, 32);
+    S.append_message(BBP_LBL("S1"), pts + 64, 32);
+    S.append_message(BBP_LBL("dom-sep"), (const uint8_t *)"r1cs-1phase", 11);
+    S.append_message(BBP_LBL("A_I2"), pts + 96, 32);
+    S.append_message(BBP_LBL("A_O2"), pts + 128, 32);
+    S.append_message(BBP_LBL("S2"), pts + 160, 32);
+    sc y = S.challenge_scalar(BBP_LBL("y"));
+    sc z = S.challenge_scalar(BBP_LBL("z"));
+    S.append_message(BBP_LBL("T_1"), pts + 192, 32);
+    S.append_message(BBP_LBL("T_3"), pts + 224, 32);
+    S.append_message(BBP_LBL("T_4"), pts + 256, 32);
+    S.append_message(BBP_LBL("T_5"), pts + 288, 32);
+    S.append_message(BBP_LBL("T_6"), pts + 320, 32);
+    sc u = S.challenge_scalar(BBP_LBL("u"));
+    sc x = S.challenge_scalar(BBP_LBL("x"));
+    S.append_message(BBP_LBL("t_x"), scal, 32);
+    S.append_message(BBP_LBL("t_x_blinding"), scal + 32, 32);
+    S.append_message(BBP_LBL("e_blinding"), scal + 64, 32);
+    sc w = S.challenge_scalar(BBP_LBL("w"));
+    S.append_message(BBP_LBL("dom-sep"), (const uint8_t *)"ipp v1", 6);
+    S.append_u64(BBP_LBL("n"), n_ipp);
+    // prefix products for the batch inversion of (u_0 .. u_{lg-1}, y), in the Montgomery domain
+    sc acc = sc_to_mont(sc_one());
+    for (uint32_t j = 0; j < lg; j++) {
+        S.append_message(BBP_LBL("L"), lr + 64 * (size_t)j, 32);
+        S.append_message(BBP_LBL("R"), lr + 64 * (size_t)j + 32, 32);
+        sc uj = S.challenge_scalar(BBP_LBL("u"));
+        c[CH_UJ0 + j] = uj;
+        c[CH_UJ0 + lg + j] = acc;          // prefix (Montgomery form), replaced by the inverse below
+        acc = sc_montmul(acc.v, sc_to_mont(uj).v);
+    }
+    sc pre_y = acc;
+    acc = sc_montmul(acc.v, sc_to_mont(y).v);
+    // verifier randomness: transcript.build_rng().finalize(rng_seed) -> one scalar
+    S.meta_ad_label(BBP_LBL("rng"));
+    S.key(seeds + 32 * (size_t)p, 32);
+    uint8_t rb[64];
+    S.fill64(rb);
+    sc r = sc_from_wide(rb);
+    // acc = (prod u_j * y) R ; invert once: x^(l-2) in the Montgomery domain
+    sc inv = sc_to_mont(sc_one());
+    for (int i = 252; i >= 0; i--) {
+        inv = sc_montmul(inv.v, inv.v);
+        uint32_t e = sc_l_limb(i >> 5);
+        if (i < 32) e = sc_l_limb(0) - 2;
+        if ((e >> (i & 31)) & 1) inv = sc_montmul(inv.v, acc.v);
+    }
+    sc yinv = sc_from_mont(sc_montmul(inv.v, pre_y.v));
+    inv = sc_montmul(inv.v, sc_to_mont(y).v);
+    sc *d = dyn + (size_t)p * dyn_stride + m;
+    for (uint32_t j = lg; j-- > 0;) {
+        sc uj = c[CH_UJ0 + j];
+        sc ujinv = sc_from_mont(sc_montmul(inv.v, c[CH_UJ0 + lg + j].v));
+        inv = sc_montmul(inv.v, sc_to_mont(uj).v);
+        c[CH_UJ0 + lg + j] = ujinv;
+        d[11 + 2 * j] = sc_mul(uj, uj);            // weight of L_j
+        d[11 + 2 * j + 1] = sc_mul(ujinv, ujinv);  // weight of R_j
+    }
+    sc xx = sc_mul(x, x), xxx = sc_mul(xx, x), rxx = sc_mul(r, xx);
+    d[0] = x; d[1] = xx; d[2] = xxx; d[3] = sc_mul(u, x); d[4] = sc_mul(u, xx); d[5] = sc_mul(u, xxx);
+    d[6] = sc_mul(r, x); d[7] = sc_mul(rxx, x); d[8] = sc_mul(rxx, xx); d[9] = sc_mul(rxx, xxx); d[10] = sc_mul(sc_mul(rxx, xx), xx);
+    sc t;
+    c[CH_Y] = y; c[CH_YINV] = yinv; c[CH_Z] = z; c[CH_X] = x; c[CH_U] = u; c[CH_W] = w; c[CH_R] = r;
+    const uint32_t *sw = (const uint32_t *)scal;
+    for (int k = 0; k < 8; k++) t.v[k] = sw[k];
+    c[CH_TX] = t;
+    for (int k = 0; k < 8; k++) t.v[k] = sw[8 + k];
+    c[CH_TXBL] = t;
+    for (int k = 0; k < 8; k++) t.v[k] = sw[16 + k];
+    c[CH_EBL] = t;
+    for (int k = 0; k < 8; k++) t.v[k] = sw[24 + k];
+    c[CH_A] = t;
+    for (int k = 0; k < 8; k++) t.v[k] = sw[32 + k];
+    c[CH_B] = t;
+    c[CH_RHO] = sc_one();
 }
 
 }  // namespace bbp

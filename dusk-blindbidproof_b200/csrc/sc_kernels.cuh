@@ -375,6 +375,11 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_verify_scalars(sc_batch B) {
         sc wV = flatten_row(B, zpow, 3 * n1 + i);
         B.dyn_out[(size_t)p * B.dyn_stride + i] = sc_from_mont(mm(rhoM, mm(wV, rx2)));
     }
+    // the transcript-dependent dynamic scalars (written unweighted by k_verify_transcript) take the batch weight here
+    for (uint32_t i = B.m + t; i < B.dyn_stride; i += BBP_SC_THREADS) {
+        sc *d = B.dyn_out + (size_t)p * B.dyn_stride + i;
+        *d = mm(rhoM, *d);   // (rho R) * d / R = rho * d
+    }
     if (t == 0) {
         sc txM = sc_to_mont(ch[CH_TX]), wM = sc_to_mont(ch[CH_W]);
         sc bs = sc_add(mm(wM, sc_sub(txM, mm(aM, bM))), mm(rM, sc_sub(mm(x2, sc_add(wc, delta)), txM)));
