@@ -797,6 +797,50 @@ inline void verify_prepare(bbp_ctx *ctx, verify_job &J, verify_prepared &P, bool
     P.live = true;
 }
 
+// Host twin of k_verify_transcript (used for small batches, where one device thread per request is latency bound):
+// fills the request's challenge block (CH_N scalars) and its dynamic scalars [m, ds), unweighted.
+inline void verify_transcript_host(const verify_prepared &P, const uint8_t rng_seed[32], sc *c, sc *dyn) {
+    const uint32_t m = P.m, lg = P.lg;
+    const uint8_t *blob = P.blob.data(), *pts = blob + 32 * (size_t)m, *lr = pts + 32 * 11, *scal = lr + 64 * (size_t)lg;
+    merlin_transcript tr("BlindBidProofGadget");
+    tr.r1cs_domain_sep();
+    for (uint32_t i = 0; i < m; i++) tr.append_point("V", blob + 32 * (size_t)i);
+    tr.append_u64("m", m);
+    tr.append_point("A_I1", pts); tr.append_point("A_O1", pts + 32); tr.append_point("S1", pts + 64);
+    tr.r1cs_1phase_domain_sep();
+    tr.append_point("A_I2", pts + 96); tr.append_point("A_O2", pts + 128); tr.append_point("S2", pts + 160);
+    sc y = tr.challenge_scalar("y"), z = tr.challenge_scalar("z");
+    tr.append_point("T_1", pts + 192); tr.append_point("T_3", pts + 224); tr.append_point("T_4", pts + 256);
+    tr.append_point("T_5", pts + 288); tr.append_point("T_6", pts + 320);
+    sc u = tr.challenge_scalar("u"), x = tr.challenge_scalar("x");
+    tr.append_message("t_x", scal, 32); tr.append_message("t_x_blinding", scal + 32, 32); tr.append_message("e_blinding", scal + 64, 32);
+    sc w = tr.challenge_scalar("w");
+    tr.innerproduct_domain_sep(P.n);
+    std::vector<sc> inv(lg + 1);
+    for (uint32_t j = 0; j < lg; j++) {
+        tr.append_point("L", lr + 64 * (size_t)j);
+        tr.append_point("R", lr + 64 * (size_t)j + 32);
+        inv[j] = c[CH_UJ0 + j] = tr.challenge_scalar("u");
+    }
+    inv[lg] = y;
+    merlin_rng rng = tr.build_rng().finalize(rng_seed);
+    sc r = rng.random_scalar();
+    sc_batch_invert(inv.data(), inv.size());
+    sc *d = dyn + m;
+    for (uint32_t j = 0; j < lg; j++) {
+        c[CH_UJ0 + lg + j] = inv[j];
+        d[11 + 2 * j] = sc_mul(c[CH_UJ0 + j], c[CH_UJ0 + j]);
+        d[11 + 2 * j + 1] = sc_mul(inv[j], inv[j]);
+    }
+    sc xx = sc_mul(x, x), xxx = sc_mul(xx, x), rxx = sc_mul(r, xx);
+    d[0] = x; d[1] = xx; d[2] = xxx; d[3] = sc_mul(u, x); d[4] = sc_mul(u, xx); d[5] = sc_mul(u, xxx);
+    d[6] = sc_mul(r, x); d[7] = sc_mul(rxx, x); d[8] = sc_mul(rxx, xx); d[9] = sc_mul(rxx, xxx); d[10] = sc_mul(sc_mul(rxx, xx), xx);
+    c[CH_Y] = y; c[CH_YINV] = inv[lg]; c[CH_Z] = z; c[CH_X] = x; c[CH_U] = u; c[CH_W] = w; c[CH_R] = r;
+    sc_from_canonical(c[CH_TX], scal); sc_from_canonical(c[CH_TXBL], scal + 32); sc_from_canonical(c[CH_EBL], scal + 64);
+    sc_from_canonical(c[CH_A], scal + 96); sc_from_canonical(c[CH_B], scal + 128);
+    c[CH_RHO] = sc_one();
+}
+
 // GPU part for prepared requests idx[0..B) that share (nc, nt). combined = false: one verdict per request (weight 1);
 // combined = true: ONE random linear combination -> a single verdict; the weights come from a Merlin transcript over one
 // digest per request — the verifier scalar r that request's own transcript yields after absorbing the whole proof, so it
@@ -837,19 +881,33 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
         (rc = h2d(ctx, ps->pub.p, h_pub, (size_t)B * T.n_pub * 32)))
         return rc;
     k_decompress_to_niels_strided<<<(B * ds + 127) / 128, 128, 0, ctx->stream>>>(ps->dyn_pts.p, ds, blob_stride, ps->dyn_niels.p, B * ds, ps->valid.p);
-    transcript_init init;
-    {
-        merlin_transcript tr("BlindBidProofGadget");   // src/blindbid/mod.rs:37
-        tr.r1cs_domain_sep();                            // Verifier::new
-        tr.export_state(init.state);
-    }
-    k_verify_transcript<<<(B + 31) / 32, 32, 0, ctx->stream>>>(init, ps->dyn_pts.p, blob_stride, ps->rng_states.p, B, m, lg, (uint64_t)n, ps->chal.as<sc>(),
-                                                               ps->dyn_sc.as<sc>(), ds);
-    ctx->launches += 2;
-    std::vector<uint8_t> valid((size_t)B * ds);
+    ctx->launches++;
+    // Fiat-Shamir replay: on the device for large batches (one thread per request, ~1.5 ms whatever the batch), on the host
+    // threads otherwise (~40 us per request per thread); BBP_DEVICE_TRANSCRIPT_MIN_BATCH overrides the crossover
+    const char *tr_env = getenv("BBP_DEVICE_TRANSCRIPT_MIN_BATCH");
+    const bool device_replay = B >= (uint32_t)(tr_env ? atoi(tr_env) : (int)(32 * host_threads()));
     std::vector<sc> rvals(combined ? B : 0);
-    if (combined)
-        BBP_CUDA_OK(cudaMemcpy2DAsync(rvals.data(), 32, ps->chal.as<sc>() + CH_R, (size_t)CH_N * 32, 32, B, cudaMemcpyDeviceToHost, ctx->stream));
+    if (device_replay) {
+        transcript_init init;
+        {
+            merlin_transcript tr("BlindBidProofGadget");   // src/blindbid/mod.rs:37
+            tr.r1cs_domain_sep();                            // Verifier::new
+            tr.export_state(init.state);
+        }
+        k_verify_transcript<<<(B + 31) / 32, 32, 0, ctx->stream>>>(init, ps->dyn_pts.p, blob_stride, ps->rng_states.p, B, m, lg, (uint64_t)n,
+                                                                   ps->chal.as<sc>(), ps->dyn_sc.as<sc>(), ds);
+        ctx->launches++;
+        if (combined)
+            BBP_CUDA_OK(cudaMemcpy2DAsync(rvals.data(), 32, ps->chal.as<sc>() + CH_R, (size_t)CH_N * 32, 32, B, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        std::vector<sc> h_chal((size_t)B * CH_N, sc_zero()), h_dyn((size_t)B * ds, sc_zero());
+        parallel_for(B, [&](size_t bi) {
+            verify_transcript_host(prep[idx[bi]], jobs[idx[bi]].rng_seed, &h_chal[bi * CH_N], &h_dyn[bi * ds]);
+            if (combined) rvals[bi] = h_chal[bi * CH_N + CH_R];
+        });
+        if ((rc = h2d(ctx, ps->chal.p, h_chal.data(), h_chal.size() * 32)) || (rc = h2d(ctx, ps->dyn_sc.p, h_dyn.data(), h_dyn.size() * 32))) return rc;
+    }
+    std::vector<uint8_t> valid((size_t)B * ds);
     if ((rc = d2h_sync(ctx, valid.data(), ps->valid.p, valid.size()))) return rc;
     trace.mark("h2d+decompress+transcripts");
 

@@ -197,9 +197,11 @@ def mutations(bid, proof, comm, tc):
     return out
 
 
-@pytest.mark.parametrize("L", [2, 8])
-def test_verify_verdicts_match_oracle(be, L):
-    """accept / reject parity with the oracle, including the error class, over honest and mutated inputs"""
+@pytest.mark.parametrize("L,replay", [(2, "host"), (8, "host"), (8, "device")])
+def test_verify_verdicts_match_oracle(be, L, replay, monkeypatch):
+    """accept / reject parity with the oracle, including the error class, over honest and mutated inputs; with the
+    Fiat-Shamir replay on the host threads (small batches) and on the device (large batches)"""
+    monkeypatch.setenv("BBP_DEVICE_TRANSCRIPT_MIN_BATCH", "1" if replay == "device" else "1000000")
     bid = make_case(50 + L, L)
     rc, proof, comm, tc = orc.blindbid_prove(bid, bid["blindings"], bid["rng_seed"])
     assert rc == 0
