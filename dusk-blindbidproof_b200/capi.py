@@ -269,19 +269,47 @@ def _verify_reqs(items):
     return arr
 
 
+class PreparedProve:
+    """bbp_prove_req array + output buffers built once (the caller's host buffers); reusable across calls."""
+
+    def __init__(self, bids):
+        self.bids = bids
+        self.arr, self.keep = _prove_reqs(bids)
+        self.n = len(bids)
+
+    def results(self):
+        out = []
+        for i, (proof, comm, tc) in enumerate(self.keep):
+            L = len(self.bids[i]["pub_list"]) // 32
+            out.append((self.arr[i].status, proof.raw[:self.arr[i].proof_len], comm.raw, tc.raw[:32 * L]))
+        return out
+
+
+class PreparedVerify:
+    """bbp_verify_req array built once; reusable across calls."""
+
+    def __init__(self, items):
+        self.items = items            # keeps the byte strings alive
+        self.arr = _verify_reqs(items)
+        self.n = len(items)
+
+    def statuses(self):
+        return [self.arr[i].status for i in range(self.n)]
+
+
 def _backend_methods():
     def set_proof_format(self, versioned):
         _chk(lib().bbp_set_proof_format(self.ctx, int(versioned)), "bbp_set_proof_format")
 
     def blindbid_prove_batch(self, bids):
-        """Proof::prove for a list of bids in one GPU pass. Returns [(status, proof, commitments, t_c)]."""
-        arr, keep = _prove_reqs(bids)
-        _chk(lib().bbp_blindbid_prove_batch(self.ctx, _sz(len(bids)), arr), "bbp_blindbid_prove_batch")
-        out = []
-        for i, (proof, comm, tc) in enumerate(keep):
-            L = len(bids[i]["pub_list"]) // 32
-            out.append((arr[i].status, proof.raw[:arr[i].proof_len], comm.raw, tc.raw[:32 * L]))
-        return out
+        """Proof::prove for a list of bids (or a PreparedProve) in one GPU pass. Returns [(status, proof, commitments, t_c)]."""
+        prep = bids if isinstance(bids, PreparedProve) else PreparedProve(bids)
+        _chk(lib().bbp_blindbid_prove_batch(self.ctx, _sz(prep.n), prep.arr), "bbp_blindbid_prove_batch")
+        return prep.results()
+
+    def blindbid_prove_prepared(self, prep):
+        """the bare C call on a PreparedProve (results stay in its buffers: prep.results())"""
+        _chk(lib().bbp_blindbid_prove_batch(self.ctx, _sz(prep.n), prep.arr), "bbp_blindbid_prove_batch")
 
     def blindbid_prove(self, bid):
         return self.blindbid_prove_batch([bid])[0]
@@ -298,18 +326,18 @@ def _backend_methods():
                                          _sz(len(item["pub_list"]) // 32), item["rng_seed"])
 
     def blindbid_verify_batch(self, items, batch_seed):
-        """One combined mega-check; returns (all_ok, statuses)."""
-        arr = _verify_reqs(items)
+        """One combined mega-check over a list of items (or a PreparedVerify); returns (all_ok, statuses)."""
+        prep = items if isinstance(items, PreparedVerify) else PreparedVerify(items)
         ok = ctypes.c_int(0)
-        _chk(lib().bbp_blindbid_verify_batch(self.ctx, _sz(len(items)), arr, batch_seed, ctypes.byref(ok)), "bbp_blindbid_verify_batch")
-        return bool(ok.value), [arr[i].status for i in range(len(items))]
+        _chk(lib().bbp_blindbid_verify_batch(self.ctx, _sz(prep.n), prep.arr, batch_seed, ctypes.byref(ok)), "bbp_blindbid_verify_batch")
+        return bool(ok.value), prep.statuses()
 
     def blindbid_verify_batch_partial(self, items, batch_seed, partial_dev_ptr):
-        arr = _verify_reqs(items)
+        prep = items if isinstance(items, PreparedVerify) else PreparedVerify(items)
         ok = ctypes.c_int(0)
-        _chk(lib().bbp_blindbid_verify_batch_partial(self.ctx, _sz(len(items)), arr, batch_seed, ctypes.c_void_p(partial_dev_ptr), ctypes.byref(ok)),
+        _chk(lib().bbp_blindbid_verify_batch_partial(self.ctx, _sz(prep.n), prep.arr, batch_seed, ctypes.c_void_p(partial_dev_ptr), ctypes.byref(ok)),
              "bbp_blindbid_verify_batch_partial")
-        return bool(ok.value), [arr[i].status for i in range(len(items))]
+        return bool(ok.value), prep.statuses()
 
     def pedersen_commit(self, values, blindings):
         n = len(values) // 32
@@ -322,7 +350,7 @@ def _backend_methods():
         _chk(lib().bbp_msm_gens(self.ctx, scalars, _sz(slot_len), _sz(n_slots), out), "bbp_msm_gens")
         return out.raw
 
-    for f in (set_proof_format, blindbid_prove_batch, blindbid_prove, blindbid_verify_each, blindbid_verify, blindbid_verify_batch,
+    for f in (set_proof_format, blindbid_prove_batch, blindbid_prove_prepared, blindbid_prove, blindbid_verify_each, blindbid_verify, blindbid_verify_batch,
               blindbid_verify_batch_partial, pedersen_commit, msm_gens):
         setattr(Backend, f.__name__, f)
 
