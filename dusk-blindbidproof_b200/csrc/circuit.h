@@ -119,7 +119,8 @@ struct evaluator {
     typedef sc LC;
     const sc *pub;                 // public value table of this proof
     const sc *committed;           // values behind the commitments
-    std::vector<sc> a_L, a_R, a_O;
+    sc *a_L, *a_R, *a_O;           // witness rows, written in place (capacity: the template's n1)
+    uint32_t count = 0;
 
     LC constant(uint32_t pv_index) const { return pub[pv_index]; }
     LC zero() const { return sc_zero(); }
@@ -128,7 +129,8 @@ struct evaluator {
     void constrain(const LC &) {}
     void multiply(const LC &left, const LC &right, LC &l, LC &r, LC &o) {
         l = left; r = right; o = sc_mul(left, right);
-        a_L.push_back(l); a_R.push_back(r); a_O.push_back(o);
+        a_L[count] = l; a_R[count] = r; a_O[count] = o;
+        count++;
     }
 };
 

@@ -507,6 +507,16 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     phase_trace trace("prove_group");
 
     // ---- phase 0: witness + V commitments
+    // the 2 n1 blinding-vector draws run on the device for large batches (one thread per proof continues the transcript RNG;
+    // the chain costs ~19 ms of latency whatever the batch; host threads draw ~2.4 ms per proof each, so the device wins
+    // once the batch exceeds about six proofs per host thread)
+    const char *rng_env = getenv("BBP_DEVICE_RNG_MIN_BATCH");   // read per call so that tests can force either path
+    const int rng_threshold = rng_env ? atoi(rng_env) : (int)(6 * host_threads());
+    const bool device_rng = (int)B >= rng_threshold;
+    // witness staging (pinned, grow-only), vector-major [a_L | a_R | a_O | s_L | s_R], each B x n1: the evaluator writes in place
+    const size_t wit_count = (size_t)B * (device_rng ? 3 : 5) * n1;
+    if ((rc = ps->h_wit.ensure(wit_count * 32))) return rc;
+    sc *wit = ps->h_wit.as<sc>();
     std::vector<sc> commit_vals((size_t)B * m * 2);
     parallel_for(B, [&](size_t bi) {
         prove_job &J = jobs[idx[bi]];
@@ -516,7 +526,7 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
         for (uint32_t i = 0; i < m; i++) { commit_vals[((size_t)bi * m + i) * 2] = H.v[i]; commit_vals[((size_t)bi * m + i) * 2 + 1] = J.blindings[i]; }
         fill_public_values(H.pub, J.seed, J.q, J.z_img, J.pub_list.data(), L);
         H.ev.pub = H.pub.data();
-        H.ev.a_L.reserve(n1); H.ev.a_R.reserve(n1); H.ev.a_O.reserve(n1);
+        H.ev.a_L = &wit[((size_t)0 * B + bi) * n1]; H.ev.a_R = &wit[((size_t)1 * B + bi) * n1]; H.ev.a_O = &wit[((size_t)2 * B + bi) * n1];
         std::vector<sc> toggles(H.v.begin() + 4, H.v.end()), items(J.pub_list.begin(), J.pub_list.end());
         proof_gadget(H.ev, H.v[0], H.v[1], H.v[3], J.q, J.z_img, J.seed, toggles, items);
     });
@@ -526,12 +536,6 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     trace.mark("gpu_V_commit");
 
     // ---- phase 1: transcript up to the blinding draws; upload witness
-    // the 2 n1 blinding-vector draws run on the device for batches (one thread per proof continues the transcript RNG)
-    // (the chain costs ~19 ms of latency whatever the batch; host threads draw ~2.4 ms per proof each, so the device wins
-    // once the batch exceeds about six proofs per host thread)
-    const char *rng_env = getenv("BBP_DEVICE_RNG_MIN_BATCH");   // read per call so that tests can force either path
-    const int rng_threshold = rng_env ? atoi(rng_env) : (int)(6 * host_threads());
-    const bool device_rng = (int)B >= rng_threshold;
     if (device_rng) {
         if ((rc = ps->h_states.ensure((size_t)B * BBP_STROBE_STATE_BYTES))) return rc;
         if (!ps->rng_stream) {
@@ -541,9 +545,6 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
         }
     }
     uint8_t *rng_states = ps->h_states.p;
-    const size_t wit_count = (size_t)B * (device_rng ? 3 : 5) * n1;
-    if ((rc = ps->h_wit.ensure(wit_count * 32))) return rc;
-    sc *wit = ps->h_wit.as<sc>();
     std::vector<sc> vbl((size_t)B * m), blind3((size_t)B * 3);
     parallel_for(B, [&](size_t bi) {
         prove_job &J = jobs[idx[bi]];
@@ -564,9 +565,7 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
         H.rng.reset(new merlin_rng(rb.finalize(J.rng_seed)));
         H.i_bl = H.rng->random_scalar(); H.o_bl = H.rng->random_scalar(); H.s_bl = H.rng->random_scalar();
         blind3[bi * 3] = H.i_bl; blind3[bi * 3 + 1] = H.o_bl; blind3[bi * 3 + 2] = H.s_bl;
-        // witness layout: vector-major [a_L | a_R | a_O | s_L | s_R], each B x n1
         auto W = [&](uint32_t k) { return &wit[((size_t)k * B + bi) * n1]; };
-        for (uint32_t i = 0; i < n1; i++) { W(0)[i] = H.ev.a_L[i]; W(1)[i] = H.ev.a_R[i]; W(2)[i] = H.ev.a_O[i]; }
         if (device_rng) {
             H.rng->export_state(&rng_states[bi * BBP_STROBE_STATE_BYTES]);
         } else {

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_commit_slots(sc_batch B, uin
 }
 
 // ---------------------------------------------------------------- prover: l / r polynomials and t_1 .. t_6
-__global__ void __launch_bounds__(BBP_SC_THREADS) k_polys(sc_batch B) {
+__global__ void __launch_bounds__(BBP_SC_THREADS, 2) k_polys(sc_batch B) {
     __shared__ sc smem[BBP_SC_THREADS];
     const uint32_t p = blockIdx.x, t = threadIdx.x, n1 = B.n1;
     const sc *zpow = B.zpow + (size_t)p * B.q, *ypow = B.ypow + (size_t)p * B.n, *yinv = B.yinvpow + (size_t)p * B.n;
@@ -326,7 +326,7 @@ __device__ inline void build_s_table(sc *stab, const sc *uj, uint32_t lg, uint32
 //   dyn_out[i] = rho * wV[i] r x^2   (coefficients of the V commitments)
 // with s[i] = prod_j u_j^(+-1) (bit (lg n - 1 - j) of i set -> u_j, else u_j^-1), uf = 1 (i < n1) | u, delta = <y^-n wR, wL>.
 // Results stay in Montgomery form; k_stat_reduce sums them over the batch and converts.
-__global__ void __launch_bounds__(BBP_SC_THREADS) k_verify_scalars(sc_batch B) {
+__global__ void __launch_bounds__(BBP_SC_THREADS, 2) k_verify_scalars(sc_batch B) {
     __shared__ sc smem[BBP_SC_THREADS];
     __shared__ sc uj[64];
     const uint32_t p = blockIdx.x, t = threadIdx.x, n = B.n, n1 = B.n1, lg = B.lg_n;
