@@ -478,6 +478,14 @@ struct prove_job {
     std::vector<uint8_t> commitments, t_c;   // 4 x 32, L x 32
 };
 
+// a toggle index beyond the list makes every toggle bit zero (the reference: `x as u64 == toggle`); the device witness
+// kernel handles that as well, this only guards the uint32 narrowing
+inline bool J0_toggle_in_range(const std::vector<prove_job> &jobs, const std::vector<size_t> &idx, uint32_t) {
+    for (size_t i : idx)
+        if (jobs[i].toggle > 0xfffffffeull) return false;
+    return true;
+}
+
 // proves jobs[idx[0..B)] — all with the same list length L
 inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::vector<size_t> &idx) {
     proto_state *ps = proto_get(ctx);
@@ -517,13 +525,24 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     const size_t wit_count = (size_t)B * (device_rng ? 3 : 5) * n1;
     if ((rc = ps->h_wit.ensure(wit_count * 32))) return rc;
     sc *wit = ps->h_wit.as<sc>();
-    std::vector<sc> commit_vals((size_t)B * m * 2);
+    // large batches evaluate the witness on the device too (one thread per proof, k_blindbid_witness); the host evaluator
+    // walks the generic gadget code and is the path for small batches
+    const bool device_witness = device_rng && J0_toggle_in_range(jobs, idx, L);
+    std::vector<sc> commit_vals((size_t)B * m * 2), wit_in(device_witness ? (size_t)B * (4 + L) : 0);
+    std::vector<uint32_t> toggles_u32(device_witness ? B : 0);
     parallel_for(B, [&](size_t bi) {
         prove_job &J = jobs[idx[bi]];
         hstate &H = hs[bi];
         H.v = {J.d, J.k, J.y, J.y_inv};
         for (uint32_t i = 0; i < L; i++) H.v.push_back(sc_from_u64((uint64_t)i == J.toggle ? 1 : 0));
         for (uint32_t i = 0; i < m; i++) { commit_vals[((size_t)bi * m + i) * 2] = H.v[i]; commit_vals[((size_t)bi * m + i) * 2 + 1] = J.blindings[i]; }
+        if (device_witness) {
+            sc *wi = &wit_in[bi * (4 + L)];
+            wi[0] = J.d; wi[1] = J.k; wi[2] = J.y_inv; wi[3] = J.seed;
+            for (uint32_t i = 0; i < L; i++) wi[4 + i] = J.pub_list[i];
+            toggles_u32[bi] = (uint32_t)J.toggle;
+            return;
+        }
         fill_public_values(H.pub, J.seed, J.q, J.z_img, J.pub_list.data(), L);
         H.ev.pub = H.pub.data();
         H.ev.a_L = &wit[((size_t)0 * B + bi) * n1]; H.ev.a_R = &wit[((size_t)1 * B + bi) * n1]; H.ev.a_O = &wit[((size_t)2 * B + bi) * n1];
@@ -583,7 +602,18 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
         (rc = ps->sH.ensure((size_t)B * n * 32)) || (rc = ps->slots.ensure((size_t)B * 3 * slot_len * 32)) || (rc = ps->ab.ensure((size_t)B * 64)) ||
         (rc = ps->msm_out.ensure((size_t)B * 3 * 32)))
         return rc;
-    if ((rc = h2d(ctx, ps->wit.p, wit, wit_count * 32)) || (rc = h2d(ctx, ps->vbl.p, vbl.data(), vbl.size() * 32)) ||
+    if (device_witness) {
+        if ((rc = ps->pub.ensure(wit_in.size() * 32 + 90 * 32 + (size_t)B * 4))) return rc;
+        sc *d_in = ps->pub.as<sc>(), *d_c = d_in + wit_in.size();
+        uint32_t *d_tg = (uint32_t *)(d_c + 90);
+        if ((rc = h2d(ctx, d_in, wit_in.data(), wit_in.size() * 32)) || (rc = h2d(ctx, d_c, mimc_constants().data(), 90 * 32)) ||
+            (rc = h2d(ctx, d_tg, toggles_u32.data(), (size_t)B * 4)))
+            return rc;
+        sc *dwit = ps->wit.as<sc>();
+        k_blindbid_witness<<<(B + 31) / 32, 32, 0, ctx->stream>>>(d_in, d_tg, d_c, B, L, n1, dwit, dwit + (size_t)B * n1, dwit + (size_t)2 * B * n1);
+        ctx->launches++;
+    } else if ((rc = h2d(ctx, ps->wit.p, wit, wit_count * 32))) return rc;
+    if ((rc = h2d(ctx, ps->vbl.p, vbl.data(), vbl.size() * 32)) ||
         (rc = h2d(ctx, ps->blind3.p, blind3.data(), blind3.size() * 32)))
         return rc;
     if (device_rng) {

@@ -144,6 +144,58 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_commit_slots(sc_batch B, uin
     }
 }
 
+// ---------------------------------------------------------------- prover: witness of the blind-bid circuit
+// One thread per proof evaluates the circuit of src/gadgets.rs natively — the same walk the host evaluator (circuit.h)
+// does through the generic gadget code — and writes the multiplier rows (a_L, a_R, a_O) straight into the witness arrays:
+//   MiMC(k, 0) -> m, MiMC(d, m) -> x, booleans t_i (1 - t_i), pairs (item_i, t_i), (t_i, x), MiMC(seed, x) -> y,
+//   MiMC(seed, m), (y, y_inv), (d, y_inv)                       [src/gadgets.rs:6-34; multiplier order = generator index]
+// in: [n_proofs][4 + L] = d, k, y_inv, seed, items[0..L); toggle[p] = index of the bidder's own item; mimc_c = 90 constants.
+struct witness_rows {
+    sc *aL, *aR, *aO;
+    uint32_t i;
+    __device__ __forceinline__ sc mul(const sc &l, const sc &r) {
+        sc o = sc_mul(l, r);
+        aL[i] = l; aR[i] = r; aO[i] = o;
+        i++;
+        return o;
+    }
+};
+__device__ inline sc mimc_rows(witness_rows &W, const sc &left, const sc &key, const sc *__restrict__ c) {
+    sc x = left;
+    for (uint32_t r = 0; r < 90; r++) {
+        sc a = sc_add(sc_add(x, key), c[r]);
+        sc a2 = W.mul(a, a);
+        sc a3 = W.mul(a2, a);
+        sc a4 = W.mul(a2, a2);
+        x = W.mul(a4, a3);
+    }
+    return sc_add(x, key);
+}
+__global__ void __launch_bounds__(32) k_blindbid_witness(const sc *__restrict__ in, const uint32_t *__restrict__ toggle, const sc *__restrict__ mimc_c,
+                                                         uint32_t n_proofs, uint32_t L, uint32_t n1, sc *__restrict__ aL, sc *__restrict__ aR, sc *__restrict__ aO) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_proofs) return;
+    const sc *v = in + (size_t)p * (4 + L);
+    const sc d = v[0], k = v[1], y_inv = v[2], seed = v[3];
+    witness_rows W = {aL + (size_t)p * n1, aR + (size_t)p * n1, aO + (size_t)p * n1, 0};
+    sc m = mimc_rows(W, k, sc_zero(), mimc_c);
+    sc x = mimc_rows(W, d, m, mimc_c);
+    const uint32_t tg = toggle[p];
+    for (uint32_t i = 0; i < L; i++) {               // boolean_gadget: t (1 - t)
+        sc t = (i == tg) ? sc_one() : sc_zero();
+        W.mul(t, sc_sub(sc_one(), t));
+    }
+    for (uint32_t i = 0; i < L; i++) {               // one_of_many: item_i * t_i, t_i * x
+        sc t = (i == tg) ? sc_one() : sc_zero();
+        W.mul(v[4 + i], t);
+        W.mul(t, x);
+    }
+    sc y = mimc_rows(W, seed, x, mimc_c);
+    mimc_rows(W, seed, m, mimc_c);
+    W.mul(y, y_inv);
+    W.mul(d, y_inv);
+}
+
 // ---------------------------------------------------------------- prover: l / r polynomials and t_1 .. t_6
 __global__ void __launch_bounds__(BBP_SC_THREADS, 2) k_polys(sc_batch B) {
     __shared__ sc smem[BBP_SC_THREADS];
