@@ -11,6 +11,9 @@
 
 namespace bbp {
 
+#ifndef BBP_KECCAK_UNROLL
+#define BBP_KECCAK_UNROLL 1
+#endif
 #define BBP_STROBE_R 166
 #define BBP_STROBE_STATE_BYTES 208   // 200 B Keccak state, pos, pos_begin, cur_flags, 5 B padding
 
@@ -22,11 +25,12 @@ __constant__ uint64_t KECCAK_RC_DEV[24] = {
 
 __device__ __forceinline__ uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
 
+static constexpr int keccak_unroll_n = BBP_KECCAK_UNROLL;
 __device__ inline void keccak_f1600_dev(uint64_t *s) {
     uint64_t a00 = s[0], a01 = s[1], a02 = s[2], a03 = s[3], a04 = s[4], a05 = s[5], a06 = s[6], a07 = s[7], a08 = s[8], a09 = s[9], a10 = s[10],
              a11 = s[11], a12 = s[12], a13 = s[13], a14 = s[14], a15 = s[15], a16 = s[16], a17 = s[17], a18 = s[18], a19 = s[19], a20 = s[20],
              a21 = s[21], a22 = s[22], a23 = s[23], a24 = s[24];
-#pragma unroll 1
+#pragma unroll (keccak_unroll_n)
     for (int r = 0; r < 24; r++) {
         uint64_t c0 = a00 ^ a05 ^ a10 ^ a15 ^ a20, c1 = a01 ^ a06 ^ a11 ^ a16 ^ a21, c2 = a02 ^ a07 ^ a12 ^ a17 ^ a22,
                  c3 = a03 ^ a08 ^ a13 ^ a18 ^ a23, c4 = a04 ^ a09 ^ a14 ^ a19 ^ a24;
