@@ -305,3 +305,24 @@ def test_batch_verify_config4_full_size(be):
         assert not ok
         assert [i for i, s in enumerate(st) if s != 0] == bad
         assert st == be.blindbid_verify_each(its)
+
+
+def test_legacy_proof_layout(be):
+    """R1CSProof::to_bytes risk R1 (SURVEY.md §8c): the legacy 14-point layout without the phase byte (1216 B) is selectable
+    and byte-identical to the oracle's legacy form; the two layouts do not verify under each other's parser"""
+    bid = make_case(42, 4)
+    try:
+        be.set_proof_format(0)
+        st, proof, comm, tc = be.blindbid_prove(bid)
+        rc, oproof, ocomm, otc = orc.blindbid_prove(bid, bid["blindings"], bid["rng_seed"], versioned=0)
+        assert st == 0 and rc == 0 and len(proof) == 1216
+        assert (proof, comm, tc) == (oproof, ocomm, otc)
+        item = verify_item(bid, proof, comm, tc)
+        assert be.blindbid_verify(item) == 0
+        assert orc.blindbid_verify(proof, comm, tc, bid["q"], bid["z_img"], bid["seed"], bid["pub_list"], item["rng_seed"], versioned=0) == 0
+        be.set_proof_format(1)
+        assert be.blindbid_verify(item) != 0        # 1216 bytes under the versioned parser: format / verification error
+        st, vproof, _, _ = be.blindbid_prove(bid)
+        assert len(vproof) == 1121 and vproof[1:1 + 96] == proof[:96] and vproof[1 + 96:] == proof[192:]
+    finally:
+        be.set_proof_format(1)
