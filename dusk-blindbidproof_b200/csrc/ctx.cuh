@@ -19,6 +19,8 @@ struct bbp_points {
 struct bbp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;    // one-shot MSMs: point upload + table build overlap the scalar-side pipeline
+    cudaEvent_t ev_table = nullptr, ev_start = nullptr;
     bbp::msm_engine msm;
     uint64_t launches = 0;
     // generators: index 0 = B, 1 = B_blinding, then G[party 0][0..cap), G[party 1][..), ..., then all H the same way, so
@@ -71,6 +73,9 @@ struct bbp_ctx {
         using namespace bbp;
         BBP_CUDA_OK(cudaSetDevice(device));
         BBP_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        BBP_CUDA_OK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        BBP_CUDA_OK(cudaEventCreateWithFlags(&ev_table, cudaEventDisableTiming));
+        BBP_CUDA_OK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
         msm.stream = stream;
         gens_capacity = gens_cap;
         party_capacity = gens_cap ? party_cap : 0;
@@ -118,7 +123,10 @@ struct bbp_ctx {
         bbp::proto_release(proto);
         proto = nullptr;
         cudaFree(d_gens_ext); cudaFree(d_gens_niels); cudaFree(d_in); cudaFree(d_out); cudaFree(d_scratch);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (ev_table) cudaEventDestroy(ev_table);
+        if (ev_start) cudaEventDestroy(ev_start);
         if (stream) cudaStreamDestroy(stream);
-        stream = nullptr;
+        stream = nullptr; copy_stream = nullptr; ev_table = ev_start = nullptr;
     }
 };

@@ -488,6 +488,8 @@ struct msm_engine {
     uint32_t *tile_sums = nullptr, *total = nullptr, *task_perm = nullptr, *len_bins = nullptr;
     uint8_t *partial = nullptr, *lvl[4] = {nullptr, nullptr, nullptr, nullptr};   // lvl: ping-pong (A, R) arrays of the bucket reduction
     uint64_t launches = 0;
+    // one-shot calls build the base table on a copy stream while recode / sort run here: the accumulation waits for this event
+    cudaEvent_t table_ready = nullptr;
     // optional per-stage timing (bbp_set_profiling): events around recode / scans / scatter+fill / accumulate /
     // chunk reduce / window reduce / combine on the launching stream
     static const int N_STAGES = 7;
@@ -595,9 +597,13 @@ struct msm_engine {
         return sh;
     }
 
-    // d_scalars: n x 32 B on device; d_table: niels table; outputs on device (either may be null)
-    int run(const msm_shape &sh, const uint8_t *d_scalars, const uint8_t *d_table, uint8_t *d_out_ext, uint8_t *d_out_compressed) {
+    // d_scalars: n x 32 B on device; d_table: niels table; outputs on device (either may be null).
+    // phase 0 = whole pipeline; 1 = scalar side only (recode, sort, task table: needs no base table); 2 = the rest. A one-shot
+    // call enqueues phase 1, then uploads and converts its points on the copy stream, then enqueues phase 2.
+    int run(const msm_shape &sh, const uint8_t *d_scalars, const uint8_t *d_table, uint8_t *d_out_ext, uint8_t *d_out_compressed, int phase = 0) {
         if (sh.n == 0) return -1;
+        size_t mt = max_tasks(sh);
+        if (phase != 2) {
         int rc = reserve(sh);
         if (rc) return rc;
         BBP_CUDA_OK(cudaMemsetAsync(hist, 0, ((size_t)sh.nkeys + 1) * 4, stream));
@@ -611,12 +617,14 @@ struct msm_engine {
         if (mark(2)) return -100;
         k_scatter<<<(sh.n + 127) / 128, 128, 0, stream>>>(digits, offs, cursor, entries, sh);
         k_task_fill<<<(sh.nkeys + 255) / 256, 256, 0, stream>>>(toffs, task_key, sh.nkeys);
-        size_t mt = max_tasks(sh);
         k_task_hist<<<(unsigned)((mt + 255) / 256), 256, 0, stream>>>(offs, toffs, task_key, len_bins, sh.nkeys, sh.S);
         k_task_bin_scan<<<1, 32, 0, stream>>>(len_bins);
         k_task_perm<<<(unsigned)((mt + 255) / 256), 256, 0, stream>>>(offs, toffs, task_key, len_bins, task_perm, sh.nkeys, sh.S);
         launches += 3;
         if (mark(3)) return -100;
+        }
+        if (phase == 1) return 0;
+        if (table_ready) BBP_CUDA_OK(cudaStreamWaitEvent(stream, table_ready, 0));
         {
             // resident CTAs per SM for the accumulation kernel (register budget 65536 / (128 * MINB)); BBP_ACC_MINB overrides
             static const int minb = [] { const char *e = getenv("BBP_ACC_MINB"); return e ? atoi(e) : 4; }();
