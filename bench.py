@@ -429,14 +429,26 @@ def run_b200(args, rank, world):
         e2e_s = time.perf_counter() - t0
         if world == 1:
             assert r == bytes(d_out.cpu().numpy())
+        # the same call shape over COMPRESSED points (optional_multiscalar_mul: 32 B per point, decompressed on the GPU)
+        h_pts_c = torch.frombuffer(bytearray(pts_c), dtype=torch.uint8).pin_memory()
+        for _ in range(2):
+            be.msm_optional_ptr(h_scalars.data_ptr(), h_pts_c.data_ptr(), n)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            rc_ = be.msm_optional_ptr(h_scalars.data_ptr(), h_pts_c.data_ptr(), n)
+        torch.cuda.synchronize()
+        e2e_c_s = time.perf_counter() - t0
+        if world == 1:
+            assert rc_ == r
         clocks = sampler.stop()
         table.free()
         blindbid = None if args.no_blindbid else run_blindbid(pkg, be, torch, dist, rank, world)
 
-    t_ms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    t_ms = torch.tensor([ms, e2e_s * 1e3, e2e_c_s * 1e3], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = t_ms.tolist()
+    ms, e2e_ms, e2e_c_ms = t_ms.tolist()
     if rank == 0:
         value = n * world * args.steps / (ms * 1e-3)
         e2e_value = n * world * e2e_steps / (e2e_ms * 1e-3)
@@ -461,7 +473,9 @@ def run_b200(args, rank, world):
                        "l2": "inputs (134 MB bases+scalars, 128 MB sort buffers) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"point-range shards x{world}, all-gather of 128 B partial sums" if world > 1 else "1 GPU"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (32 + 128), "d2h_bytes_per_step": 32,
-                    "call": "bbp_msm_vartime(host scalars, host extended points) incl. niels table build"},
+                    "call": "bbp_msm_vartime(host scalars, host extended points) incl. niels table build",
+                    "compressed_points": {"value": n * world * e2e_steps / (e2e_c_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * 64,
+                                          "call": "bbp_msm_optional(host scalars, host compressed points) incl. decompression on the GPU"}},
             "gpu_launches": launches,
             "roofline": {"bound": "int32-multiply", "kernel": "k_accumulate", "achieved": achieved / 1e12, "peak": peak_imad / 1e12,
                          "unit": "T IMAD-eq/s", "frac": achieved / peak_imad, "traffic": traffic,

@@ -151,6 +151,15 @@ class Backend:
         _chk(lib().bbp_msm_vartime(self.ctx, ctypes.c_void_p(scalars_host_ptr), ctypes.c_void_p(points_ext_host_ptr), _sz(n), out), "bbp_msm_vartime")
         return out.raw
 
+    def msm_optional_ptr(self, scalars_host_ptr, points_compressed_host_ptr, n):
+        """bbp_msm_optional on raw host pointers; None when a point fails to decompress."""
+        out = _out(32)
+        rc = lib().bbp_msm_optional(self.ctx, ctypes.c_void_p(scalars_host_ptr), ctypes.c_void_p(points_compressed_host_ptr), _sz(n), out)
+        if rc == BBP_ERR_DECOMPRESS:
+            return None
+        _chk(rc, "bbp_msm_optional")
+        return out.raw
+
     # ---- measurement hooks
     def set_profiling(self, on):
         _chk(lib().bbp_set_profiling(self.ctx, int(on)), "bbp_set_profiling")
