@@ -232,26 +232,30 @@ static int msm_oneshot(bbp_ctx *ctx, const uint8_t *scalars, const uint8_t *poin
     BBP_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_start, 0));
     msm_shape sh = msm_engine::make_shape((uint32_t)n, (uint32_t)n, (uint32_t)n, false, 0, 0, 0);
     if ((rc = ctx->msm.run(sh, ctx->d_in, d_table, nullptr, ctx->d_out, 1))) return rc;   // scalar side, enqueued before the point copies
-    if (compressed) BBP_CUDA_OK(cudaMemsetAsync(d_valid, 1, 4, ctx->copy_stream));
+    BBP_CUDA_OK(cudaStreamWaitEvent(ctx->conv_stream, ctx->ev_start, 0));
+    if (compressed) BBP_CUDA_OK(cudaMemsetAsync(d_valid, 1, 4, ctx->conv_stream));
     const size_t n_chunks = n >= (1u << 16) ? 8 : 1;
     const size_t chunk = ((n + n_chunks - 1) / n_chunks + BBP_NIELS_BATCH - 1) / BBP_NIELS_BATCH * BBP_NIELS_BATCH;
-    for (size_t off = 0; off < n; off += chunk) {
+    size_t ci = 0;
+    for (size_t off = 0; off < n; off += chunk, ci++) {
         size_t cnt = std::min(chunk, n - off);
         BBP_CUDA_OK(cudaMemcpyAsync(d_pts + off * pt_bytes, points + off * pt_bytes, cnt * pt_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        BBP_CUDA_OK(cudaEventRecord(ctx->ev_chunk[ci], ctx->copy_stream));
+        BBP_CUDA_OK(cudaStreamWaitEvent(ctx->conv_stream, ctx->ev_chunk[ci], 0));
         if (compressed) {
-            k_decompress_to_niels<<<(unsigned)((cnt + 127) / 128), 128, 0, ctx->copy_stream>>>((const uint32_t *)(d_pts + off * 32), d_table + off * 96,
+            k_decompress_to_niels<<<(unsigned)((cnt + 127) / 128), 128, 0, ctx->conv_stream>>>((const uint32_t *)(d_pts + off * 32), d_table + off * 96,
                                                                                              (uint32_t)cnt, d_valid, nullptr);
         } else {
             size_t threads = (cnt + BBP_NIELS_BATCH - 1) / BBP_NIELS_BATCH;
-            k_ext_to_niels<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->copy_stream>>>(d_pts + off * 128, d_table + off * 96, (uint32_t)cnt);
+            k_ext_to_niels<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->conv_stream>>>(d_pts + off * 128, d_table + off * 96, (uint32_t)cnt);
         }
         ctx->launches++;
     }
-    BBP_CUDA_OK(cudaEventRecord(ctx->ev_table, ctx->copy_stream));
+    BBP_CUDA_OK(cudaEventRecord(ctx->ev_table, ctx->conv_stream));
     ctx->msm.table_ready = ctx->ev_table;
     rc = ctx->msm.run(sh, ctx->d_in, d_table, nullptr, ctx->d_out, 2);
     ctx->msm.table_ready = nullptr;
-    if (rc) { cudaStreamSynchronize(ctx->copy_stream); return rc; }
+    if (rc) { cudaStreamSynchronize(ctx->conv_stream); return rc; }
     if (compressed) BBP_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_table, 0));
     uint8_t res[32];
     BBP_CUDA_OK(cudaMemcpyAsync(res, ctx->d_out, 32, cudaMemcpyDeviceToHost, ctx->stream));

@@ -19,8 +19,9 @@ struct bbp_points {
 struct bbp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;    // one-shot MSMs: point upload + table build overlap the scalar-side pipeline
-    cudaEvent_t ev_table = nullptr, ev_start = nullptr;
+    cudaStream_t copy_stream = nullptr;    // one-shot MSMs: point upload (copy_stream) and table build (conv_stream) overlap
+    cudaStream_t conv_stream = nullptr;    // the scalar-side pipeline; uploads are never queued behind a conversion kernel
+    cudaEvent_t ev_table = nullptr, ev_start = nullptr, ev_chunk[8] = {};
     bbp::msm_engine msm;
     uint64_t launches = 0;
     // generators: index 0 = B, 1 = B_blinding, then G[party 0][0..cap), G[party 1][..), ..., then all H the same way, so
@@ -74,6 +75,8 @@ struct bbp_ctx {
         BBP_CUDA_OK(cudaSetDevice(device));
         BBP_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         BBP_CUDA_OK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        BBP_CUDA_OK(cudaStreamCreateWithFlags(&conv_stream, cudaStreamNonBlocking));
+        for (auto &e : ev_chunk) BBP_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         BBP_CUDA_OK(cudaEventCreateWithFlags(&ev_table, cudaEventDisableTiming));
         BBP_CUDA_OK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
         msm.stream = stream;
@@ -124,6 +127,9 @@ struct bbp_ctx {
         proto = nullptr;
         cudaFree(d_gens_ext); cudaFree(d_gens_niels); cudaFree(d_in); cudaFree(d_out); cudaFree(d_scratch);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (conv_stream) cudaStreamDestroy(conv_stream);
+        for (auto &e : ev_chunk) if (e) { cudaEventDestroy(e); e = nullptr; }
+        conv_stream = nullptr;
         if (ev_table) cudaEventDestroy(ev_table);
         if (ev_start) cudaEventDestroy(ev_start);
         if (stream) cudaStreamDestroy(stream);
