@@ -1,6 +1,5 @@
 """CPU-side checks of the drop-in boundary: libbbp_b200.so loads, exports every symbol include/bbp.h declares, and
 refuses to run without a GPU (no CPU fallback). No compute calls here."""
-import ctypes
 import os
 import re
 import subprocess

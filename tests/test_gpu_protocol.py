@@ -1,7 +1,6 @@
 """GPU parity, protocol layer: Pedersen commitments, generator-table MSMs, the blind-bid prover (proof bytes identical
 to the oracle's under the same blindings / rng seed — BASELINE config 3) and verifier (same verdicts as the oracle on
 honest, mutated and malformed proofs — configs 1, 4). Everything goes through the C ABI."""
-import ctypes
 import hashlib
 
 import pytest

@@ -1,5 +1,5 @@
 """Overlap host and GPU phases by proving sub-batches on several contexts (one thread each) of the same GPU."""
-import sys, os, time, threading, hashlib
+import sys, os, time, threading
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
