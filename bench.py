@@ -311,6 +311,44 @@ def run_blindbid(pkg, be, torch, dist, rank, world, n_prove=1024, n_verify=1024,
     }
 
 
+def run_rangeproof(pkg, torch, dist, rank, world, device, n_proofs=256, m=64, nbits=64, reps=2):
+    """BASELINE config 5: aggregated 64-bit range proofs, m = 64 parties (4096-element inner-product argument, 1056-byte
+    proofs), n_proofs aggregated proofs per GPU in one batched pass (replicas across GPUs): prove, then verify."""
+    be = pkg.Backend(device=device, gens_capacity=nbits, party_capacity=m)
+    vals = [[int.from_bytes(shake(b"rp-v" + bytes([rank & 255, k & 255, i]), 8), "little") for i in range(m)] for k in range(n_proofs)]
+    bls = b"".join(le32(int.from_bytes(shake(b"rp-bl" + bytes([rank & 255, k & 255, i]), 64), "little") % LO) for k in range(n_proofs) for i in range(m))
+    seeds = b"".join(hashlib.sha256(b"rp%d-%d" % (rank, k)).digest() for k in range(n_proofs))
+    st, proofs, Vs = be.rangeproof_prove_batch(vals, bls, m, nbits, seeds)      # warm-up (tables, allocations)
+    assert not any(st) and len(proofs[0]) == 32 * (9 + 2 * 12)
+    vseeds = bytes(range(32)) * n_proofs
+    assert be.rangeproof_verify_batch(proofs, Vs, m, nbits, vseeds) == [0] * n_proofs
+
+    def tmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        st, proofs2, _ = be.rangeproof_prove_batch(vals, bls, m, nbits, seeds)
+    prove_s = tmax((time.perf_counter() - t0) / reps)
+    assert proofs2 == proofs
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        vst = be.rangeproof_verify_batch(proofs, Vs, m, nbits, vseeds)
+    verify_s = tmax((time.perf_counter() - t0) / reps)
+    assert vst == [0] * n_proofs
+    be.close()
+    return {"parties": m, "bits": nbits, "ipp_len": m * nbits, "proof_bytes": len(proofs[0]), "batch_per_gpu": n_proofs,
+            "prove": {"value": world * n_proofs / prove_s, "unit": "aggregated proofs/s", "ms_per_batch": 1e3 * prove_s},
+            "verify": {"value": world * n_proofs / verify_s, "unit": "aggregated proofs/s", "ms_per_batch": 1e3 * verify_s},
+            "range_statements_per_s_prove": world * n_proofs * m / prove_s}
+
+
 def cpu_blindbid_rates(cores, L=8):
     """oracle prove / verify on `cores` threads, one request per thread (ctypes releases the GIL)"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -444,6 +482,7 @@ def run_b200(args, rank, world):
         clocks = sampler.stop()
         table.free()
         blindbid = None if args.no_blindbid else run_blindbid(pkg, be, torch, dist, rank, world)
+        rangeproof = None if args.no_blindbid else run_rangeproof(pkg, torch, dist, rank, world, local)
 
     t_ms = torch.tensor([ms, e2e_s * 1e3, e2e_c_s * 1e3], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -489,6 +528,8 @@ def run_b200(args, rank, world):
         }
         if blindbid is not None:
             line["blindbid"] = blindbid
+        if rangeproof is not None:
+            line["rangeproof_m64"] = rangeproof
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             rate, secs = cpu_msm_rate(1 << 18, cores, 2)
