@@ -4,6 +4,10 @@
 // (SURVEY.md §2.2 U6, §8 a-4, a-5, a-7). Call sites in the reference: src/blindbid/proof.rs:50-88,
 // src/blindbid/verify.rs:51-88, src/gadgets.rs (multiply / constrain).
 // Only the one-phase (no randomized constraints) flow the reference circuit exercises is restated.
+// PARITY STATUS: the group / field / scalar / Merlin layers underneath are pinned (RFC 9496, libsodium, Merlin's vector:
+// tests/test_oracle_primitives.py); at PROOF-BYTE level parity is UNPINNED — the reference ships no tests or vectors, its
+// Rust dependencies cannot be built here, so transcript labels, draw order and the R1CSProof byte layout are restated from
+// the pinned upstream revision and checked only for self-consistency (SURVEY.md §8c risks R1-R4).
 // RNG contract: the 32 "external" bytes that the reference draws from thread_rng in
 // TranscriptRngBuilder::finalize are an explicit argument.
 #pragma once

@@ -2,6 +2,7 @@
 // bulletproofs 1.0.4 aggregated range proofs: RangeProof::{prove_multiple, verify_multiple} with the
 // dealer/party MPC run in-process. The reference itself has no call site;
 // BASELINE.json configs[4] names it (m = 64 parties x n = 64 bits => 4096-point IPP).
+// PARITY STATUS: proof-byte level parity UNPINNED (no reference vectors; see r1cs.h). 
 // RNG contract: upstream draws from the caller's rng directly (not a TranscriptRng). Here the rng is the
 // SHAKE256 stream of a 32-byte seed, consumed 64 bytes per Scalar::random in upstream's draw order
 // (per party j: a_blinding, s_blinding, s_L[0..n), s_R[0..n); then per party: t_1_blinding, t_2_blinding).
