@@ -210,6 +210,62 @@ __global__ void __launch_bounds__(128) k_wide_reduce(const uint32_t *__restrict_
     out[(size_t)(d / per_vec) * vec_stride + (size_t)p * per_vec + d % per_vec] = sc_add(lo, hi);
 }
 
+// ---------------------------------------------------------------- SHAKE256 draw stream on the device (aggregated range proofs)
+// The range-proof prover draws 2 m (1 + n) + 2 m scalars per proof from SHAKE256(seed) (rangeproof.cuh RNG contract):
+// one thread per proof squeezes the whole stream (one Keccak-f per 136 bytes, state in registers), writing raw 64-byte
+// draws; k_rp_draw_scatter reduces them mod l in parallel and routes them to s_L / s_R or to the small per-party list the
+// host sums (a_blinding, s_blinding, t_1 / t_2 blindings).
+__global__ void __launch_bounds__(32) k_shake_draws(const uint8_t *__restrict__ seeds, uint32_t n_proofs, uint32_t n_draws, uint32_t *__restrict__ raw) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_proofs) return;
+    uint64_t r[25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) r[i] = 0;
+    const uint64_t *sd = (const uint64_t *)(seeds + 32 * (size_t)p);
+    r[0] = sd[0]; r[1] = sd[1]; r[2] = sd[2]; r[3] = sd[3];
+    r[4] ^= 0x1fULL;                       // SHAKE domain separation + first pad bit right after the 32 absorbed bytes
+    r[16] ^= 0x8000000000000000ULL;        // last pad bit at byte 135 (rate 136)
+    keccak_f1600_dev(r);
+    uint64_t *out = (uint64_t *)(raw + (size_t)p * n_draws * 16);
+    const size_t total_words = (size_t)n_draws * 8;   // 64-bit words to produce
+    size_t w = 0;
+    while (w < total_words) {
+#pragma unroll
+        for (int i = 0; i < 17; i++)
+            if (w + i < total_words) out[w + i] = r[i];
+        w += 17;
+        if (w < total_words) keccak_f1600_dev(r);
+    }
+}
+// draw d of proof p: party j = d / (2 + 2 n) for d < m (2 + 2 n): slot 0 = a_blinding, 1 = s_blinding, then s_L, s_R;
+// the last 2 m draws are (t_1, t_2) blindings per party. small: [n_proofs][4][m] = a, s, t1, t2 blindings.
+__global__ void __launch_bounds__(128) k_rp_draw_scatter(const uint32_t *__restrict__ raw, uint32_t n_proofs, uint32_t m, uint32_t nbits, sc *__restrict__ sL,
+                                                         sc *__restrict__ sR, sc *__restrict__ small) {
+    const uint32_t per_party = 2 + 2 * nbits, n_draws = m * per_party + 2 * m;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n_proofs * n_draws) return;
+    uint32_t p = (uint32_t)(i / n_draws), d = (uint32_t)(i % n_draws);
+    uint32_t w[16];
+    const uint4 *q = (const uint4 *)(raw + i * 16);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { uint4 v = q[k]; w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
+    sc lo = sc_reduce_words(w);
+    sc r2 = sc_r2();
+    sc hi = sc_montmul(w + 8, r2.v);
+    sc val = sc_add(lo, hi);
+    const size_t nm = (size_t)m * nbits;
+    if (d < m * per_party) {
+        uint32_t j = d / per_party, e = d % per_party;
+        if (e == 0) small[((size_t)p * 4 + 0) * m + j] = val;
+        else if (e == 1) small[((size_t)p * 4 + 1) * m + j] = val;
+        else if (e < 2 + nbits) sL[(size_t)p * nm + (size_t)j * nbits + (e - 2)] = val;
+        else sR[(size_t)p * nm + (size_t)j * nbits + (e - 2 - nbits)] = val;
+    } else {
+        uint32_t t = d - m * per_party, j = t / 2;
+        small[((size_t)p * 4 + 2 + (t & 1)) * m + j] = val;
+    }
+}
+
 // ---------------------------------------------------------------- the verifier's transcript replay on the device
 // One thread per request replays Verifier::verify's Fiat-Shamir transcript from the request's blob
 //   [V_0..V_{m-1} | A_I1 A_O1 S1 A_I2 A_O2 S2 | T_1 T_3 T_4 T_5 T_6 | L_0 R_0 .. | t_x t_x_blinding e_blinding | a b]   (32 B each)

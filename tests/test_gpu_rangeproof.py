@@ -68,11 +68,13 @@ def test_rangeproof_small_matches_oracle():
     be.close()
 
 
-@pytest.mark.parametrize("hybrid", ["0", "2"])
-def test_rangeproof_config5_shape(hybrid, monkeypatch):
+@pytest.mark.parametrize("hybrid,device_rng", [("0", "1000000"), ("2", "1000000"), ("2", "1")])
+def test_rangeproof_config5_shape(hybrid, device_rng, monkeypatch):
     """m = 64, n = 64: 4096-element IPP, 12 rounds, 1056-byte proof, byte-identical to the oracle; batch of 3; with the
-    plain and the hybrid (materialised bases) inner-product argument"""
+    plain and the hybrid (materialised bases) inner-product argument, and with the SHAKE256 draw stream squeezed on the
+    host or on the device"""
     monkeypatch.setenv("BBP_IPP_HYBRID", hybrid)
+    monkeypatch.setenv("BBP_DEVICE_RNG_MIN_BATCH", device_rng)
     be = backend(64, 64)
     seeds = [hashlib.sha256(b"rp%d" % i).digest() for i in range(3)]
     vals = [[from_le(hashlib.shake_256(b"rp-v" + bytes([i, k])).digest(8)) for i in range(64)] for k in range(3)]
