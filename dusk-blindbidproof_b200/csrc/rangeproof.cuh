@@ -303,7 +303,14 @@ inline int rp_verify_group(bbp_ctx *ctx, std::vector<rp_verify_job> &jobs, uint3
         for (size_t j = 0; j < lg_p; j++) { ch[CH_UJ0 + j] = uj[j]; ch[CH_UJ0 + lg_p + j] = allinv[j]; }
         // B and B_blinding coefficients
         sc zz = sc_mul(z, z);
-        auto sum_pow = [&](const sc &base, size_t cnt) { sc s = sc_zero(), e = sc_one(); for (size_t k = 0; k < cnt; k++) { s = sc_add(s, e); e = sc_mul(e, base); } return s; };
+        // 1 + base + ... + base^(cnt-1): geometric series in closed form for long ranges (cnt = n m = 4096 for y), plain loop otherwise
+        auto sum_pow = [&](const sc &base, size_t cnt) {
+            sc bm1 = sc_sub(base, sc_one());
+            if (cnt >= 64 && !sc_iszero(bm1)) return sc_mul(sc_sub(sc_pow_u64(base, cnt), sc_one()), sc_invert(bm1));
+            sc s = sc_zero(), e = sc_one();
+            for (size_t k = 0; k < cnt; k++) { s = sc_add(s, e); e = sc_mul(e, base); }
+            return s;
+        };
         sc sum_y = sum_pow(y, nm), sum_2 = sum_pow(sc_from_u64(2), nbits), sum_z = sum_pow(z, m);
         sc delta = sc_sub(sc_mul(sc_sub(z, zz), sum_y), sc_mul(sc_mul(sc_mul(zz, z), sum_2), sum_z));
         ch[CH_TX] = sc_add(sc_mul(w, sc_sub(t_x, sc_mul(a, b))), sc_mul(c, sc_sub(delta, t_x)));
