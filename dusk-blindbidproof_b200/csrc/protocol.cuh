@@ -215,6 +215,8 @@ struct proto_state {
     uint8_t *wtable2 = nullptr;    // same with WT2_C-bit windows
     uint32_t *colmap = nullptr;    // compact slot -> generator column map of the materialisation MSM
     uint32_t colmap_n = 0, colmap_gcols = 0;
+    uint32_t *ipp_colmap = nullptr;   // early IPP rounds, compact slots: lg n maps of 2 (1 + n) generator columns (L slot, R slot)
+    uint32_t ipp_colmap_n = 0, ipp_colmap_gcols = 0;
     dev_buf fext, ftab;            // materialised folded bases: extended, then niels (+ B at the tail)
     dev_buf chal, zpow, ypow, yinvpow, wit, vbl, blind3, poly, tout, a, b, sG, sH, slots, ab, pub, dyn_sc, dyn_pts, dyn_niels, stat, stat_red,
         msm_out, msm_ext, flags, valid, commit_in, commit_out, rng_states, rng_raw;
@@ -232,7 +234,7 @@ inline proto_state *proto_get(bbp_ctx *ctx) {
 void proto_release(proto_state *ps) {
     if (!ps) return;
     for (auto &kv : ps->templates) { cudaFree(kv.second.row_ptr); cudaFree(kv.second.entries); cudaFree(kv.second.const_j); cudaFree(kv.second.const_idx); }
-    cudaFree(ps->comb); cudaFree(ps->wtable); cudaFree(ps->wtable2); cudaFree(ps->colmap);
+    cudaFree(ps->comb); cudaFree(ps->wtable); cudaFree(ps->wtable2); cudaFree(ps->colmap); cudaFree(ps->ipp_colmap);
     ps->fext.release(); ps->ftab.release();
     dev_buf *all[] = {&ps->chal, &ps->zpow, &ps->ypow, &ps->yinvpow, &ps->wit, &ps->vbl, &ps->blind3, &ps->poly, &ps->tout, &ps->a, &ps->b, &ps->sG, &ps->sH,
                       &ps->slots, &ps->ab, &ps->pub, &ps->dyn_sc, &ps->dyn_pts, &ps->dyn_niels, &ps->stat, &ps->stat_red, &ps->msm_out, &ps->msm_ext,
@@ -345,6 +347,31 @@ inline int ipp_rounds(bbp_ctx *ctx, sc_batch &SB, uint32_t P, std::vector<sc> &c
     int rc;
     std::vector<uint8_t> lr((size_t)P * 64);
     SB.fac_n = n; SB.late = 0;
+    const char *cp_env = getenv("BBP_IPP_COMPACT");
+    SB.compact = (cp_env ? atoi(cp_env) : 1) && n >= 4;
+    const uint32_t cslot = 1 + n;
+    if (SB.compact && (ps->ipp_colmap_n != n || ps->ipp_colmap_gcols != gcols)) {
+        // round j, slot s (0 = L, 1 = R), entry e: e = 0 -> B; then n/2 G columns and n/2 H columns, block by block
+        std::vector<uint32_t> cm((size_t)lg * 2 * cslot);
+        for (uint32_t j = 0; j < lg; j++) {
+            const uint32_t nj = n >> j, nh = nj >> 1, half = n >> 1;
+            for (uint32_t s = 0; s < 2; s++) {
+                uint32_t *o = &cm[((size_t)j * 2 + s) * cslot];
+                o[0] = 0;
+                for (uint32_t e = 0; e < n; e++) {
+                    uint32_t fam = e >= half, tt = e % half, blk = tt / nh, off = tt % nh, lo = blk * nj + off, hi = lo + nh;
+                    uint32_t idx = (s == 0) ? (fam == 0 ? hi : lo) : (fam == 0 ? lo : hi);
+                    o[1 + e] = 2 + fam * gcols + idx;
+                }
+            }
+        }
+        cudaFree(ps->ipp_colmap);
+        ps->ipp_colmap = nullptr;
+        BBP_CUDA_OK(cudaMalloc(&ps->ipp_colmap, cm.size() * 4));
+        BBP_CUDA_OK(cudaMemcpyAsync(ps->ipp_colmap, cm.data(), cm.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        ps->ipp_colmap_n = n; ps->ipp_colmap_gcols = gcols;
+    }
     if ((rc = ps->msm_out.ensure((size_t)P * 64))) return rc;
     for (uint32_t j = 0; j < lg; j++) {
         uint32_t mode = 0;
@@ -382,7 +409,11 @@ inline int ipp_rounds(bbp_ctx *ctx, sc_batch &SB, uint32_t P, std::vector<sc> &c
         }
         k_ipp_round<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB, j, mode);
         ctx->launches++;
-        if (!SB.late) {
+        if (!SB.late && SB.compact) {
+            msm_shape sh = msm_engine::make_shape(2 * P * cslot, cslot, cslot, true, WT_C, WT_W, (uint32_t)ctx->n_gens);
+            sh.ref_mode = 1; sh.colmap = ps->ipp_colmap + (size_t)j * 2 * cslot; sh.colmap_len = 2 * cslot;
+            if ((rc = ctx->msm.run(sh, (const uint8_t *)SB.slots, ps->wtable, nullptr, ps->msm_out.p))) return rc;
+        } else if (!SB.late) {
             if ((rc = msm_gens_device(ctx, SB.slots, slot_len, 2 * P, ps->msm_out.p, nullptr))) return rc;
         } else {
             const uint32_t sl = 2 * nf + 1;

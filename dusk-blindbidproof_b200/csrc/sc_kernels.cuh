@@ -55,6 +55,8 @@ struct sc_batch {
     // hybrid IPP: after the first rounds the folded bases ARE materialised once (n_f per family), later rounds work on them
     uint32_t fac_n;                            // length of the live part of sG / sH (n, or n_f after materialisation)
     uint32_t late;                             // 0: slots over [B, B_bl, G, H] of the generator table; 1: [F_G, F_H, B]
+    uint32_t compact;                          // early rounds: 1 = slots hold only the non-zero half of the columns
+                                               // ([B | n/2 G terms | n/2 H terms], addressed through a per-round column map)
     sc *mat;                                   // [n_proofs][2 n] compact scalars of the materialisation MSM
     // aggregated range proofs (bulletproofs RangeProof::prove_multiple / verify_multiple)
     const uint64_t *rp_values;                 // [n_proofs][rp_m]
@@ -296,6 +298,24 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_ipp_round(sc_batch B, uint32
     }
     cl = block_sum_sc(cl, smem);
     cr = block_sum_sc(cr, smem);
+    if (B.compact && !B.late) {
+        // compact early-round slots: L = [c_L w | a_lo * G_hi | b_hi * H_lo], R = [c_R w | a_hi * G_lo | b_lo * H_hi], n/2 terms each,
+        // enumerated block by block (tt = block * nh + off); the engine maps entry e to its generator column (ipp_colmap)
+        const uint32_t slot_len = 1 + n, half = n >> 1;
+        sc *sl = B.slots + (size_t)(2 * p) * slot_len, *sr = sl + slot_len;
+        if (t == 0) {
+            sc wM = sc_to_mont(ch[CH_W]);
+            sl[0] = sc_from_mont(mm(cl, wM)); sr[0] = sc_from_mont(mm(cr, wM));
+        }
+        for (uint32_t tt = t; tt < half; tt += BBP_SC_THREADS) {
+            uint32_t blk = tt / nh, off = tt % nh, lo = blk * nj + off, hi = lo + nh;
+            sl[1 + tt] = sc_from_mont(mm(a[off], sG[hi]));
+            sl[1 + half + tt] = sc_from_mont(mm(b[off + nh], sH[lo]));
+            sr[1 + tt] = sc_from_mont(mm(a[off + nh], sG[lo]));
+            sr[1 + half + tt] = sc_from_mont(mm(b[off], sH[hi]));
+        }
+        return;
+    }
     // slot layout: early rounds [B, B_bl, G[0..gc), H[0..gc)]; late rounds [F_G[0..fn), F_H[0..fn), B]
     const uint32_t gc = B.late ? fn : B.gcols, hdr = B.late ? 0 : 2, slot_len = B.late ? 2 * fn + 1 : 2 + 2 * gc;
     sc *sl = B.slots + (size_t)(2 * p) * slot_len, *sr = sl + slot_len;
