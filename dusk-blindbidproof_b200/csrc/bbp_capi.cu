@@ -35,7 +35,12 @@ void bbp_free(bbp_ctx *ctx) {
     delete ctx;
 }
 
-uint64_t bbp_launch_count(const bbp_ctx *ctx) { return ctx ? ctx->launches + ctx->msm.launches : 0; }
+uint64_t bbp_launch_count(const bbp_ctx *ctx) {
+    if (!ctx) return 0;
+    uint64_t n = ctx->launches + ctx->msm.launches;
+    for (const bbp_ctx *l : ctx->lanes) n += l->launches + l->msm.launches;
+    return n;
+}
 uint64_t bbp_stream(const bbp_ctx *ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
 int bbp_sync(bbp_ctx *ctx) {
     if (!ctx) return BBP_ERR_INPUT;

@@ -3,6 +3,7 @@
 // (src/blindbid/mod.rs:34-40: PedersenGens::default(), BulletproofGens::new(2048, 1)); here it is built once on the
 // GPU (SHAKE256 stream on the host, Elligator maps + additions in k_from_uniform) and stays in HBM.
 #pragma once
+#include <vector>
 #include "../../include/bbp.h"
 #include "codec.cuh"
 #include "keccak.h"
@@ -33,6 +34,9 @@ struct bbp_ctx {
     uint8_t pc_compressed[64];
     // protocol layer state (templates, tables, scratch): protocol.cuh
     bbp::proto_state *proto = nullptr;
+    // sibling contexts on the same device (own streams, scratch and tables) that large batched prove calls are split
+    // over, one host thread each, so that one lane's host phases and round trips hide behind the others' kernels
+    std::vector<bbp_ctx *> lanes;
     // staging
     uint8_t *d_in = nullptr, *d_out = nullptr, *d_scratch = nullptr;
     size_t cap_in = 0, cap_out = 0, cap_scratch = 0;
@@ -121,6 +125,8 @@ struct bbp_ctx {
 
     void destroy() {
         cudaSetDevice(device);
+        for (bbp_ctx *l : lanes) { l->destroy(); delete l; }
+        lanes.clear();
         if (stream) cudaStreamSynchronize(stream);
         msm.release();
         bbp::proto_release(proto);

@@ -785,6 +785,28 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     return 0;
 }
 
+// Lanes a large prove batch is split over (BBP_PROVE_LANES, default 3; 1 = off). The proof bytes do not depend on it:
+// requests are independent and every per-request draw is keyed by the request's own seed.
+inline size_t prove_lanes() {
+    const char *e = getenv("BBP_PROVE_LANES");
+    int v = e ? atoi(e) : 3;
+    return (size_t)std::min(std::max(v, 1), 8);
+}
+
+inline int prove_lane_ctx(bbp_ctx *ctx, size_t k, bbp_ctx **out) {
+    if (k == 0) { *out = ctx; return 0; }
+    while (ctx->lanes.size() < k) {
+        bbp_ctx *l = new bbp_ctx();
+        l->device = ctx->device;
+        int rc = l->init(ctx->gens_capacity, ctx->party_capacity);
+        if (rc) { l->destroy(); delete l; return rc; }
+        ctx->lanes.push_back(l);
+    }
+    *out = ctx->lanes[k - 1];
+    proto_get(*out)->proof_versioned = proto_get(ctx)->proof_versioned;
+    return 0;
+}
+
 // Proof::prove for a batch of requests; groups by list length
 inline int prove_batch(bbp_ctx *ctx, std::vector<prove_job> &jobs) {
     std::map<size_t, std::vector<size_t>> groups;
@@ -794,14 +816,45 @@ inline int prove_batch(bbp_ctx *ctx, std::vector<prove_job> &jobs) {
         if (L == 0 || J.blindings.size() != 4 + L) { J.status = BBP_ERR_INPUT; continue; }   // the reference panics (gadgets.rs:103)
         groups[L].push_back(i);
     }
+    // parts: at most 1024 proofs each (bounds the device footprint), cut evenly; several parts run on parallel lanes
+    // (cutting a batch of <= 1024 measured no gain: smaller launches lose what the overlap wins)
+    const size_t K = prove_lanes();
+    const char *pe = getenv("BBP_PROVE_PART");   // tests shrink the part size to drive the lanes with a handful of requests
+    const size_t part_max = pe ? (size_t)std::min(std::max(atoi(pe), 1), 1024) : 1024;
+    std::vector<std::vector<size_t>> parts;
     for (auto &g : groups) {
-        // bound the device footprint: at most 1024 proofs per launch group
-        for (size_t off = 0; off < g.second.size(); off += 1024) {
-            std::vector<size_t> part(g.second.begin() + off, g.second.begin() + std::min(g.second.size(), off + 1024));
+        const size_t sz = g.second.size(), cuts = (sz + part_max - 1) / part_max, per = (sz + cuts - 1) / cuts;
+        for (size_t off = 0; off < sz; off += per) parts.emplace_back(g.second.begin() + off, g.second.begin() + std::min(sz, off + per));
+    }
+    const size_t n_lanes = std::min(K, parts.size());
+    if (n_lanes <= 1) {
+        for (auto &part : parts) {
             int rc = prove_group(ctx, jobs, part);
             if (rc) return rc;
         }
+        return 0;
     }
+    std::vector<bbp_ctx *> lane(n_lanes);
+    for (size_t k = 0; k < n_lanes; k++) {
+        int rc = prove_lane_ctx(ctx, k, &lane[k]);
+        if (rc) return rc;
+    }
+    std::atomic<size_t> next{0};
+    std::vector<int> rcs(n_lanes, 0);
+    auto work = [&](size_t k) {
+        cudaSetDevice(ctx->device);
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= parts.size()) return;
+            int rc = prove_group(lane[k], jobs, parts[i]);
+            if (rc) { rcs[k] = rc; return; }
+        }
+    };
+    std::vector<std::thread> th;
+    for (size_t k = 1; k < n_lanes; k++) th.emplace_back(work, k);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int rc : rcs) if (rc) return rc;
     return 0;
 }
 

@@ -144,6 +144,26 @@ def test_prove_batch_device_rng_matches_oracle(be, monkeypatch):
             assert be.blindbid_prove(bid) == (st, proof, comm, tc)
 
 
+def test_prove_batch_lanes_match_oracle(be, monkeypatch):
+    """batches above the part size (1024; shrunk here) are cut into parts proved concurrently on sibling contexts of the
+    same GPU: the bytes must not depend on the cut, and the launch counter must include the sibling contexts"""
+    cases = [make_case(500 + i, L) for i, L in enumerate([2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 5, 5, 5, 5])]
+    monkeypatch.setenv("BBP_PROVE_PART", "4")
+    monkeypatch.setenv("BBP_PROVE_LANES", "3")
+    l0 = be.launch_count()
+    outs = be.blindbid_prove_batch(cases)
+    l1 = be.launch_count()
+    monkeypatch.setenv("BBP_PROVE_LANES", "1")
+    serial = be.blindbid_prove_batch(cases)
+    l2 = be.launch_count()
+    assert outs == serial
+    assert l1 - l0 == l2 - l1 > 0
+    for i in (0, 3, 4, 9, 10, 13):
+        bid = cases[i]
+        rc, oproof, ocomm, otc = orc.blindbid_prove(bid, bid["blindings"], bid["rng_seed"])
+        assert rc == 0 and outs[i] == (0, oproof, ocomm, otc), i
+
+
 def mutations(bid, proof, comm, tc):
     """(name, item) pairs; each must be rejected. Mirrors SURVEY.md §4.4-3."""
     out = []
