@@ -440,11 +440,13 @@ int bbp_blindbid_prove(bbp_ctx *ctx, const uint8_t d[32], const uint8_t k[32], c
 }
 
 static int load_verify_jobs(size_t n, bbp_verify_req *reqs, std::vector<verify_job> &jobs, std::vector<size_t> &map) {
-    for (size_t i = 0; i < n; i++) {
+    std::vector<verify_job> all(n);
+    std::vector<uint8_t> good(n, 0);
+    parallel_for(n, [&](size_t i) {
         bbp_verify_req &R = reqs[i];
         R.status = BBP_ERR_INPUT;
-        if (!R.proof || !R.commitments || !R.t_c || !R.score || !R.z_img || !R.seed || (!R.pub_list && R.L) || !R.rng_seed) continue;
-        verify_job J;
+        if (!R.proof || !R.commitments || !R.t_c || !R.score || !R.z_img || !R.seed || (!R.pub_list && R.L) || !R.rng_seed) return;
+        verify_job &J = all[i];
         J.proof.assign(R.proof, R.proof + R.proof_len);
         J.commitments.assign(R.commitments, R.commitments + 32 * R.n_commitments);
         J.t_c.assign(R.t_c, R.t_c + 32 * R.n_t_c);
@@ -452,9 +454,18 @@ static int load_verify_jobs(size_t n, bbp_verify_req *reqs, std::vector<verify_j
         J.pub_list.resize(R.L);
         for (size_t k = 0; k < R.L; k++) J.pub_list[k] = sc_from_bits(R.pub_list + 32 * k);   // src/blindbid/verify.rs:112-116
         memcpy(J.rng_seed, R.rng_seed, 32);
-        map.push_back(i);
-        jobs.push_back(std::move(J));
+        good[i] = 1;
+    });
+    bool every = true;
+    for (size_t i = 0; i < n; i++) every = every && good[i];
+    if (every) {
+        jobs = std::move(all);
+        map.resize(n);
+        for (size_t i = 0; i < n; i++) map[i] = i;
+        return 0;
     }
+    for (size_t i = 0; i < n; i++)
+        if (good[i]) { map.push_back(i); jobs.push_back(std::move(all[i])); }
     return 0;
 }
 
@@ -486,14 +497,17 @@ int bbp_blindbid_verify(bbp_ctx *ctx, const uint8_t *proof, size_t proof_len, co
 int bbp_blindbid_verify_batch(bbp_ctx *ctx, size_t n, bbp_verify_req *reqs, const uint8_t batch_seed[32], int *all_ok) {
     if (!ctx || !reqs || n == 0 || !batch_seed) return BBP_ERR_INPUT;
     cudaSetDevice(ctx->device);
+    phase_trace tc("bbp_blindbid_verify_batch");
     std::vector<verify_job> jobs;
     std::vector<size_t> map;
     load_verify_jobs(n, reqs, jobs, map);
+    tc.mark("load_requests");
     int ok = 1;
     if (!jobs.empty()) {
         int rc = verify_batch(ctx, jobs, batch_seed, &ok, false, nullptr);
         if (rc) return rc;
     }
+    tc.mark("verify_batch");
     for (size_t k = 0; k < jobs.size(); k++) reqs[map[k]].status = jobs[k].status;
     if (jobs.size() != n) ok = 0;
     if (all_ok) *all_ok = ok;

@@ -201,6 +201,7 @@ struct host_buf {
 struct dev_template {
     std::shared_ptr<const circuit_template> tpl;
     uint32_t *row_ptr = nullptr, *entries = nullptr, *const_j = nullptr, *const_idx = nullptr;
+    uint32_t n_long = 0, long_rows[BBP_MAX_LONG] = {};   // the longest CSR rows among wL / wR / wO (sc_kernels.cuh: flatten_long_rows)
 };
 
 static const uint32_t WT_C = 11, WT_W = 24;   // window table over the generators: 24 windows of 11 bits (264 >= 254 bits)
@@ -289,6 +290,16 @@ inline int proto_template(bbp_ctx *ctx, uint32_t n_commit, uint32_t n_toggle, de
         BBP_CUDA_OK(cudaMemcpyAsync(dt.const_j, t.const_j.data(), t.const_j.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         BBP_CUDA_OK(cudaMemcpyAsync(dt.const_idx, t.const_idx.data(), t.const_idx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        {
+            std::vector<std::pair<uint32_t, uint32_t>> lens;   // (length, row) of rows above the threshold, longest first
+            for (uint32_t r = 0; r < 3 * t.n1; r++) {
+                uint32_t len = t.row_ptr[r + 1] - t.row_ptr[r];
+                if (len > BBP_LONG_ROW) lens.emplace_back(len, r);
+            }
+            std::sort(lens.rbegin(), lens.rend());
+            dt.n_long = (uint32_t)std::min<size_t>(lens.size(), BBP_MAX_LONG);
+            for (uint32_t k = 0; k < dt.n_long; k++) dt.long_rows[k] = lens[k].second;
+        }
         it = ps->templates.emplace(key, dt).first;
     }
     *out = &it->second;
@@ -665,6 +676,8 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     memset(&SB, 0, sizeof SB);
     SB.n_proofs = B; SB.n1 = n1; SB.q = T.q; SB.m = m; SB.n = n; SB.lg_n = lg; SB.n_pub = T.n_pub; SB.gcols = gcols;
     SB.row_ptr = dt->row_ptr; SB.entries = dt->entries; SB.const_j = dt->const_j; SB.const_idx = dt->const_idx; SB.n_const = (uint32_t)T.const_j.size();
+    SB.n_long = dt->n_long;
+    memcpy(SB.long_rows, dt->long_rows, sizeof SB.long_rows);
     SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>();
     const sc *dw = ps->wit.as<sc>();
     const size_t vs = (size_t)B * n1;
@@ -785,15 +798,26 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     return 0;
 }
 
-// Lanes a large prove batch is split over (BBP_PROVE_LANES, default 3; 1 = off). The proof bytes do not depend on it:
-// requests are independent and every per-request draw is keyed by the request's own seed.
-inline size_t prove_lanes() {
+// Lanes: sibling contexts of the same GPU that the 1024-request parts of a larger batch run on concurrently, one host
+// thread each (BBP_PROVE_LANES, default 3; 1 = off). No result byte or verdict depends on the cut: requests are
+// independent, every per-request draw is keyed by the request's own seed, and a batch verification of several parts is
+// the conjunction of one random linear combination per part.
+inline size_t batch_lanes() {
     const char *e = getenv("BBP_PROVE_LANES");
     int v = e ? atoi(e) : 3;
     return (size_t)std::min(std::max(v, 1), 8);
 }
+inline size_t batch_part_max() {
+    const char *pe = getenv("BBP_PROVE_PART");   // tests shrink the part size to drive the lanes with a handful of requests
+    return pe ? (size_t)std::min(std::max(atoi(pe), 1), 1024) : 1024;
+}
+// even cuts of at most part_max
+inline void cut_parts(const std::vector<size_t> &idx, size_t part_max, std::vector<std::vector<size_t>> &parts) {
+    const size_t sz = idx.size(), cuts = (sz + part_max - 1) / part_max, per = (sz + cuts - 1) / cuts;
+    for (size_t off = 0; off < sz; off += per) parts.emplace_back(idx.begin() + off, idx.begin() + std::min(sz, off + per));
+}
 
-inline int prove_lane_ctx(bbp_ctx *ctx, size_t k, bbp_ctx **out) {
+inline int lane_ctx(bbp_ctx *ctx, size_t k, bbp_ctx **out) {
     if (k == 0) { *out = ctx; return 0; }
     while (ctx->lanes.size() < k) {
         bbp_ctx *l = new bbp_ctx();
@@ -804,6 +828,41 @@ inline int prove_lane_ctx(bbp_ctx *ctx, size_t k, bbp_ctx **out) {
     }
     *out = ctx->lanes[k - 1];
     proto_get(*out)->proof_versioned = proto_get(ctx)->proof_versioned;
+    return 0;
+}
+
+// fn(lane context, part index) for every part; parts are handed out dynamically to min(lanes, parts) host threads
+template <class F>
+inline int run_on_lanes(bbp_ctx *ctx, size_t n_parts, F fn) {
+    const size_t n_lanes = std::min(batch_lanes(), n_parts);
+    if (n_lanes <= 1) {
+        for (size_t i = 0; i < n_parts; i++) {
+            int rc = fn(ctx, i);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    std::vector<bbp_ctx *> lane(n_lanes);
+    for (size_t k = 0; k < n_lanes; k++) {
+        int rc = lane_ctx(ctx, k, &lane[k]);
+        if (rc) return rc;
+    }
+    std::atomic<size_t> next{0};
+    std::vector<int> rcs(n_lanes, 0);
+    auto work = [&](size_t k) {
+        cudaSetDevice(ctx->device);
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= n_parts) return;
+            int rc = fn(lane[k], i);
+            if (rc) { rcs[k] = rc; return; }
+        }
+    };
+    std::vector<std::thread> th;
+    for (size_t k = 1; k < n_lanes; k++) th.emplace_back(work, k);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int rc : rcs) if (rc) return rc;
     return 0;
 }
 
@@ -818,44 +877,9 @@ inline int prove_batch(bbp_ctx *ctx, std::vector<prove_job> &jobs) {
     }
     // parts: at most 1024 proofs each (bounds the device footprint), cut evenly; several parts run on parallel lanes
     // (cutting a batch of <= 1024 measured no gain: smaller launches lose what the overlap wins)
-    const size_t K = prove_lanes();
-    const char *pe = getenv("BBP_PROVE_PART");   // tests shrink the part size to drive the lanes with a handful of requests
-    const size_t part_max = pe ? (size_t)std::min(std::max(atoi(pe), 1), 1024) : 1024;
     std::vector<std::vector<size_t>> parts;
-    for (auto &g : groups) {
-        const size_t sz = g.second.size(), cuts = (sz + part_max - 1) / part_max, per = (sz + cuts - 1) / cuts;
-        for (size_t off = 0; off < sz; off += per) parts.emplace_back(g.second.begin() + off, g.second.begin() + std::min(sz, off + per));
-    }
-    const size_t n_lanes = std::min(K, parts.size());
-    if (n_lanes <= 1) {
-        for (auto &part : parts) {
-            int rc = prove_group(ctx, jobs, part);
-            if (rc) return rc;
-        }
-        return 0;
-    }
-    std::vector<bbp_ctx *> lane(n_lanes);
-    for (size_t k = 0; k < n_lanes; k++) {
-        int rc = prove_lane_ctx(ctx, k, &lane[k]);
-        if (rc) return rc;
-    }
-    std::atomic<size_t> next{0};
-    std::vector<int> rcs(n_lanes, 0);
-    auto work = [&](size_t k) {
-        cudaSetDevice(ctx->device);
-        for (;;) {
-            size_t i = next.fetch_add(1);
-            if (i >= parts.size()) return;
-            int rc = prove_group(lane[k], jobs, parts[i]);
-            if (rc) { rcs[k] = rc; return; }
-        }
-    };
-    std::vector<std::thread> th;
-    for (size_t k = 1; k < n_lanes; k++) th.emplace_back(work, k);
-    work(0);
-    for (auto &t : th) t.join();
-    for (int rc : rcs) if (rc) return rc;
-    return 0;
+    for (auto &g : groups) cut_parts(g.second, batch_part_max(), parts);
+    return run_on_lanes(ctx, parts.size(), [&](bbp_ctx *c, size_t i) { return prove_group(c, jobs, parts[i]); });
 }
 
 
@@ -1054,13 +1078,19 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     memset(&SB, 0, sizeof SB);
     SB.n_proofs = B; SB.n1 = n1; SB.q = T.q; SB.m = m; SB.n = n; SB.lg_n = lg; SB.n_pub = T.n_pub; SB.gcols = gcols;
     SB.row_ptr = dt->row_ptr; SB.entries = dt->entries; SB.const_j = dt->const_j; SB.const_idx = dt->const_idx; SB.n_const = (uint32_t)T.const_j.size();
+    SB.n_long = dt->n_long;
+    memcpy(SB.long_rows, dt->long_rows, sizeof SB.long_rows);
     SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>();
     SB.pub = ps->pub.as<sc>(); SB.dyn_out = ps->dyn_sc.as<sc>(); SB.dyn_stride = ds; SB.stat = ps->stat.as<sc>();
     SB.stab = ps->sG.as<sc>();
+    SB.skip_ypow = 1;
     k_powers<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
     k_verify_scalars<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
-    k_stat_reduce<<<dim3((slot_len + BBP_SC_THREADS - 1) / BBP_SC_THREADS, n_groups), BBP_SC_THREADS, 0, ctx->stream>>>(SB.stat, combined ? B : 1, slot_len,
-                                                                                                                         ps->stat_red.as<sc>());
+    if (combined && B >= 32)
+        k_stat_reduce_wide<<<dim3((slot_len + 15) / 16, n_groups), 256, 0, ctx->stream>>>(SB.stat, B, slot_len, ps->stat_red.as<sc>());
+    else
+        k_stat_reduce<<<dim3((slot_len + BBP_SC_THREADS - 1) / BBP_SC_THREADS, n_groups), BBP_SC_THREADS, 0, ctx->stream>>>(SB.stat, combined ? B : 1, slot_len,
+                                                                                                                             ps->stat_red.as<sc>());
     ctx->launches += 3;
     // static bases: one fixed-table slot per group; dynamic bases: one variable-base slot per group
     uint8_t *ext = ps->msm_ext.p;
@@ -1099,15 +1129,12 @@ inline int verify_each(bbp_ctx *ctx, std::vector<verify_job> &jobs) {
     std::vector<verify_prepared> prep(jobs.size());
     std::map<uint64_t, std::vector<size_t>> groups;
     verify_prepare_all(ctx, jobs, prep, groups);
-    for (auto &g : groups) {
-        for (size_t off = 0; off < g.second.size(); off += 1024) {
-            std::vector<size_t> part(g.second.begin() + off, g.second.begin() + std::min(g.second.size(), off + 1024));
-            std::vector<uint8_t> verdicts;
-            int rc = verify_group(ctx, jobs, prep, part, false, nullptr, verdicts, nullptr);
-            if (rc) return rc;
-        }
-    }
-    return 0;
+    std::vector<std::vector<size_t>> parts;
+    for (auto &g : groups) cut_parts(g.second, batch_part_max(), parts);
+    return run_on_lanes(ctx, parts.size(), [&](bbp_ctx *c, size_t i) {
+        std::vector<uint8_t> verdicts;
+        return verify_group(c, jobs, prep, parts[i], false, nullptr, verdicts, nullptr);
+    });
 }
 
 // Batch verification: one random linear combination of the mega-checks of all requests of a
@@ -1119,24 +1146,30 @@ inline int verify_batch(bbp_ctx *ctx, std::vector<verify_job> &jobs, const uint8
     std::vector<verify_prepared> prep(jobs.size());
     std::map<uint64_t, std::vector<size_t>> groups;
     verify_prepare_all(ctx, jobs, prep, groups);
-    bool ok = true;
     if (partial_only && groups.size() > 1) return BBP_ERR_INPUT;   // sharded mode expects one circuit shape per call
+    // one combination per part of at most 1024 requests (the sharded mode keeps its single combination: its partial sum
+    // is what the other GPUs add to); the parts run on parallel lanes
+    std::vector<std::vector<size_t>> parts;
     for (auto &g : groups) {
-        std::vector<uint8_t> verdicts;
-        int rc = verify_group(ctx, jobs, prep, g.second, true, batch_seed, verdicts, d_partial_ext);
-        if (rc) return rc;
-        if (!verdicts[0] && !partial_only) {   // the combination failed: find the culprits with one per-request pass
-            for (size_t i : g.second) jobs[i].status = 0;
-            for (size_t off = 0; off < g.second.size(); off += 1024) {
-                std::vector<size_t> part;
-                for (size_t k = off; k < std::min(g.second.size(), off + 1024); k++) part.push_back(g.second[k]);
-                std::vector<uint8_t> v2;
-                rc = verify_group(ctx, jobs, prep, part, false, nullptr, v2, nullptr);
-                if (rc) return rc;
-            }
-        }
-        ok = ok && verdicts[0];
+        if (partial_only) parts.push_back(g.second);
+        else cut_parts(g.second, batch_part_max(), parts);
     }
+    std::vector<uint8_t> part_ok(parts.size(), 0);
+    int rc = run_on_lanes(ctx, partial_only ? std::min<size_t>(parts.size(), 1) : parts.size(), [&](bbp_ctx *c, size_t i) {
+        std::vector<uint8_t> verdicts;
+        int r = verify_group(c, jobs, prep, parts[i], true, batch_seed, verdicts, d_partial_ext);
+        if (r) return r;
+        part_ok[i] = verdicts[0];
+        if (!verdicts[0] && !partial_only) {   // the combination failed: find the culprits with one per-request pass
+            for (size_t k : parts[i]) jobs[k].status = 0;
+            std::vector<uint8_t> v2;
+            if ((r = verify_group(c, jobs, prep, parts[i], false, nullptr, v2, nullptr))) return r;
+        }
+        return 0;
+    });
+    if (rc) return rc;
+    bool ok = true;
+    for (uint8_t v : part_ok) ok = ok && v;
     for (auto &J : jobs) ok = ok && (J.status == 0 || partial_only);
     if (all_ok) *all_ok = ok ? 1 : 0;
     return 0;

@@ -370,6 +370,7 @@ inline int rp_verify_group(bbp_ctx *ctx, std::vector<rp_verify_job> &jobs, uint3
     SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>(); SB.stat = ps->stat.as<sc>();
     if ((rc = ps->sG.ensure((size_t)P * nm * 32))) return rc;
     SB.stab = ps->sG.as<sc>();
+    SB.skip_ypow = 1;
     k_powers<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
     k_rp_verify_scalars<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
     k_stat_reduce<<<dim3((slot_len + BBP_SC_THREADS - 1) / BBP_SC_THREADS, P), BBP_SC_THREADS, 0, ctx->stream>>>(SB.stat, 1, slot_len, ps->stat_red.as<sc>());

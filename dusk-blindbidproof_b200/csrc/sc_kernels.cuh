@@ -19,6 +19,8 @@
 namespace bbp {
 
 #define BBP_SC_THREADS 256
+#define BBP_MAX_LONG 8      // long CSR rows handled block-cooperatively
+#define BBP_LONG_ROW 24     // a row counts as long above this many entries
 
 // per-proof challenge block (normal form, 32 B each)
 enum chal_slot : uint32_t {
@@ -33,6 +35,8 @@ struct sc_batch {
     uint32_t gcols;                            // generator columns per family in the table (capacity x parties >= n): slot
                                                // layout [B, B_blinding, G[0..gcols), H[0..gcols)], slot length 2 + 2 gcols
     const uint32_t *row_ptr, *entries;         // circuit template CSR (shared by the batch)
+    uint32_t skip_ypow;                        // verifiers need only z^j and y^-i
+    uint32_t n_long, long_rows[BBP_MAX_LONG];  // the few CSR rows long enough to be summed by the whole block (see flatten_long_rows)
     const uint32_t *const_j, *const_idx;       // constant terms (verifier)
     uint32_t n_const;
     const sc *chal;                            // [n_proofs][CH_N]
@@ -68,8 +72,9 @@ __device__ __forceinline__ sc mm(const sc &a, const sc &b) { return sc_montmul(a
 
 // base^e in the Montgomery domain, e < 2^16
 __device__ inline sc sc_pow_small_mont(const sc &baseM, uint32_t e) {
-    sc r = sc_mont_one();
-    for (int bit = 15; bit >= 0; bit--) {
+    if (e == 0) return sc_mont_one();
+    sc r = baseM;
+    for (int bit = 30 - __clz(e); bit >= 0; bit--) {
         r = mm(r, r);
         if ((e >> bit) & 1) r = mm(r, baseM);
     }
@@ -91,26 +96,49 @@ __device__ inline sc block_sum_sc(sc v, sc *smem) {
 }
 
 // ---------------------------------------------------------------- power tables
-// zpow[j] = z^(j+1), j < q ; ypow[i] = y^i, yinvpow[i] = y^-i, i < n. Each thread raises to its chunk start, then walks.
+// zpow[j] = z^(j+1), j < q ; ypow[i] = y^i (unless B.skip_ypow), yinvpow[i] = y^-i, i < n. Thread t owns one chunk of each
+// sequence; its first element is first * (base^chunk)^t, assembled from the eight shared powers (base^chunk)^(2^k) by the
+// bits of t (<= 8 products instead of a square-and-multiply ladder per thread), then it walks with one product per element.
 __global__ void __launch_bounds__(BBP_SC_THREADS) k_powers(sc_batch B) {
+    static_assert(BBP_SC_THREADS == 256, "chunk starts are assembled from 8 bits of the thread index");
+    __shared__ sc r2k[3][8];
     const uint32_t p = blockIdx.x, t = threadIdx.x;
     const sc *ch = B.chal + (size_t)p * CH_N;
-    sc zM = sc_to_mont(ch[CH_Z]), yM = sc_to_mont(ch[CH_Y]), yiM = sc_to_mont(ch[CH_YINV]);
+    const uint32_t zc = (B.q + BBP_SC_THREADS - 1) / BBP_SC_THREADS, yc = (B.n + BBP_SC_THREADS - 1) / BBP_SC_THREADS;
+    if ((t & 31) == 0 && t < 96) {   // one thread of three different warps: z, y, y^-1
+        const uint32_t s = t >> 5;
+        if (s == 0 ? B.q > 0 : (s == 1 ? !B.skip_ypow : true)) {
+            sc r = sc_pow_small_mont(sc_to_mont(ch[s == 0 ? CH_Z : s == 1 ? CH_Y : CH_YINV]), s == 0 ? zc : yc);
+            for (uint32_t k = 0; k < 8; k++) { r2k[s][k] = r; r = mm(r, r); }
+        }
+    }
+    __syncthreads();
+    auto chunk_first = [&](uint32_t s, sc cur) {
+        for (uint32_t k = 0; k < 8; k++)
+            if ((t >> k) & 1) cur = mm(cur, r2k[s][k]);
+        return cur;
+    };
     {
-        uint32_t chunk = (B.q + BBP_SC_THREADS - 1) / BBP_SC_THREADS, j0 = t * chunk, j1 = min(j0 + chunk, B.q);
+        uint32_t j0 = t * zc, j1 = min(j0 + zc, B.q);
         if (j0 < j1) {
-            sc cur = sc_pow_small_mont(zM, j0 + 1);
+            sc zM = sc_to_mont(ch[CH_Z]);
+            sc cur = chunk_first(0, zM);
             sc *out = B.zpow + (size_t)p * B.q;
             for (uint32_t j = j0; j < j1; j++) { out[j] = cur; cur = mm(cur, zM); }
         }
     }
-    {
-        uint32_t chunk = (B.n + BBP_SC_THREADS - 1) / BBP_SC_THREADS, i0 = t * chunk, i1 = min(i0 + chunk, B.n);
-        if (i0 < i1) {
-            sc cy = sc_pow_small_mont(yM, i0), ci = sc_pow_small_mont(yiM, i0);
-            sc *oy = B.ypow + (size_t)p * B.n, *oi = B.yinvpow + (size_t)p * B.n;
-            for (uint32_t i = i0; i < i1; i++) { oy[i] = cy; oi[i] = ci; cy = mm(cy, yM); ci = mm(ci, yiM); }
+    uint32_t i0 = t * yc, i1 = min(i0 + yc, B.n);
+    if (i0 < i1) {
+        if (!B.skip_ypow) {
+            sc yM = sc_to_mont(ch[CH_Y]);
+            sc cy = chunk_first(1, sc_mont_one());
+            sc *oy = B.ypow + (size_t)p * B.n;
+            for (uint32_t i = i0; i < i1; i++) { oy[i] = cy; cy = mm(cy, yM); }
         }
+        sc yiM = sc_to_mont(ch[CH_YINV]);
+        sc ci = chunk_first(2, sc_mont_one());
+        sc *oi = B.yinvpow + (size_t)p * B.n;
+        for (uint32_t i = i0; i < i1; i++) { oi[i] = ci; ci = mm(ci, yiM); }
     }
 }
 
@@ -123,6 +151,29 @@ __device__ __forceinline__ sc flatten_row(const sc_batch &B, const sc *zpow, uin
         acc = (v >> 31) ? sc_sub(acc, zp) : sc_add(acc, zp);
     }
     return acc;
+}
+
+// A wire that feeds many constraints has a long row (the blind-bid circuit has one a_O wire in 820 constraints and one in
+// 279, every other row has <= 19 entries); walked by one thread it would bound the whole block, so the rows listed in
+// B.long_rows are summed by all threads first and looked up afterwards.
+__device__ inline void flatten_long_rows(const sc_batch &B, const sc *zpow, sc *long_val, sc *smem) {
+    for (uint32_t k = 0; k < B.n_long; k++) {
+        const uint32_t row = B.long_rows[k];
+        sc acc = sc_zero();
+        for (uint32_t e = B.row_ptr[row] + threadIdx.x; e < B.row_ptr[row + 1]; e += BBP_SC_THREADS) {
+            uint32_t v = B.entries[e];
+            const sc &zp = zpow[v & 0x7fffffffu];
+            acc = (v >> 31) ? sc_sub(acc, zp) : sc_add(acc, zp);
+        }
+        acc = block_sum_sc(acc, smem);
+        if (threadIdx.x == 0) long_val[k] = acc;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ sc flatten_row_l(const sc_batch &B, const sc *zpow, uint32_t row, const sc *long_val) {
+    for (uint32_t k = 0; k < B.n_long; k++)
+        if (B.long_rows[k] == row) return long_val[k];
+    return flatten_row(B, zpow, row);
 }
 
 // ---------------------------------------------------------------- prover: commitment scalar slots
@@ -204,9 +255,11 @@ __global__ void __launch_bounds__(BBP_SC_THREADS, 2) k_polys(sc_batch B) {
     const uint32_t p = blockIdx.x, t = threadIdx.x, n1 = B.n1;
     const sc *zpow = B.zpow + (size_t)p * B.q, *ypow = B.ypow + (size_t)p * B.n, *yinv = B.yinvpow + (size_t)p * B.n;
     sc *poly = B.poly + (size_t)p * 6 * n1;
+    __shared__ sc long_val[BBP_MAX_LONG];
+    flatten_long_rows(B, zpow, long_val, smem);
     sc t1 = sc_zero(), t2 = t1, t3 = t1, t4 = t1, t5 = t1, t6 = t1;
     for (uint32_t i = t; i < n1; i += BBP_SC_THREADS) {
-        sc wL = flatten_row(B, zpow, i), wR = flatten_row(B, zpow, n1 + i), wO = flatten_row(B, zpow, 2 * n1 + i);
+        sc wL = flatten_row_l(B, zpow, i, long_val), wR = flatten_row_l(B, zpow, n1 + i, long_val), wO = flatten_row_l(B, zpow, 2 * n1 + i, long_val);
         size_t k = (size_t)p * n1 + i;
         sc aL = sc_to_mont(B.aL[k]), aR = sc_to_mont(B.aR[k]), aO = sc_to_mont(B.aO[k]), sL = sc_to_mont(B.sL[k]), sR = sc_to_mont(B.sR[k]);
         sc l1 = sc_add(aL, mm(yinv[i], wR));
@@ -401,6 +454,7 @@ __device__ inline void build_s_table(sc *stab, const sc *uj, uint32_t lg, uint32
 __global__ void __launch_bounds__(BBP_SC_THREADS, 2) k_verify_scalars(sc_batch B) {
     __shared__ sc smem[BBP_SC_THREADS];
     __shared__ sc uj[64];
+    __shared__ sc long_val[BBP_MAX_LONG];
     const uint32_t p = blockIdx.x, t = threadIdx.x, n = B.n, n1 = B.n1, lg = B.lg_n;
     const sc *ch = B.chal + (size_t)p * CH_N;
     const sc *zpow = B.zpow + (size_t)p * B.q, *yinv = B.yinvpow + (size_t)p * n;
@@ -422,23 +476,27 @@ __global__ void __launch_bounds__(BBP_SC_THREADS, 2) k_verify_scalars(sc_batch B
     wc = block_sum_sc(wc, smem);
     sc delta = sc_zero();
     sc *stab = B.stab + (size_t)p * n;
+    flatten_long_rows(B, zpow, long_val, smem);
     build_s_table(stab, uj, lg, n);
+    // rho and uf are folded into per-thread constants so that a column costs 8 products below n1 and 3 above:
+    //   g = (ru x) ywR - (ru a) s,   h = y^-i ((ru x) wL + ru wO - (ru b) s_rev) - ru,   ru = rho uf
+    const sc ruU = mm(rhoM, uM);
+    const sc rx = mm(rhoM, xM), ra1 = mm(rhoM, aM), rb1 = mm(rhoM, bM), raU = mm(ruU, aM), rbU = mm(ruU, bM);
     for (uint32_t i = t; i < n; i += BBP_SC_THREADS) {
         sc s = stab[i], srev = stab[n - 1 - i];
         sc g, h;
-        sc uf = (i < n1) ? one : uM;
         if (i < n1) {
-            sc wL = flatten_row(B, zpow, i), wR = flatten_row(B, zpow, n1 + i), wO = flatten_row(B, zpow, 2 * n1 + i);
+            sc wL = flatten_row_l(B, zpow, i, long_val), wR = flatten_row_l(B, zpow, n1 + i, long_val), wO = flatten_row_l(B, zpow, 2 * n1 + i, long_val);
             sc ywR = mm(yinv[i], wR);
             delta = sc_add(delta, mm(ywR, wL));
-            g = sc_sub(mm(xM, ywR), mm(aM, s));
-            h = sc_sub(mm(yinv[i], sc_sub(sc_add(mm(xM, wL), wO), mm(bM, srev))), one);
+            g = sc_sub(mm(rx, ywR), mm(ra1, s));
+            h = sc_sub(mm(yinv[i], sc_sub(sc_add(mm(rx, wL), mm(rhoM, wO)), mm(rb1, srev))), rhoM);
         } else {
-            g = sc_neg(mm(aM, s));
-            h = sc_sub(sc_neg(mm(yinv[i], mm(bM, srev))), one);
+            g = sc_neg(mm(raU, s));
+            h = sc_sub(sc_neg(mm(yinv[i], mm(rbU, srev))), ruU);
         }
-        stat[2 + i] = mm(rhoM, mm(uf, g));
-        stat[2 + gc + i] = mm(rhoM, mm(uf, h));
+        stat[2 + i] = g;
+        stat[2 + gc + i] = h;
     }
     delta = block_sum_sc(delta, smem);
     sc rM = sc_to_mont(ch[CH_R]);
@@ -571,6 +629,25 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_stat_reduce(const sc *__rest
     const sc *base = stat + (size_t)g * group_size * slot_len;
     for (uint32_t p = 0; p < group_size; p++) acc = sc_add(acc, base[(size_t)p * slot_len + i]);
     out[(size_t)g * slot_len + i] = sc_from_mont(acc);
+}
+
+// the same for large groups: 16 columns x 16 proof slices per block, so that a batch-wide sum is not 4098 threads walking
+// the whole batch one proof at a time
+__global__ void __launch_bounds__(256) k_stat_reduce_wide(const sc *__restrict__ stat, uint32_t group_size, uint32_t slot_len, sc *__restrict__ out) {
+    __shared__ sc part[16][16];
+    const uint32_t col = threadIdx.x & 15, slice = threadIdx.x >> 4, i = blockIdx.x * 16 + col, g = blockIdx.y;
+    sc acc = sc_zero();
+    if (i < slot_len) {
+        const sc *base = stat + (size_t)g * group_size * slot_len + i;
+        for (uint32_t p = slice; p < group_size; p += 16) acc = sc_add(acc, base[(size_t)p * slot_len]);
+    }
+    part[slice][col] = acc;
+    __syncthreads();
+    for (uint32_t s = 8; s >= 1; s >>= 1) {
+        if (slice < s) part[slice][col] = sc_add(part[slice][col], part[slice + s][col]);
+        __syncthreads();
+    }
+    if (slice == 0 && i < slot_len) out[(size_t)g * slot_len + i] = sc_from_mont(part[0][col]);
 }
 
 }  // namespace bbp

@@ -264,8 +264,14 @@ def test_generator_capacity_limits(be):
     assert be.blindbid_verify(verify_item(bid, gproof, gcomm, gtc)) == 0
 
 
-def test_batch_verify_equals_and_of_singles(be):
-    """BASELINE config 4 at test size: combined check verdict == AND of single verdicts, with 0 / 1 / k bad proofs"""
+@pytest.mark.parametrize("part", [None, 7])
+def test_batch_verify_equals_and_of_singles(be, part, monkeypatch):
+    """BASELINE config 4 at test size: combined check verdict == AND of single verdicts, with 0 / 1 / k bad proofs.
+    part = 7 shrinks the 1024-request part size, so the batch is cut into four parts verified concurrently on sibling
+    contexts ("lanes"), one combination per part."""
+    if part:
+        monkeypatch.setenv("BBP_PROVE_PART", str(part))
+        monkeypatch.setenv("BBP_PROVE_LANES", "3")
     n = 24
     cases = [make_case(200 + i, 8) for i in range(n)]
     outs = be.blindbid_prove_batch(cases)
