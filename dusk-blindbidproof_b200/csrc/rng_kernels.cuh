@@ -61,7 +61,10 @@ struct strobe_dev {
     uint64_t st[25];
     uint32_t pos, pos_begin;
     __device__ uint8_t *bytes() { return (uint8_t *)st; }
-    __device__ void run_f() {
+    // The permutation and the two composite operations are real calls: inlined, the 50-odd transcript operations of the
+    // verifier replay grew k_verify_transcript to 131 k SASS instructions and a third of its issue slots went to
+    // instruction-cache misses (one warp per SM has nothing to hide them behind).
+    __device__ __noinline__ void run_f() {
         uint8_t *s = bytes();
         s[pos] ^= (uint8_t)pos_begin;
         s[pos + 1] ^= 0x04;
@@ -87,7 +90,7 @@ struct strobe_dev {
     __device__ void meta_ad_len(uint32_t len) {   // meta_ad(LE32(len), more = true): continues the running meta_ad
         absorb_byte((uint8_t)len); absorb_byte((uint8_t)(len >> 8)); absorb_byte((uint8_t)(len >> 16)); absorb_byte((uint8_t)(len >> 24));
     }
-    __device__ void append_message(const char *label, uint32_t llen, const uint8_t *msg, uint32_t n) {
+    __device__ __noinline__ void append_message(const char *label, uint32_t llen, const uint8_t *msg, uint32_t n) {
         meta_ad_label(label, llen);
         meta_ad_len(n);
         begin_op(2);                        // ad
@@ -116,7 +119,7 @@ struct strobe_dev {
         }
     }
     // TranscriptProtocol::challenge_scalar: 64 challenge bytes, wide-reduced
-    __device__ sc challenge_scalar(const char *label, uint32_t llen) {
+    __device__ __noinline__ sc challenge_scalar(const char *label, uint32_t llen) {
         meta_ad_label(label, llen);
         meta_ad_len(64);
         uint8_t b[64];

@@ -68,7 +68,12 @@ struct sc_batch {
 };
 
 __device__ __forceinline__ sc sc_mont_one() { return sc_to_mont(sc_one()); }
-__device__ __forceinline__ sc mm(const sc &a, const sc &b) { return sc_montmul(a.v, b.v); }
+#ifndef BBP_MM_INLINE
+#define BBP_MM_ATTR __noinline__
+#else
+#define BBP_MM_ATTR __forceinline__
+#endif
+__device__ BBP_MM_ATTR sc mm(sc a, sc b) { return sc_montmul(a.v, b.v); }
 
 // base^e in the Montgomery domain, e < 2^16
 __device__ inline sc sc_pow_small_mont(const sc &baseM, uint32_t e) {
