@@ -82,8 +82,19 @@ class Backend:
 
     def close(self):
         if self.ctx:
-            lib().bbp_free(self.ctx)
+            if getattr(self, "_owner", None) is None:   # lanes belong to the context that created them
+                lib().bbp_free(self.ctx)
             self.ctx = ctypes.c_void_p()
+
+    def lane(self, k):
+        """k-th sibling context of the same GPU (bbp_lane): own stream, engine and scratch; k = 0 is this context."""
+        if k == 0:
+            return self
+        h = ctypes.c_void_p()
+        _chk(lib().bbp_lane(self.ctx, ctypes.c_uint32(k), ctypes.byref(h)), "bbp_lane")
+        view = Backend.__new__(Backend)
+        view.ctx, view.device, view._owner = h, self.device, self   # keeps the owner alive
+        return view
 
     def __del__(self):
         try:

@@ -46,7 +46,14 @@ int bbp_sync(bbp_ctx *ctx) {
     if (!ctx) return BBP_ERR_INPUT;
     cudaSetDevice(ctx->device);
     BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    for (bbp_ctx *l : ctx->lanes) BBP_CUDA_OK(cudaStreamSynchronize(l->stream));
     return BBP_OK;
+}
+
+int bbp_lane(bbp_ctx *ctx, uint32_t k, bbp_ctx **lane) {
+    if (!ctx || !lane || k > 7) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    return lane_ctx(ctx, k, lane);
 }
 
 int bbp_pedersen_gens(bbp_ctx *ctx, uint8_t B[32], uint8_t B_blinding[32]) {

@@ -47,7 +47,16 @@ void bbp_free(bbp_ctx *ctx);
 uint64_t bbp_launch_count(const bbp_ctx *ctx);
 /* the CUDA stream all work of this context is enqueued on (cudaStream_t as an integer), for event timing */
 uint64_t bbp_stream(const bbp_ctx *ctx);
-int bbp_sync(bbp_ctx *ctx);
+int bbp_sync(bbp_ctx *ctx);   /* waits for the context's stream and for those of its lanes */
+/* Lanes: sibling contexts on the same device, created on first use, owned by `ctx` (freed with it; never pass one to
+ * bbp_free). k = 0 is `ctx` itself, k <= 7. Each lane has its own stream, MSM engine and scratch, so independent calls
+ * issued on different lanes overlap on the GPU: the latency-bound tail of one MSM (bucket reduction, Horner chain) runs
+ * beside the bucket accumulation of the next, and one call's host<->device copies beside another's kernels. Read-only
+ * inputs (bbp_points tables, device scalar buffers) may be shared between lanes once the call that produced them has
+ * completed (bbp_sync). The batched prove / verify entry points use the same lanes internally for batches above 1024
+ * requests. One host thread per lane at a time (no reference counterpart: the reference is one CPU thread per request,
+ * src/futures/main.rs:52-62). */
+int bbp_lane(bbp_ctx *ctx, uint32_t k, bbp_ctx **lane);
 
 /* ---- measurement hooks (bench.py): per-stage MSM timing with CUDA events on the context stream, the MSM plan for a
  * size, and the measured integer-multiply ceiling of the device (no reference counterpart) */

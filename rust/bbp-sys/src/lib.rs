@@ -65,6 +65,7 @@ extern "C" {
     pub fn bbp_init(out: *mut *mut bbp_ctx, device: c_int, gens_capacity: u32, party_capacity: u32) -> c_int;
     pub fn bbp_free(ctx: *mut bbp_ctx);
     pub fn bbp_sync(ctx: *mut bbp_ctx) -> c_int;
+    pub fn bbp_lane(ctx: *mut bbp_ctx, k: u32, lane: *mut *mut bbp_ctx) -> c_int;
     pub fn bbp_launch_count(ctx: *const bbp_ctx) -> u64;
     pub fn bbp_stream(ctx: *const bbp_ctx) -> u64;
     pub fn bbp_set_proof_format(ctx: *mut bbp_ctx, versioned: c_int) -> c_int;

@@ -169,3 +169,38 @@ def test_msm_full_size_properties(be):
         sums[i % period] += from_le(scs[32 * i:32 * i + 32])
     folded = b"".join(le(s % L_ORDER) for s in sums)
     assert be.msm_optional(scs, rep) == orc.msm(folded, pts[:32 * period], algo=1, threads=8)
+
+
+def test_msm_lanes_agree_and_overlap(be):
+    """bbp_lane: sibling contexts of the same GPU give the same bytes as the owning context, sequentially and when
+    three host threads call them at once (each lane has its own stream, engine and scratch); the owner's launch counter
+    includes the lanes'."""
+    import threading
+    from gpu_util import gpu_random_points
+    n = 5000
+    pts = gpu_random_points(77, n)
+    scs = orc.random_scalars(78, n)
+    want = orc.msm(scs, pts)
+    lanes = [be.lane(k) for k in range(3)]
+    assert lanes[0] is be
+    l0 = be.launch_count()
+    assert [b.msm_optional(scs, pts) for b in lanes] == [want] * 3
+    assert be.launch_count() - l0 >= 3 * 10
+    got = [[None] * 4 for _ in lanes]
+
+    def worker(k):
+        for r in range(4):
+            got[k][r] = lanes[k].msm_optional(scs, pts)
+
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(3)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert all(x == want for row in got for x in row)
+    # a table built on the owner is usable from a lane once the owner has been synchronised
+    ext, valid = be.decompress(pts)
+    table = be.points_from_extended(ext)
+    be.sync()
+    assert lanes[2].msm_points(scs, table) == want
+    table.free()
