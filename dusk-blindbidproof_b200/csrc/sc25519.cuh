@@ -7,6 +7,9 @@
 #include <cstdint>
 #include <cstring>
 #include "curve_consts.inc"
+#ifdef __CUDACC__
+#include "fe25519.cuh"   // the 8 x 8 limb product (IMAD.WIDE carry chains) is shared with the field layer
+#endif
 
 #ifdef __CUDACC__
 #define BBP_HD __host__ __device__ __forceinline__
@@ -118,9 +121,100 @@ inline sc sc_montmul_host64(const uint32_t *a32, const uint32_t *b32) {
     return r;
 }
 #endif
+#if defined(__CUDACC__)
+// -l^-1 mod 2^256 and c = l - 2^252 (125 bits)
+#define SC_NPRIME_LIMBS {0x12547e1bu, 0xd2b51da3u, 0xfdba84ffu, 0xb1a206f2u, 0xffa36beau, 0x14e75438u, 0x6fe91836u, 0x9db6c6f2u}
+#define SC_C_LIMBS {0x5cf5d3edu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu}
+
+// r[0..11] = a[0..7] * b[0..3]: the first four rows of fe_mul_wide's even / odd column scheme
+__device__ __forceinline__ void sc_mul_8x4_wide(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    uint32_t ev[12], od[11];
+    mul4(ev, a[0], a[2], a[4], a[6], b[0]);
+    mul4(od, a[1], a[3], a[5], a[7], b[0]);
+    od[8] = mad4_cc(od, a[0], a[2], a[4], a[6], b[1]);
+    mad4_top_fresh(ev + 2, a[1], a[3], a[5], a[7], b[1]);
+    ev[10] = mad4_cc(ev + 2, a[0], a[2], a[4], a[6], b[2]);
+    mad4_top_half(od + 2, a[1], a[3], a[5], a[7], b[2]);
+    od[10] = mad4_cc(od + 2, a[0], a[2], a[4], a[6], b[3]);
+    mad4_top_half(ev + 4, a[1], a[3], a[5], a[7], b[3]);
+    r[0] = ev[0];
+    asm("add.cc.u32 %0, %11, %22;\n\t"
+        "addc.cc.u32 %1, %12, %23;\n\t"
+        "addc.cc.u32 %2, %13, %24;\n\t"
+        "addc.cc.u32 %3, %14, %25;\n\t"
+        "addc.cc.u32 %4, %15, %26;\n\t"
+        "addc.cc.u32 %5, %16, %27;\n\t"
+        "addc.cc.u32 %6, %17, %28;\n\t"
+        "addc.cc.u32 %7, %18, %29;\n\t"
+        "addc.cc.u32 %8, %19, %30;\n\t"
+        "addc.cc.u32 %9, %20, %31;\n\t"
+        "addc.u32 %10, %21, %32;"
+        : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11])
+        : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(ev[8]), "r"(ev[9]), "r"(ev[10]), "r"(ev[11]),
+          "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]), "r"(od[8]), "r"(od[9]), "r"(od[10]));
+}
+
+// Montgomery product on the device, separated-operand form: T = a b (16 limbs, the field layer's product);
+// M = T_lo * (-l^-1) mod 2^256; T + M l has zero low half, and with l = 2^252 + c
+//   (T + M l) / 2^256 = T_hi + floor((M c + M 2^252) / 2^256) + [T_lo != 0].
+// ~160 IMAD.WIDE against ~350 mixed IMAD / IADD3 instructions of the limb-serial CIOS loop it replaces.
+__device__ __forceinline__ sc sc_montmul_dev(const uint32_t *a, const uint32_t *b) {
+    const uint32_t np[8] = SC_NPRIME_LIMBS, cl[4] = SC_C_LIMBS;
+    uint32_t T[16], W[16], P[12];
+    fe_mul_wide(T, a, b);
+    fe_mul_wide(W, T, np);                    // only W[0..7] = M is used; the dead high rows are dropped by ptxas
+    sc_mul_8x4_wide(P, W, cl);
+    // Q = M << 252: Q[7] = M0 << 28, Q[8 + j] = (M[j] >> 4) | (M[j + 1] << 28), Q[15] = M7 >> 4
+    uint32_t q7 = W[0] << 28, Q[8];
+#pragma unroll
+    for (int j = 0; j < 7; j++) Q[j] = (W[j] >> 4) | (W[j + 1] << 28);
+    Q[7] = W[7] >> 4;
+    uint32_t lo_nonzero = (T[0] | T[1] | T[2] | T[3] | T[4] | T[5] | T[6] | T[7]) != 0 ? 1u : 0u;
+    sc r;
+    uint32_t dummy;
+    // U_hi = P[8..11] + Q + carry(P[7] + q7);   R = T_hi + U_hi + lo_nonzero
+    asm("add.cc.u32 %8, %9, %10;\n\t"          // carry out of limb 7 of P + Q
+        "addc.cc.u32 %0, %11, %15;\n\t"
+        "addc.cc.u32 %1, %12, %16;\n\t"
+        "addc.cc.u32 %2, %13, %17;\n\t"
+        "addc.cc.u32 %3, %14, %18;\n\t"
+        "addc.cc.u32 %4, %19, 0;\n\t"
+        "addc.cc.u32 %5, %20, 0;\n\t"
+        "addc.cc.u32 %6, %21, 0;\n\t"
+        "addc.u32 %7, %22, 0;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]), "=r"(dummy)
+        : "r"(P[7]), "r"(q7), "r"(P[8]), "r"(P[9]), "r"(P[10]), "r"(P[11]), "r"(Q[0]), "r"(Q[1]), "r"(Q[2]), "r"(Q[3]), "r"(Q[4]), "r"(Q[5]), "r"(Q[6]),
+          "r"(Q[7]));
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t"
+        "addc.cc.u32 %5, %5, 0;\n\t"
+        "addc.cc.u32 %6, %6, 0;\n\t"
+        "addc.u32 %7, %7, 0;"
+        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7])
+        : "r"(lo_nonzero));
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32 %7, %7, %15;"
+        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7])
+        : "r"(T[8]), "r"(T[9]), "r"(T[10]), "r"(T[11]), "r"(T[12]), "r"(T[13]), "r"(T[14]), "r"(T[15]));
+    if (sc_geq_l(r.v)) sc_sub_l(r.v);
+    return r;
+}
+#endif
+
 BBP_HD sc sc_montmul(const uint32_t *a, const uint32_t *b) {
 #if !defined(__CUDA_ARCH__)
     return sc_montmul_host64(a, b);
+#elif !defined(BBP_SC_CIOS)
+    return sc_montmul_dev(a, b);
 #else
     uint32_t t[10];
 #pragma unroll
