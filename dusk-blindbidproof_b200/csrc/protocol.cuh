@@ -25,6 +25,7 @@
 #include "fixedbase.cuh"
 #include "rng_kernels.cuh"
 #include "sc_kernels.cuh"
+#include "small_msm.cuh"
 
 namespace bbp {
 
@@ -216,6 +217,8 @@ struct proto_state {
     uint8_t *wtable2 = nullptr;    // same with WT2_C-bit windows
     uint32_t *colmap = nullptr;    // compact slot -> generator column map of the materialisation MSM
     uint32_t colmap_n = 0, colmap_gcols = 0;
+    uint8_t *dtable = nullptr;     // digit-multiple table of the latency path (small_msm.cuh), built on first use
+    dev_buf sm_partial;
     uint32_t *ipp_colmap = nullptr;   // early IPP rounds, compact slots: lg n maps of 2 (1 + n) generator columns (L slot, R slot)
     uint32_t ipp_colmap_n = 0, ipp_colmap_gcols = 0;
     dev_buf fext, ftab;            // materialised folded bases: extended, then niels (+ B at the tail)
@@ -235,7 +238,8 @@ inline proto_state *proto_get(bbp_ctx *ctx) {
 void proto_release(proto_state *ps) {
     if (!ps) return;
     for (auto &kv : ps->templates) { cudaFree(kv.second.row_ptr); cudaFree(kv.second.entries); cudaFree(kv.second.const_j); cudaFree(kv.second.const_idx); }
-    cudaFree(ps->comb); cudaFree(ps->wtable); cudaFree(ps->wtable2); cudaFree(ps->colmap); cudaFree(ps->ipp_colmap);
+    cudaFree(ps->comb); cudaFree(ps->wtable); cudaFree(ps->wtable2); cudaFree(ps->colmap); cudaFree(ps->ipp_colmap); cudaFree(ps->dtable);
+    ps->sm_partial.release();
     ps->fext.release(); ps->ftab.release();
     dev_buf *all[] = {&ps->chal, &ps->zpow, &ps->ypow, &ps->yinvpow, &ps->wit, &ps->vbl, &ps->blind3, &ps->poly, &ps->tout, &ps->a, &ps->b, &ps->sG, &ps->sH,
                       &ps->slots, &ps->ab, &ps->pub, &ps->dyn_sc, &ps->dyn_pts, &ps->dyn_niels, &ps->stat, &ps->stat_red, &ps->msm_out, &ps->msm_ext,
@@ -333,9 +337,36 @@ inline int pedersen_commit_host(bbp_ctx *ctx, const sc *vals, size_t n, uint8_t 
 
 // n_slots MSMs over the generator window table; scalars: n_slots x slot_len on the device (slot_len <= n_gens, column i
 // of a slot multiplies generator i). Results: compressed (n_slots x 32 B) and / or extended (n_slots x 128 B), on device.
+// Small problems take the latency path (small_msm.cuh): two launches instead of the engine's ~20. The crossover is in
+// total terms (BBP_SMALL_MSM_MAX, default 32768 = the IPP rounds of up to 8 proofs; 0 disables the path).
+inline bool small_msm_ok(size_t total_terms) {
+    const char *e = getenv("BBP_SMALL_MSM_MAX");
+    return total_terms <= (size_t)(e ? atol(e) : 32768);
+}
+inline int msm_gens_small(bbp_ctx *ctx, const sc *d_scalars, uint32_t slot_len, uint32_t n_slots, const uint32_t *colmap, uint32_t colmap_slots,
+                          uint8_t *d_out_compressed, uint8_t *d_out_ext) {
+    proto_state *ps = proto_get(ctx);
+    if (!ps->dtable) {
+        const size_t entries = (size_t)SM_W * ctx->n_gens;
+        BBP_CUDA_OK(cudaMalloc(&ps->dtable, entries * SM_D * 96));
+        k_build_digit_table<<<(unsigned)((entries + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_gens_ext, ps->dtable, (uint32_t)ctx->n_gens);
+        ctx->launches++;
+    }
+    const uint32_t chunks = (slot_len + SM_THREADS / SM_GROUPS - 1) / (SM_THREADS / SM_GROUPS);
+    int rc;
+    if ((rc = ps->sm_partial.ensure((size_t)n_slots * chunks * 128))) return rc;
+    k_small_msm_partial<<<dim3(chunks, n_slots), SM_THREADS, 0, ctx->stream>>>(d_scalars, slot_len, ps->dtable, (uint32_t)ctx->n_gens, colmap,
+                                                                                 colmap_slots ? colmap_slots : 1, ps->sm_partial.p);
+    k_small_msm_final<<<n_slots, SM_THREADS, 0, ctx->stream>>>(ps->sm_partial.p, chunks, d_out_ext, d_out_compressed);
+    ctx->launches += 2;
+    BBP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 inline int msm_gens_device(bbp_ctx *ctx, const sc *d_scalars, uint32_t slot_len, uint32_t n_slots, uint8_t *d_out_compressed, uint8_t *d_out_ext) {
     proto_state *ps = proto_get(ctx);
     if (slot_len > ctx->n_gens || !ps->wtable) return BBP_ERR_INVALID_GENERATORS_LENGTH;
+    if (small_msm_ok((size_t)n_slots * slot_len)) return msm_gens_small(ctx, d_scalars, slot_len, n_slots, nullptr, 0, d_out_compressed, d_out_ext);
     msm_shape sh = msm_engine::make_shape(n_slots * slot_len, slot_len, slot_len, true, WT_C, WT_W, (uint32_t)ctx->n_gens);
     return ctx->msm.run(sh, (const uint8_t *)d_scalars, ps->wtable, d_out_ext, d_out_compressed);
 }
@@ -420,7 +451,9 @@ inline int ipp_rounds(bbp_ctx *ctx, sc_batch &SB, uint32_t P, std::vector<sc> &c
         }
         k_ipp_round<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB, j, mode);
         ctx->launches++;
-        if (!SB.late && SB.compact) {
+        if (!SB.late && SB.compact && small_msm_ok((size_t)2 * P * cslot)) {
+            if ((rc = msm_gens_small(ctx, SB.slots, cslot, 2 * P, ps->ipp_colmap + (size_t)j * 2 * cslot, 2, ps->msm_out.p, nullptr))) return rc;
+        } else if (!SB.late && SB.compact) {
             msm_shape sh = msm_engine::make_shape(2 * P * cslot, cslot, cslot, true, WT_C, WT_W, (uint32_t)ctx->n_gens);
             sh.ref_mode = 1; sh.colmap = ps->ipp_colmap + (size_t)j * 2 * cslot; sh.colmap_len = 2 * cslot;
             if ((rc = ctx->msm.run(sh, (const uint8_t *)SB.slots, ps->wtable, nullptr, ps->msm_out.p))) return rc;

@@ -96,9 +96,14 @@ def test_msm_over_generator_table(be):
         assert got[32 * k:32 * k + 32] == orc.msm(two[64 * k:64 * k + 64], B + Bb, algo=0)
 
 
+@pytest.mark.parametrize("small_msm", ["latency path", "engine"])
 @pytest.mark.parametrize("L", [1, 2, 8])
-def test_prove_bytes_identical_to_oracle(be, L):
-    """BASELINE config 3: proof bytes, commitments and toggle commitments equal the oracle's under fixed blindings / rng."""
+def test_prove_bytes_identical_to_oracle(be, L, small_msm, monkeypatch):
+    """BASELINE config 3: proof bytes, commitments and toggle commitments equal the oracle's under fixed blindings / rng.
+    Single requests take the two-launch digit-table MSMs (small_msm.cuh) by default; BBP_SMALL_MSM_MAX=0 sends the same
+    request through the bucket engine."""
+    if small_msm == "engine":
+        monkeypatch.setenv("BBP_SMALL_MSM_MAX", "0")
     bid = make_case(L, L)
     rc, proof, comm, tc = orc.blindbid_prove(bid, bid["blindings"], bid["rng_seed"])
     assert rc == 0
