@@ -338,10 +338,12 @@ inline int pedersen_commit_host(bbp_ctx *ctx, const sc *vals, size_t n, uint8_t 
 // n_slots MSMs over the generator window table; scalars: n_slots x slot_len on the device (slot_len <= n_gens, column i
 // of a slot multiplies generator i). Results: compressed (n_slots x 32 B) and / or extended (n_slots x 128 B), on device.
 // Small problems take the latency path (small_msm.cuh): two launches instead of the engine's ~20. The crossover is in
-// total terms (BBP_SMALL_MSM_MAX, default 32768 = the IPP rounds of up to 8 proofs; 0 disables the path).
+// total terms (BBP_SMALL_MSM_MAX, default 66000 = the IPP rounds of up to 16 proofs, the commitments of up to 5; measured:
+// 6.0 / 6.9 / 7.9 / 9.1 ms per prove call at batch 1 / 2 / 4 / 8 against 9.3 / 9.6 / 10.3 / 11.6 through the engine, equal
+// from 16 on; 0 disables the path).
 inline bool small_msm_ok(size_t total_terms) {
     const char *e = getenv("BBP_SMALL_MSM_MAX");
-    return total_terms <= (size_t)(e ? atol(e) : 32768);
+    return total_terms <= (size_t)(e ? atol(e) : 66000);
 }
 inline int msm_gens_small(bbp_ctx *ctx, const sc *d_scalars, uint32_t slot_len, uint32_t n_slots, const uint32_t *colmap, uint32_t colmap_slots,
                           uint8_t *d_out_compressed, uint8_t *d_out_ext) {

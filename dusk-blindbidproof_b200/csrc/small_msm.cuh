@@ -18,8 +18,8 @@
 namespace bbp {
 
 static const uint32_t SM_C = 5, SM_W = 51, SM_D = 16;    // window bits, windows (255 >= 253 bits), multiples per window
-static const uint32_t SM_GROUPS = 4;                     // threads per term, each takes the windows w = g (mod 4)
-static const uint32_t SM_THREADS = 128;
+static const uint32_t SM_GROUPS = 4;                     // warps per block; warp g takes the windows w = g (mod 4) of the block's 32 terms
+static const uint32_t SM_THREADS = 32 * SM_GROUPS;
 
 // out[((w * n + i) * 16 + (d - 1))] = niels(d * 2^(5w) * P_i); one thread per (w, i)
 __global__ void __launch_bounds__(128) k_build_digit_table(const uint8_t *__restrict__ in_ext, uint8_t *__restrict__ out, uint32_t n) {
@@ -57,14 +57,15 @@ __device__ inline ge sm_block_fold(ge acc, ge *sh) {
     return sh[0];
 }
 
-// grid (chunks, slots); block = 32 terms x 4 window groups. scalars: [n_slots][slot_len] reduced, normal form.
+// grid (chunks, slots); block = 4 window groups (warps) x 32 terms. scalars: [n_slots][slot_len] reduced, normal form.
 // Entry e of a slot multiplies generator column colmap[(slot % colmap_slots) * slot_len + e] (or e without a map).
 __global__ void __launch_bounds__(SM_THREADS) k_small_msm_partial(const sc *__restrict__ scalars, uint32_t slot_len, const uint8_t *__restrict__ table,
                                                                    uint32_t n_gens, const uint32_t *__restrict__ colmap, uint32_t colmap_slots,
                                                                    uint8_t *__restrict__ partial) {
     __shared__ ge sh[SM_THREADS];
-    const uint32_t slot = blockIdx.y, t = threadIdx.x, g = t & (SM_GROUPS - 1);
-    const uint32_t e = blockIdx.x * (SM_THREADS / SM_GROUPS) + (t / SM_GROUPS);
+    // the window group is the warp index, so that a warp's lanes (32 different terms) all add at the same windows
+    const uint32_t slot = blockIdx.y, t = threadIdx.x, g = t >> 5;
+    const uint32_t e = blockIdx.x * (SM_THREADS / SM_GROUPS) + (t & 31);
     ge acc = ge_identity();
     if (e < slot_len) {
         sc s = scalars[(size_t)slot * slot_len + e];
