@@ -283,6 +283,14 @@ inline int rp_verify_group(bbp_ctx *ctx, std::vector<rp_verify_job> &jobs, uint3
         sc w = tr.challenge_scalar("w");
         shake_scalar_rng crng(J.rng_seed);
         sc c = crng.random_scalar();
+        // this request's weight in a combined check of several requests: a second secret stream, keyed by the request's
+        // seed and its position in the batch (callers may hand the same seed to every request)
+        uint8_t wseed[32];
+        memcpy(wseed, J.rng_seed, 32);
+        for (int k = 0; k < 8; k++) wseed[24 + k] ^= (uint8_t)((uint64_t)(i + 1) >> (8 * k));
+        shake_scalar_rng wrng(wseed);
+        wrng.random_scalar();
+        sc rho = wrng.random_scalar();
         if (nm != ((size_t)1 << lg_p)) return;
         tr.innerproduct_domain_sep(nm);
         std::vector<sc> uj(lg_p);
@@ -300,6 +308,7 @@ inline int rp_verify_group(bbp_ctx *ctx, std::vector<rp_verify_job> &jobs, uint3
         std::vector<sc> &ch = chal_all[i];
         ch.assign(CH_N, sc_zero());
         ch[CH_Y] = y; ch[CH_YINV] = allinv[lg_p]; ch[CH_Z] = z; ch[CH_X] = x; ch[CH_W] = w; ch[CH_A] = a; ch[CH_B] = b; ch[CH_RHO] = sc_one();
+        ch[CH_R] = rho;
         for (size_t j = 0; j < lg_p; j++) { ch[CH_UJ0 + j] = uj[j]; ch[CH_UJ0 + lg_p + j] = allinv[j]; }
         // B and B_blinding coefficients
         sc zz = sc_mul(z, z);
@@ -350,39 +359,67 @@ inline int rp_verify_group(bbp_ctx *ctx, std::vector<rp_verify_job> &jobs, uint3
     ctx->launches++;
     std::vector<uint8_t> valid((size_t)P * ds);
     if ((rc = d2h_sync(ctx, valid.data(), ps->valid.p, valid.size()))) return rc;
-    std::vector<sc> chal((size_t)P * CH_N), dyn((size_t)P * ds);
     std::vector<uint8_t> alive(P, 1);
-    for (uint32_t k = 0; k < P; k++) {
+    for (uint32_t k = 0; k < P; k++)
         for (uint32_t t = 0; t < ds; t++) if (!valid[(size_t)k * ds + t]) alive[k] = 0;
-        std::vector<sc> &ch = chal_all[live[k]];
-        if (!alive[k]) { ch[CH_RHO] = sc_zero(); ch[CH_TX] = sc_zero(); ch[CH_TXBL] = sc_zero(); }
-        memcpy(&chal[(size_t)k * CH_N], ch.data(), (size_t)CH_N * 32);
-        for (uint32_t t = 0; t < ds; t++) dyn[(size_t)k * ds + t] = alive[k] ? dyn_all[live[k]][t] : sc_zero();
-    }
-    if ((rc = ps->chal.ensure(chal.size() * 32)) || (rc = ps->dyn_sc.ensure(dyn.size() * 32)) || (rc = ps->zpow.ensure(32)) ||
+    if ((rc = ps->chal.ensure((size_t)P * CH_N * 32)) || (rc = ps->dyn_sc.ensure((size_t)P * ds * 32)) || (rc = ps->zpow.ensure(32)) ||
         (rc = ps->ypow.ensure((size_t)P * nm * 32)) || (rc = ps->yinvpow.ensure((size_t)P * nm * 32)) || (rc = ps->stat.ensure((size_t)P * slot_len * 32)) ||
-        (rc = ps->stat_red.ensure((size_t)P * slot_len * 32)) || (rc = ps->msm_ext.ensure((size_t)2 * P * 128)) || (rc = ps->flags.ensure(P)))
+        (rc = ps->stat_red.ensure((size_t)P * slot_len * 32)) || (rc = ps->msm_ext.ensure((size_t)2 * P * 128)) || (rc = ps->flags.ensure(P)) ||
+        (rc = ps->sG.ensure((size_t)P * nm * 32)))
         return rc;
-    if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32)) || (rc = h2d(ctx, ps->dyn_sc.p, dyn.data(), dyn.size() * 32))) return rc;
-    sc_batch SB;
-    memset(&SB, 0, sizeof SB);
-    SB.n_proofs = P; SB.n = nm; SB.lg_n = lg; SB.gcols = gcols; SB.rp_bits = nbits; SB.rp_m = m; SB.q = 0;
-    SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>(); SB.stat = ps->stat.as<sc>();
-    if ((rc = ps->sG.ensure((size_t)P * nm * 32))) return rc;
-    SB.stab = ps->sG.as<sc>();
-    SB.skip_ypow = 1;
-    k_powers<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
-    k_rp_verify_scalars<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
-    k_stat_reduce<<<dim3((slot_len + BBP_SC_THREADS - 1) / BBP_SC_THREADS, P), BBP_SC_THREADS, 0, ctx->stream>>>(SB.stat, 1, slot_len, ps->stat_red.as<sc>());
-    ctx->launches += 3;
-    uint8_t *ext = ps->msm_ext.p;
-    if ((rc = msm_gens_device(ctx, ps->stat_red.as<sc>(), slot_len, P, nullptr, ext))) return rc;
-    msm_shape sh = msm_engine::make_shape(P * ds, ds, P * ds, false, 0, 0, 0);
-    if ((rc = ctx->msm.run(sh, ps->dyn_sc.p, ps->dyn_niels.p, ext + (size_t)P * 128, nullptr))) return rc;
-    k_group_sum_identity<<<(P + 63) / 64, 64, 0, ctx->stream>>>(ext, P, 2, P, ps->flags.p, nullptr);
-    ctx->launches++;
-    std::vector<uint8_t> fl(P);
-    if ((rc = d2h_sync(ctx, fl.data(), ps->flags.p, P))) return rc;
+    // One pass over the P live requests. combined = false: P independent mega-checks (the semantics of verify_multiple).
+    // combined = true: ONE check of the random linear combination sum_k rho_k * check_k (rho_k from request k's own secret
+    // stream): the 8194 static-base columns are summed over the batch into a single slot, the dynamic points form one
+    // variable-base MSM. fl gets one flag per group (1 or P).
+    std::vector<sc> chal((size_t)P * CH_N), dyn((size_t)P * ds);
+    auto pass = [&](bool combined, std::vector<uint8_t> &fl) -> int {
+        int r;
+        const uint32_t n_groups = combined ? 1 : P;
+        parallel_for(P, [&](size_t k) {
+            const std::vector<sc> &src = chal_all[live[k]];
+            sc *ch = &chal[k * CH_N];
+            memcpy(ch, src.data(), (size_t)CH_N * 32);
+            sc rho = alive[k] ? (combined ? src[CH_R] : sc_one()) : sc_zero();
+            ch[CH_RHO] = rho;
+            ch[CH_TX] = sc_mul(rho, src[CH_TX]);
+            ch[CH_TXBL] = sc_mul(rho, src[CH_TXBL]);
+            for (uint32_t t = 0; t < ds; t++) dyn[k * ds + t] = sc_mul(rho, dyn_all[live[k]][t]);
+        });
+        if ((r = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32)) || (r = h2d(ctx, ps->dyn_sc.p, dyn.data(), dyn.size() * 32))) return r;
+        sc_batch SB;
+        memset(&SB, 0, sizeof SB);
+        SB.n_proofs = P; SB.n = nm; SB.lg_n = lg; SB.gcols = gcols; SB.rp_bits = nbits; SB.rp_m = m; SB.q = 0;
+        SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>(); SB.stat = ps->stat.as<sc>();
+        SB.stab = ps->sG.as<sc>();
+        SB.skip_ypow = 1;
+        k_powers<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+        k_rp_verify_scalars<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+        if (combined && P >= 32)
+            k_stat_reduce_wide<<<dim3((slot_len + 15) / 16, 1), 256, 0, ctx->stream>>>(SB.stat, P, slot_len, ps->stat_red.as<sc>());
+        else
+            k_stat_reduce<<<dim3((slot_len + BBP_SC_THREADS - 1) / BBP_SC_THREADS, n_groups), BBP_SC_THREADS, 0, ctx->stream>>>(SB.stat, combined ? P : 1, slot_len,
+                                                                                                                                 ps->stat_red.as<sc>());
+        ctx->launches += 3;
+        uint8_t *ext = ps->msm_ext.p;
+        if ((r = msm_gens_device(ctx, ps->stat_red.as<sc>(), slot_len, n_groups, nullptr, ext))) return r;
+        msm_shape sh = msm_engine::make_shape(P * ds, combined ? P * ds : ds, P * ds, false, 0, 0, 0);
+        if ((r = ctx->msm.run(sh, ps->dyn_sc.p, ps->dyn_niels.p, ext + (size_t)n_groups * 128, nullptr))) return r;
+        k_group_sum_identity<<<(n_groups + 63) / 64, 64, 0, ctx->stream>>>(ext, n_groups, 2, n_groups, ps->flags.p, nullptr);
+        ctx->launches++;
+        fl.resize(n_groups);
+        return d2h_sync(ctx, fl.data(), ps->flags.p, n_groups);
+    };
+    std::vector<uint8_t> fl;
+    const char *cb_env = getenv("BBP_RP_COMBINED");   // 0 = always the per-request pass (tests run both)
+    const bool try_combined = P >= 2 && (cb_env ? atoi(cb_env) != 0 : true);
+    if (try_combined) {
+        if ((rc = pass(true, fl))) return rc;
+        if (fl[0]) {   // the combination is the identity: every live request verifies
+            for (uint32_t k = 0; k < P; k++) jobs[live[k]].status = alive[k] ? 0 : BBP_ERR_VERIFICATION;
+            return 0;
+        }
+    }
+    if ((rc = pass(false, fl))) return rc;
     for (uint32_t k = 0; k < P; k++) jobs[live[k]].status = (alive[k] && fl[k]) ? 0 : BBP_ERR_VERIFICATION;
     return 0;
 }

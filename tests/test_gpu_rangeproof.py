@@ -85,7 +85,16 @@ def test_rangeproof_config5_shape(hybrid, device_rng, monkeypatch):
     assert rc == 0 and len(proof) == 1056
     assert proofs[0] == proof and Vs[0] == V
     assert oracle_verify(proofs[2], Vs[2], 64, RNG) == 0
-    assert be.rangeproof_verify_batch(proofs, Vs, 64, 64, RNG * 3) == [0, 0, 0]
     bad = [proofs[0], proofs[1][:200] + bytes([proofs[1][200] ^ 1]) + proofs[1][201:], proofs[2]]
-    assert be.rangeproof_verify_batch(bad, Vs, 64, 64, RNG * 3) == [0, oracle_verify(bad[1], Vs[1], 64, RNG), 0]
+    want_bad = [0, oracle_verify(bad[1], Vs[1], 64, RNG), 0]
+    assert want_bad[1] != 0
+    # batches are first checked as ONE random linear combination (accept all if it is the identity), then per request if
+    # that fails; BBP_RP_COMBINED=0 goes straight to the per-request pass: same verdicts either way
+    for combined in ("1", "0"):
+        monkeypatch.setenv("BBP_RP_COMBINED", combined)
+        assert be.rangeproof_verify_batch(proofs, Vs, 64, 64, RNG * 3) == [0, 0, 0]
+        assert be.rangeproof_verify_batch(bad, Vs, 64, 64, RNG * 3) == want_bad
+        # a commitment swapped between two requests breaks both
+        swapped = [Vs[1], Vs[0], Vs[2]]
+        assert be.rangeproof_verify_batch(proofs, swapped, 64, 64, RNG * 3) == [-3, -3, 0]
     be.close()
