@@ -562,13 +562,16 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_rp_polys(sc_batch B) {
     const sc *ch = B.chal + (size_t)p * CH_N, *ypow = B.ypow + (size_t)p * n;
     sc *poly = B.poly + (size_t)p * 4 * n;
     sc zM = sc_to_mont(ch[CH_Z]), one = sc_mont_one();
+    __shared__ sc zz[64], two[64];   // z^(2+j) for the first 64 parties, 2^i for the (at most 64) bits
+    if (t < 64) { zz[t] = sc_pow_small_mont(zM, 2 + t); two[t] = sc_to_mont(sc_from_u64(1ull << t)); }
+    __syncthreads();
     sc t0 = sc_zero(), t1 = t0, t2 = t0;
     for (uint32_t k = t; k < n; k += BBP_SC_THREADS) {
         uint32_t j = k / B.rp_bits, i = k % B.rp_bits, bit = rp_bit(B, p, k);
         sc aL = bit ? one : sc_zero(), aR = bit ? sc_zero() : sc_neg(one);
         sc sL = sc_to_mont(B.sL[(size_t)p * n + k]), sR = sc_to_mont(B.sR[(size_t)p * n + k]);
-        sc zz_j = sc_pow_small_mont(zM, 2 + j);
-        sc two_i = sc_to_mont(sc_from_u64(1ull << i));
+        sc zz_j = j < 64 ? zz[j] : sc_pow_small_mont(zM, 2 + j);
+        sc two_i = two[i];
         sc l0 = sc_sub(aL, zM);
         sc r0 = sc_add(mm(ypow[k], sc_add(aR, zM)), mm(zz_j, two_i));
         sc r1 = mm(ypow[k], sR);
@@ -610,12 +613,14 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_rp_verify_scalars(sc_batch B
     sc *stat = B.stat + (size_t)p * (2 + 2 * gc);
     for (uint32_t i = n + t; i < gc; i += BBP_SC_THREADS) { stat[2 + i] = sc_zero(); stat[2 + gc + i] = sc_zero(); }
     sc *stab = B.stab + (size_t)p * n;
-    build_s_table(stab, uj, lg, n);
+    __shared__ sc zz[64], two[64];   // z^(2+j) for the first 64 parties, 2^i for the (at most 64) bits
+    if (t < 64) { zz[t] = sc_pow_small_mont(zM, 2 + t); two[t] = sc_to_mont(sc_from_u64(1ull << t)); }
+    build_s_table(stab, uj, lg, n);   // synchronises the block
     for (uint32_t k = t; k < n; k += BBP_SC_THREADS) {
         sc s = stab[k], srev = stab[n - 1 - k];
         uint32_t j = k / B.rp_bits, i = k % B.rp_bits;
-        sc zz_j = sc_pow_small_mont(zM, 2 + j);
-        sc two_i = sc_to_mont(sc_from_u64(1ull << i));
+        sc zz_j = j < 64 ? zz[j] : sc_pow_small_mont(zM, 2 + j);
+        sc two_i = two[i];
         sc g = sc_sub(sc_neg(zM), mm(aM, s));
         sc h = sc_add(zM, mm(yinv[k], sc_sub(mm(zz_j, two_i), mm(bM, srev))));
         stat[2 + k] = mm(rhoM, g);
