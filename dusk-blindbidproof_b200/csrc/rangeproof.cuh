@@ -18,6 +18,12 @@ namespace bbp {
 struct shake_scalar_rng {
     keccak_sponge s;
     explicit shake_scalar_rng(const uint8_t seed[32]) : s(shake256_new()) { s.absorb(seed, 32); }
+    // party j's stream of a prover: SHAKE256(seed || LE32(j))
+    shake_scalar_rng(const uint8_t seed[32], uint32_t party) : s(shake256_new()) {
+        uint8_t le[4] = {(uint8_t)party, (uint8_t)(party >> 8), (uint8_t)(party >> 16), (uint8_t)(party >> 24)};
+        s.absorb(seed, 32);
+        s.absorb(le, 4);
+    }
     sc random_scalar() {
         uint8_t b[64];
         s.squeeze(b, 64);
@@ -60,40 +66,43 @@ inline int rp_prove_group(bbp_ctx *ctx, std::vector<rp_prove_job> &jobs, uint32_
     if ((rc = proto_tables(ctx))) return rc;
     struct hstate {
         std::unique_ptr<merlin_transcript> tr;
-        std::unique_ptr<shake_scalar_rng> rng;
+        std::vector<shake_scalar_rng> rng;   // one stream per party (host path)
         sc sum_a, sum_s, sum_t1, sum_t2, y, z, x;
         uint8_t A[32], S[32], T1[32], T2[32];
         sc t_x, t_x_bl, e_bl;
         std::vector<uint8_t> LR;
     };
     std::vector<hstate> hs(P);
-    // ---- party draws, V commitments. Large batches squeeze the SHAKE256 draw streams on the device (one thread per
-    // proof, ~12 ms whatever the batch, against ~3.5 ms per proof per host thread) and land s_L / s_R directly in HBM.
+    phase_trace trace("rp_prove_group");
+    // ---- party draws, V commitments. Every party has its own SHAKE256 stream (seed || party index); large batches
+    // squeeze them on the device, one thread per (proof, party), and land s_L / s_R directly in HBM.
     const char *rng_env = getenv("BBP_DEVICE_RNG_MIN_BATCH");
     const bool device_rng = (int)P >= (rng_env ? atoi(rng_env) : (int)(4 * host_threads()));
     std::vector<sc> sLR(device_rng ? 0 : (size_t)2 * P * nm), blind3((size_t)P * 3, sc_zero()), cv((size_t)P * m * 2);
     std::vector<uint64_t> vals((size_t)P * m);
     std::vector<sc> small(device_rng ? (size_t)P * 4 * m : 0);
     if (device_rng) {
-        const uint32_t n_draws = m * (2 + 2 * nbits) + 2 * m;
+        const uint32_t per_party = 4 + 2 * nbits, n_draws = m * per_party;
         std::vector<uint8_t> seeds((size_t)P * 32);
         for (uint32_t pi = 0; pi < P; pi++) memcpy(&seeds[(size_t)pi * 32], jobs[pi].rng_seed, 32);
         if ((rc = ps->rng_states.ensure(seeds.size())) || (rc = ps->rng_raw.ensure((size_t)P * n_draws * 64)) || (rc = ps->wit.ensure((size_t)2 * P * nm * 32)) ||
             (rc = ps->stat_red.ensure(small.size() * 32)))
             return rc;
         if ((rc = h2d(ctx, ps->rng_states.p, seeds.data(), seeds.size()))) return rc;
-        k_shake_draws<<<(P + 31) / 32, 32, 0, ctx->stream>>>(ps->rng_states.p, P, n_draws, ps->rng_raw.as<uint32_t>());
+        k_shake_draws<<<(P * m + 63) / 64, 64, 0, ctx->stream>>>(ps->rng_states.p, P, m, per_party, ps->rng_raw.as<uint32_t>());
         k_rp_draw_scatter<<<(unsigned)(((size_t)P * n_draws + 127) / 128), 128, 0, ctx->stream>>>(ps->rng_raw.as<uint32_t>(), P, m, nbits, ps->wit.as<sc>(),
                                                                                                   ps->wit.as<sc>() + (size_t)P * nm, ps->stat_red.as<sc>());
         ctx->launches += 2;
         BBP_CUDA_OK(cudaMemcpyAsync(small.data(), ps->stat_red.p, small.size() * 32, cudaMemcpyDeviceToHost, ctx->stream));
         BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        trace.mark("gpu_shake_draws");
     }
     parallel_for(P, [&](size_t pi) {
         rp_prove_job &J = jobs[pi];
         hstate &H = hs[pi];
         H.sum_a = sc_zero(); H.sum_s = sc_zero(); H.sum_t1 = sc_zero(); H.sum_t2 = sc_zero();
-        if (!device_rng) H.rng.reset(new shake_scalar_rng(J.rng_seed));
+        if (!device_rng)
+            for (uint32_t j = 0; j < m; j++) H.rng.emplace_back(J.rng_seed, j);
         for (uint32_t j = 0; j < m; j++) {
             vals[pi * m + j] = J.values[j];
             cv[(pi * m + j) * 2] = sc_from_u64(J.values[j]);
@@ -104,15 +113,17 @@ inline int rp_prove_group(bbp_ctx *ctx, std::vector<rp_prove_job> &jobs, uint32_
                 H.sum_t1 = sc_add(H.sum_t1, sm[2 * m + j]); H.sum_t2 = sc_add(H.sum_t2, sm[3 * m + j]);
                 continue;
             }
-            H.sum_a = sc_add(H.sum_a, H.rng->random_scalar());
-            H.sum_s = sc_add(H.sum_s, H.rng->random_scalar());
-            for (uint32_t i = 0; i < nbits; i++) sLR[(size_t)pi * nm + j * nbits + i] = H.rng->random_scalar();
-            for (uint32_t i = 0; i < nbits; i++) sLR[(size_t)(P + pi) * nm + j * nbits + i] = H.rng->random_scalar();
+            H.sum_a = sc_add(H.sum_a, H.rng[j].random_scalar());
+            H.sum_s = sc_add(H.sum_s, H.rng[j].random_scalar());
+            for (uint32_t i = 0; i < nbits; i++) sLR[(size_t)pi * nm + j * nbits + i] = H.rng[j].random_scalar();
+            for (uint32_t i = 0; i < nbits; i++) sLR[(size_t)(P + pi) * nm + j * nbits + i] = H.rng[j].random_scalar();
         }
         blind3[pi * 3] = H.sum_a; blind3[pi * 3 + 1] = H.sum_s;
     });
     std::vector<uint8_t> V((size_t)P * m * 32);
+    trace.mark("host_draws");
     if ((rc = pedersen_commit_host(ctx, cv.data(), (size_t)P * m, V.data()))) return rc;
+    trace.mark("gpu_V_commit");
 
     if ((rc = ps->chal.ensure((size_t)P * CH_N * 32)) || (rc = ps->zpow.ensure(32)) || (rc = ps->ypow.ensure((size_t)P * nm * 32)) ||
         (rc = ps->yinvpow.ensure((size_t)P * nm * 32)) || (rc = ps->wit.ensure((size_t)2 * P * nm * 32)) || (rc = ps->blind3.ensure((size_t)P * 96)) ||
@@ -139,6 +150,7 @@ inline int rp_prove_group(bbp_ctx *ctx, std::vector<rp_prove_job> &jobs, uint32_
     if ((rc = msm_gens_device(ctx, SB.slots, slot_len, 2 * P, ps->msm_out.p, nullptr))) return rc;
     std::vector<uint8_t> as((size_t)P * 64);
     if ((rc = d2h_sync(ctx, as.data(), ps->msm_out.p, as.size()))) return rc;
+    trace.mark("gpu_A_S_msm");
     std::vector<sc> chal((size_t)P * CH_N, sc_zero());
     parallel_for(P, [&](size_t pi) {
         rp_prove_job &J = jobs[pi];
@@ -156,8 +168,8 @@ inline int rp_prove_group(bbp_ctx *ctx, std::vector<rp_prove_job> &jobs, uint32_
         c[CH_Y] = H.y; c[CH_Z] = H.z; c[CH_YINV] = sc_invert(H.y);
         if (!device_rng) {
             for (uint32_t j = 0; j < m; j++) {
-                H.sum_t1 = sc_add(H.sum_t1, H.rng->random_scalar());
-                H.sum_t2 = sc_add(H.sum_t2, H.rng->random_scalar());
+                H.sum_t1 = sc_add(H.sum_t1, H.rng[j].random_scalar());
+                H.sum_t2 = sc_add(H.sum_t2, H.rng[j].random_scalar());
             }
         }
     });
@@ -167,6 +179,7 @@ inline int rp_prove_group(bbp_ctx *ctx, std::vector<rp_prove_job> &jobs, uint32_
     ctx->launches += 2;
     std::vector<sc> tout((size_t)P * 8);
     if ((rc = d2h_sync(ctx, tout.data(), ps->tout.p, tout.size() * 32))) return rc;
+    trace.mark("yz+gpu_polys");
     // ---- T_1, T_2
     std::vector<sc> tv((size_t)P * 4);
     for (uint32_t pi = 0; pi < P; pi++) {
@@ -175,6 +188,7 @@ inline int rp_prove_group(bbp_ctx *ctx, std::vector<rp_prove_job> &jobs, uint32_
     }
     std::vector<uint8_t> Tp((size_t)P * 64);
     if ((rc = pedersen_commit_host(ctx, tv.data(), (size_t)P * 2, Tp.data()))) return rc;
+    trace.mark("gpu_T_commit");
     parallel_for(P, [&](size_t pi) {
         rp_prove_job &J = jobs[pi];
         hstate &H = hs[pi];
@@ -202,7 +216,7 @@ inline int rp_prove_group(bbp_ctx *ctx, std::vector<rp_prove_job> &jobs, uint32_
     if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32))) return rc;
     k_rp_ipp_init<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
     ctx->launches++;
-    phase_trace trace("rp_prove_group");
+    trace.mark("host_xw");
     rc = ipp_rounds(ctx, SB, P, chal, [&](uint32_t j, const std::vector<uint8_t> &lr) {
         parallel_chunks(P, [&](size_t lo, size_t hi) {
             std::vector<sc> inv(hi - lo);

@@ -215,22 +215,25 @@ __global__ void __launch_bounds__(128) k_wide_reduce(const uint32_t *__restrict_
 
 // ---------------------------------------------------------------- SHAKE256 draw stream on the device (aggregated range proofs)
 // The range-proof prover draws 2 m (1 + n) + 2 m scalars per proof from SHAKE256(seed) (rangeproof.cuh RNG contract):
-// one thread per proof squeezes the whole stream (one Keccak-f per 136 bytes, state in registers), writing raw 64-byte
-// draws; k_rp_draw_scatter reduces them mod l in parallel and routes them to s_L / s_R or to the small per-party list the
-// host sums (a_blinding, s_blinding, t_1 / t_2 blindings).
-__global__ void __launch_bounds__(32) k_shake_draws(const uint8_t *__restrict__ seeds, uint32_t n_proofs, uint32_t n_draws, uint32_t *__restrict__ raw) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_proofs) return;
+// one thread per (proof, party) squeezes that party's stream SHAKE256(seed || LE32(party)) (one Keccak-f per 136 bytes,
+// state in registers), writing raw 64-byte draws; k_rp_draw_scatter reduces them mod l in parallel and routes them to
+// s_L / s_R or to the small per-party list the host sums (a_blinding, s_blinding, t_1 / t_2 blindings).
+// raw: [n_proofs][m][per_party][16 words], per_party = 4 + 2 nbits.
+__global__ void __launch_bounds__(64) k_shake_draws(const uint8_t *__restrict__ seeds, uint32_t n_proofs, uint32_t m, uint32_t per_party,
+                                                    uint32_t *__restrict__ raw) {
+    uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_proofs * m) return;
+    const uint32_t p = idx / m, j = idx % m;
     uint64_t r[25];
 #pragma unroll
     for (int i = 0; i < 25; i++) r[i] = 0;
     const uint64_t *sd = (const uint64_t *)(seeds + 32 * (size_t)p);
     r[0] = sd[0]; r[1] = sd[1]; r[2] = sd[2]; r[3] = sd[3];
-    r[4] ^= 0x1fULL;                       // SHAKE domain separation + first pad bit right after the 32 absorbed bytes
+    r[4] = (uint64_t)j | (0x1fULL << 32);  // LE32(party), then SHAKE domain separation + first pad bit after the 36 absorbed bytes
     r[16] ^= 0x8000000000000000ULL;        // last pad bit at byte 135 (rate 136)
     keccak_f1600_dev(r);
-    uint64_t *out = (uint64_t *)(raw + (size_t)p * n_draws * 16);
-    const size_t total_words = (size_t)n_draws * 8;   // 64-bit words to produce
+    uint64_t *out = (uint64_t *)(raw + (size_t)idx * per_party * 16);
+    const size_t total_words = (size_t)per_party * 8;   // 64-bit words to produce
     size_t w = 0;
     while (w < total_words) {
 #pragma unroll
@@ -240,14 +243,14 @@ __global__ void __launch_bounds__(32) k_shake_draws(const uint8_t *__restrict__ 
         if (w < total_words) keccak_f1600_dev(r);
     }
 }
-// draw d of proof p: party j = d / (2 + 2 n) for d < m (2 + 2 n): slot 0 = a_blinding, 1 = s_blinding, then s_L, s_R;
-// the last 2 m draws are (t_1, t_2) blindings per party. small: [n_proofs][4][m] = a, s, t1, t2 blindings.
+// draw e of party j of proof p: 0 = a_blinding, 1 = s_blinding, then s_L[0..n), s_R[0..n), then t_1 / t_2 blindings.
+// small: [n_proofs][4][m] = a, s, t1, t2 blindings.
 __global__ void __launch_bounds__(128) k_rp_draw_scatter(const uint32_t *__restrict__ raw, uint32_t n_proofs, uint32_t m, uint32_t nbits, sc *__restrict__ sL,
                                                          sc *__restrict__ sR, sc *__restrict__ small) {
-    const uint32_t per_party = 2 + 2 * nbits, n_draws = m * per_party + 2 * m;
+    const uint32_t per_party = 4 + 2 * nbits;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)n_proofs * n_draws) return;
-    uint32_t p = (uint32_t)(i / n_draws), d = (uint32_t)(i % n_draws);
+    if (i >= (size_t)n_proofs * m * per_party) return;
+    uint32_t e = (uint32_t)(i % per_party), j = (uint32_t)((i / per_party) % m), p = (uint32_t)(i / ((size_t)per_party * m));
     uint32_t w[16];
     const uint4 *q = (const uint4 *)(raw + i * 16);
 #pragma unroll
@@ -257,16 +260,11 @@ __global__ void __launch_bounds__(128) k_rp_draw_scatter(const uint32_t *__restr
     sc hi = sc_montmul(w + 8, r2.v);
     sc val = sc_add(lo, hi);
     const size_t nm = (size_t)m * nbits;
-    if (d < m * per_party) {
-        uint32_t j = d / per_party, e = d % per_party;
-        if (e == 0) small[((size_t)p * 4 + 0) * m + j] = val;
-        else if (e == 1) small[((size_t)p * 4 + 1) * m + j] = val;
-        else if (e < 2 + nbits) sL[(size_t)p * nm + (size_t)j * nbits + (e - 2)] = val;
-        else sR[(size_t)p * nm + (size_t)j * nbits + (e - 2 - nbits)] = val;
-    } else {
-        uint32_t t = d - m * per_party, j = t / 2;
-        small[((size_t)p * 4 + 2 + (t & 1)) * m + j] = val;
-    }
+    if (e == 0) small[((size_t)p * 4 + 0) * m + j] = val;
+    else if (e == 1) small[((size_t)p * 4 + 1) * m + j] = val;
+    else if (e < 2 + nbits) sL[(size_t)p * nm + (size_t)j * nbits + (e - 2)] = val;
+    else if (e < 2 + 2 * nbits) sR[(size_t)p * nm + (size_t)j * nbits + (e - 2 - nbits)] = val;
+    else small[((size_t)p * 4 + 2 + (e - 2 - 2 * nbits)) * m + j] = val;
 }
 
 // ---------------------------------------------------------------- the verifier's transcript replay on the device

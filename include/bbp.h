@@ -167,7 +167,8 @@ int bbp_blindbid_circuit_shape(size_t n_commitments, size_t n_toggles, size_t ou
 /* ---- aggregated range proofs: bulletproofs RangeProof::prove_multiple / verify_multiple (BASELINE.json configs[4]; the
  * reference itself has no call site). m values of nbits bits each (nbits in {8,16,32,64}, m a power of two);
  * the context must have been created with bbp_init(device, nbits, parties >= m). Proof = 32 * (9 + 2 lg(nbits m)) bytes.
- * RNG contract: rng_seed keys a SHAKE256 stream that replaces the caller's rng of upstream (draw order as upstream).
+ * RNG contract: upstream hands every party an rng; here party j draws from the SHAKE256 stream of (rng_seed || LE32(j)),
+ * 64 bytes per scalar in upstream's per-party order (a_blinding, s_blinding, s_L, s_R, then t_1 / t_2 blindings).
  * Transcript label "bbp-rangeproof". */
 int bbp_rangeproof_prove_multiple(bbp_ctx *ctx, const uint64_t *values, const uint8_t *blindings, size_t m, size_t nbits, const uint8_t rng_seed[32],
                                   uint8_t *proof_out, size_t *proof_len, uint8_t *commitments_out /* m x 32 */);

@@ -3,10 +3,11 @@
 // dealer/party MPC run in-process. The reference itself has no call site;
 // BASELINE.json configs[4] names it (m = 64 parties x n = 64 bits => 4096-point IPP).
 // PARITY STATUS: proof-byte level parity UNPINNED (no reference vectors; see r1cs.h). 
-// RNG contract: upstream draws from the caller's rng directly (not a TranscriptRng). Here the rng is the
-// SHAKE256 stream of a 32-byte seed, consumed 64 bytes per Scalar::random in upstream's draw order
-// (per party j: a_blinding, s_blinding, s_L[0..n), s_R[0..n); then per party: t_1_blinding, t_2_blinding).
-// The verifier's batching scalar c is the first 64 bytes of SHAKE256(rng32), wide-reduced.
+// RNG contract: upstream draws from the caller's rng directly (not a TranscriptRng): every party owns an rng
+// (Party::new(.., rng)). Here party j's rng is the SHAKE256 stream of (32-byte seed || LE32(j)), consumed 64 bytes
+// per Scalar::random in upstream's per-party draw order: a_blinding, s_blinding, s_L[0..n), s_R[0..n), then (after
+// the y, z challenges) t_1_blinding, t_2_blinding. Independent per-party streams are what lets the product squeeze
+// them in parallel. The verifier's batching scalar c is the first 64 bytes of SHAKE256(rng32), wide-reduced.
 #pragma once
 #include "gens.h"
 #include "ipp.h"
@@ -18,6 +19,11 @@ namespace orc {
 struct shake_rng {
     shake256 s;
     explicit shake_rng(const uint8_t seed[32]) { s.absorb(seed, 32); }
+    shake_rng(const uint8_t seed[32], uint32_t party) {
+        uint8_t le[4] = {(uint8_t)party, (uint8_t)(party >> 8), (uint8_t)(party >> 16), (uint8_t)(party >> 24)};
+        s.absorb(seed, 32);
+        s.absorb(le, 4);
+    }
     sc random_scalar() {
         uint8_t b[64];
         s.squeeze(b, 64);
@@ -48,7 +54,8 @@ static inline int rangeproof_prove_multiple(const std::vector<uint64_t> &values,
     pedersen_gens pc;
     bulletproof_gens bp(n, m);
     transcript tr("bbp-rangeproof");   // caller-chosen label; the product uses the same one
-    shake_rng rng(rng_seed);
+    std::vector<shake_rng> rngs;
+    for (size_t j = 0; j < m; j++) rngs.emplace_back(rng_seed, (uint32_t)j);
 
     tr.rangeproof_domain_sep(n, m);
     struct party { sc a_bl, s_bl; std::vector<sc> s_L, s_R; ge A, S; sc t1_bl, t2_bl, t0, t1, t2; std::vector<sc> l0, l1, r0, r1; };
@@ -57,17 +64,17 @@ static inline int rangeproof_prove_multiple(const std::vector<uint64_t> &values,
     for (size_t j = 0; j < m; j++) {
         party &p = P[j];
         V_out[j] = ge_compress32(pc.commit(sc_from_u64(values[j]), blindings[j]));
-        p.a_bl = rng.random_scalar();
+        p.a_bl = rngs[j].random_scalar();
         ge A = ge_scalarmul(p.a_bl, pc.B_blinding);
         for (size_t i = 0; i < n; i++) {
             if ((values[j] >> i) & 1) A = ge_add(A, bp.G[j][i]);
             else A = ge_sub(A, bp.H[j][i]);
         }
         p.A = A;
-        p.s_bl = rng.random_scalar();
+        p.s_bl = rngs[j].random_scalar();
         p.s_L.resize(n); p.s_R.resize(n);
-        for (size_t i = 0; i < n; i++) p.s_L[i] = rng.random_scalar();
-        for (size_t i = 0; i < n; i++) p.s_R[i] = rng.random_scalar();
+        for (size_t i = 0; i < n; i++) p.s_L[i] = rngs[j].random_scalar();
+        for (size_t i = 0; i < n; i++) p.s_R[i] = rngs[j].random_scalar();
         std::vector<sc> ss; std::vector<ge> pp;
         ss.push_back(p.s_bl); pp.push_back(pc.B_blinding);
         for (size_t i = 0; i < n; i++) { ss.push_back(p.s_L[i]); pp.push_back(bp.G[j][i]); }
@@ -103,8 +110,8 @@ static inline int rangeproof_prove_multiple(const std::vector<uint64_t> &values,
         p.t0 = sc_inner_product(p.l0.data(), p.r0.data(), n);
         p.t2 = sc_inner_product(p.l1.data(), p.r1.data(), n);
         p.t1 = sc_add(sc_inner_product(p.l0.data(), p.r1.data(), n), sc_inner_product(p.l1.data(), p.r0.data(), n));
-        p.t1_bl = rng.random_scalar();
-        p.t2_bl = rng.random_scalar();
+        p.t1_bl = rngs[j].random_scalar();
+        p.t2_bl = rngs[j].random_scalar();
         T1 = ge_add(T1, pc.commit(p.t1, p.t1_bl));
         T2 = ge_add(T2, pc.commit(p.t2, p.t2_bl));
     }
