@@ -325,11 +325,20 @@ inline int d2h_sync(bbp_ctx *ctx, void *dst, const void *src, size_t bytes) {
 }
 
 // n commitments v*B + r*B_blinding; vals = n x (value, blinding) reduced scalars on the host; out = n x 32 B on the host
+inline bool small_msm_ok(size_t total_terms);
+inline int msm_gens_small(bbp_ctx *ctx, const sc *d_scalars, uint32_t slot_len, uint32_t n_slots, const uint32_t *colmap, uint32_t colmap_slots,
+                          uint8_t *d_out_compressed, uint8_t *d_out_ext);
 inline int pedersen_commit_host(bbp_ctx *ctx, const sc *vals, size_t n, uint8_t *out) {
     proto_state *ps = proto_get(ctx);
     int rc;
     if ((rc = ps->commit_in.ensure(n * 64)) || (rc = ps->commit_out.ensure(n * 32))) return rc;
     if ((rc = h2d(ctx, ps->commit_in.p, vals, n * 64))) return rc;
+    if (n <= 64 && small_msm_ok(2 * n)) {
+        // a handful of commitments (one request's V or T points): the comb kernel is a 128-addition chain per thread
+        // (~0.4 ms); as two-column slots [B, B_blinding] of the latency path the additions spread over four warps
+        if ((rc = msm_gens_small(ctx, ps->commit_in.as<sc>(), 2, (uint32_t)n, nullptr, 0, ps->commit_out.p, nullptr))) return rc;
+        return d2h_sync(ctx, out, ps->commit_out.p, n * 32);
+    }
     k_pedersen_commit<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ps->commit_in.as<sc>(), ps->comb, ps->commit_out.as<uint32_t>(), (uint32_t)n);
     ctx->launches++;
     return d2h_sync(ctx, out, ps->commit_out.p, n * 32);
