@@ -66,4 +66,14 @@ __global__ void __launch_bounds__(64) k_group_sum_identity(const uint8_t *__rest
     if (out_compressed) ge_compress_words(out_compressed + 8 * (size_t)g, acc);
 }
 
+// out[g] = sum over parts of partial[part][g], g < n_groups (extended points, 128 B each): folds the per-lane partial
+// sums of a sharded batch verification into the one this GPU contributes
+__global__ void __launch_bounds__(32) k_partial_fold(const uint8_t *__restrict__ partial, uint32_t n_parts, uint32_t n_groups, uint8_t *__restrict__ out) {
+    uint32_t g = threadIdx.x;
+    if (g >= n_groups) return;
+    ge acc = ge_load(partial + 128 * (size_t)g);
+    for (uint32_t k = 1; k < n_parts; k++) acc = ge_add(acc, ge_load(partial + 128 * ((size_t)k * n_groups + g)));
+    ge_store(out + 128 * (size_t)g, acc);
+}
+
 }  // namespace bbp

@@ -218,7 +218,7 @@ struct proto_state {
     uint32_t *colmap = nullptr;    // compact slot -> generator column map of the materialisation MSM
     uint32_t colmap_n = 0, colmap_gcols = 0;
     uint8_t *dtable = nullptr;     // digit-multiple table of the latency path (small_msm.cuh), built on first use
-    dev_buf sm_partial;
+    dev_buf sm_partial, lane_partials;
     uint32_t *ipp_colmap = nullptr;   // early IPP rounds, compact slots: lg n maps of 2 (1 + n) generator columns (L slot, R slot)
     uint32_t ipp_colmap_n = 0, ipp_colmap_gcols = 0;
     dev_buf fext, ftab;            // materialised folded bases: extended, then niels (+ B at the tail)
@@ -239,7 +239,7 @@ void proto_release(proto_state *ps) {
     if (!ps) return;
     for (auto &kv : ps->templates) { cudaFree(kv.second.row_ptr); cudaFree(kv.second.entries); cudaFree(kv.second.const_j); cudaFree(kv.second.const_idx); }
     cudaFree(ps->comb); cudaFree(ps->wtable); cudaFree(ps->wtable2); cudaFree(ps->colmap); cudaFree(ps->ipp_colmap); cudaFree(ps->dtable);
-    ps->sm_partial.release();
+    ps->sm_partial.release(); ps->lane_partials.release();
     ps->fext.release(); ps->ftab.release();
     dev_buf *all[] = {&ps->chal, &ps->zpow, &ps->ypow, &ps->yinvpow, &ps->wit, &ps->vbl, &ps->blind3, &ps->poly, &ps->tout, &ps->a, &ps->b, &ps->sG, &ps->sH,
                       &ps->slots, &ps->ab, &ps->pub, &ps->dyn_sc, &ps->dyn_pts, &ps->dyn_niels, &ps->stat, &ps->stat_red, &ps->msm_out, &ps->msm_ext,
@@ -1198,18 +1198,20 @@ inline int verify_batch(bbp_ctx *ctx, std::vector<verify_job> &jobs, const uint8
     std::map<uint64_t, std::vector<size_t>> groups;
     verify_prepare_all(ctx, jobs, prep, groups);
     if (partial_only && groups.size() > 1) return BBP_ERR_INPUT;   // sharded mode expects one circuit shape per call
-    // one combination per part of at most 1024 requests (the sharded mode keeps its single combination: its partial sum
-    // is what the other GPUs add to); the parts run on parallel lanes
+    // one combination per part of at most 1024 requests; the parts run on parallel lanes. In the sharded mode every part
+    // leaves its partial sum (static | dynamic, 2 x 128 B) in a scratch row and the rows are folded into the one partial
+    // this GPU contributes to the cross-GPU sum.
     std::vector<std::vector<size_t>> parts;
-    for (auto &g : groups) {
-        if (partial_only) { parts.push_back(g.second); continue; }
-        // like a prove batch, a single part of 768..1024 requests runs as two halves on two lanes (5.4 against 6.4 ms)
-        cut_parts(g.second, single_part_max(g.second.size()), parts);
+    for (auto &g : groups) cut_parts(g.second, single_part_max(g.second.size()), parts);
+    proto_state *ps0 = proto_get(ctx);
+    if (partial_only && !parts.empty()) {
+        int r = ps0->lane_partials.ensure(parts.size() * 256);
+        if (r) return r;
     }
     std::vector<uint8_t> part_ok(parts.size(), 0);
-    int rc = run_on_lanes(ctx, partial_only ? std::min<size_t>(parts.size(), 1) : parts.size(), [&](bbp_ctx *c, size_t i) {
+    int rc = run_on_lanes(ctx, parts.size(), [&](bbp_ctx *c, size_t i) {
         std::vector<uint8_t> verdicts;
-        int r = verify_group(c, jobs, prep, parts[i], true, batch_seed, verdicts, d_partial_ext);
+        int r = verify_group(c, jobs, prep, parts[i], true, batch_seed, verdicts, partial_only ? ps0->lane_partials.p + 256 * i : nullptr);
         if (r) return r;
         part_ok[i] = verdicts[0];
         if (!verdicts[0] && !partial_only) {   // the combination failed: find the culprits with one per-request pass
@@ -1219,6 +1221,19 @@ inline int verify_batch(bbp_ctx *ctx, std::vector<verify_job> &jobs, const uint8
         }
         return 0;
     });
+    if (!rc && partial_only && !parts.empty()) {
+        // every lane has synchronised its own stream inside verify_group, so the rows are complete
+        k_partial_fold<<<1, 32, 0, ctx->stream>>>(ps0->lane_partials.p, (uint32_t)parts.size(), 2, d_partial_ext);
+        ctx->launches++;
+        BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (!rc && partial_only && parts.empty()) {   // no live request: this GPU contributes the identity twice
+        uint8_t id[256];
+        memset(id, 0, sizeof id);
+        id[32] = 1; id[64] = 1; id[128 + 32] = 1; id[128 + 64] = 1;   // (X, Y, Z, T) = (0, 1, 1, 0)
+        BBP_CUDA_OK(cudaMemcpyAsync(d_partial_ext, id, 256, cudaMemcpyHostToDevice, ctx->stream));
+        BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    }
     if (rc) return rc;
     bool ok = true;
     for (uint8_t v : part_ok) ok = ok && v;

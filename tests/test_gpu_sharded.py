@@ -47,8 +47,13 @@ def test_point_range_sharded_msm_equals_single(ranks):
     assert bytes(d_out.cpu().numpy()) == want
 
 
-def test_proof_range_sharded_batch_verify(ranks):
+@pytest.mark.parametrize("part", [None, 2])
+def test_proof_range_sharded_batch_verify(ranks, part, monkeypatch):
+    """part = 2 shrinks the 1024-request part size: every rank then verifies its 3 requests as two parts on two lanes
+    and folds their partial sums into the one it contributes"""
     import torch
+    if part:
+        monkeypatch.setenv("BBP_PROVE_PART", str(part))
     pkg, ctxs = ranks
     world = 3
     L = 4
