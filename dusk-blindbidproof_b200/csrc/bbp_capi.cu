@@ -398,10 +398,16 @@ int bbp_blindbid_prove_batch(bbp_ctx *ctx, size_t n, bbp_prove_req *reqs) {
         R.status = BBP_ERR_INPUT;
         R.proof_len = 0;
         if (!R.d || !R.k || !R.y || !R.y_inv || !R.q || !R.z_img || !R.seed || !R.pub_list || !R.blindings || !R.rng_seed || !R.proof_out ||
-            !R.commitments_out || !R.t_c_out || R.L == 0 || R.toggle >= R.L + (uint64_t)0x100000000ull)
+            !R.commitments_out || !R.t_c_out || R.L == 0)
             continue;
-        J.d = load_scalar(R.d); J.k = load_scalar(R.k); J.y = load_scalar(R.y); J.y_inv = load_scalar(R.y_inv);
-        J.q = load_scalar(R.q); J.z_img = load_scalar(R.z_img); J.seed = load_scalar(R.seed);
+        // any toggle is accepted, as in the reference (`i as u64 == toggle`, src/blindbid/proof.rs:60-66): an index beyond the
+        // list makes every toggle bit zero and yields a proof that cannot verify, not an error.
+        // d .. seed arrive through serde in the reference (src/blindbid/proof.rs:100-106), which rejects non-canonical scalars
+        if (!sc_from_canonical(J.d, R.d) || !sc_from_canonical(J.k, R.k) || !sc_from_canonical(J.y, R.y) || !sc_from_canonical(J.y_inv, R.y_inv) ||
+            !sc_from_canonical(J.q, R.q) || !sc_from_canonical(J.z_img, R.z_img) || !sc_from_canonical(J.seed, R.seed)) {
+            R.status = BBP_ERR_FORMAT;
+            continue;
+        }
         J.pub_list.resize(R.L);
         for (size_t k = 0; k < R.L; k++) J.pub_list[k] = sc_from_bits(R.pub_list + 32 * k);   // Bid::from (src/blindbid/bid.rs:20-29)
         J.toggle = R.toggle;
@@ -457,7 +463,8 @@ static int load_verify_jobs(size_t n, bbp_verify_req *reqs, std::vector<verify_j
         J.proof.assign(R.proof, R.proof + R.proof_len);
         J.commitments.assign(R.commitments, R.commitments + 32 * R.n_commitments);
         J.t_c.assign(R.t_c, R.t_c + 32 * R.n_t_c);
-        J.score = load_scalar(R.score); J.z_img = load_scalar(R.z_img); J.seed = load_scalar(R.seed);
+        // serde-decoded in the reference (src/blindbid/verify.rs:100-102): canonical encodings only
+        if (!sc_from_canonical(J.score, R.score) || !sc_from_canonical(J.z_img, R.z_img) || !sc_from_canonical(J.seed, R.seed)) { R.status = BBP_ERR_FORMAT; return; }
         J.pub_list.resize(R.L);
         for (size_t k = 0; k < R.L; k++) J.pub_list[k] = sc_from_bits(R.pub_list + 32 * k);   // src/blindbid/verify.rs:112-116
         memcpy(J.rng_seed, R.rng_seed, 32);
@@ -527,11 +534,13 @@ int bbp_blindbid_verify_batch_partial(bbp_ctx *ctx, size_t n, bbp_verify_req *re
     std::vector<verify_job> jobs;
     std::vector<size_t> map;
     load_verify_jobs(n, reqs, jobs, map);
-    if (jobs.size() != n) return BBP_ERR_INPUT;
     int ok = 1;
+    // requests refused while loading (null pointers, non-canonical scalars) keep their status and clear the local flag;
+    // the remaining ones still form this GPU's partial sum (the identity when none is left)
     int rc = verify_batch(ctx, jobs, batch_seed, &ok, true, (uint8_t *)partial_ext_device);
     if (rc) return rc;
     for (size_t k = 0; k < jobs.size(); k++) reqs[map[k]].status = jobs[k].status;
+    if (jobs.size() != n) ok = 0;
     if (local_ok) *local_ok = ok;
     return BBP_OK;
 }
@@ -550,9 +559,13 @@ int bbp_mimc_constants(uint8_t out[90 * 32]) {
 }
 
 int bbp_blindbid_circuit_shape(size_t n_commitments, size_t n_toggles, size_t out[3]) {
-    if (!out || n_commitments < 4 || n_toggles < 1 || n_toggles > 100000) return BBP_ERR_INPUT;
-    std::shared_ptr<const circuit_template> t = blindbid_template((uint32_t)n_commitments, (uint32_t)n_toggles);
-    out[0] = t->n1; out[1] = t->q; out[2] = t->m;
+    if (!out || n_commitments < 4 || n_toggles < 1 || n_toggles > BLINDBID_MAX_TOGGLES || n_commitments > BLINDBID_MAX_COMMITMENTS) return BBP_ERR_INPUT;
+    if (n_toggles <= 256) {   // small circuits are recorded for real (what the tests compare with the formulas and the oracle)
+        std::shared_ptr<const circuit_template> t = blindbid_template((uint32_t)n_commitments, (uint32_t)n_toggles);
+        out[0] = t->n1; out[1] = t->q; out[2] = t->m;
+        return (t->n1 == blindbid_n1((uint32_t)n_toggles) && t->q == blindbid_q((uint32_t)n_toggles)) ? BBP_OK : BBP_ERR_INPUT;
+    }
+    out[0] = blindbid_n1((uint32_t)n_toggles); out[1] = blindbid_q((uint32_t)n_toggles); out[2] = n_commitments + n_toggles;
     return BBP_OK;
 }
 

@@ -83,8 +83,25 @@ struct recorder {
         for (auto x : b.t) { x.neg = !x.neg; a.t.push_back(x); }
         return a;
     }
-    void constrain(const LC &lc) {
+    // Terms that cancel inside one constraint (+t and -t of the same variable or constant) are dropped before they reach
+    // the CSR: the toggle-sum constraints of one_of_many_gadget (src/gadgets.rs:119) are sum[i-1] + t_i - sum[i] with
+    // sum[i] = sum[i-1] + t_i, i.e. 2i + 1 pairs that all cancel — O(L^2) entries that contribute exactly zero to every
+    // flattened weight. The constraint still takes its index j (its z power), so nothing else moves.
+    static void cancel(const LC &lc, std::vector<sym_term> &out) {
+        std::map<uint64_t, int32_t> net;   // (is_const, ref) -> signed multiplicity
+        for (auto &x : lc.t) net[((uint64_t)x.is_const << 32) | x.ref] += x.neg ? -1 : 1;
+        for (auto &x : lc.t) {
+            auto it = net.find(((uint64_t)x.is_const << 32) | x.ref);
+            if (it->second == 0) continue;
+            bool neg = it->second < 0;
+            for (int32_t k = 0; k < (neg ? -it->second : it->second); k++) out.push_back({x.ref, x.is_const, neg});
+            it->second = 0;
+        }
+    }
+    void constrain(const LC &lc_in) {
         uint32_t j = n_con++;
+        sym_lc lc;
+        cancel(lc_in, lc.t);
         for (auto &x : lc.t) {
             if (x.is_const) {
                 tpl->const_j.push_back(j | (x.neg ? 0x80000000u : 0u));
@@ -207,6 +224,14 @@ void proof_gadget(CS &cs, const typename CS::LC &d, const typename CS::LC &k, co
 // ---- template cache -------------------------------------------------------------------------------------------------
 // Wiring as in src/blindbid/proof.rs:74-85 / verify.rs:74-85: d = V[0], k = V[1], y_inv = V[3] (V[2], the commitment to
 // y, is committed but never wired), toggles = V[n_commit ..], items = the first n_toggle public list entries.
+// shape of the circuit without building it: n1 = 4 MiMC x 90 rounds x 4 + L booleans + 2 L membership + 2 score multipliers,
+// q = 2 n1 + 1 + 2 + (L - 1) + 1 + L + L constraints, m = commitments + toggles
+inline uint32_t blindbid_n1(uint32_t n_toggle) { return 16 * MIMC_ROUNDS + 3 * n_toggle + 2; }
+inline uint32_t blindbid_q(uint32_t n_toggle) { return 2 * blindbid_n1(n_toggle) + 3 + 3 * n_toggle; }
+static const uint32_t BLINDBID_MAX_TOGGLES = 1u << 16;      // the recorder's toggle-sum LCs are O(L^2) terms while being built
+static const uint32_t BLINDBID_MAX_COMMITMENTS = 1u << 16;
+static const size_t TEMPLATE_CACHE_MAX = 64;                // (n_commit, n_toggle) comes from untrusted requests: bounded cache
+
 inline std::shared_ptr<const circuit_template> blindbid_template(uint32_t n_commit, uint32_t n_toggle) {
     static std::mutex mu;
     static std::map<uint64_t, std::shared_ptr<const circuit_template>> cache;
@@ -214,6 +239,7 @@ inline std::shared_ptr<const circuit_template> blindbid_template(uint32_t n_comm
     uint64_t key = ((uint64_t)n_commit << 32) | n_toggle;
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
+    if (cache.size() >= TEMPLATE_CACHE_MAX) cache.clear();   // shared_ptr keeps templates in use alive
     auto tpl = std::make_shared<circuit_template>();
     tpl->n_commit = n_commit; tpl->n_toggle = n_toggle;
     tpl->m = n_commit + n_toggle;

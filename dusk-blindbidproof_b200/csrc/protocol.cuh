@@ -282,6 +282,11 @@ inline int proto_template(bbp_ctx *ctx, uint32_t n_commit, uint32_t n_toggle, de
     uint64_t key = ((uint64_t)n_commit << 32) | n_toggle;
     auto it = ps->templates.find(key);
     if (it == ps->templates.end()) {
+        if (ps->templates.size() >= TEMPLATE_CACHE_MAX) {   // keyed by request-chosen counts: bounded (no call holds a pointer across calls)
+            BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+            for (auto &kv : ps->templates) { cudaFree(kv.second.row_ptr); cudaFree(kv.second.entries); cudaFree(kv.second.const_j); cudaFree(kv.second.const_idx); }
+            ps->templates.clear();
+        }
         dev_template dt;
         dt.tpl = blindbid_template(n_commit, n_toggle);
         const circuit_template &t = *dt.tpl;
@@ -579,15 +584,16 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     const uint32_t L = (uint32_t)jobs[idx[0]].pub_list.size();
     int rc;
     if ((rc = proto_tables(ctx))) return rc;
+    // the capacity check comes BEFORE the template is built: L is the caller's, the template costs O(L^2) to record
+    if (L > BLINDBID_MAX_TOGGLES || next_pow2_u32(blindbid_n1(L)) > ctx->gens_capacity || ctx->party_capacity < 1) {
+        for (size_t i : idx) jobs[i].status = BBP_ERR_INVALID_GENERATORS_LENGTH;   // bp_gens.gens_capacity < padded_n
+        return 0;
+    }
     dev_template *dt;
     if ((rc = proto_template(ctx, 4, L, &dt))) return rc;
     const circuit_template &T = *dt->tpl;
     const uint32_t n1 = T.n1, m = T.m, n = next_pow2_u32(n1), lg = log2_u32(n);
     const uint32_t gcols = ctx->gens_capacity * ctx->party_capacity, slot_len = 2 + 2 * gcols;
-    if (n > ctx->gens_capacity || ctx->party_capacity < 1) {   // bp_gens.gens_capacity < padded_n -> InvalidGeneratorsLength
-        for (size_t i : idx) jobs[i].status = BBP_ERR_INVALID_GENERATORS_LENGTH;
-        return 0;
-    }
 
     struct hstate {
         std::unique_ptr<merlin_transcript> tr;
@@ -962,11 +968,15 @@ inline void verify_prepare(bbp_ctx *ctx, verify_job &J, verify_prepared &P, bool
     P.nc = (uint32_t)(J.commitments.size() / 32); P.nt = (uint32_t)(J.t_c.size() / 32);
     // the reference indexes vars[0], vars[1], vars[3] and toggle[0], items[i] (panics otherwise: SURVEY.md §5)
     if (P.nc < 4 || P.nt < 1 || J.pub_list.size() < P.nt) { J.status = BBP_ERR_FORMAT; return; }
+    if (P.nc > BLINDBID_MAX_COMMITMENTS) { J.status = BBP_ERR_INPUT; return; }   // no reference counterpart: bounds the per-request work
+    const bool too_many_toggles = P.nt > BLINDBID_MAX_TOGGLES;                   // reported as the capacity error, in its place below
+    if (too_many_toggles) P.nt = BLINDBID_MAX_TOGGLES;
     P.m = P.nc + P.nt;
-    std::shared_ptr<const circuit_template> tpl = blindbid_template(P.nc, P.nt);
-    P.n1 = tpl->n1; P.n = next_pow2_u32(P.n1); P.lg = log2_u32(P.n);
+    // n1 by its formula: the template (O(nt^2) to record, cached per (nc, nt)) is only built for requests that pass the
+    // generator-capacity check below, i.e. nt <= 202 for BulletproofGens::new(2048, 1)
+    P.n1 = blindbid_n1(P.nt); P.n = next_pow2_u32(P.n1); P.lg = log2_u32(P.n);
     if (all_zero32(pf.A_I1) || all_zero32(pf.A_O1) || all_zero32(pf.S1)) { J.status = BBP_ERR_VERIFICATION; return; }
-    if (P.n > ctx->gens_capacity || ctx->party_capacity < 1) { J.status = BBP_ERR_INVALID_GENERATORS_LENGTH; return; }
+    if (too_many_toggles || P.n > ctx->gens_capacity || ctx->party_capacity < 1) { J.status = BBP_ERR_INVALID_GENERATORS_LENGTH; return; }
     if (all_zero32(pf.T_1) || all_zero32(pf.T_3) || all_zero32(pf.T_4) || all_zero32(pf.T_5) || all_zero32(pf.T_6)) { J.status = BBP_ERR_VERIFICATION; return; }
     // InnerProductProof::verification_scalars
     uint32_t lg_p = (uint32_t)(pf.LR.size() / 64);
@@ -1192,7 +1202,9 @@ inline int verify_each(bbp_ctx *ctx, std::vector<verify_job> &jobs) {
 // circuit shape. If the combination is the identity every live request is accepted; otherwise the requests are
 // re-checked individually, so the verdicts always equal those of verify_each.
 // partial_only: stop after the combined pass and leave this GPU's partial sum (static | dynamic, 2 x 128 B extended) in
-// d_partial_ext for a cross-GPU reduction (proof-range sharding); *all_ok then reports the local verdict.
+// d_partial_ext for a cross-GPU reduction (proof-range sharding); *all_ok then reports the local verdict:
+// every local request passed the host checks and decompressed AND the local combination is the identity. The whole batch
+// verifies iff every rank's local flag is set and the sum of all partials is the identity.
 inline int verify_batch(bbp_ctx *ctx, std::vector<verify_job> &jobs, const uint8_t batch_seed[32], int *all_ok, bool partial_only, uint8_t *d_partial_ext) {
     std::vector<verify_prepared> prep(jobs.size());
     std::map<uint64_t, std::vector<size_t>> groups;
@@ -1237,7 +1249,10 @@ inline int verify_batch(bbp_ctx *ctx, std::vector<verify_job> &jobs, const uint8
     if (rc) return rc;
     bool ok = true;
     for (uint8_t v : part_ok) ok = ok && v;
-    for (auto &J : jobs) ok = ok && (J.status == 0 || partial_only);
+    // a request that failed a host check (format, identity point, non-canonical scalar, wrong IPP length) or whose points do
+    // not decompress never entered a combination: it must fail the batch in BOTH modes (in the sharded mode the caller
+    // ANDs this flag over the ranks next to the identity test of the summed partials)
+    for (auto &J : jobs) ok = ok && J.status == 0;
     if (all_ok) *all_ok = ok ? 1 : 0;
     return 0;
 }

@@ -6,10 +6,14 @@
 //
 // Generator requirement: the context must hold BulletproofGens::new(n_bits, >= m), i.e. bbp_init(device, n_bits, parties),
 // so that the aggregated G / H vectors are contiguous column ranges of the resident table.
-// RNG contract: upstream draws from the caller's rng (not a TranscriptRng); here the rng is the SHAKE256 stream of the
-// caller's 32-byte seed, 64 bytes per Scalar::random in upstream's draw order (per party: a_blinding, s_blinding,
-// s_L[0..n), s_R[0..n); then per party: t_1 blinding, t_2 blinding). The verifier's batching scalar c is the first
-// draw of SHAKE256(rng32). Transcript label: "bbp-rangeproof" (caller-chosen in upstream).
+// RNG contract: upstream draws from the caller's rng (not a TranscriptRng). Here party j draws from the SHAKE256 stream of
+// (seed || v_blinding_j (32 B) || LE64(value_j) || LE32(j)), 64 bytes per Scalar::random in upstream's draw order (per
+// party: a_blinding, s_blinding, s_L[0..n), s_R[0..n); then t_1 blinding, t_2 blinding): the stream is keyed with the
+// party's witness, so a seed handed in twice with different values does not repeat the nonces (which would leak the
+// values and blindings). The verifier's equation-merging scalar c and its batch weight rho are the first two scalars
+// of transcript.build_rng().finalize(seed) taken after the WHOLE proof has been absorbed: bound to every proof byte and
+// to the caller's secret seed. Seeds must be secret; prover seeds should be fresh. Transcript label: "bbp-rangeproof"
+// (caller-chosen in upstream).
 #pragma once
 #include "protocol.cuh"
 
@@ -18,11 +22,15 @@ namespace bbp {
 struct shake_scalar_rng {
     keccak_sponge s;
     explicit shake_scalar_rng(const uint8_t seed[32]) : s(shake256_new()) { s.absorb(seed, 32); }
-    // party j's stream of a prover: SHAKE256(seed || LE32(j))
-    shake_scalar_rng(const uint8_t seed[32], uint32_t party) : s(shake256_new()) {
-        uint8_t le[4] = {(uint8_t)party, (uint8_t)(party >> 8), (uint8_t)(party >> 16), (uint8_t)(party >> 24)};
+    // party j's stream of a prover: SHAKE256(seed || v_blinding_j || LE64(value_j) || LE32(j))
+    shake_scalar_rng(const uint8_t seed[32], const sc &v_blinding, uint64_t value, uint32_t party) : s(shake256_new()) {
+        uint8_t bl[32], tail[12];
+        sc_tobytes(bl, v_blinding);
+        for (int i = 0; i < 8; i++) tail[i] = (uint8_t)(value >> (8 * i));
+        for (int i = 0; i < 4; i++) tail[8 + i] = (uint8_t)(party >> (8 * i));
         s.absorb(seed, 32);
-        s.absorb(le, 4);
+        s.absorb(bl, 32);
+        s.absorb(tail, 12);
     }
     sc random_scalar() {
         uint8_t b[64];
@@ -83,13 +91,22 @@ inline int rp_prove_group(bbp_ctx *ctx, std::vector<rp_prove_job> &jobs, uint32_
     std::vector<sc> small(device_rng ? (size_t)P * 4 * m : 0);
     if (device_rng) {
         const uint32_t per_party = 4 + 2 * nbits, n_draws = m * per_party;
-        std::vector<uint8_t> seeds((size_t)P * 32);
-        for (uint32_t pi = 0; pi < P; pi++) memcpy(&seeds[(size_t)pi * 32], jobs[pi].rng_seed, 32);
+        // per proof: seed (32 B); per (proof, party): v_blinding (32 B) | value (8 B) — what each party's stream is keyed with
+        std::vector<uint8_t> seeds((size_t)P * 32 + (size_t)P * m * 40);
+        uint8_t *wk = seeds.data() + (size_t)P * 32;
+        for (uint32_t pi = 0; pi < P; pi++) {
+            memcpy(&seeds[(size_t)pi * 32], jobs[pi].rng_seed, 32);
+            for (uint32_t j = 0; j < m; j++) {
+                uint8_t *o = wk + ((size_t)pi * m + j) * 40;
+                sc_tobytes(o, jobs[pi].blindings[j]);
+                memcpy(o + 32, &jobs[pi].values[j], 8);
+            }
+        }
         if ((rc = ps->rng_states.ensure(seeds.size())) || (rc = ps->rng_raw.ensure((size_t)P * n_draws * 64)) || (rc = ps->wit.ensure((size_t)2 * P * nm * 32)) ||
             (rc = ps->stat_red.ensure(small.size() * 32)))
             return rc;
         if ((rc = h2d(ctx, ps->rng_states.p, seeds.data(), seeds.size()))) return rc;
-        k_shake_draws<<<(P * m + 63) / 64, 64, 0, ctx->stream>>>(ps->rng_states.p, P, m, per_party, ps->rng_raw.as<uint32_t>());
+        k_shake_draws<<<(P * m + 63) / 64, 64, 0, ctx->stream>>>(ps->rng_states.p, ps->rng_states.p + (size_t)P * 32, P, m, per_party, ps->rng_raw.as<uint32_t>());
         k_rp_draw_scatter<<<(unsigned)(((size_t)P * n_draws + 127) / 128), 128, 0, ctx->stream>>>(ps->rng_raw.as<uint32_t>(), P, m, nbits, ps->wit.as<sc>(),
                                                                                                   ps->wit.as<sc>() + (size_t)P * nm, ps->stat_red.as<sc>());
         ctx->launches += 2;
@@ -102,7 +119,7 @@ inline int rp_prove_group(bbp_ctx *ctx, std::vector<rp_prove_job> &jobs, uint32_
         hstate &H = hs[pi];
         H.sum_a = sc_zero(); H.sum_s = sc_zero(); H.sum_t1 = sc_zero(); H.sum_t2 = sc_zero();
         if (!device_rng)
-            for (uint32_t j = 0; j < m; j++) H.rng.emplace_back(J.rng_seed, j);
+            for (uint32_t j = 0; j < m; j++) H.rng.emplace_back(J.rng_seed, J.blindings[j], J.values[j], j);
         for (uint32_t j = 0; j < m; j++) {
             vals[pi * m + j] = J.values[j];
             cv[(pi * m + j) * 2] = sc_from_u64(J.values[j]);
@@ -295,16 +312,6 @@ inline int rp_verify_group(bbp_ctx *ctx, std::vector<rp_verify_job> &jobs, uint3
         tr.append_scalar("t_x_blinding", t_x_bl);
         tr.append_scalar("e_blinding", e_bl);
         sc w = tr.challenge_scalar("w");
-        shake_scalar_rng crng(J.rng_seed);
-        sc c = crng.random_scalar();
-        // this request's weight in a combined check of several requests: a second secret stream, keyed by the request's
-        // seed and its position in the batch (callers may hand the same seed to every request)
-        uint8_t wseed[32];
-        memcpy(wseed, J.rng_seed, 32);
-        for (int k = 0; k < 8; k++) wseed[24 + k] ^= (uint8_t)((uint64_t)(i + 1) >> (8 * k));
-        shake_scalar_rng wrng(wseed);
-        wrng.random_scalar();
-        sc rho = wrng.random_scalar();
         if (nm != ((size_t)1 << lg_p)) return;
         tr.innerproduct_domain_sep(nm);
         std::vector<sc> uj(lg_p);
@@ -312,6 +319,12 @@ inline int rp_verify_group(bbp_ctx *ctx, std::vector<rp_verify_job> &jobs, uint3
             if (!tr.validate_and_append_point("L", LR + 64 * j) || !tr.validate_and_append_point("R", LR + 64 * j + 32)) return;
             uj[j] = tr.challenge_scalar("u");
         }
+        // verifier randomness, drawn once the transcript has absorbed every proof byte: c merges the two verification
+        // equations, rho is this request's weight in a combined check of several requests. Both depend on the proof AND on
+        // the caller's secret seed (callers may hand the same seed to every request: the transcripts differ).
+        merlin_rng vrng = tr.build_rng().finalize(J.rng_seed);
+        sc c = vrng.random_scalar();
+        sc rho = vrng.random_scalar();
         std::vector<sc> all(uj);
         all.push_back(y);
         std::vector<sc> pre(all.size()), allinv(all.size());

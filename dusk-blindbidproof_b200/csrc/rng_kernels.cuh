@@ -214,13 +214,14 @@ __global__ void __launch_bounds__(128) k_wide_reduce(const uint32_t *__restrict_
 }
 
 // ---------------------------------------------------------------- SHAKE256 draw stream on the device (aggregated range proofs)
-// The range-proof prover draws 2 m (1 + n) + 2 m scalars per proof from SHAKE256(seed) (rangeproof.cuh RNG contract):
-// one thread per (proof, party) squeezes that party's stream SHAKE256(seed || LE32(party)) (one Keccak-f per 136 bytes,
-// state in registers), writing raw 64-byte draws; k_rp_draw_scatter reduces them mod l in parallel and routes them to
+// The range-proof prover draws 2 m (1 + n) + 2 m scalars per proof from SHAKE256 streams (rangeproof.cuh RNG contract):
+// one thread per (proof, party) squeezes that party's stream SHAKE256(seed || v_blinding || LE64(value) || LE32(party))
+// (76 absorbed bytes; one Keccak-f per 136 bytes, state in registers), writing raw 64-byte draws; k_rp_draw_scatter reduces them mod l in parallel and routes them to
 // s_L / s_R or to the small per-party list the host sums (a_blinding, s_blinding, t_1 / t_2 blindings).
 // raw: [n_proofs][m][per_party][16 words], per_party = 4 + 2 nbits.
-__global__ void __launch_bounds__(64) k_shake_draws(const uint8_t *__restrict__ seeds, uint32_t n_proofs, uint32_t m, uint32_t per_party,
-                                                    uint32_t *__restrict__ raw) {
+// wkeys: [n_proofs][m] x 40 B = the party's v_blinding (32 B canonical) and value (LE64)
+__global__ void __launch_bounds__(64) k_shake_draws(const uint8_t *__restrict__ seeds, const uint8_t *__restrict__ wkeys, uint32_t n_proofs, uint32_t m,
+                                                    uint32_t per_party, uint32_t *__restrict__ raw) {
     uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_proofs * m) return;
     const uint32_t p = idx / m, j = idx % m;
@@ -228,8 +229,11 @@ __global__ void __launch_bounds__(64) k_shake_draws(const uint8_t *__restrict__ 
 #pragma unroll
     for (int i = 0; i < 25; i++) r[i] = 0;
     const uint64_t *sd = (const uint64_t *)(seeds + 32 * (size_t)p);
+    const uint64_t *wk = (const uint64_t *)(wkeys + 40 * (size_t)idx);
     r[0] = sd[0]; r[1] = sd[1]; r[2] = sd[2]; r[3] = sd[3];
-    r[4] = (uint64_t)j | (0x1fULL << 32);  // LE32(party), then SHAKE domain separation + first pad bit after the 36 absorbed bytes
+    r[4] = wk[0]; r[5] = wk[1]; r[6] = wk[2]; r[7] = wk[3];   // v_blinding
+    r[8] = wk[4];                                               // LE64(value)
+    r[9] = (uint64_t)j | (0x1fULL << 32);  // LE32(party), then SHAKE domain separation + first pad bit after the 76 absorbed bytes
     r[16] ^= 0x8000000000000000ULL;        // last pad bit at byte 135 (rate 136)
     keccak_f1600_dev(r);
     uint64_t *out = (uint64_t *)(raw + (size_t)idx * per_party * 16);

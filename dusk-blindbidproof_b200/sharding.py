@@ -48,7 +48,18 @@ def sharded_batch_verify(be, dist, items, batch_seed, d_partial, d_gather, d_out
     if world == 1:
         ok, _ = be.blindbid_verify_batch(items, batch_seed)
         return ok
-    be.blindbid_verify_batch_partial(items, batch_seed, d_partial.data_ptr())
+    local_ok, _ = be.blindbid_verify_batch_partial(items, batch_seed, d_partial.data_ptr())
     gather_partials(dist, d_partial, d_gather)
     be.sum_compress_device(d_gather.data_ptr(), 2 * world, d_out.data_ptr())
-    return bytes(d_out.cpu().numpy()) == bytes(32)
+    return combine_verdicts(dist, local_ok, d_out)
+
+
+def combine_verdicts(dist, local_ok, d_out):
+    """Verdict of a sharded batch verification: the summed partials compress to the identity (32 zero bytes in d_out) AND
+    every rank's local flag is set. Requests a rank rejected before the combination (malformed proof, point that does not
+    decompress) never enter its partial sum, so the identity test alone would accept them; the flag travels in one MIN
+    all-reduce next to the all-gather of the partials."""
+    flag = torch.tensor([1 if local_ok else 0], dtype=torch.int32, device=d_out.device)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item()) and bytes(d_out.cpu().numpy()) == bytes(32)

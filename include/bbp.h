@@ -114,12 +114,15 @@ int bbp_from_uniform_bytes(bbp_ctx *ctx, const uint8_t *bytes64, size_t n, uint8
  * RNG contract replacing thread_rng (proof.rs:53,64 and the two finalize(&mut thread_rng()) sites inside bulletproofs):
  * the caller supplies the 4+L commitment blindings and the 32 "external randomness" bytes keyed into the TranscriptRng.
  * With those fixed every output byte is a deterministic function of the inputs.
- * Scalars d .. seed: any 32 bytes, reduced mod l. pub_list items: Scalar::from_bits semantics (bid.rs:27, verify.rs:115). */
+ * Scalars d .. seed (and score, z_img, seed of a verification): canonical encodings only (< l), as the reference's serde
+ * decoding enforces (proof.rs:100-106, verify.rs:100-102): BBP_ERR_FORMAT otherwise. pub_list items: Scalar::from_bits
+ * semantics (bid.rs:27, verify.rs:115). Blindings: any 32 bytes, reduced mod l. toggle: any value; an index beyond the list
+ * yields (as in the reference) a proof that does not verify. */
 typedef struct bbp_prove_req {
     const uint8_t *d, *k, *y, *y_inv, *q, *z_img, *seed; /* 32 B each */
     const uint8_t *pub_list;                             /* L x 32 B */
     size_t L;                                            /* >= 1 (the reference panics on an empty list) */
-    uint64_t toggle;                                     /* index of the bidder's own item */
+    uint64_t toggle;                                     /* index of the bidder's own item (>= L: all toggle bits zero) */
     const uint8_t *blindings;                            /* (4 + L) x 32 B */
     const uint8_t *rng_seed;                             /* 32 B */
     uint8_t *proof_out;                                  /* R1CSProof::to_bytes() */
@@ -156,7 +159,9 @@ int bbp_blindbid_verify_each(bbp_ctx *ctx, size_t n, bbp_verify_req *reqs);
 int bbp_blindbid_verify_batch(bbp_ctx *ctx, size_t n, bbp_verify_req *reqs, const uint8_t batch_seed[32], int *all_ok);
 /* proof-range sharding across GPUs: runs only the combined pass over this GPU's requests and leaves its
  * partial sums (2 x 128 B extended points: static-base part, dynamic part) in HBM at partial_ext_device for the all-gather;
- * the whole batch verifies iff the sum of all GPUs' partials is the identity (bbp_sum_compress_device -> 32 zero bytes). */
+ * Requests rejected before the combination (malformed proof, identity point, point that fails to decompress) do not
+ * enter the partial sum: they clear *local_ok and set reqs[i].status. The whole batch verifies iff EVERY rank reports
+ * *local_ok = 1 AND the sum of all GPUs' partials is the identity (bbp_sum_compress_device -> 32 zero bytes). */
 int bbp_blindbid_verify_batch_partial(bbp_ctx *ctx, size_t n, bbp_verify_req *reqs, const uint8_t batch_seed[32], void *partial_ext_device, int *local_ok);
 /* native MiMC-x^7 hash the circuit constrains (src/gadgets.rs:37-68) and its constants (src/blindbid/mod.rs:7-24): host helpers */
 int bbp_mimc_hash(const uint8_t left[32], const uint8_t right[32], uint8_t out[32]);
@@ -167,8 +172,12 @@ int bbp_blindbid_circuit_shape(size_t n_commitments, size_t n_toggles, size_t ou
 /* ---- aggregated range proofs: bulletproofs RangeProof::prove_multiple / verify_multiple (BASELINE.json configs[4]; the
  * reference itself has no call site). m values of nbits bits each (nbits in {8,16,32,64}, m a power of two);
  * the context must have been created with bbp_init(device, nbits, parties >= m). Proof = 32 * (9 + 2 lg(nbits m)) bytes.
- * RNG contract: upstream hands every party an rng; here party j draws from the SHAKE256 stream of (rng_seed || LE32(j)),
- * 64 bytes per scalar in upstream's per-party order (a_blinding, s_blinding, s_L, s_R, then t_1 / t_2 blindings).
+ * RNG contract: upstream hands every party an rng; here party j draws from the SHAKE256 stream of
+ * (rng_seed || v_blinding_j || LE64(value_j) || LE32(j)), 64 bytes per scalar in upstream's per-party order (a_blinding,
+ * s_blinding, s_L, s_R, then t_1 / t_2 blindings). The stream is keyed with the party's witness, so a seed reused with other
+ * values does not repeat nonces; prover seeds must still be SECRET and should be fresh per proof. The verifier's merging
+ * scalar c and batch weight come from transcript.build_rng().finalize(rng_seed) after the whole proof has been absorbed:
+ * verifier seeds must be SECRET (unpredictable to whoever supplies the proofs); the same seed may serve every request.
  * Transcript label "bbp-rangeproof". */
 int bbp_rangeproof_prove_multiple(bbp_ctx *ctx, const uint64_t *values, const uint8_t *blindings, size_t m, size_t nbits, const uint8_t rng_seed[32],
                                   uint8_t *proof_out, size_t *proof_len, uint8_t *commitments_out /* m x 32 */);

@@ -4,10 +4,13 @@
 // BASELINE.json configs[4] names it (m = 64 parties x n = 64 bits => 4096-point IPP).
 // PARITY STATUS: proof-byte level parity UNPINNED (no reference vectors; see r1cs.h). 
 // RNG contract: upstream draws from the caller's rng directly (not a TranscriptRng): every party owns an rng
-// (Party::new(.., rng)). Here party j's rng is the SHAKE256 stream of (32-byte seed || LE32(j)), consumed 64 bytes
-// per Scalar::random in upstream's per-party draw order: a_blinding, s_blinding, s_L[0..n), s_R[0..n), then (after
-// the y, z challenges) t_1_blinding, t_2_blinding. Independent per-party streams are what lets the product squeeze
-// them in parallel. The verifier's batching scalar c is the first 64 bytes of SHAKE256(rng32), wide-reduced.
+// (Party::new(.., rng)). Here party j's rng is the SHAKE256 stream of (32-byte seed || v_blinding_j (32 B canonical) ||
+// LE64(value_j) || LE32(j)) — keyed with the party's witness, so that a seed reused for a different value set does not
+// repeat the nonces — consumed 64 bytes per Scalar::random in upstream's per-party draw order: a_blinding, s_blinding,
+// s_L[0..n), s_R[0..n), then (after the y, z challenges) t_1_blinding, t_2_blinding. Independent per-party streams are
+// what lets the product squeeze them in parallel. The verifier's batching scalar c is the first scalar of
+// transcript.build_rng().finalize(rng32) taken AFTER the whole proof (all L_j, R_j included) has been absorbed, so it is
+// bound to every proof byte as well as to the caller's secret seed.
 #pragma once
 #include "gens.h"
 #include "ipp.h"
@@ -19,10 +22,14 @@ namespace orc {
 struct shake_rng {
     shake256 s;
     explicit shake_rng(const uint8_t seed[32]) { s.absorb(seed, 32); }
-    shake_rng(const uint8_t seed[32], uint32_t party) {
-        uint8_t le[4] = {(uint8_t)party, (uint8_t)(party >> 8), (uint8_t)(party >> 16), (uint8_t)(party >> 24)};
+    shake_rng(const uint8_t seed[32], const sc &v_blinding, uint64_t value, uint32_t party) {
+        uint8_t bl[32], tail[12];
+        sc_tobytes(bl, v_blinding);
+        for (int i = 0; i < 8; i++) tail[i] = (uint8_t)(value >> (8 * i));
+        for (int i = 0; i < 4; i++) tail[8 + i] = (uint8_t)(party >> (8 * i));
         s.absorb(seed, 32);
-        s.absorb(le, 4);
+        s.absorb(bl, 32);
+        s.absorb(tail, 12);
     }
     sc random_scalar() {
         uint8_t b[64];
@@ -55,7 +62,7 @@ static inline int rangeproof_prove_multiple(const std::vector<uint64_t> &values,
     bulletproof_gens bp(n, m);
     transcript tr("bbp-rangeproof");   // caller-chosen label; the product uses the same one
     std::vector<shake_rng> rngs;
-    for (size_t j = 0; j < m; j++) rngs.emplace_back(rng_seed, (uint32_t)j);
+    for (size_t j = 0; j < m; j++) rngs.emplace_back(rng_seed, blindings[j], values[j], (uint32_t)j);
 
     tr.rangeproof_domain_sep(n, m);
     struct party { sc a_bl, s_bl; std::vector<sc> s_L, s_R; ge A, S; sc t1_bl, t2_bl, t0, t1, t2; std::vector<sc> l0, l1, r0, r1; };
@@ -188,13 +195,13 @@ static inline int rangeproof_verify_multiple(const uint8_t *proof, size_t len, c
     tr.append_scalar("t_x_blinding", t_x_bl);
     tr.append_scalar("e_blinding", e_bl);
     sc w = tr.challenge_scalar("w");
-    sc c;
-    {
-        shake_rng r(rng32);
-        c = r.random_scalar();
-    }
     std::vector<sc> x_sq, x_inv_sq, s;
     if (!ipp_verification_scalars(ipp, n * m, tr, x_sq, x_inv_sq, s)) return -3;
+    sc c;
+    {
+        transcript_rng r = tr.build_rng().finalize(rng32);
+        c = r.random_scalar();
+    }
     sc a = ipp.a, b = ipp.b;
     size_t nm = n * m;
 

@@ -89,3 +89,18 @@ def test_proof_range_sharded_batch_verify(ranks, part, monkeypatch):
     ok, local = run(bad)
     assert not ok and local == [True, False, True]      # only the shard holding request 4 fails locally
     assert ctxs[1].blindbid_verify_each(bad)[4] != 0
+    # requests rejected BEFORE the combination never enter a partial sum: the sum of the partials is still the identity,
+    # so the verdict has to come from the per-rank flags (sharding.combine_verdicts ANDs them over the ranks)
+    for mutate in ("malformed", "undecompressable"):
+        bad = [dict(x) for x in items]
+        p = bytearray(bad[7]["proof"])
+        if mutate == "malformed":
+            p = p[:-5]                                   # R1CSProof::from_bytes -> FormatError
+        else:
+            p[97:129] = b"\x01" + bytes(31)             # T_1 (after the phase byte and A_I1, A_O1, S1) := an odd s: no valid encoding
+        bad[7]["proof"] = bytes(p)
+        sum_is_identity, local = run(bad)
+        assert local == [True, True, False], (mutate, local)
+        assert not (sum_is_identity and all(local))
+        want = ctxs[0].blindbid_verify_each(bad)
+        assert want[7] != 0 and all(w == 0 for i, w in enumerate(want) if i != 7)
