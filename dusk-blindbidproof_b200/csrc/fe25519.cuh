@@ -37,7 +37,7 @@ BBP_DEV uint32_t mad4_cc(uint32_t *c, uint32_t x0, uint32_t x1, uint32_t x2, uin
         "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
         "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
         "addc.u32 %8, 0, 0;"
-        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7]), "=r"(cy)
+        : "+&r"(c[0]), "+&r"(c[1]), "+&r"(c[2]), "+&r"(c[3]), "+&r"(c[4]), "+&r"(c[5]), "+&r"(c[6]), "+&r"(c[7]), "=&r"(cy)
         : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
     return cy;
 }
@@ -51,7 +51,7 @@ BBP_DEV void mad4_top_fresh(uint32_t *c, uint32_t x0, uint32_t x1, uint32_t x2, 
         "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
         "madc.lo.cc.u32 %6, %11, %12, 0;\n\t"
         "madc.hi.u32 %7, %11, %12, 0;"
-        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "=r"(c[6]), "=r"(c[7])
+        : "+&r"(c[0]), "+&r"(c[1]), "+&r"(c[2]), "+&r"(c[3]), "+&r"(c[4]), "+&r"(c[5]), "=&r"(c[6]), "=&r"(c[7])
         : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
 }
 // same, where c[7] has not been written yet and c[6] holds a previous carry-out
@@ -64,7 +64,7 @@ BBP_DEV void mad4_top_half(uint32_t *c, uint32_t x0, uint32_t x1, uint32_t x2, u
         "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
         "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
         "madc.hi.u32 %7, %11, %12, 0;"
-        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "=r"(c[7])
+        : "+&r"(c[0]), "+&r"(c[1]), "+&r"(c[2]), "+&r"(c[3]), "+&r"(c[4]), "+&r"(c[5]), "+&r"(c[6]), "=&r"(c[7])
         : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
 }
 // c[0..7] = {x0,x1,x2,x3} * y (four independent 32x32->64 products)
@@ -113,12 +113,158 @@ BBP_DEV void fe_mul_wide(uint32_t *r, const uint32_t *a, const uint32_t *b) {
         "addc.cc.u32 %12, %27, %42;\n\t"
         "addc.cc.u32 %13, %28, %43;\n\t"
         "addc.u32 %14, %29, %44;"
-        : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(r[8]), "=&r"(r[9]), "=&r"(r[10]),
+          "=&r"(r[11]), "=&r"(r[12]), "=&r"(r[13]), "=&r"(r[14]), "=&r"(r[15])
         : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(ev[8]), "r"(ev[9]), "r"(ev[10]),
           "r"(ev[11]), "r"(ev[12]), "r"(ev[13]), "r"(ev[14]), "r"(ev[15]),
           "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]), "r"(od[8]), "r"(od[9]),
           "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]));
+}
+
+// ---- dedicated squaring: 28 off-diagonal products (doubled by one funnel-shift pass) + 8 diagonal ones = 36 IMAD.WIDE against
+// the 64 of fe_mul_wide. Chains of 1..3 products over the same even / odd column accumulators as the multiplication; the
+// suffix says what the top of the chain meets: _cc = every slot already written, carry out returned; _top_fresh = the last
+// product's two slots are unwritten; _top_half = its low slot holds an earlier carry-out, its high slot is unwritten.
+BBP_DEV void mul3(uint32_t *c, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t y) {
+    uint64_t p0 = (uint64_t)x0 * y, p1 = (uint64_t)x1 * y, p2 = (uint64_t)x2 * y;
+    c[0] = (uint32_t)p0; c[1] = (uint32_t)(p0 >> 32);
+    c[2] = (uint32_t)p1; c[3] = (uint32_t)(p1 >> 32);
+    c[4] = (uint32_t)p2; c[5] = (uint32_t)(p2 >> 32);
+}
+BBP_DEV uint32_t mad3_cc(uint32_t *c, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t y) {
+    uint32_t cy;
+    asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+        "addc.u32 %6, 0, 0;"
+        : "+&r"(c[0]), "+&r"(c[1]), "+&r"(c[2]), "+&r"(c[3]), "+&r"(c[4]), "+&r"(c[5]), "=&r"(cy)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(y));
+    return cy;
+}
+BBP_DEV uint32_t mad2_cc(uint32_t *c, uint32_t x0, uint32_t x1, uint32_t y) {
+    uint32_t cy;
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "+&r"(c[0]), "+&r"(c[1]), "+&r"(c[2]), "+&r"(c[3]), "=&r"(cy)
+        : "r"(x0), "r"(x1), "r"(y));
+    return cy;
+}
+BBP_DEV uint32_t mad1_cc(uint32_t *c, uint32_t x0, uint32_t y) {
+    uint32_t cy;
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, 0, 0;"
+        : "+&r"(c[0]), "+&r"(c[1]), "=&r"(cy)
+        : "r"(x0), "r"(y));
+    return cy;
+}
+BBP_DEV void mad3_top_fresh(uint32_t *c, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t y) {
+    asm("mad.lo.cc.u32 %0, %6, %9, %0;\n\t"
+        "madc.hi.cc.u32 %1, %6, %9, %1;\n\t"
+        "madc.lo.cc.u32 %2, %7, %9, %2;\n\t"
+        "madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
+        "madc.lo.cc.u32 %4, %8, %9, 0;\n\t"
+        "madc.hi.u32 %5, %8, %9, 0;"
+        : "+&r"(c[0]), "+&r"(c[1]), "+&r"(c[2]), "+&r"(c[3]), "=&r"(c[4]), "=&r"(c[5])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(y));
+}
+BBP_DEV void mad3_top_half(uint32_t *c, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t y) {
+    asm("mad.lo.cc.u32 %0, %6, %9, %0;\n\t"
+        "madc.hi.cc.u32 %1, %6, %9, %1;\n\t"
+        "madc.lo.cc.u32 %2, %7, %9, %2;\n\t"
+        "madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
+        "madc.lo.cc.u32 %4, %8, %9, %4;\n\t"
+        "madc.hi.u32 %5, %8, %9, 0;"
+        : "+&r"(c[0]), "+&r"(c[1]), "+&r"(c[2]), "+&r"(c[3]), "+&r"(c[4]), "=&r"(c[5])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(y));
+}
+BBP_DEV void mad2_top_half(uint32_t *c, uint32_t x0, uint32_t x1, uint32_t y) {
+    asm("mad.lo.cc.u32 %0, %4, %6, %0;\n\t"
+        "madc.hi.cc.u32 %1, %4, %6, %1;\n\t"
+        "madc.lo.cc.u32 %2, %5, %6, %2;\n\t"
+        "madc.hi.u32 %3, %5, %6, 0;"
+        : "+&r"(c[0]), "+&r"(c[1]), "+&r"(c[2]), "=&r"(c[3])
+        : "r"(x0), "r"(x1), "r"(y));
+}
+BBP_DEV void mad1_top_half(uint32_t *c, uint32_t x0, uint32_t y) {
+    asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\t"
+        "madc.hi.u32 %1, %2, %3, 0;"
+        : "+&r"(c[0]), "=&r"(c[1])
+        : "r"(x0), "r"(y));
+}
+
+// 512-bit square r[0..15] = a * a. ev[k] is the limb of column k, od[k] the limb of column k + 1 (off-diagonal sums only).
+BBP_DEV void fe_sq_wide(uint32_t *r, const uint32_t *a) {
+    uint32_t ev[14], od[14];
+    mul4(od, a[1], a[3], a[5], a[7], a[0]);                   // columns 1, 3, 5, 7
+    mul3(ev + 2, a[2], a[4], a[6], a[0]);                     // columns 2, 4, 6
+    od[8] = mad3_cc(od + 2, a[2], a[4], a[6], a[1]);          // columns 3, 5, 7
+    mad3_top_fresh(ev + 4, a[3], a[5], a[7], a[1]);           // columns 4, 6, 8
+    mad3_top_half(od + 4, a[3], a[5], a[7], a[2]);            // columns 5, 7, 9
+    ev[10] = mad2_cc(ev + 6, a[4], a[6], a[2]);               // columns 6, 8
+    od[10] = mad2_cc(od + 6, a[4], a[6], a[3]);               // columns 7, 9
+    mad2_top_half(ev + 8, a[5], a[7], a[3]);                  // columns 8, 10
+    mad2_top_half(od + 8, a[5], a[7], a[4]);                  // columns 9, 11
+    ev[12] = mad1_cc(ev + 10, a[6], a[4]);                    // column 10
+    od[12] = mad1_cc(od + 10, a[6], a[5]);                    // column 11
+    mad1_top_half(ev + 12, a[7], a[5]);                       // column 12
+    mad1_top_half(od + 12, a[7], a[6]);                       // column 13
+    // s = ev + (od << 32): limbs 1 .. 14 (limb 0 and limb 15 of the off-diagonal sum are zero)
+    uint32_t s[15];
+    s[1] = od[0];
+    asm("add.cc.u32 %0, %13, %25;\n\t"
+        "addc.cc.u32 %1, %14, %26;\n\t"
+        "addc.cc.u32 %2, %15, %27;\n\t"
+        "addc.cc.u32 %3, %16, %28;\n\t"
+        "addc.cc.u32 %4, %17, %29;\n\t"
+        "addc.cc.u32 %5, %18, %30;\n\t"
+        "addc.cc.u32 %6, %19, %31;\n\t"
+        "addc.cc.u32 %7, %20, %32;\n\t"
+        "addc.cc.u32 %8, %21, %33;\n\t"
+        "addc.cc.u32 %9, %22, %34;\n\t"
+        "addc.cc.u32 %10, %23, %35;\n\t"
+        "addc.cc.u32 %11, %24, %36;\n\t"
+        "addc.u32 %12, %37, 0;"
+        : "=&r"(s[2]), "=&r"(s[3]), "=&r"(s[4]), "=&r"(s[5]), "=&r"(s[6]), "=&r"(s[7]), "=&r"(s[8]), "=&r"(s[9]), "=&r"(s[10]), "=&r"(s[11]), "=&r"(s[12]),
+          "=&r"(s[13]), "=&r"(s[14])
+        : "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(ev[8]), "r"(ev[9]), "r"(ev[10]), "r"(ev[11]), "r"(ev[12]),
+          "r"(ev[13]),
+          "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]), "r"(od[8]), "r"(od[9]), "r"(od[10]), "r"(od[11]),
+          "r"(od[12]), "r"(od[13]));
+    // t = 2 s by independent funnel shifts (no carry chain), then r = t + sum_i a_i^2 2^(64 i): the diagonal products ride
+    // the final addition as eight multiply-add pairs
+    uint32_t t[16];
+    t[1] = s[1] << 1;
+#pragma unroll
+    for (int k = 2; k < 15; k++) t[k] = __funnelshift_l(s[k - 1], s[k], 1);
+    t[15] = s[14] >> 31;
+    asm("mad.lo.cc.u32 %0, %16, %16, 0;\n\t"
+        "madc.hi.cc.u32 %1, %16, %16, %24;\n\t"
+        "madc.lo.cc.u32 %2, %17, %17, %25;\n\t"
+        "madc.hi.cc.u32 %3, %17, %17, %26;\n\t"
+        "madc.lo.cc.u32 %4, %18, %18, %27;\n\t"
+        "madc.hi.cc.u32 %5, %18, %18, %28;\n\t"
+        "madc.lo.cc.u32 %6, %19, %19, %29;\n\t"
+        "madc.hi.cc.u32 %7, %19, %19, %30;\n\t"
+        "madc.lo.cc.u32 %8, %20, %20, %31;\n\t"
+        "madc.hi.cc.u32 %9, %20, %20, %32;\n\t"
+        "madc.lo.cc.u32 %10, %21, %21, %33;\n\t"
+        "madc.hi.cc.u32 %11, %21, %21, %34;\n\t"
+        "madc.lo.cc.u32 %12, %22, %22, %35;\n\t"
+        "madc.hi.cc.u32 %13, %22, %22, %36;\n\t"
+        "madc.lo.cc.u32 %14, %23, %23, %37;\n\t"
+        "madc.hi.u32 %15, %23, %23, %38;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(r[8]), "=&r"(r[9]), "=&r"(r[10]),
+          "=&r"(r[11]), "=&r"(r[12]), "=&r"(r[13]), "=&r"(r[14]), "=&r"(r[15])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]), "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]),
+          "r"(t[13]), "r"(t[14]), "r"(t[15]));
 }
 
 // 512-bit value -> fe: lo + 38*hi, then fold the small overflow twice
@@ -137,7 +283,7 @@ BBP_DEV fe fe_reduce_wide(const uint32_t *r) {
         "addc.cc.u32 %5, %5, %13;\n\t"
         "addc.cc.u32 %6, %6, %14;\n\t"
         "addc.u32 %7, %7, %15;"
-        : "+r"(lo[1]), "+r"(lo[2]), "+r"(lo[3]), "+r"(lo[4]), "+r"(lo[5]), "+r"(lo[6]), "+r"(lo[7]), "+r"(top)
+        : "+&r"(lo[1]), "+&r"(lo[2]), "+&r"(lo[3]), "+&r"(lo[4]), "+&r"(lo[5]), "+&r"(lo[6]), "+&r"(lo[7]), "+&r"(top)
         : "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
     // top <= 39; lo += 38*top
     uint32_t t = top * 38u, c2;
@@ -150,7 +296,7 @@ BBP_DEV fe fe_reduce_wide(const uint32_t *r) {
         "addc.cc.u32 %6, %6, 0;\n\t"
         "addc.cc.u32 %7, %7, 0;\n\t"
         "addc.u32 %8, 0, 0;"
-        : "+r"(lo[0]), "+r"(lo[1]), "+r"(lo[2]), "+r"(lo[3]), "+r"(lo[4]), "+r"(lo[5]), "+r"(lo[6]), "+r"(lo[7]), "=r"(c2)
+        : "+&r"(lo[0]), "+&r"(lo[1]), "+&r"(lo[2]), "+&r"(lo[3]), "+&r"(lo[4]), "+&r"(lo[5]), "+&r"(lo[6]), "+&r"(lo[7]), "=&r"(c2)
         : "r"(t));
     lo[0] += (0u - c2) & 38u;   // after a wrap the value is < 1482, so this cannot carry
 #pragma unroll
@@ -163,7 +309,15 @@ BBP_DEV fe fe_mul(const fe &a, const fe &b) {
     fe_mul_wide(r, a.v, b.v);
     return fe_reduce_wide(r);
 }
+#ifndef BBP_SQ_VIA_MUL
+BBP_DEV fe fe_sq(const fe &a) {
+    uint32_t r[16];
+    fe_sq_wide(r, a.v);
+    return fe_reduce_wide(r);
+}
+#else
 BBP_DEV fe fe_sq(const fe &a) { return fe_mul(a, a); }
+#endif
 
 BBP_DEV fe fe_add(const fe &a, const fe &b) {
     fe r;
@@ -177,7 +331,7 @@ BBP_DEV fe fe_add(const fe &a, const fe &b) {
         "addc.cc.u32 %6, %15, %23;\n\t"
         "addc.cc.u32 %7, %16, %24;\n\t"
         "addc.u32 %8, 0, 0;"
-        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]), "=r"(c)
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]), "=&r"(r.v[7]), "=&r"(c)
         : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
           "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
     uint32_t t = (0u - c) & 38u, c2;
@@ -190,7 +344,7 @@ BBP_DEV fe fe_add(const fe &a, const fe &b) {
         "addc.cc.u32 %6, %6, 0;\n\t"
         "addc.cc.u32 %7, %7, 0;\n\t"
         "addc.u32 %8, 0, 0;"
-        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]), "=r"(c2)
+        : "+&r"(r.v[0]), "+&r"(r.v[1]), "+&r"(r.v[2]), "+&r"(r.v[3]), "+&r"(r.v[4]), "+&r"(r.v[5]), "+&r"(r.v[6]), "+&r"(r.v[7]), "=&r"(c2)
         : "r"(t));
     r.v[0] += (0u - c2) & 38u;
     return r;
@@ -208,7 +362,7 @@ BBP_DEV fe fe_sub(const fe &a, const fe &b) {
         "subc.cc.u32 %6, %15, %23;\n\t"
         "subc.cc.u32 %7, %16, %24;\n\t"
         "subc.u32 %8, 0, 0;"
-        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]), "=r"(bw)
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]), "=&r"(r.v[7]), "=&r"(bw)
         : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
           "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
     // bw = 0 or 0xffffffff; a - b + 2^256 = a - b + 38 (mod p), so take the 38 back off
@@ -222,7 +376,7 @@ BBP_DEV fe fe_sub(const fe &a, const fe &b) {
         "subc.cc.u32 %6, %6, 0;\n\t"
         "subc.cc.u32 %7, %7, 0;\n\t"
         "subc.u32 %8, 0, 0;"
-        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]), "=r"(b2)
+        : "+&r"(r.v[0]), "+&r"(r.v[1]), "+&r"(r.v[2]), "+&r"(r.v[3]), "+&r"(r.v[4]), "+&r"(r.v[5]), "+&r"(r.v[6]), "+&r"(r.v[7]), "=&r"(b2)
         : "r"(t));
     r.v[0] -= b2 & 38u;   // after a second wrap the value is >= 2^256 - 38, so this cannot borrow
     return r;
@@ -254,7 +408,7 @@ BBP_DEV fe fe_canon(const fe &a) {
         "addc.cc.u32 %5, %5, 0;\n\t"
         "addc.cc.u32 %6, %6, 0;\n\t"
         "addc.u32 %7, %7, 0;"
-        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7])
+        : "+&r"(r.v[0]), "+&r"(r.v[1]), "+&r"(r.v[2]), "+&r"(r.v[3]), "+&r"(r.v[4]), "+&r"(r.v[5]), "+&r"(r.v[6]), "+&r"(r.v[7])
         : "r"(t));
     // q = 1 iff v >= p, i.e. iff v + 19 >= 2^255
     fe s;
@@ -266,7 +420,7 @@ BBP_DEV fe fe_canon(const fe &a) {
         "addc.cc.u32 %5, %13, 0;\n\t"
         "addc.cc.u32 %6, %14, 0;\n\t"
         "addc.u32 %7, %15, 0;"
-        : "=r"(s.v[0]), "=r"(s.v[1]), "=r"(s.v[2]), "=r"(s.v[3]), "=r"(s.v[4]), "=r"(s.v[5]), "=r"(s.v[6]), "=r"(s.v[7])
+        : "=&r"(s.v[0]), "=&r"(s.v[1]), "=&r"(s.v[2]), "=&r"(s.v[3]), "=&r"(s.v[4]), "=&r"(s.v[5]), "=&r"(s.v[6]), "=&r"(s.v[7])
         : "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7]));
     bool ge_p = (s.v[7] >> 31) != 0;
     s.v[7] &= 0x7fffffffu;

@@ -41,6 +41,9 @@ inline size_t host_threads() {
     }();
     return hw;
 }
+// BBP_KECCAK_THREAD=1 selects the one-thread-per-sponge Keccak kernels (k_rng_draws, k_verify_transcript) instead of the
+// warp-cooperative ones; read per call so that the tests can compare both
+inline bool keccak_per_thread() { const char *e = getenv("BBP_KECCAK_THREAD"); return e && atoi(e) != 0; }
 // Persistent host worker pool (one per process): the per-proof phases are short (tens of microseconds per proof), so
 // spawning threads per phase would cost as much as the phase. Workers sleep on a condition variable between phases.
 class host_pool {
@@ -607,11 +610,11 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     phase_trace trace("prove_group");
 
     // ---- phase 0: witness + V commitments
-    // the 2 n1 blinding-vector draws run on the device for large batches (one thread per proof continues the transcript RNG;
-    // the chain costs ~19 ms of latency whatever the batch; host threads draw ~2.4 ms per proof each, so the device wins
-    // once the batch exceeds about six proofs per host thread)
+    // the 2 n1 blinding-vector draws run on the device for large batches (one warp per proof continues the transcript RNG;
+    // the chain is a few ms of latency whatever the batch; host threads draw ~2.4 ms per proof each, so the device wins
+    // once the batch exceeds about two proofs per host thread)
     const char *rng_env = getenv("BBP_DEVICE_RNG_MIN_BATCH");   // read per call so that tests can force either path
-    const int rng_threshold = rng_env ? atoi(rng_env) : (int)(6 * host_threads());
+    const int rng_threshold = rng_env ? atoi(rng_env) : (int)(2 * host_threads());
     const bool device_rng = (int)B >= rng_threshold;
     // witness staging (pinned, grow-only), vector-major [a_L | a_R | a_O | s_L | s_R], each B x n1: the evaluator writes in place
     const size_t wit_count = (size_t)B * (device_rng ? 3 : 5) * n1;
@@ -715,7 +718,10 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
         BBP_CUDA_OK(cudaEventRecord(ps->ev_up, ctx->stream));
         BBP_CUDA_OK(cudaStreamWaitEvent(ps->rng_stream, ps->ev_up, 0));
         if ((rc = ps->rng_raw.ensure((size_t)B * 2 * n1 * 64))) return rc;
-        k_rng_draws<<<(B + 31) / 32, 32, 0, ps->rng_stream>>>(ps->rng_states.p, B, 2 * n1, ps->rng_raw.as<uint32_t>());
+        if (keccak_per_thread())
+            k_rng_draws<<<(B + 31) / 32, 32, 0, ps->rng_stream>>>(ps->rng_states.p, B, 2 * n1, ps->rng_raw.as<uint32_t>());
+        else   // one warp per proof
+            k_rng_draws_warp<<<(B + 3) / 4, 128, 0, ps->rng_stream>>>(ps->rng_states.p, B, 2 * n1, ps->rng_raw.as<uint32_t>());
         k_wide_reduce<<<(unsigned)(((size_t)B * 2 * n1 + 127) / 128), 128, 0, ps->rng_stream>>>(ps->rng_raw.as<uint32_t>(), B, 2 * n1, n1, (size_t)B * n1,
                                                                                                  ps->wit.as<sc>() + (size_t)3 * B * n1);
         ctx->launches += 2;
@@ -1080,10 +1086,10 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
         return rc;
     k_decompress_to_niels_strided<<<(B * ds + 127) / 128, 128, 0, ctx->stream>>>(ps->dyn_pts.p, ds, blob_stride, ps->dyn_niels.p, B * ds, ps->valid.p);
     ctx->launches++;
-    // Fiat-Shamir replay: on the device for large batches (one thread per request, ~1.5 ms whatever the batch), on the host
+    // Fiat-Shamir replay: on the device for large batches (one warp per request, ~0.2 ms whatever the batch), on the host
     // threads otherwise (~40 us per request per thread); BBP_DEVICE_TRANSCRIPT_MIN_BATCH overrides the crossover
     const char *tr_env = getenv("BBP_DEVICE_TRANSCRIPT_MIN_BATCH");
-    const bool device_replay = B >= (uint32_t)(tr_env ? atoi(tr_env) : (int)(32 * host_threads()));
+    const bool device_replay = B >= (uint32_t)(tr_env ? atoi(tr_env) : (int)(8 * host_threads()));
     std::vector<sc> rvals(combined ? B : 0);
     if (device_replay) {
         transcript_init init;
@@ -1092,8 +1098,12 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
             tr.r1cs_domain_sep();                            // Verifier::new
             tr.export_state(init.state);
         }
-        k_verify_transcript<<<(B + 31) / 32, 32, 0, ctx->stream>>>(init, ps->dyn_pts.p, blob_stride, ps->rng_states.p, B, m, lg, (uint64_t)n,
-                                                                   ps->chal.as<sc>(), ps->dyn_sc.as<sc>(), ds);
+        if (keccak_per_thread())
+            k_verify_transcript<<<(B + 31) / 32, 32, 0, ctx->stream>>>(init, ps->dyn_pts.p, blob_stride, ps->rng_states.p, B, m, lg, (uint64_t)n,
+                                                                       ps->chal.as<sc>(), ps->dyn_sc.as<sc>(), ds);
+        else   // one warp per request
+            k_verify_transcript_warp<<<(B + 3) / 4, 128, 0, ctx->stream>>>(init, ps->dyn_pts.p, blob_stride, ps->rng_states.p, B, m, lg, (uint64_t)n,
+                                                                           ps->chal.as<sc>(), ps->dyn_sc.as<sc>(), ds);
         ctx->launches++;
         if (combined)
             BBP_CUDA_OK(cudaMemcpy2DAsync(rvals.data(), 32, ps->chal.as<sc>() + CH_R, (size_t)CH_N * 32, 32, B, cudaMemcpyDeviceToHost, ctx->stream));

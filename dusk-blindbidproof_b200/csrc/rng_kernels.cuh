@@ -140,6 +140,172 @@ struct strobe_dev {
     }
 };
 
+// ---------------------------------------------------------------- warp-cooperative Keccak-f[1600] and STROBE-128
+// One WARP advances one sponge: lane i < 25 holds state lane i = x + 5 y in two registers. A round is two gather steps by
+// warp shuffles and a handful of logic instructions per thread:
+//   theta   each lane fetches the five lanes of column x-1 and the five of column x+1 (10 64-bit shuffles), D = C[x-1] ^ rotl(C[x+1], 1)
+//   rho     every lane rotates its own word by its own offset
+//   pi+chi  lane (X, Y) fetches the rotated words that pi moves to (X, Y), (X+1, Y), (X+2, Y) (3 shuffles) and combines them
+//   iota    lane 0
+// against ~5000 dependent logic instructions of one thread walking all 25 lanes. The dependent path of a round is ~100
+// clocks, and a batch of B sponges is B warps spread over all SMs instead of B / 32 (one thread per sponge left 16 warps on
+// 148 SMs for 512 requests: a pure latency chain, 26 % of the prover's and 34 % of the batch verifier's GPU time).
+__constant__ uint8_t KECCAK_RHO_LANE[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+    uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+struct keccak_warp {
+    int m_base, p_base, s0, s1, s2;   // source lanes of the two gathers
+    uint32_t rot;                     // rho offset of the lane's own word
+    uint64_t iota_mask;               // all ones on lane 0
+    __device__ __forceinline__ void init(uint32_t lane) {
+        const uint32_t i = lane < 25 ? lane : lane - 25;   // the seven idle lanes shadow lanes 0..6 (their results are never read)
+        const uint32_t x = i % 5, y = i / 5;
+        m_base = (int)((x + 4) % 5); p_base = (int)((x + 1) % 5);
+        const uint32_t x1 = (x + 1) % 5, x2 = (x + 2) % 5;
+        s0 = (int)((x + 3 * y) % 5 + 5 * x); s1 = (int)((x1 + 3 * y) % 5 + 5 * x1); s2 = (int)((x2 + 3 * y) % 5 + 5 * x2);
+        rot = KECCAK_RHO_LANE[i];
+        iota_mask = lane == 0 ? ~0ull : 0ull;
+    }
+    __device__ __forceinline__ uint64_t rotl_own(uint64_t v) const {
+        uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+        if (rot & 32) { uint32_t t = lo; lo = hi; hi = t; }
+        const uint32_t r = rot & 31;
+        uint32_t nlo = __funnelshift_l(hi, lo, r), nhi = __funnelshift_l(lo, hi, r);
+        return ((uint64_t)nhi << 32) | nlo;
+    }
+    __device__ __forceinline__ uint64_t permute(uint64_t a) const {
+#pragma unroll 2
+        for (int r = 0; r < 24; r++) {
+            uint64_t cm = shfl64(a, m_base) ^ shfl64(a, m_base + 5) ^ shfl64(a, m_base + 10) ^ shfl64(a, m_base + 15) ^ shfl64(a, m_base + 20);
+            uint64_t cp = shfl64(a, p_base) ^ shfl64(a, p_base + 5) ^ shfl64(a, p_base + 10) ^ shfl64(a, p_base + 15) ^ shfl64(a, p_base + 20);
+            uint64_t c = rotl_own(a ^ cm ^ rotl64(cp, 1));
+            uint64_t b0 = shfl64(c, s0), b1 = shfl64(c, s1), b2 = shfl64(c, s2);
+            a = b0 ^ (~b1 & b2) ^ (KECCAK_RC_DEV[r] & iota_mask);
+        }
+        return a;
+    }
+};
+
+// STROBE-128 with the sponge state of one warp in shared memory (200 bytes, 8-byte aligned, owned by the warp): absorb /
+// overwrite / squeeze touch the bytes lane-parallel, the permutation runs on registers (keccak_warp). pos / pos_begin are
+// warp-uniform. Bit-exact twin of strobe_dev and of keccak.h's strobe128.
+struct strobe_warp {
+    uint8_t *st;
+    uint32_t pos, pos_begin, lane;
+    keccak_warp K;
+    __device__ __forceinline__ void attach(uint8_t *smem_state, uint32_t lane_) { st = smem_state; lane = lane_; K.init(lane_); }
+    // 208-byte exported state (keccak.h export_state) from generic memory
+    __device__ __forceinline__ void load(const uint8_t *src) {
+        if (lane < 25) ((uint64_t *)st)[lane] = ((const uint64_t *)src)[lane];
+        pos = src[200]; pos_begin = src[201];
+        __syncwarp();
+    }
+    __device__ __forceinline__ void store(uint8_t *dst, uint8_t cur_flags) {
+        __syncwarp();
+        if (lane < 25) ((uint64_t *)dst)[lane] = ((const uint64_t *)st)[lane];
+        if (lane == 0) { dst[200] = (uint8_t)pos; dst[201] = (uint8_t)pos_begin; dst[202] = cur_flags; }
+    }
+    __device__ __noinline__ void run_f() {
+        if (lane == 0) { st[pos] ^= (uint8_t)pos_begin; st[pos + 1] ^= 0x04; st[BBP_STROBE_R + 1] ^= 0x80; }
+        __syncwarp();
+        uint64_t a = ((const uint64_t *)st)[lane < 25 ? lane : lane - 25];
+        a = K.permute(a);
+        if (lane < 25) ((uint64_t *)st)[lane] = a;
+        __syncwarp();
+        pos = 0; pos_begin = 0;
+    }
+    __device__ __forceinline__ void absorb_byte(uint8_t b) {
+        if (lane == 0) st[pos] ^= b;
+        __syncwarp();
+        if (++pos == BBP_STROBE_R) run_f();
+    }
+    // up to 16 warp-uniform bytes held in (lo, hi), little-endian
+    __device__ __forceinline__ void absorb_packed(uint64_t lo, uint64_t hi, uint32_t n) {
+        if (pos + n < BBP_STROBE_R) {
+            if (lane < n) st[pos + lane] ^= (uint8_t)((lane < 8 ? lo >> (8 * lane) : hi >> (8 * (lane - 8))) & 0xff);
+            __syncwarp();
+            pos += n;
+            return;
+        }
+        for (uint32_t i = 0; i < n; i++) absorb_byte((uint8_t)((i < 8 ? lo >> (8 * i) : hi >> (8 * (i - 8))) & 0xff));
+    }
+    __device__ __forceinline__ void absorb(const uint8_t *d, uint32_t n) {
+        while (n) {
+            const uint32_t chunk = min(n, BBP_STROBE_R - pos);
+            for (uint32_t i = lane; i < chunk; i += 32) st[pos + i] ^= d[i];
+            __syncwarp();
+            pos += chunk; d += chunk; n -= chunk;
+            if (pos == BBP_STROBE_R) run_f();
+        }
+    }
+    __device__ __forceinline__ void begin_op(uint8_t flags) {
+        const uint32_t old_begin = pos_begin;
+        pos_begin = pos + 1;
+        absorb_packed((uint64_t)old_begin | ((uint64_t)flags << 8), 0, 2);
+        if ((flags & (4 | 32)) && pos != 0) run_f();   // FLAG_C | FLAG_K
+    }
+    __device__ __forceinline__ void meta_ad_label(const char *label, uint32_t n) { begin_op(16 | 2); absorb((const uint8_t *)label, n); }
+    __device__ __forceinline__ void meta_ad_len(uint32_t len) { absorb_packed(len, 0, 4); }
+    __device__ __noinline__ void append_message(const char *label, uint32_t llen, const uint8_t *msg, uint32_t n) {
+        meta_ad_label(label, llen);
+        meta_ad_len(n);
+        begin_op(2);
+        absorb(msg, n);
+    }
+    __device__ __forceinline__ void append_u64(const char *label, uint32_t llen, uint64_t x) {
+        meta_ad_label(label, llen);
+        meta_ad_len(8);
+        begin_op(2);
+        absorb_packed(x, 0, 8);
+    }
+    // prf(64): after begin_op with FLAG_C the position is 0, so the 64 bytes are state lanes 0..7; every lane gets all 16 words
+    __device__ __forceinline__ void prf64(uint32_t w[16]) {
+        begin_op(1 | 2 | 4);
+        const uint32_t *s32 = (const uint32_t *)st;
+#pragma unroll
+        for (int i = 0; i < 16; i++) w[i] = s32[i];
+        __syncwarp();
+        if (lane < 16) ((uint32_t *)st)[lane] = 0;
+        __syncwarp();
+        pos = 64;
+    }
+    // key(32 bytes): begin_op(A | C) leaves pos = 0, then the bytes overwrite state bytes 0..31
+    __device__ __forceinline__ void key32(const uint8_t *d) {
+        begin_op(2 | 4);
+        if (lane < 32) st[lane] = d[lane];
+        __syncwarp();
+        pos = 32;
+    }
+    __device__ __noinline__ sc challenge_scalar(const char *label, uint32_t llen) {
+        meta_ad_label(label, llen);
+        meta_ad_len(64);
+        uint32_t w[16];
+        prf64(w);
+        return sc_from_wide_words(w);
+    }
+    // TranscriptRng::fill_bytes(64)
+    __device__ __forceinline__ void fill64(uint32_t w[16]) {
+        begin_op(16 | 2);
+        absorb_packed(64, 0, 4);
+        prf64(w);
+    }
+    // the same, lane i < 16 receiving output word i only
+    __device__ __forceinline__ uint32_t fill64_word() {
+        begin_op(16 | 2);
+        absorb_packed(64, 0, 4);
+        begin_op(1 | 2 | 4);
+        const uint32_t v = ((const uint32_t *)st)[lane & 15];
+        __syncwarp();
+        if (lane < 16) ((uint32_t *)st)[lane] = 0;
+        __syncwarp();
+        pos = 64;
+        return v;
+    }
+};
+
 // Steady state of consecutive 64-byte draws: every draw starts at pos = 64, pos_begin = 0 (the previous prf squeezed lanes
 // 0..7 after a permutation), so the STROBE framing of one draw is a fixed pattern of byte XORs:
 //   bytes 64..71 (lane 8):  old_begin = 0, flags M|A = 0x12, LE32(64), old_begin = 65, flags I|A|C = 0x07
@@ -194,6 +360,42 @@ __global__ void __launch_bounds__(32) k_rng_draws(uint8_t *__restrict__ states, 
     for (int i = 0; i < 25; i++) o[i] = S.st[i];
     uint8_t *ot = states + (size_t)p * BBP_STROBE_STATE_BYTES + 200;
     ot[0] = (uint8_t)S.pos; ot[1] = (uint8_t)S.pos_begin; ot[2] = 1 | 2 | 4;   // cur_flags after a prf
+}
+
+// The same chain with one WARP per proof (keccak_warp): the generic path runs on the shared-memory sponge until the steady
+// state is reached, then the state lives in the lanes' registers; lanes 0..7 store the 64 output bytes of a draw as one
+// coalesced 64-byte row. 4 proofs per block.
+__global__ void __launch_bounds__(128) k_rng_draws_warp(uint8_t *__restrict__ states, uint32_t n_proofs, uint32_t n_draws, uint32_t *__restrict__ raw) {
+    __shared__ uint64_t sm_state[4][26];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t p = blockIdx.x * 4 + warp;
+    if (p >= n_proofs) return;   // whole warps leave together
+    strobe_warp S;
+    S.attach((uint8_t *)sm_state[warp], lane);
+    S.load(states + (size_t)p * BBP_STROBE_STATE_BYTES);
+    uint32_t *out = raw + (size_t)p * n_draws * 16;
+    uint32_t d = 0;
+    for (; d < n_draws && !(S.pos == 64 && S.pos_begin == 0); d++) {
+        const uint32_t v = S.fill64_word();
+        if (lane < 16) out[(size_t)d * 16 + lane] = v;
+    }
+    if (d < n_draws) {
+        uint64_t a = ((const uint64_t *)S.st)[lane < 25 ? lane : lane - 25];
+        const uint64_t frame = lane == 8 ? BBP_STROBE_DRAW_LANE8 : lane == 9 ? BBP_STROBE_DRAW_LANE9 : lane == 20 ? BBP_STROBE_DRAW_LANE20 : 0ull;
+        const bool is_out = lane < 8;
+#pragma unroll 1
+        for (; d < n_draws; d++) {
+            a = S.K.permute(a ^ frame);
+            if (is_out) {
+                ((uint2 *)(out + (size_t)d * 16))[lane] = make_uint2((uint32_t)a, (uint32_t)(a >> 32));
+                a = 0;
+            }
+        }
+        __syncwarp();
+        if (lane < 25) ((uint64_t *)S.st)[lane] = a;
+        __syncwarp();
+    }
+    S.store(states + (size_t)p * BBP_STROBE_STATE_BYTES, 1 | 2 | 4);   // cur_flags after a prf
 }
 
 // Scalar::from_bytes_mod_order_wide over the raw draws: draw d of proof p -> out[(d / per_vec) * vec_stride + p * per_vec + d % per_vec]
@@ -358,6 +560,115 @@ __global__ void __launch_bounds__(32) k_verify_transcript(transcript_init init, 
         d[11 + 2 * j] = sc_mul(uj, uj);            // weight of L_j
         d[11 + 2 * j + 1] = sc_mul(ujinv, ujinv);  // weight of R_j
     }
+    sc xx = sc_mul(x, x), xxx = sc_mul(xx, x), rxx = sc_mul(r, xx);
+    d[0] = x; d[1] = xx; d[2] = xxx; d[3] = sc_mul(u, x); d[4] = sc_mul(u, xx); d[5] = sc_mul(u, xxx);
+    d[6] = sc_mul(r, x); d[7] = sc_mul(rxx, x); d[8] = sc_mul(rxx, xx); d[9] = sc_mul(rxx, xxx); d[10] = sc_mul(sc_mul(rxx, xx), xx);
+    sc t;
+    c[CH_Y] = y; c[CH_YINV] = yinv; c[CH_Z] = z; c[CH_X] = x; c[CH_U] = u; c[CH_W] = w; c[CH_R] = r;
+    const uint32_t *sw = (const uint32_t *)scal;
+    for (int k = 0; k < 8; k++) t.v[k] = sw[k];
+    c[CH_TX] = t;
+    for (int k = 0; k < 8; k++) t.v[k] = sw[8 + k];
+    c[CH_TXBL] = t;
+    for (int k = 0; k < 8; k++) t.v[k] = sw[16 + k];
+    c[CH_EBL] = t;
+    for (int k = 0; k < 8; k++) t.v[k] = sw[24 + k];
+    c[CH_A] = t;
+    for (int k = 0; k < 8; k++) t.v[k] = sw[32 + k];
+    c[CH_B] = t;
+    c[CH_RHO] = sc_one();
+}
+
+// The same replay with one WARP per request (strobe_warp / keccak_warp): the ~50 permutations and ~60 transcript operations
+// of a request run lane-parallel; the scalar arithmetic that follows (challenge reductions, one batched inversion, the
+// dynamic-point weights) is computed redundantly by every lane (uniform control flow) and stored by lane 0. 4 requests per block.
+__global__ void __launch_bounds__(128) k_verify_transcript_warp(transcript_init init, const uint8_t *__restrict__ blobs, uint32_t blob_stride,
+                                                                const uint8_t *__restrict__ seeds, uint32_t n_req, uint32_t m, uint32_t lg, uint64_t n_ipp,
+                                                                sc *__restrict__ chal, sc *__restrict__ dyn, uint32_t dyn_stride) {
+    __shared__ uint64_t sm_state[4][26];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t p = blockIdx.x * 4 + warp;
+    if (p >= n_req) return;   // whole warps leave together
+    strobe_warp S;
+    S.attach((uint8_t *)sm_state[warp], lane);
+    S.load(init.state);
+    const bool lead = lane == 0;
+    const uint8_t *blob = blobs + (size_t)p * blob_stride;
+    const uint8_t *pts = blob + 32 * (size_t)m;                   // A_I1 ...
+    const uint8_t *lr = pts + 32 * 11;
+    const uint8_t *scal = lr + 64 * (size_t)lg;                   // t_x, t_x_blinding, e_blinding, a, b
+    sc *c = chal + (size_t)p * CH_N;
+    for (uint32_t i = 0; i < m; i++) S.append_message(BBP_LBL("V"), blob + 32 * (size_t)i, 32);
+    S.append_u64(BBP_LBL("m"), m);
+    S.append_message(BBP_LBL("A_I1"), pts, 32);
+    S.append_message(BBP_LBL("A_O1"), pts + 32, 32);
+    S.append_message(BBP_LBL("S1"), pts + 64, 32);
+    S.append_message(BBP_LBL("dom-sep"), (const uint8_t *)"r1cs-1phase", 11);
+    S.append_message(BBP_LBL("A_I2"), pts + 96, 32);
+    S.append_message(BBP_LBL("A_O2"), pts + 128, 32);
+    S.append_message(BBP_LBL("S2"), pts + 160, 32);
+    sc y = S.challenge_scalar(BBP_LBL("y"));
+    sc z = S.challenge_scalar(BBP_LBL("z"));
+    S.append_message(BBP_LBL("T_1"), pts + 192, 32);
+    S.append_message(BBP_LBL("T_3"), pts + 224, 32);
+    S.append_message(BBP_LBL("T_4"), pts + 256, 32);
+    S.append_message(BBP_LBL("T_5"), pts + 288, 32);
+    S.append_message(BBP_LBL("T_6"), pts + 320, 32);
+    sc u = S.challenge_scalar(BBP_LBL("u"));
+    sc x = S.challenge_scalar(BBP_LBL("x"));
+    S.append_message(BBP_LBL("t_x"), scal, 32);
+    S.append_message(BBP_LBL("t_x_blinding"), scal + 32, 32);
+    S.append_message(BBP_LBL("e_blinding"), scal + 64, 32);
+    sc w = S.challenge_scalar(BBP_LBL("w"));
+    S.append_message(BBP_LBL("dom-sep"), (const uint8_t *)"ipp v1", 6);
+    S.append_u64(BBP_LBL("n"), n_ipp);
+    // prefix products for the batch inversion of (u_0 .. u_{lg-1}, y), in the Montgomery domain
+    sc acc = sc_to_mont(sc_one());
+    for (uint32_t j = 0; j < lg; j++) {
+        S.append_message(BBP_LBL("L"), lr + 64 * (size_t)j, 32);
+        S.append_message(BBP_LBL("R"), lr + 64 * (size_t)j + 32, 32);
+        sc uj = S.challenge_scalar(BBP_LBL("u"));
+        if (lead) {
+            c[CH_UJ0 + j] = uj;
+            c[CH_UJ0 + lg + j] = acc;      // prefix (Montgomery form), replaced by the inverse below
+        }
+        acc = mm(acc, sc_to_mont(uj));
+    }
+    __syncwarp();                          // lane 0's stores to c[] are read back by every lane below
+    sc pre_y = acc;
+    acc = mm(acc, sc_to_mont(y));
+    // verifier randomness: transcript.build_rng().finalize(rng_seed) -> one scalar
+    S.meta_ad_label(BBP_LBL("rng"));
+    S.key32(seeds + 32 * (size_t)p);
+    uint32_t rw[16];
+    S.fill64(rw);
+    sc r = sc_from_wide_words(rw);
+    // acc = (prod u_j * y) R ; invert once: x^(l-2) in the Montgomery domain
+    sc inv = sc_to_mont(sc_one());
+#pragma unroll 1
+    for (int i = 252; i >= 0; i--) {
+        inv = mm(inv, inv);
+        uint32_t e = sc_l_limb(i >> 5);
+        if (i < 32) e = sc_l_limb(0) - 2;
+        if ((e >> (i & 31)) & 1) inv = mm(inv, acc);
+    }
+    sc yinv = sc_from_mont(mm(inv, pre_y));
+    inv = mm(inv, sc_to_mont(y));
+    sc *d = dyn + (size_t)p * dyn_stride + m;
+#pragma unroll 1
+    for (uint32_t j = lg; j-- > 0;) {
+        sc uj = c[CH_UJ0 + j];
+        sc ujinv = sc_from_mont(mm(inv, c[CH_UJ0 + lg + j]));
+        inv = mm(inv, sc_to_mont(uj));
+        sc w_l = sc_mul(uj, uj), w_r = sc_mul(ujinv, ujinv);
+        __syncwarp();                      // every lane has read c[CH_UJ0 + lg + j] before lane 0 overwrites it
+        if (lead) {
+            c[CH_UJ0 + lg + j] = ujinv;
+            d[11 + 2 * j] = w_l;           // weight of L_j
+            d[11 + 2 * j + 1] = w_r;       // weight of R_j
+        }
+    }
+    if (!lead) return;
     sc xx = sc_mul(x, x), xxx = sc_mul(xx, x), rxx = sc_mul(r, xx);
     d[0] = x; d[1] = xx; d[2] = xxx; d[3] = sc_mul(u, x); d[4] = sc_mul(u, xx); d[5] = sc_mul(u, xxx);
     d[6] = sc_mul(r, x); d[7] = sc_mul(rxx, x); d[8] = sc_mul(rxx, xx); d[9] = sc_mul(rxx, xxx); d[10] = sc_mul(sc_mul(rxx, xx), xx);

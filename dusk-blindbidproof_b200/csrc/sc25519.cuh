@@ -149,7 +149,7 @@ __device__ __forceinline__ void sc_mul_8x4_wide(uint32_t *r, const uint32_t *a, 
         "addc.cc.u32 %8, %19, %30;\n\t"
         "addc.cc.u32 %9, %20, %31;\n\t"
         "addc.u32 %10, %21, %32;"
-        : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11])
+        : "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(r[8]), "=&r"(r[9]), "=&r"(r[10]), "=&r"(r[11])
         : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(ev[8]), "r"(ev[9]), "r"(ev[10]), "r"(ev[11]),
           "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]), "r"(od[8]), "r"(od[9]), "r"(od[10]));
 }
@@ -182,7 +182,7 @@ __device__ __forceinline__ sc sc_montmul_dev(const uint32_t *a, const uint32_t *
         "addc.cc.u32 %5, %20, 0;\n\t"
         "addc.cc.u32 %6, %21, 0;\n\t"
         "addc.u32 %7, %22, 0;"
-        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]), "=r"(dummy)
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]), "=&r"(r.v[7]), "=&r"(dummy)
         : "r"(P[7]), "r"(q7), "r"(P[8]), "r"(P[9]), "r"(P[10]), "r"(P[11]), "r"(Q[0]), "r"(Q[1]), "r"(Q[2]), "r"(Q[3]), "r"(Q[4]), "r"(Q[5]), "r"(Q[6]),
           "r"(Q[7]));
     asm("add.cc.u32 %0, %0, %8;\n\t"
@@ -193,7 +193,7 @@ __device__ __forceinline__ sc sc_montmul_dev(const uint32_t *a, const uint32_t *
         "addc.cc.u32 %5, %5, 0;\n\t"
         "addc.cc.u32 %6, %6, 0;\n\t"
         "addc.u32 %7, %7, 0;"
-        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7])
+        : "+&r"(r.v[0]), "+&r"(r.v[1]), "+&r"(r.v[2]), "+&r"(r.v[3]), "+&r"(r.v[4]), "+&r"(r.v[5]), "+&r"(r.v[6]), "+&r"(r.v[7])
         : "r"(lo_nonzero));
     asm("add.cc.u32 %0, %0, %8;\n\t"
         "addc.cc.u32 %1, %1, %9;\n\t"
@@ -203,7 +203,7 @@ __device__ __forceinline__ sc sc_montmul_dev(const uint32_t *a, const uint32_t *
         "addc.cc.u32 %5, %5, %13;\n\t"
         "addc.cc.u32 %6, %6, %14;\n\t"
         "addc.u32 %7, %7, %15;"
-        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7])
+        : "+&r"(r.v[0]), "+&r"(r.v[1]), "+&r"(r.v[2]), "+&r"(r.v[3]), "+&r"(r.v[4]), "+&r"(r.v[5]), "+&r"(r.v[6]), "+&r"(r.v[7])
         : "r"(T[8]), "r"(T[9]), "r"(T[10]), "r"(T[11]), "r"(T[12]), "r"(T[13]), "r"(T[14]), "r"(T[15]));
     if (sc_geq_l(r.v)) sc_sub_l(r.v);
     return r;
@@ -285,6 +285,13 @@ BBP_HD sc sc_from_wide(const uint8_t *in) {
     for (int i = 0; i < 8; i++) w[i] = (uint32_t)in[32 + 4 * i] | ((uint32_t)in[33 + 4 * i] << 8) | ((uint32_t)in[34 + 4 * i] << 16) | ((uint32_t)in[35 + 4 * i] << 24);
     sc r2 = sc_r2();
     sc hi = sc_montmul(w, r2.v);      // hi * 2^256 mod l
+    return sc_add(lo, hi);
+}
+// the same from 16 little-endian words
+BBP_HD sc sc_from_wide_words(const uint32_t *w) {
+    sc lo = sc_reduce_words(w);
+    sc r2 = sc_r2();
+    sc hi = sc_montmul(w + 8, r2.v);
     return sc_add(lo, hi);
 }
 BBP_HD bool sc_from_canonical(sc &out, const uint8_t *in) {

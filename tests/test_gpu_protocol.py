@@ -130,11 +130,13 @@ def test_prove_batch_mixed_lengths(be):
         assert (proof, comm, tc) == (oproof, ocomm, otc)
 
 
-def test_prove_batch_device_rng_matches_oracle(be, monkeypatch):
-    """large batches continue the TranscriptRng on the device (rng_kernels.cuh) and switch the inner-product argument to
-    its hybrid form (materialised folded bases): bytes must still equal the oracle's, and equal what the host-RNG /
-    plain path (single request) produces"""
+@pytest.mark.parametrize("keccak", ["warp", "thread"])
+def test_prove_batch_device_rng_matches_oracle(be, keccak, monkeypatch):
+    """large batches continue the TranscriptRng on the device (rng_kernels.cuh: one warp per proof, or the older
+    one-thread-per-proof kernel) and switch the inner-product argument to its hybrid form (materialised folded bases):
+    bytes must still equal the oracle's, and equal what the host-RNG / plain path (single request) produces"""
     cases = [make_case(300 + i, 3) for i in range(12)]
+    monkeypatch.setenv("BBP_KECCAK_THREAD", "1" if keccak == "thread" else "0")
     monkeypatch.setenv("BBP_DEVICE_RNG_MIN_BATCH", "8")
     monkeypatch.setenv("BBP_IPP_HYBRID", "2")
     outs = be.blindbid_prove_batch(cases)
@@ -221,11 +223,13 @@ def mutations(bid, proof, comm, tc):
     return out
 
 
-@pytest.mark.parametrize("L,replay", [(2, "host"), (8, "host"), (8, "device")])
+@pytest.mark.parametrize("L,replay", [(2, "host"), (8, "host"), (8, "device"), (3, "device"), (8, "device-thread")])
 def test_verify_verdicts_match_oracle(be, L, replay, monkeypatch):
     """accept / reject parity with the oracle, including the error class, over honest and mutated inputs; with the
-    Fiat-Shamir replay on the host threads (small batches) and on the device (large batches)"""
-    monkeypatch.setenv("BBP_DEVICE_TRANSCRIPT_MIN_BATCH", "1" if replay == "device" else "1000000")
+    Fiat-Shamir replay on the host threads (small batches) and on the device (large batches: one warp per request, or
+    the older one-thread-per-request kernel)"""
+    monkeypatch.setenv("BBP_DEVICE_TRANSCRIPT_MIN_BATCH", "1" if replay.startswith("device") else "1000000")
+    monkeypatch.setenv("BBP_KECCAK_THREAD", "1" if replay == "device-thread" else "0")
     bid = make_case(50 + L, L)
     rc, proof, comm, tc = orc.blindbid_prove(bid, bid["blindings"], bid["rng_seed"])
     assert rc == 0
@@ -254,6 +258,26 @@ def test_non_member_bid_does_not_verify(be):
     assert rc == 0 and st == 0 and (gproof, gcomm, gtc) == (proof, comm, tc)
     item = verify_item(bid, gproof, gcomm, gtc)
     assert oracle_verify(item) != 0 and be.blindbid_verify(item) == oracle_verify(item)
+
+
+def test_toggle_beyond_list_and_non_canonical_inputs(be):
+    """the reference accepts any toggle (`i as u64 == toggle`): an index beyond the list gives all-zero toggle bits and a
+    proof that does not verify — same bytes as the oracle's; serde-decoded scalars must be canonical (FormatError)"""
+    bid = make_case(95, 4)
+    bid["toggle"] = 9
+    rc, proof, comm, tc = orc.blindbid_prove(bid, bid["blindings"], bid["rng_seed"])
+    st, gproof, gcomm, gtc = be.blindbid_prove(bid)
+    assert rc == 0 and st == 0 and (gproof, gcomm, gtc) == (proof, comm, tc)
+    item = verify_item(bid, gproof, gcomm, gtc)
+    assert oracle_verify(item) != 0 and be.blindbid_verify(item) == oracle_verify(item)
+    good = make_case(96, 2)
+    bad = dict(good); bad["k"] = le(L_ORDER + 5)
+    assert be.blindbid_prove(bad)[0] == -2
+    st, p, c, t = be.blindbid_prove(good)
+    it = verify_item(good, p, c, t)
+    assert be.blindbid_verify(it) == 0
+    it["seed"] = le(from_le(good["seed"]) + L_ORDER)
+    assert be.blindbid_verify(it) == -2
 
 
 def test_generator_capacity_limits(be):
