@@ -238,6 +238,12 @@ class Backend:
         _chk(lib().bbp_test_ge(self.ctx, a, b, _sz(n), int(op), out), "bbp_test_ge")
         return out.raw
 
+    def test_batch_weights(self, r, batch_seed):
+        n = len(r) // 32
+        out = _out(32 * n)
+        _chk(lib().bbp_test_batch_weights(self.ctx, r, _sz(n), batch_seed, out), "bbp_test_batch_weights")
+        return out.raw
+
 
 # ---------------------------------------------------------------------------------------------- blind-bid entry points
 class ProveReq(ctypes.Structure):

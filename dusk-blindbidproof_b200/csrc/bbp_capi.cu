@@ -352,6 +352,28 @@ int bbp_test_fe(bbp_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, int 
     return e == cudaSuccess ? BBP_OK : BBP_ERR_CUDA;
 }
 
+int bbp_test_batch_weights(bbp_ctx *ctx, const uint8_t *r, size_t n, const uint8_t batch_seed[32], uint8_t *out) {
+    if (!ctx || !r || !batch_seed || !out || n == 0 || n > (1u << 24)) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    std::vector<sc> chal(n * CH_N, sc_zero());
+    for (size_t i = 0; i < n; i++)
+        if (!sc_from_canonical(chal[i * CH_N + CH_R], r + 32 * i)) return BBP_ERR_FORMAT;
+    uint8_t *d = nullptr;
+    const size_t chal_bytes = n * CH_N * 32, dig_bytes = (n / 32 + 1) * 32;
+    BBP_CUDA_OK(cudaMalloc(&d, chal_bytes + dig_bytes + 32 + n));
+    uint8_t *d_dig = d + chal_bytes, *d_seed = d_dig + dig_bytes, *d_valid = d_seed + 32;
+    cudaMemcpyAsync(d, chal.data(), chal_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_seed, batch_seed, 32, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemsetAsync(d_valid, 1, n, ctx->stream);
+    k_batch_weight_digests<<<(unsigned)((n + 31) / 32), 32, 0, ctx->stream>>>((const sc *)d, (uint32_t)n, (uint64_t *)d_dig);
+    k_batch_weights<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((sc *)d, d_valid, 1, (uint32_t)n, (const uint64_t *)d_dig, d_seed, 1u);
+    ctx->launches += 2;
+    cudaMemcpy2DAsync(out, 32, d + (size_t)CH_RHO * 32, (size_t)CH_N * 32, 32, n, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    return e == cudaSuccess ? BBP_OK : BBP_ERR_CUDA;
+}
+
 int bbp_test_ge(bbp_ctx *ctx, const uint8_t *a_compressed, const uint8_t *b_compressed, size_t n, int op, uint8_t *out_compressed) {
     if (!ctx || !a_compressed || !b_compressed || !out_compressed || n == 0) return BBP_ERR_INPUT;
     cudaSetDevice(ctx->device);

@@ -169,6 +169,32 @@ struct phase_trace {
     }
 };
 
+// BBP_TRACE=1: device timeline of one stream-ordered sequence (events between kernels, read after the final sync)
+struct event_timeline {
+    bool on;
+    std::vector<std::pair<const char *, cudaEvent_t>> ev;
+    event_timeline() : on(getenv("BBP_TRACE") != nullptr) {}
+    void mark(const char *name, cudaStream_t st) {
+        if (!on) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, st);
+        ev.push_back({name, e});
+    }
+    void report(const char *what) {   // call after the streams have been synchronised
+        if (!on || ev.empty()) return;
+        fprintf(stderr, "[bbp timeline] %s (ms since %s):", what, ev[0].first);
+        for (size_t i = 1; i < ev.size(); i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[0].second, ev[i].second);
+            fprintf(stderr, " %s=%.3f", ev[i].first, ms);
+        }
+        fprintf(stderr, "\n");
+        for (auto &e : ev) cudaEventDestroy(e.second);
+        ev.clear();
+    }
+};
+
 struct dev_buf {
     uint8_t *p = nullptr;
     size_t cap = 0;
@@ -226,12 +252,26 @@ struct proto_state {
     uint32_t ipp_colmap_n = 0, ipp_colmap_gcols = 0;
     dev_buf fext, ftab;            // materialised folded bases: extended, then niels (+ B at the tail)
     dev_buf chal, zpow, ypow, yinvpow, wit, vbl, blind3, poly, tout, a, b, sG, sH, slots, ab, pub, dyn_sc, dyn_pts, dyn_niels, stat, stat_red,
-        msm_out, msm_ext, flags, valid, commit_in, commit_out, rng_states, rng_raw;
+        msm_out, msm_ext, flags, valid, commit_in, commit_out, rng_states, rng_raw, bw_digests;
     host_buf h_wit, h_states;
     cudaStream_t rng_stream = nullptr;   // the device TranscriptRng chain runs beside the A_I1 / A_O1 commitments
-    cudaEvent_t ev_up = nullptr, ev_rng = nullptr;
+    cudaEvent_t ev_up = nullptr, ev_rng = nullptr, ev_dyn = nullptr;
     int proof_versioned = 1;       // R1CSProof::to_bytes layout (SURVEY.md §8c risk R1): 1 = leading phase byte, 0 = legacy 14-point form
 };
+
+inline int proto_side_stream(proto_state *ps) {
+    if (!ps->rng_stream) {
+        // highest priority: what runs here are latency chains of few warps (the RNG chain, the variable-base MSM of a
+        // verification); their blocks should take the first free slots beside the wide scalar kernels of the main stream
+        int prio_lo = 0, prio_hi = 0;
+        BBP_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        BBP_CUDA_OK(cudaStreamCreateWithPriority(&ps->rng_stream, cudaStreamNonBlocking, prio_hi));
+        BBP_CUDA_OK(cudaEventCreateWithFlags(&ps->ev_up, cudaEventDisableTiming));
+        BBP_CUDA_OK(cudaEventCreateWithFlags(&ps->ev_rng, cudaEventDisableTiming));
+        BBP_CUDA_OK(cudaEventCreateWithFlags(&ps->ev_dyn, cudaEventDisableTiming));
+    }
+    return 0;
+}
 
 inline proto_state *proto_get(bbp_ctx *ctx) {
     if (!ctx->proto) ctx->proto = new proto_state();
@@ -246,12 +286,13 @@ void proto_release(proto_state *ps) {
     ps->fext.release(); ps->ftab.release();
     dev_buf *all[] = {&ps->chal, &ps->zpow, &ps->ypow, &ps->yinvpow, &ps->wit, &ps->vbl, &ps->blind3, &ps->poly, &ps->tout, &ps->a, &ps->b, &ps->sG, &ps->sH,
                       &ps->slots, &ps->ab, &ps->pub, &ps->dyn_sc, &ps->dyn_pts, &ps->dyn_niels, &ps->stat, &ps->stat_red, &ps->msm_out, &ps->msm_ext,
-                      &ps->flags, &ps->valid, &ps->commit_in, &ps->commit_out, &ps->rng_states, &ps->rng_raw};
+                      &ps->flags, &ps->valid, &ps->commit_in, &ps->commit_out, &ps->rng_states, &ps->rng_raw, &ps->bw_digests};
     for (dev_buf *b : all) b->release();
     ps->h_wit.release(); ps->h_states.release();
     if (ps->rng_stream) cudaStreamDestroy(ps->rng_stream);
     if (ps->ev_up) cudaEventDestroy(ps->ev_up);
     if (ps->ev_rng) cudaEventDestroy(ps->ev_rng);
+    if (ps->ev_dyn) cudaEventDestroy(ps->ev_dyn);
     delete ps;
 }
 
@@ -653,9 +694,7 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     if (device_rng) {
         if ((rc = ps->h_states.ensure((size_t)B * BBP_STROBE_STATE_BYTES))) return rc;
         if (!ps->rng_stream) {
-            BBP_CUDA_OK(cudaStreamCreateWithFlags(&ps->rng_stream, cudaStreamNonBlocking));
-            BBP_CUDA_OK(cudaEventCreateWithFlags(&ps->ev_up, cudaEventDisableTiming));
-            BBP_CUDA_OK(cudaEventCreateWithFlags(&ps->ev_rng, cudaEventDisableTiming));
+            if ((rc = proto_side_stream(ps))) return rc;
         }
     }
     uint8_t *rng_states = ps->h_states.p;
@@ -772,7 +811,7 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32))) return rc;
 
     // ---- phase 4 (GPU): power tables, flattened constraints, l / r polynomials, t_1 .. t_6
-    k_powers<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+    k_powers<<<B, BBP_SC_THREADS, k_powers_smem(SB.q, SB.n), ctx->stream>>>(SB);
     k_polys<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
     ctx->launches += 2;
     std::vector<sc> tout((size_t)B * 8);
@@ -1064,33 +1103,52 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     const uint32_t ds = m + 11 + 2 * lg, blob_stride = 32 * (ds + 5);
     const uint32_t n_groups = combined ? 1 : B;
     phase_trace trace(combined ? "verify_group(combined)" : "verify_group(each)");
+    event_timeline tl;
 
     // ---- upload blobs, seeds, public values; decompress the dynamic points; replay the transcripts
-    if ((rc = ps->h_wit.ensure((size_t)B * (blob_stride + 32 + (size_t)T.n_pub * 32)))) return rc;
-    uint8_t *h_blobs = ps->h_wit.p, *h_seeds = h_blobs + (size_t)B * blob_stride;
-    sc *h_pub = (sc *)(h_seeds + (size_t)B * 32);
+    if ((rc = ps->h_wit.ensure((size_t)B * (blob_stride + 32 + (size_t)T.n_pub * 32) + 32))) return rc;
+    uint8_t *h_blobs = ps->h_wit.p, *h_seeds = h_blobs + (size_t)B * blob_stride;   // B request seeds, then the batch seed
+    sc *h_pub = (sc *)(h_seeds + (size_t)(B + 1) * 32);
+    if (combined) memcpy(h_seeds + (size_t)B * 32, batch_seed, 32); else memset(h_seeds + (size_t)B * 32, 0, 32);
     parallel_for(B, [&](size_t bi) {
         const verify_prepared &P = prep[idx[bi]];
         memcpy(h_blobs + bi * blob_stride, P.blob.data(), blob_stride);
         memcpy(h_seeds + bi * 32, jobs[idx[bi]].rng_seed, 32);
         memcpy(h_pub + bi * T.n_pub, P.pub.data(), (size_t)T.n_pub * 32);
     });
-    if ((rc = ps->dyn_pts.ensure((size_t)B * blob_stride)) || (rc = ps->rng_states.ensure((size_t)B * 32)) || (rc = ps->pub.ensure((size_t)B * T.n_pub * 32)) ||
-        (rc = ps->dyn_niels.ensure((size_t)B * ds * 96)) || (rc = ps->valid.ensure((size_t)B * ds)) || (rc = ps->chal.ensure((size_t)B * CH_N * 32)) ||
+    if ((rc = ps->dyn_pts.ensure((size_t)B * blob_stride)) || (rc = ps->rng_states.ensure((size_t)(B + 1) * 32)) || (rc = ps->pub.ensure((size_t)B * T.n_pub * 32)) ||
+        (rc = ps->bw_digests.ensure((size_t)(B / 32 + 1) * 32)) || (rc = ps->dyn_niels.ensure((size_t)B * ds * 96)) || (rc = ps->valid.ensure((size_t)B * ds)) || (rc = ps->chal.ensure((size_t)B * CH_N * 32)) ||
         (rc = ps->dyn_sc.ensure((size_t)B * ds * 32)) || (rc = ps->zpow.ensure((size_t)B * T.q * 32)) || (rc = ps->ypow.ensure((size_t)B * n * 32)) ||
         (rc = ps->yinvpow.ensure((size_t)B * n * 32)) || (rc = ps->stat.ensure((size_t)B * slot_len * 32)) || (rc = ps->sG.ensure((size_t)B * n * 32)) ||
         (rc = ps->stat_red.ensure((size_t)n_groups * slot_len * 32)) || (rc = ps->msm_ext.ensure((size_t)2 * n_groups * 128)) || (rc = ps->flags.ensure(n_groups)))
         return rc;
-    if ((rc = h2d(ctx, ps->dyn_pts.p, h_blobs, (size_t)B * blob_stride)) || (rc = h2d(ctx, ps->rng_states.p, h_seeds, (size_t)B * 32)) ||
+    trace.mark("stage");
+    tl.mark("start", ctx->stream);
+    if ((rc = h2d(ctx, ps->dyn_pts.p, h_blobs, (size_t)B * blob_stride)) || (rc = h2d(ctx, ps->rng_states.p, h_seeds, (size_t)(B + 1) * 32)) ||
         (rc = h2d(ctx, ps->pub.p, h_pub, (size_t)B * T.n_pub * 32)))
         return rc;
-    k_decompress_to_niels_strided<<<(B * ds + 127) / 128, 128, 0, ctx->stream>>>(ps->dyn_pts.p, ds, blob_stride, ps->dyn_niels.p, B * ds, ps->valid.p);
+    // Two streams: the variable-base MSM over the requests' own points (decompression, then the bucket engine) runs on the
+    // side stream; transcript replay, weights, power tables, scalar assembly and the static-base MSM run on the main one.
+    // The side stream only waits for the weighted dynamic scalars (k_dyn_weights). If the static-base MSM itself needs
+    // the bucket engine (per-request checks of a large group, or the latency path switched off) both share the main stream.
+    const uint32_t n_stat_slots = combined ? 1 : B;
+    const char *ds_env = getenv("BBP_VERIFY_STREAMS");   // 1 = everything on the main stream (tests compare both)
+    const bool two_streams = small_msm_ok((size_t)n_stat_slots * slot_len) && !(ds_env && atoi(ds_env) == 1);
+    cudaStream_t side = ctx->stream;
+    if (two_streams) {
+        if ((rc = proto_side_stream(ps))) return rc;
+        side = ps->rng_stream;
+        BBP_CUDA_OK(cudaEventRecord(ps->ev_up, ctx->stream));
+        BBP_CUDA_OK(cudaStreamWaitEvent(side, ps->ev_up, 0));
+    }
+    tl.mark("uploaded", ctx->stream);
+    k_decompress_to_niels_strided<<<(B * ds + 127) / 128, 128, 0, side>>>(ps->dyn_pts.p, ds, blob_stride, ps->dyn_niels.p, B * ds, ps->valid.p);
     ctx->launches++;
+    tl.mark("side:decompressed", side);
     // Fiat-Shamir replay: on the device for large batches (one warp per request, ~0.2 ms whatever the batch), on the host
     // threads otherwise (~40 us per request per thread); BBP_DEVICE_TRANSCRIPT_MIN_BATCH overrides the crossover
     const char *tr_env = getenv("BBP_DEVICE_TRANSCRIPT_MIN_BATCH");
     const bool device_replay = B >= (uint32_t)(tr_env ? atoi(tr_env) : (int)(8 * host_threads()));
-    std::vector<sc> rvals(combined ? B : 0);
     if (device_replay) {
         transcript_init init;
         {
@@ -1105,45 +1163,34 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
             k_verify_transcript_warp<<<(B + 3) / 4, 128, 0, ctx->stream>>>(init, ps->dyn_pts.p, blob_stride, ps->rng_states.p, B, m, lg, (uint64_t)n,
                                                                            ps->chal.as<sc>(), ps->dyn_sc.as<sc>(), ds);
         ctx->launches++;
-        if (combined)
-            BBP_CUDA_OK(cudaMemcpy2DAsync(rvals.data(), 32, ps->chal.as<sc>() + CH_R, (size_t)CH_N * 32, 32, B, cudaMemcpyDeviceToHost, ctx->stream));
     } else {
-        std::vector<sc> h_chal((size_t)B * CH_N, sc_zero()), h_dyn((size_t)B * ds, sc_zero());
+        // pinned staging: the copies below are asynchronous and nothing waits for them before the end of the group
+        if ((rc = ps->h_states.ensure(((size_t)B * CH_N + (size_t)B * ds) * 32))) return rc;
+        sc *h_chal = (sc *)ps->h_states.p, *h_dyn = h_chal + (size_t)B * CH_N;
         parallel_for(B, [&](size_t bi) {
+            for (uint32_t k = 0; k < CH_N; k++) h_chal[bi * CH_N + k] = sc_zero();
+            for (uint32_t k = 0; k < ds; k++) h_dyn[bi * ds + k] = sc_zero();
             verify_transcript_host(prep[idx[bi]], jobs[idx[bi]].rng_seed, &h_chal[bi * CH_N], &h_dyn[bi * ds]);
-            if (combined) rvals[bi] = h_chal[bi * CH_N + CH_R];
         });
-        if ((rc = h2d(ctx, ps->chal.p, h_chal.data(), h_chal.size() * 32)) || (rc = h2d(ctx, ps->dyn_sc.p, h_dyn.data(), h_dyn.size() * 32))) return rc;
+        if ((rc = h2d(ctx, ps->chal.p, h_chal, (size_t)B * CH_N * 32)) || (rc = h2d(ctx, ps->dyn_sc.p, h_dyn, (size_t)B * ds * 32))) return rc;
     }
-    std::vector<uint8_t> valid((size_t)B * ds);
-    if ((rc = d2h_sync(ctx, valid.data(), ps->valid.p, valid.size()))) return rc;
-    trace.mark("h2d+decompress+transcripts");
+    trace.mark("h2d+decompress+transcripts(launch)");
+    tl.mark("transcripts", ctx->stream);
 
-    // ---- weights
-    std::vector<uint8_t> alive(B, 1);
-    std::vector<sc> rho(B, sc_one());
-    bool any_dead = false;
-    for (uint32_t bi = 0; bi < B; bi++) {
-        for (uint32_t k = 0; k < ds; k++)
-            if (!valid[(size_t)bi * ds + k]) alive[bi] = 0;
-        if (!alive[bi]) { jobs[idx[bi]].status = BBP_ERR_VERIFICATION; rho[bi] = sc_zero(); any_dead = true; }   // optional_multiscalar_mul -> None
-    }
+    // ---- weights, on the device (rng_kernels.cuh): 0 for a request with a point that does not decompress, else 1 (per-request
+    // checks) or the request's share of the batch's random linear combination. No host round trip: the whole group is one
+    // asynchronous sequence on the stream, synchronised once at the end.
     if (combined) {
-        merlin_transcript bt("bbp batch verification");
-        bt.append_u64("n", B);
-        for (uint32_t bi = 0; bi < B; bi++) {
-            uint8_t dg[32];
-            sc_tobytes(dg, rvals[bi]);
-            bt.append_message("proof", dg, 32);
-        }
-        merlin_rng brng = bt.build_rng().finalize(batch_seed);
-        for (uint32_t bi = 0; bi < B; bi++) {
-            sc w = brng.random_scalar();
-            if (alive[bi]) rho[bi] = w;
-        }
+        k_batch_weight_digests<<<(B + 31) / 32, 32, 0, ctx->stream>>>(ps->chal.as<sc>(), B, ps->bw_digests.as<uint64_t>());
+        ctx->launches++;
     }
-    if (combined || any_dead)
-        BBP_CUDA_OK(cudaMemcpy2DAsync(ps->chal.as<sc>() + CH_RHO, (size_t)CH_N * 32, rho.data(), 32, 32, B, cudaMemcpyHostToDevice, ctx->stream));
+    if (two_streams) {   // the validity flags come from the decompression on the side stream
+        BBP_CUDA_OK(cudaEventRecord(ps->ev_rng, side));
+        BBP_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ps->ev_rng, 0));
+    }
+    k_batch_weights<<<(B + 127) / 128, 128, 0, ctx->stream>>>(ps->chal.as<sc>(), ps->valid.p, ds, B, ps->bw_digests.as<uint64_t>(),
+                                                              ps->rng_states.p + (size_t)B * 32, combined ? 1u : 0u);
+    ctx->launches++;
 
     sc_batch SB;
     memset(&SB, 0, sizeof SB);
@@ -1155,31 +1202,58 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     SB.pub = ps->pub.as<sc>(); SB.dyn_out = ps->dyn_sc.as<sc>(); SB.dyn_stride = ds; SB.stat = ps->stat.as<sc>();
     SB.stab = ps->sG.as<sc>();
     SB.skip_ypow = 1;
-    k_powers<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
-    k_verify_scalars<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+    SB.dyn_done = 1;
+    k_dyn_weights<<<B, 64, 0, ctx->stream>>>(SB);
+    ctx->launches++;
+    tl.mark("weights", ctx->stream);
+    uint8_t *ext = ps->msm_ext.p;
+    const uint32_t dyn_total = B * ds, per_slot = combined ? dyn_total : ds;
+    {   // dynamic bases: one variable-base slot per group, on the side stream
+        if (two_streams) {
+            BBP_CUDA_OK(cudaEventRecord(ps->ev_dyn, ctx->stream));
+            BBP_CUDA_OK(cudaStreamWaitEvent(side, ps->ev_dyn, 0));
+        }
+        msm_shape sh = msm_engine::make_shape(dyn_total, per_slot, dyn_total, false, 0, 0, 0);
+        cudaStream_t engine_stream = ctx->msm.stream;
+        ctx->msm.stream = side;
+        rc = ctx->msm.run(sh, ps->dyn_sc.p, ps->dyn_niels.p, ext + (size_t)n_groups * 128, nullptr);
+        ctx->msm.stream = engine_stream;
+        if (rc) return rc;
+        if (two_streams) BBP_CUDA_OK(cudaEventRecord(ps->ev_up, side));
+        tl.mark("side:dyn_msm", side);
+    }
+    k_powers<<<B, BBP_SC_THREADS, k_powers_smem(SB.q, SB.n), ctx->stream>>>(SB);
+    tl.mark("powers", ctx->stream);
+    k_verify_scalars<<<B, BBP_SC_THREADS, k_verify_scalars_smem(SB.n, SB.lg_n), ctx->stream>>>(SB);
     if (combined && B >= 32)
         k_stat_reduce_wide<<<dim3((slot_len + 15) / 16, n_groups), 256, 0, ctx->stream>>>(SB.stat, B, slot_len, ps->stat_red.as<sc>());
     else
         k_stat_reduce<<<dim3((slot_len + BBP_SC_THREADS - 1) / BBP_SC_THREADS, n_groups), BBP_SC_THREADS, 0, ctx->stream>>>(SB.stat, combined ? B : 1, slot_len,
                                                                                                                              ps->stat_red.as<sc>());
     ctx->launches += 3;
-    // static bases: one fixed-table slot per group; dynamic bases: one variable-base slot per group
-    uint8_t *ext = ps->msm_ext.p;
+    tl.mark("scalars+reduce", ctx->stream);
+    // static bases: one fixed-table slot per group
     if ((rc = msm_gens_device(ctx, ps->stat_red.as<sc>(), slot_len, n_groups, nullptr, ext))) return rc;
-    uint32_t dyn_total = B * ds, per_slot = combined ? dyn_total : ds;
-    msm_shape sh = msm_engine::make_shape(dyn_total, per_slot, dyn_total, false, 0, 0, 0);
-    if ((rc = ctx->msm.run(sh, ps->dyn_sc.p, ps->dyn_niels.p, ext + (size_t)n_groups * 128, nullptr))) return rc;
+    tl.mark("static_msm", ctx->stream);
+    if (two_streams) BBP_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ps->ev_up, 0));   // join: the dynamic-base sum
     k_group_sum_identity<<<(n_groups + 63) / 64, 64, 0, ctx->stream>>>(ext, n_groups, 2, n_groups, ps->flags.p, nullptr);
     ctx->launches++;
     if (combined && d_partial_ext) BBP_CUDA_OK(cudaMemcpyAsync(d_partial_ext, ext, 256, cudaMemcpyDeviceToDevice, ctx->stream));
-    std::vector<uint8_t> fl(n_groups);
+    std::vector<uint8_t> fl(n_groups), valid((size_t)B * ds);
+    BBP_CUDA_OK(cudaMemcpyAsync(valid.data(), ps->valid.p, valid.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    trace.mark("launched");
+    tl.mark("end", ctx->stream);
     if ((rc = d2h_sync(ctx, fl.data(), ps->flags.p, n_groups))) return rc;
-    trace.mark("gpu_scalars+msm");
+    trace.mark("sync");
+    tl.report(combined ? "verify_group(combined)" : "verify_group(each)");
     verdicts.assign(n_groups, 0);
     for (uint32_t g = 0; g < n_groups; g++) verdicts[g] = fl[g];
-    if (!combined)
-        for (uint32_t bi = 0; bi < B; bi++)
-            if (alive[bi]) jobs[idx[bi]].status = fl[bi] ? 0 : BBP_ERR_VERIFICATION;
+    for (uint32_t bi = 0; bi < B; bi++) {
+        bool alive = true;
+        for (uint32_t k = 0; k < ds; k++) alive = alive && valid[(size_t)bi * ds + k];
+        if (!alive) jobs[idx[bi]].status = BBP_ERR_VERIFICATION;   // optional_multiscalar_mul -> None
+        else if (!combined) jobs[idx[bi]].status = fl[bi] ? 0 : BBP_ERR_VERIFICATION;
+    }
     return 0;
 }
 

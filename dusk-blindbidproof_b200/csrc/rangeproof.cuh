@@ -191,7 +191,7 @@ inline int rp_prove_group(bbp_ctx *ctx, std::vector<rp_prove_job> &jobs, uint32_
         }
     });
     if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32))) return rc;
-    k_powers<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+    k_powers<<<P, BBP_SC_THREADS, k_powers_smem(SB.q, SB.n), ctx->stream>>>(SB);
     k_rp_polys<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
     ctx->launches += 2;
     std::vector<sc> tout((size_t)P * 8);
@@ -419,7 +419,7 @@ inline int rp_verify_group(bbp_ctx *ctx, std::vector<rp_verify_job> &jobs, uint3
         SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>(); SB.stat = ps->stat.as<sc>();
         SB.stab = ps->sG.as<sc>();
         SB.skip_ypow = 1;
-        k_powers<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+        k_powers<<<P, BBP_SC_THREADS, k_powers_smem(SB.q, SB.n), ctx->stream>>>(SB);
         k_rp_verify_scalars<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
         if (combined && P >= 32)
             k_stat_reduce_wide<<<dim3((slot_len + 15) / 16, 1), 256, 0, ctx->stream>>>(SB.stat, P, slot_len, ps->stat_red.as<sc>());

@@ -688,4 +688,99 @@ __global__ void __launch_bounds__(128) k_verify_transcript_warp(transcript_init 
     c[CH_RHO] = sc_one();
 }
 
+
+// ---------------------------------------------------------------- batch-verification weights on the device
+// The random linear combination of a batch verification needs one secret, proof-binding weight per request. Deriving them
+// on the host meant a device -> host -> device round trip in the middle of every batch (the digests r_i come out of the
+// transcript replay, the weights go into the scalar assembly) plus ~B serial Keccak permutations on one host thread. Here
+// they are a two-level SHAKE256 tree, all on the launching stream (hashlib-reproducible: tests/test_gpu_protocol.py):
+//   h_g   = SHAKE256(LBL_H || LE64(g) || LE64(cnt_g) || r_{32g} || ... || r_{32g+cnt_g-1})[0..32)        one warp per 32 requests
+//   D     = SHAKE256(LBL_D || batch_seed || LE64(B) || h_0 || ... || h_{G-1})[0..32)                      one warp (per block)
+//   rho_i = from_bytes_mod_order_wide(SHAKE256(LBL_W || D || LE64(i))[0..64))                              one thread per request
+// r_i = the verifier scalar request i's own transcript yields after absorbing its whole proof (binds every proof byte),
+// batch_seed = the caller's secret. A request with a point that failed to decompress gets weight zero (its status is
+// reported separately). Labels are 32 bytes, zero padded.
+__device__ __forceinline__ uint64_t bw_label_word(int which, uint32_t w) {
+    // "bbp batch digest v1", "bbp batch root v1", "bbp batch weight v1" as little-endian 64-bit words
+    const char *s = which == 0 ? "bbp batch digest v1\0\0\0\0\0\0\0\0\0\0\0\0\0" : which == 1 ? "bbp batch root v1\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0" : "bbp batch weight v1\0\0\0\0\0\0\0\0\0\0\0\0\0";
+    uint64_t v = 0;
+    for (int k = 7; k >= 0; k--) v = (v << 8) | (uint8_t)s[8 * w + k];
+    return v;
+}
+// SHAKE256 (rate 136 = 17 lanes) of a message given as 64-bit words (n_words of them), state spread over the warp's lanes
+// (keccak_warp); returns this lane's state word after the last permutation (lanes 0..7 = the first 64 output bytes).
+template <class F>
+__device__ __forceinline__ uint64_t shake256_warp_words(const keccak_warp &K, uint32_t lane, uint32_t n_words, F word) {
+    uint64_t a = 0;
+    const uint32_t n_blocks = n_words / 17 + 1;
+#pragma unroll 1
+    for (uint32_t blk = 0; blk < n_blocks; blk++) {
+        uint64_t w = 0;
+        if (lane < 17) {
+            const uint32_t wi = 17 * blk + lane;
+            if (wi < n_words) w = word(wi);
+            else if (wi == n_words) w = 0x1full;                           // SHAKE domain bits + first pad bit
+            if (blk == n_blocks - 1 && lane == 16) w ^= 0x80ull << 56;     // last pad bit
+        }
+        a = K.permute(a ^ w);
+    }
+    return a;
+}
+__global__ void __launch_bounds__(32) k_batch_weight_digests(const sc *__restrict__ chal, uint32_t n_req, uint64_t *__restrict__ digests) {
+    const uint32_t g = blockIdx.x, lane = threadIdx.x;
+    const uint32_t cnt = min(32u, n_req - 32 * g);
+    keccak_warp K;
+    K.init(lane);
+    const uint64_t a = shake256_warp_words(K, lane, 6 + 4 * cnt, [&](uint32_t w) -> uint64_t {
+        if (w < 4) return bw_label_word(0, w);
+        if (w == 4) return g;
+        if (w == 5) return cnt;
+        const uint32_t i = 32 * g + (w - 6) / 4, k = (w - 6) % 4;
+        const sc &r = chal[(size_t)i * CH_N + CH_R];
+        return (uint64_t)r.v[2 * k] | ((uint64_t)r.v[2 * k + 1] << 32);
+    });
+    if (lane < 4) digests[4 * (size_t)g + lane] = a;
+}
+// combined = 0: weights 1 (0 for a request with an invalid point), no hashing
+__global__ void __launch_bounds__(128) k_batch_weights(sc *__restrict__ chal, const uint8_t *__restrict__ valid, uint32_t ds, uint32_t n_req,
+                                                       const uint64_t *__restrict__ digests, const uint8_t *__restrict__ seed, uint32_t combined) {
+    __shared__ uint64_t root[4];
+    const uint32_t lane = threadIdx.x & 31;
+    if (combined && threadIdx.x < 32) {
+        keccak_warp K;
+        K.init(lane);
+        const uint32_t G = (n_req + 31) / 32;
+        const uint64_t *s64 = (const uint64_t *)seed;
+        const uint64_t a = shake256_warp_words(K, lane, 9 + 4 * G, [&](uint32_t w) -> uint64_t {
+            if (w < 4) return bw_label_word(1, w);
+            if (w < 8) return s64[w - 4];
+            if (w == 8) return n_req;
+            return digests[w - 9];
+        });
+        if (lane < 4) root[lane] = a;
+    }
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_req) return;
+    bool alive = true;
+    for (uint32_t k = 0; k < ds; k++) alive = alive && valid[(size_t)i * ds + k] != 0;
+    sc rho = sc_one();
+    if (combined) {
+        uint64_t st[25];
+#pragma unroll
+        for (int k = 0; k < 25; k++) st[k] = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { st[k] = bw_label_word(2, k); st[4 + k] = root[k]; }
+        st[8] = i;
+        st[9] = 0x1full;
+        st[16] = 0x80ull << 56;
+        keccak_f1600_dev(st);
+        uint32_t w[16];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { w[2 * k] = (uint32_t)st[k]; w[2 * k + 1] = (uint32_t)(st[k] >> 32); }
+        rho = sc_from_wide_words(w);
+    }
+    chal[(size_t)i * CH_N + CH_RHO] = alive ? rho : sc_zero();
+}
+
 }  // namespace bbp

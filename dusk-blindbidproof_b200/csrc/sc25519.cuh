@@ -55,17 +55,6 @@ BBP_HD void sc_sub_l(uint32_t *a) {
         borrow = (t >> 32) & 1;
     }
 }
-BBP_HD sc sc_add(const sc &a, const sc &b) {
-    sc r;
-    uint64_t c = 0;
-    for (int i = 0; i < 8; i++) {
-        c += (uint64_t)a.v[i] + b.v[i];
-        r.v[i] = (uint32_t)c;
-        c >>= 32;
-    }
-    if (sc_geq_l(r.v)) sc_sub_l(r.v);   // a, b < l < 2^253: no overflow out of 256 bits
-    return r;
-}
 BBP_HD sc sc_neg(const sc &a) {
     if (sc_iszero(a)) return a;
     sc r;
@@ -77,7 +66,84 @@ BBP_HD sc sc_neg(const sc &a) {
     }
     return r;
 }
-BBP_HD sc sc_sub(const sc &a, const sc &b) { return sc_add(a, sc_neg(b)); }
+BBP_HD sc sc_add(const sc &a, const sc &b) {
+#ifdef __CUDA_ARCH__
+    // branch-free: r = a + b (a, b < l < 2^253: no carry out), t = r - l, keep r when the subtraction borrows
+    uint32_t r[8], t[8], bw;
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=&r"(t[0]), "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]), "=&r"(bw)
+        : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(sc_l_limb(0)), "r"(sc_l_limb(1)), "r"(sc_l_limb(2)), "r"(sc_l_limb(3)), "r"(sc_l_limb(4)), "r"(sc_l_limb(5)), "r"(sc_l_limb(6)), "r"(sc_l_limb(7)));
+    sc o;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o.v[i] = bw ? r[i] : t[i];
+    return o;
+#else
+    sc r;
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)a.v[i] + b.v[i];
+        r.v[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    if (sc_geq_l(r.v)) sc_sub_l(r.v);   // a, b < l < 2^253: no overflow out of 256 bits
+    return r;
+#endif
+}
+BBP_HD sc sc_sub(const sc &a, const sc &b) {
+#ifdef __CUDA_ARCH__
+    // branch-free: r = a - b, then add l back when the subtraction borrowed (a, b < l)
+    uint32_t r[8], bw;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(bw)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    sc o;
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=&r"(o.v[0]), "=&r"(o.v[1]), "=&r"(o.v[2]), "=&r"(o.v[3]), "=&r"(o.v[4]), "=&r"(o.v[5]), "=&r"(o.v[6]), "=&r"(o.v[7])
+        : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(sc_l_limb(0) & bw), "r"(sc_l_limb(1) & bw), "r"(sc_l_limb(2) & bw), "r"(sc_l_limb(3) & bw), "r"(sc_l_limb(4) & bw), "r"(sc_l_limb(5) & bw),
+          "r"(sc_l_limb(6) & bw), "r"(sc_l_limb(7) & bw));
+    return o;
+#else
+    return sc_add(a, sc_neg(b));
+#endif
+}
+
 
 // Montgomery product a*b/2^256 mod l; inputs < 2^256 with a*b < l*2^256; output < l
 #if !defined(__CUDA_ARCH__)

@@ -54,6 +54,7 @@ struct sc_batch {
     const sc *pub;                             // [n_proofs][n_pub] public value tables (normal form)
     sc *dyn_out;                               // [n_proofs][dyn_stride]: first m entries = rho * wV[i] * r * x^2 (written here)
     uint32_t dyn_stride;
+    uint32_t dyn_done;                         // 1: k_dyn_weights has already written dyn_out (k_verify_scalars leaves it alone)
     sc *stat;                                  // [n_proofs][2 + 2 gcols] rho-weighted static-base scalars (Montgomery)
     sc *stab;                                  // [n_proofs][n] scratch: the IPP verification vector s (Montgomery)
     // hybrid IPP: after the first rounds the folded bases ARE materialised once (n_f per family), later rounds work on them
@@ -101,51 +102,59 @@ __device__ inline sc block_sum_sc(sc v, sc *smem) {
 }
 
 // ---------------------------------------------------------------- power tables
-// zpow[j] = z^(j+1), j < q ; ypow[i] = y^i (unless B.skip_ypow), yinvpow[i] = y^-i, i < n. Thread t owns one chunk of each
-// sequence; its first element is first * (base^chunk)^t, assembled from the eight shared powers (base^chunk)^(2^k) by the
-// bits of t (<= 8 products instead of a square-and-multiply ladder per thread), then it walks with one product per element.
+// zpow[j] = z^(j+1), j < q ; ypow[i] = y^i (unless B.skip_ypow), yinvpow[i] = y^-i, i < n. Two-level product form: with
+// i = hi * 64 + lo, base^i = lo_tab[lo] * hi_tab[hi], lo_tab[lo] = base^lo (64 entries), hi_tab[hi] = (base^64)^hi; both
+// small tables are assembled from the squaring chain base^(2^k) by the bits of their index, so an element costs ONE
+// product and all of them are independent (the first version walked a chunk per thread: one product per element plus
+// eight per thread to reach the chunk start, 9 k products per proof against 5.6 k here, on a 20-product dependency chain).
+#define BBP_POW_LO_BITS 6
+#define BBP_POW_MAX_HI 1024   // sequences of up to 65536 elements
 __global__ void __launch_bounds__(BBP_SC_THREADS) k_powers(sc_batch B) {
-    static_assert(BBP_SC_THREADS == 256, "chunk starts are assembled from 8 bits of the thread index");
-    __shared__ sc r2k[3][8];
+    __shared__ sc sq[3][16];                     // base^(2^k)
+    __shared__ sc lo_tab[3][1 << BBP_POW_LO_BITS];
+    extern __shared__ sc hi_tab[];               // [3][n_hi]
     const uint32_t p = blockIdx.x, t = threadIdx.x;
     const sc *ch = B.chal + (size_t)p * CH_N;
-    const uint32_t zc = (B.q + BBP_SC_THREADS - 1) / BBP_SC_THREADS, yc = (B.n + BBP_SC_THREADS - 1) / BBP_SC_THREADS;
+    const uint32_t len[3] = {B.q ? B.q + 1 : 0u, B.skip_ypow ? 0u : B.n, B.n};   // z needs exponents 1 .. q
+    uint32_t n_hi_max = 0;
+    for (int s = 0; s < 3; s++) n_hi_max = max(n_hi_max, (len[s] + 63) >> BBP_POW_LO_BITS);
     if ((t & 31) == 0 && t < 96) {   // one thread of three different warps: z, y, y^-1
         const uint32_t s = t >> 5;
-        if (s == 0 ? B.q > 0 : (s == 1 ? !B.skip_ypow : true)) {
-            sc r = sc_pow_small_mont(sc_to_mont(ch[s == 0 ? CH_Z : s == 1 ? CH_Y : CH_YINV]), s == 0 ? zc : yc);
-            for (uint32_t k = 0; k < 8; k++) { r2k[s][k] = r; r = mm(r, r); }
+        if (len[s]) {
+            sc r = sc_to_mont(ch[s == 0 ? CH_Z : s == 1 ? CH_Y : CH_YINV]);
+            for (uint32_t k = 0; k < 16; k++) { sq[s][k] = r; r = mm(r, r); }
         }
     }
     __syncthreads();
-    auto chunk_first = [&](uint32_t s, sc cur) {
-        for (uint32_t k = 0; k < 8; k++)
-            if ((t >> k) & 1) cur = mm(cur, r2k[s][k]);
-        return cur;
-    };
-    {
-        uint32_t j0 = t * zc, j1 = min(j0 + zc, B.q);
-        if (j0 < j1) {
-            sc zM = sc_to_mont(ch[CH_Z]);
-            sc cur = chunk_first(0, zM);
-            sc *out = B.zpow + (size_t)p * B.q;
-            for (uint32_t j = j0; j < j1; j++) { out[j] = cur; cur = mm(cur, zM); }
-        }
+    // small tables: entry e of lo_tab = prod over the bits of e of sq[k]; entry e of hi_tab = the same with sq[6 + k]
+    for (uint32_t w = t; w < 3 * ((1u << BBP_POW_LO_BITS) + n_hi_max); w += BBP_SC_THREADS) {
+        const uint32_t s = w / ((1u << BBP_POW_LO_BITS) + n_hi_max), e0 = w % ((1u << BBP_POW_LO_BITS) + n_hi_max);
+        if (!len[s]) continue;
+        const bool is_hi = e0 >= (1u << BBP_POW_LO_BITS);
+        const uint32_t e = is_hi ? e0 - (1u << BBP_POW_LO_BITS) : e0;
+        sc acc = sc_mont_one();
+        bool first = true;
+        for (uint32_t k = 0; k < 10; k++)
+            if ((e >> k) & 1) {
+                const sc &f = sq[s][(is_hi ? BBP_POW_LO_BITS : 0) + k];
+                acc = first ? f : mm(acc, f);
+                first = false;
+            }
+        if (is_hi) hi_tab[s * n_hi_max + e] = acc; else lo_tab[s][e] = acc;
     }
-    uint32_t i0 = t * yc, i1 = min(i0 + yc, B.n);
-    if (i0 < i1) {
-        if (!B.skip_ypow) {
-            sc yM = sc_to_mont(ch[CH_Y]);
-            sc cy = chunk_first(1, sc_mont_one());
-            sc *oy = B.ypow + (size_t)p * B.n;
-            for (uint32_t i = i0; i < i1; i++) { oy[i] = cy; cy = mm(cy, yM); }
+    __syncthreads();
+    sc *out[3] = {B.zpow + (size_t)p * B.q, B.ypow + (size_t)p * B.n, B.yinvpow + (size_t)p * B.n};
+    for (int s = 0; s < 3; s++) {
+        if (!len[s]) continue;
+        const uint32_t first = s == 0 ? 1u : 0u;   // zpow[j] holds exponent j + 1
+        for (uint32_t i = first + t; i < len[s]; i += BBP_SC_THREADS) {
+            const uint32_t lo = i & ((1u << BBP_POW_LO_BITS) - 1), hi = i >> BBP_POW_LO_BITS;
+            sc v = hi == 0 ? lo_tab[s][lo] : (lo == 0 ? hi_tab[s * n_hi_max + hi] : mm(lo_tab[s][lo], hi_tab[s * n_hi_max + hi]));
+            out[s][i - first] = v;
         }
-        sc yiM = sc_to_mont(ch[CH_YINV]);
-        sc ci = chunk_first(2, sc_mont_one());
-        sc *oi = B.yinvpow + (size_t)p * B.n;
-        for (uint32_t i = i0; i < i1; i++) { oi[i] = ci; ci = mm(ci, yiM); }
     }
 }
+inline size_t k_powers_smem(uint32_t q, uint32_t n) { return (size_t)3 * (((q + 1 > n ? q + 1 : n) + 63) >> BBP_POW_LO_BITS) * sizeof(sc); }
 
 // signed sum of z powers over one CSR row (Montgomery form)
 __device__ __forceinline__ sc flatten_row(const sc_batch &B, const sc *zpow, uint32_t row) {
@@ -447,6 +456,34 @@ __device__ inline void build_s_table(sc *stab, const sc *uj, uint32_t lg, uint32
     }
 }
 
+// The same vector in product form: s[i] = s_lo[i mod 2^lo_bits] * s_hi[i >> lo_bits] (s is a product over the bits of i), so
+// the verifier never materialises it: a * s[i] = s_lo[.] * (a s_hi)[.] is one product against the two (table build + use)
+// of the recurrence. Each factor table is built by the same doubling recurrence on its own bits, in shared memory.
+// s_lo: 2^lo_bits entries, s_hi: 2^(lg - lo_bits) entries. Synchronises the block.
+__device__ inline void build_s_factors(sc *s_lo, sc *s_hi, const sc *uj, uint32_t lg, uint32_t lo_bits) {
+    const uint32_t t = threadIdx.x, hi_bits = lg - lo_bits;
+    if (t < 2) {
+        // t = 0: bits 0 .. lo_bits-1 (challenges u_{lg-1} .. u_{lg-lo_bits}); t = 1: the rest
+        sc acc = sc_mont_one();
+        const uint32_t b0 = t ? lo_bits : 0, b1 = t ? lg : lo_bits;
+        for (uint32_t b = b0; b < b1; b++) acc = mm(acc, uj[lg + (lg - 1 - b)]);
+        (t ? s_hi : s_lo)[0] = acc;
+    }
+    __syncthreads();
+    for (uint32_t b = 0; b < max(lo_bits, hi_bits); b++) {
+        const uint32_t half = 1u << b;
+        if (b < lo_bits) {
+            sc usq = mm(uj[lg - 1 - b], uj[lg - 1 - b]);
+            for (uint32_t i = half + t; i < 2 * half; i += BBP_SC_THREADS) s_lo[i] = mm(s_lo[i - half], usq);
+        }
+        if (b < hi_bits) {
+            sc usq = mm(uj[lg - 1 - lo_bits - b], uj[lg - 1 - lo_bits - b]);
+            for (uint32_t i = half + t; i < 2 * half; i += BBP_SC_THREADS) s_hi[i] = mm(s_hi[i - half], usq);
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------- verifier scalar assembly
 // Per proof (weight rho, 1 for a single verification):
 //   stat[0]   (B)          rho * ( w (t_x - a b) + r (x^2 (wc + delta) - t_x) )
@@ -456,17 +493,21 @@ __device__ inline void build_s_table(sc *stab, const sc *uj, uint32_t lg, uint32
 //   dyn_out[i] = rho * wV[i] r x^2   (coefficients of the V commitments)
 // with s[i] = prod_j u_j^(+-1) (bit (lg n - 1 - j) of i set -> u_j, else u_j^-1), uf = 1 (i < n1) | u, delta = <y^-n wR, wL>.
 // Results stay in Montgomery form; k_stat_reduce sums them over the batch and converts.
+#define BBP_S_LO_BITS 8      // s_lo has min(n, 256) entries: with i = t + 256 k its index is constant per thread
+#define BBP_S_MAX_HI 256     // n <= 65536
 __global__ void __launch_bounds__(BBP_SC_THREADS, 2) k_verify_scalars(sc_batch B) {
     __shared__ sc smem[BBP_SC_THREADS];
     __shared__ sc uj[64];
     __shared__ sc long_val[BBP_MAX_LONG];
+    __shared__ sc s_lo[1 << BBP_S_LO_BITS];
+    extern __shared__ sc s_hi_all[];            // [5][n_hi]: s_hi, then rho a s_hi, rho b s_hi, rho u a s_hi, rho u b s_hi
     const uint32_t p = blockIdx.x, t = threadIdx.x, n = B.n, n1 = B.n1, lg = B.lg_n;
+    const uint32_t lo_bits = min(lg, (uint32_t)BBP_S_LO_BITS), n_lo = 1u << lo_bits, n_hi = n >> lo_bits;
     const sc *ch = B.chal + (size_t)p * CH_N;
     const sc *zpow = B.zpow + (size_t)p * B.q, *yinv = B.yinvpow + (size_t)p * n;
     if (t < 2 * lg) uj[t] = sc_to_mont(ch[CH_UJ0 + t]);   // u_0..u_{lg-1}, then u_0^-1..u_{lg-1}^-1
     __syncthreads();
-    sc xM = sc_to_mont(ch[CH_X]), uM = sc_to_mont(ch[CH_U]), aM = sc_to_mont(ch[CH_A]), bM = sc_to_mont(ch[CH_B]);
-    sc rhoM = sc_to_mont(ch[CH_RHO]), one = sc_mont_one();
+    const sc xM = sc_to_mont(ch[CH_X]), rhoM = sc_to_mont(ch[CH_RHO]);
     const uint32_t gc = B.gcols;
     sc *stat = B.stat + (size_t)p * (2 + 2 * gc);
     for (uint32_t i = n + t; i < gc; i += BBP_SC_THREADS) { stat[2 + i] = sc_zero(); stat[2 + gc + i] = sc_zero(); }
@@ -480,25 +521,37 @@ __global__ void __launch_bounds__(BBP_SC_THREADS, 2) k_verify_scalars(sc_batch B
     }
     wc = block_sum_sc(wc, smem);
     sc delta = sc_zero();
-    sc *stab = B.stab + (size_t)p * n;
     flatten_long_rows(B, zpow, long_val, smem);
-    build_s_table(stab, uj, lg, n);
-    // rho and uf are folded into per-thread constants so that a column costs 8 products below n1 and 3 above:
-    //   g = (ru x) ywR - (ru a) s,   h = y^-i ((ru x) wL + ru wO - (ru b) s_rev) - ru,   ru = rho uf
-    const sc ruU = mm(rhoM, uM);
-    const sc rx = mm(rhoM, xM), ra1 = mm(rhoM, aM), rb1 = mm(rhoM, bM), raU = mm(ruU, aM), rbU = mm(ruU, bM);
+    sc *s_hi = s_hi_all;
+    build_s_factors(s_lo, s_hi, uj, lg, lo_bits);
+    // rho, a / b and uf are folded into four copies of the (small) high factor table, so that a column costs 8 products
+    // below n1 and 3 above:  g = (rho x) ywR - s_lo (rho a s_hi),  h = y^-i ((rho x) wL + rho wO - s_lo' (rho b s_hi')) - rho
+    {
+        const sc uM = sc_to_mont(ch[CH_U]), aM = sc_to_mont(ch[CH_A]), bM = sc_to_mont(ch[CH_B]);
+        const sc ra = mm(rhoM, aM), rb = mm(rhoM, bM);
+        for (uint32_t w = t; w < 4 * n_hi; w += BBP_SC_THREADS) {
+            const uint32_t k = w / n_hi, h = w % n_hi;
+            sc f = (k & 1) ? rb : ra;
+            if (k >= 2) f = mm(f, uM);
+            s_hi_all[(1 + k) * n_hi + h] = mm(f, s_hi[h]);
+        }
+    }
+    __syncthreads();
+    const sc rx = mm(rhoM, xM), ruU = mm(rhoM, sc_to_mont(ch[CH_U]));
+    const sc *hi_a = s_hi_all + n_hi, *hi_b = s_hi_all + 2 * n_hi, *hi_au = s_hi_all + 3 * n_hi, *hi_bu = s_hi_all + 4 * n_hi;
     for (uint32_t i = t; i < n; i += BBP_SC_THREADS) {
-        sc s = stab[i], srev = stab[n - 1 - i];
+        const uint32_t lo = i & (n_lo - 1), hi = i >> lo_bits;   // reversed index n - 1 - i: (n_lo - 1 - lo, n_hi - 1 - hi)
         sc g, h;
         if (i < n1) {
             sc wL = flatten_row_l(B, zpow, i, long_val), wR = flatten_row_l(B, zpow, n1 + i, long_val), wO = flatten_row_l(B, zpow, 2 * n1 + i, long_val);
-            sc ywR = mm(yinv[i], wR);
+            const sc yi = yinv[i];
+            sc ywR = mm(yi, wR);
             delta = sc_add(delta, mm(ywR, wL));
-            g = sc_sub(mm(rx, ywR), mm(ra1, s));
-            h = sc_sub(mm(yinv[i], sc_sub(sc_add(mm(rx, wL), mm(rhoM, wO)), mm(rb1, srev))), rhoM);
+            g = sc_sub(mm(rx, ywR), mm(s_lo[lo], hi_a[hi]));
+            h = sc_sub(mm(yi, sc_sub(sc_add(mm(rx, wL), mm(rhoM, wO)), mm(s_lo[n_lo - 1 - lo], hi_b[n_hi - 1 - hi]))), rhoM);
         } else {
-            g = sc_neg(mm(raU, s));
-            h = sc_sub(sc_neg(mm(yinv[i], mm(rbU, srev))), ruU);
+            g = sc_neg(mm(s_lo[lo], hi_au[hi]));
+            h = sc_sub(sc_neg(mm(yinv[i], mm(s_lo[n_lo - 1 - lo], hi_bu[n_hi - 1 - hi]))), ruU);
         }
         stat[2 + i] = g;
         stat[2 + gc + i] = h;
@@ -506,21 +559,59 @@ __global__ void __launch_bounds__(BBP_SC_THREADS, 2) k_verify_scalars(sc_batch B
     delta = block_sum_sc(delta, smem);
     sc rM = sc_to_mont(ch[CH_R]);
     sc x2 = mm(xM, xM), rx2 = mm(rM, x2);
-    for (uint32_t i = t; i < B.m; i += BBP_SC_THREADS) {
-        sc wV = flatten_row(B, zpow, 3 * n1 + i);
-        B.dyn_out[(size_t)p * B.dyn_stride + i] = sc_from_mont(mm(rhoM, mm(wV, rx2)));
-    }
-    // the transcript-dependent dynamic scalars (written unweighted by k_verify_transcript) take the batch weight here
-    for (uint32_t i = B.m + t; i < B.dyn_stride; i += BBP_SC_THREADS) {
-        sc *d = B.dyn_out + (size_t)p * B.dyn_stride + i;
-        *d = mm(rhoM, *d);   // (rho R) * d / R = rho * d
+    if (!B.dyn_done) {
+        for (uint32_t i = t; i < B.m; i += BBP_SC_THREADS) {
+            sc wV = flatten_row(B, zpow, 3 * n1 + i);
+            B.dyn_out[(size_t)p * B.dyn_stride + i] = sc_from_mont(mm(rhoM, mm(wV, rx2)));
+        }
+        // the transcript-dependent dynamic scalars (written unweighted by k_verify_transcript) take the batch weight here
+        for (uint32_t i = B.m + t; i < B.dyn_stride; i += BBP_SC_THREADS) {
+            sc *d = B.dyn_out + (size_t)p * B.dyn_stride + i;
+            *d = mm(rhoM, *d);   // (rho R) * d / R = rho * d
+        }
     }
     if (t == 0) {
-        sc txM = sc_to_mont(ch[CH_TX]), wM = sc_to_mont(ch[CH_W]);
+        sc txM = sc_to_mont(ch[CH_TX]), wM = sc_to_mont(ch[CH_W]), aM = sc_to_mont(ch[CH_A]), bM = sc_to_mont(ch[CH_B]);
         sc bs = sc_add(mm(wM, sc_sub(txM, mm(aM, bM))), mm(rM, sc_sub(mm(x2, sc_add(wc, delta)), txM)));
         sc bbs = sc_sub(sc_neg(sc_to_mont(ch[CH_EBL])), mm(rM, sc_to_mont(ch[CH_TXBL])));
         stat[0] = mm(rhoM, bs);
         stat[1] = mm(rhoM, bbs);
+    }
+}
+inline size_t k_verify_scalars_smem(uint32_t n, uint32_t lg) { return (size_t)5 * (n >> (lg < BBP_S_LO_BITS ? lg : BBP_S_LO_BITS)) * sizeof(sc); }
+
+// The dynamic-point scalars alone, without the power tables: dyn_out[i] = rho wV[i] r x^2 for the m commitments (the few
+// z powers a V row needs are assembled from z^(2^k) by the bits of the exponent) and rho * d for the transcript-dependent
+// ones. Lets the variable-base MSM over a request's own points start on a second stream while k_powers / k_verify_scalars
+// (which only feed the static-base MSM) are still running. One block per request.
+__global__ void __launch_bounds__(64) k_dyn_weights(sc_batch B) {
+    __shared__ sc z2k[16];
+    const uint32_t p = blockIdx.x, t = threadIdx.x;
+    const sc *ch = B.chal + (size_t)p * CH_N;
+    if (t == 0) {
+        sc r = sc_to_mont(ch[CH_Z]);
+        for (uint32_t k = 0; k < 16; k++) { z2k[k] = r; r = mm(r, r); }
+    }
+    __syncthreads();
+    const sc rhoM = sc_to_mont(ch[CH_RHO]);
+    for (uint32_t i = t; i < B.dyn_stride; i += 64) {
+        sc *d = B.dyn_out + (size_t)p * B.dyn_stride + i;
+        if (i < B.m) {
+            const uint32_t row = 3 * B.n1 + i;
+            sc acc = sc_zero();
+            for (uint32_t e = B.row_ptr[row]; e < B.row_ptr[row + 1]; e++) {
+                const uint32_t v = B.entries[e], ex = (v & 0x7fffffffu) + 1;   // zpow[j] = z^(j+1)
+                sc zp = sc_mont_one();
+                for (uint32_t k = 0; k < 16; k++)
+                    if ((ex >> k) & 1) zp = mm(zp, z2k[k]);
+                acc = (v >> 31) ? sc_sub(acc, zp) : sc_add(acc, zp);
+            }
+            const sc xM = sc_to_mont(ch[CH_X]);
+            const sc rx2 = mm(sc_to_mont(ch[CH_R]), mm(xM, xM));
+            *d = sc_from_mont(mm(rhoM, mm(acc, rx2)));
+        } else {
+            *d = mm(rhoM, *d);   // (rho R) * d / R = rho * d
+        }
     }
 }
 

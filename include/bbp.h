@@ -203,6 +203,9 @@ int bbp_msm_gens(bbp_ctx *ctx, const uint8_t *scalars, size_t slot_len, size_t n
 int bbp_test_fe(bbp_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, int op, uint8_t *out);
 /* op: 0 add, 1 double(a), 2 mixed add via niels(b), 3 mixed sub via niels(b), 4 niels(b) -> extended; compressed output */
 int bbp_test_ge(bbp_ctx *ctx, const uint8_t *a_compressed, const uint8_t *b_compressed, size_t n, int op, uint8_t *out_compressed);
+/* weights of a batch verification's random linear combination (csrc/rng_kernels.cuh: k_batch_weights), from the n
+ * per-request digests r (n x 32 B canonical scalars) and the caller's batch seed; out = n x 32 B canonical scalars */
+int bbp_test_batch_weights(bbp_ctx *ctx, const uint8_t *r, size_t n, const uint8_t batch_seed[32], uint8_t *out);
 
 #ifdef __cplusplus
 }

@@ -293,11 +293,15 @@ def test_generator_capacity_limits(be):
     assert be.blindbid_verify(verify_item(bid, gproof, gcomm, gtc)) == 0
 
 
-@pytest.mark.parametrize("part", [None, 7])
+@pytest.mark.parametrize("part", [None, 7, -1])
 def test_batch_verify_equals_and_of_singles(be, part, monkeypatch):
     """BASELINE config 4 at test size: combined check verdict == AND of single verdicts, with 0 / 1 / k bad proofs.
     part = 7 shrinks the 1024-request part size, so the batch is cut into four parts verified concurrently on sibling
-    contexts ("lanes"), one combination per part."""
+    contexts ("lanes"), one combination per part. part = -1 keeps the whole group on one stream (default: the
+    variable-base MSM over the requests' own points runs on a second stream beside the scalar assembly)."""
+    if part == -1:
+        monkeypatch.setenv("BBP_VERIFY_STREAMS", "1")
+        part = None
     if part:
         monkeypatch.setenv("BBP_PROVE_PART", str(part))
         monkeypatch.setenv("BBP_PROVE_LANES", "3")
@@ -328,6 +332,30 @@ def test_batch_verify_equals_and_of_singles(be, part, monkeypatch):
     its[3]["proof"] = its[3]["proof"][:-1]
     ok, st = be.blindbid_verify_batch(its, seed32("batch2"))
     assert not ok and st[3] == -2 and all(s == 0 for i, s in enumerate(st) if i != 3)
+    # a request with a point that does not decompress gets weight zero on the device and its own status; the rest pass
+    its = [dict(x) for x in items]
+    p = bytearray(its[11]["proof"]); p[1] |= 1; its[11]["proof"] = bytes(p)
+    assert oracle_verify(its[11]) != 0
+    ok, st = be.blindbid_verify_batch(its, seed32("batch3"))
+    assert not ok and st[11] == oracle_verify(its[11]) and all(s == 0 for i, s in enumerate(st) if i != 11)
+    assert st == be.blindbid_verify_each(its)
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 100, 1024])
+def test_batch_weights_are_the_documented_shake_tree(be, n):
+    """The weights of a batch verification's random linear combination are derived on the device (rng_kernels.cuh:
+    k_batch_weight_digests / k_batch_weights); hashlib restates the two-level SHAKE256 tree."""
+    r = orc.random_scalars(4242 + n, n)
+    seed = seed32("weights")
+    lbl = lambda t: t.encode().ljust(32, b"\0")
+    G = (n + 31) // 32
+    hs = b""
+    for g in range(G):
+        cnt = min(32, n - 32 * g)
+        hs += hashlib.shake_256(lbl("bbp batch digest v1") + g.to_bytes(8, "little") + cnt.to_bytes(8, "little") + r[1024 * g:1024 * g + 32 * cnt]).digest(32)
+    root = hashlib.shake_256(lbl("bbp batch root v1") + seed + n.to_bytes(8, "little") + hs).digest(32)
+    want = b"".join(le(from_le(hashlib.shake_256(lbl("bbp batch weight v1") + root + i.to_bytes(8, "little")).digest(64)) % L_ORDER) for i in range(n))
+    assert be.test_batch_weights(r, seed) == want
 
 
 def test_batch_verify_config4_full_size(be):
