@@ -245,6 +245,78 @@ class Backend:
         return out.raw
 
 
+# ---------------------------------------------------------------------------------------------- generic bulletproofs surface
+class CsStruct(ctypes.Structure):
+    _fields_ = [("n_multipliers", ctypes.c_uint32), ("n_commitments", ctypes.c_uint32), ("n_constraints", ctypes.c_uint32),
+                ("con_ptr", ctypes.POINTER(ctypes.c_uint32)), ("term_var", ctypes.POINTER(ctypes.c_uint32)), ("term_coeff", ctypes.c_char_p)]
+
+
+class Transcript:
+    """merlin::Transcript over the C ABI (bbp_transcript_*)."""
+
+    def __init__(self, label=None, _handle=None):
+        lib().bbp_transcript_new.restype = ctypes.c_void_p
+        lib().bbp_transcript_clone.restype = ctypes.c_void_p
+        self.h = _handle if _handle is not None else lib().bbp_transcript_new(label, _sz(len(label)))
+        if not self.h:
+            raise BbpError(BBP_ERR_INPUT, "bbp_transcript_new")
+
+    def clone(self):
+        return Transcript(_handle=lib().bbp_transcript_clone(ctypes.c_void_p(self.h)))
+
+    def append_message(self, label, msg):
+        _chk(lib().bbp_transcript_append_message(ctypes.c_void_p(self.h), label, _sz(len(label)), msg, _sz(len(msg))), "bbp_transcript_append_message")
+
+    def append_u64(self, label, x):
+        _chk(lib().bbp_transcript_append_u64(ctypes.c_void_p(self.h), label, _sz(len(label)), ctypes.c_uint64(x)), "bbp_transcript_append_u64")
+
+    def challenge_bytes(self, label, n):
+        out = _out(n)
+        _chk(lib().bbp_transcript_challenge_bytes(ctypes.c_void_p(self.h), label, _sz(len(label)), out, _sz(n)), "bbp_transcript_challenge_bytes")
+        return out.raw
+
+    def __del__(self):
+        try:
+            lib().bbp_transcript_free.restype = None
+            lib().bbp_transcript_free(ctypes.c_void_p(self.h))
+        except Exception:
+            pass
+
+
+def _cs_struct(cs):
+    """cs = dict(n_mul, m, con_ptr[q + 1], term_var[], term_coeff bytes) -> (CsStruct, keep-alive tuple)"""
+    con_ptr = (ctypes.c_uint32 * len(cs["con_ptr"]))(*cs["con_ptr"])
+    term_var = (ctypes.c_uint32 * max(1, len(cs["term_var"])))(*cs["term_var"])
+    st = CsStruct(cs["n_mul"], cs["m"], len(cs["con_ptr"]) - 1, con_ptr, term_var, cs["term_coeff"])
+    return st, (con_ptr, term_var)
+
+
+def _generic_methods():
+    def r1cs_prove(self, transcript, cs, a_L, a_R, a_O, v, v_blinding, rng_seed):
+        """Prover::prove over a flattened circuit; returns (status, proof, V). The transcript is advanced."""
+        st, keep = _cs_struct(cs)
+        V = _out(32 * max(1, cs["m"]))
+        proof = _out(8192)
+        plen = ctypes.c_size_t(8192)
+        rc = lib().bbp_r1cs_prove(self.ctx, ctypes.c_void_p(transcript.h), ctypes.byref(st), a_L, a_R, a_O, v, v_blinding, rng_seed, V, proof, ctypes.byref(plen))
+        if rc != 0:
+            return rc, None, None
+        return 0, proof.raw[:plen.value], V.raw[:32 * cs["m"]]
+
+    def r1cs_verify(self, transcript, cs, proof, V, rng_seed):
+        st, keep = _cs_struct(cs)
+        return lib().bbp_r1cs_verify(self.ctx, ctypes.c_void_p(transcript.h), ctypes.byref(st), proof, _sz(len(proof)), V, rng_seed)
+
+    def ipp_create(self, transcript, w, Gf, Hf, a, b):
+        n = len(a) // 32
+        out = _out(64 * n.bit_length() + 64)
+        olen = ctypes.c_size_t(len(out))
+        _chk(lib().bbp_ipp_create(self.ctx, ctypes.c_void_p(transcript.h), w, Gf, Hf, a, b, _sz(n), out, ctypes.byref(olen)), "bbp_ipp_create")
+        return out.raw[:olen.value]
+
+    return dict(r1cs_prove=r1cs_prove, r1cs_verify=r1cs_verify, ipp_create=ipp_create)
+
+
 # ---------------------------------------------------------------------------------------------- blind-bid entry points
 class ProveReq(ctypes.Structure):
     _fields_ = [(n, ctypes.c_char_p) for n in ("d", "k", "y", "y_inv", "q", "z_img", "seed", "pub_list")] + [
@@ -382,6 +454,8 @@ def _backend_methods():
 
 
 _backend_methods()
+for _name, _fn in _generic_methods().items():
+    setattr(Backend, _name, _fn)
 
 
 # host-only helpers of the library (no GPU needed)

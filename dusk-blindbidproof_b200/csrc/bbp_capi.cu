@@ -336,6 +336,98 @@ int bbp_from_uniform_bytes(bbp_ctx *ctx, const uint8_t *bytes64, size_t n, uint8
     return BBP_OK;
 }
 
+// ---------------------------------------------------------------- generic bulletproofs surface
+struct bbp_transcript {
+    merlin_transcript tr;
+    bbp_transcript(const void *label, size_t n) : tr(label, n) {}
+    explicit bbp_transcript(const merlin_transcript &o) : tr(o) {}
+};
+bbp_transcript *bbp_transcript_new(const uint8_t *label, size_t label_len) {
+    if (!label && label_len) return nullptr;
+    return new (std::nothrow) bbp_transcript(label ? (const void *)label : (const void *)"", label_len);
+}
+bbp_transcript *bbp_transcript_clone(const bbp_transcript *t) { return t ? new (std::nothrow) bbp_transcript(t->tr) : nullptr; }
+void bbp_transcript_free(bbp_transcript *t) { delete t; }
+int bbp_transcript_append_message(bbp_transcript *t, const uint8_t *label, size_t label_len, const uint8_t *msg, size_t msg_len) {
+    if (!t || (!label && label_len) || (!msg && msg_len) || msg_len > 0xffffffffull) return BBP_ERR_INPUT;
+    t->tr.append_message_l(label, label_len, msg, msg_len);
+    return BBP_OK;
+}
+int bbp_transcript_append_u64(bbp_transcript *t, const uint8_t *label, size_t label_len, uint64_t x) {
+    uint8_t b[8];
+    for (int i = 0; i < 8; i++) b[i] = (uint8_t)(x >> (8 * i));
+    return bbp_transcript_append_message(t, label, label_len, b, 8);
+}
+int bbp_transcript_challenge_bytes(bbp_transcript *t, const uint8_t *label, size_t label_len, uint8_t *out, size_t out_len) {
+    if (!t || (!label && label_len) || (!out && out_len) || out_len > 0xffffffffull) return BBP_ERR_INPUT;
+    t->tr.challenge_bytes_l(label, label_len, out, out_len);
+    return BBP_OK;
+}
+
+static bool load_canonical(std::vector<sc> &out, const uint8_t *in, size_t n) {
+    out.resize(n);
+    for (size_t i = 0; i < n; i++)
+        if (!sc_from_canonical(out[i], in + 32 * i)) return false;
+    return true;
+}
+
+int bbp_r1cs_prove(bbp_ctx *ctx, bbp_transcript *t, const bbp_cs *cs, const uint8_t *a_L, const uint8_t *a_R, const uint8_t *a_O, const uint8_t *v,
+                   const uint8_t *v_blinding, const uint8_t rng_seed[32], uint8_t *V_out, uint8_t *proof_out, size_t *proof_len) {
+    if (!ctx || !t || !cs || !a_L || !a_R || !a_O || !rng_seed || !proof_out || !proof_len) return BBP_ERR_INPUT;
+    if (cs->n_commitments && (!v || !v_blinding)) return BBP_ERR_INPUT;
+    if (!cs->con_ptr || (cs->n_constraints && cs->con_ptr[cs->n_constraints] && (!cs->term_var || !cs->term_coeff))) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    generic_cs G;
+    int rc = generic_cs_build(G, cs->n_multipliers, cs->n_commitments, cs->n_constraints, cs->con_ptr, cs->term_var, cs->term_coeff);
+    if (rc) return rc;
+    std::vector<sc> aL, aR, aO, vv, bl;
+    if (!load_canonical(aL, a_L, cs->n_multipliers) || !load_canonical(aR, a_R, cs->n_multipliers) || !load_canonical(aO, a_O, cs->n_multipliers) ||
+        !load_canonical(vv, v, cs->n_commitments) || !load_canonical(bl, v_blinding, cs->n_commitments))
+        return BBP_ERR_FORMAT;
+    std::vector<uint8_t> proof;
+    int status = 0;
+    rc = r1cs_prove_generic(ctx, t->tr, G, aL.data(), aR.data(), aO.data(), vv.data(), bl.data(), rng_seed, V_out, proof, &status);
+    if (rc) return rc;
+    if (status) return status;
+    const size_t cap = *proof_len;
+    *proof_len = proof.size();
+    if (cap < proof.size()) return BBP_ERR_INPUT;
+    memcpy(proof_out, proof.data(), proof.size());
+    return BBP_OK;
+}
+
+int bbp_r1cs_verify(bbp_ctx *ctx, bbp_transcript *t, const bbp_cs *cs, const uint8_t *proof, size_t proof_len, const uint8_t *V,
+                    const uint8_t rng_seed[32]) {
+    if (!ctx || !t || !cs || (!proof && proof_len) || !rng_seed || (cs->n_commitments && !V)) return BBP_ERR_INPUT;
+    if (!cs->con_ptr || (cs->n_constraints && cs->con_ptr[cs->n_constraints] && (!cs->term_var || !cs->term_coeff))) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    generic_cs G;
+    int rc = generic_cs_build(G, cs->n_multipliers, cs->n_commitments, cs->n_constraints, cs->con_ptr, cs->term_var, cs->term_coeff);
+    if (rc) return rc;
+    int status = 0;
+    rc = r1cs_verify_generic(ctx, t->tr, G, proof, proof_len, V, rng_seed, &status);
+    return rc ? rc : status;
+}
+
+int bbp_ipp_create(bbp_ctx *ctx, bbp_transcript *t, const uint8_t w[32], const uint8_t *G_factors, const uint8_t *H_factors, const uint8_t *a,
+                   const uint8_t *b, size_t n, uint8_t *proof_out, size_t *proof_len) {
+    if (!ctx || !t || !w || !G_factors || !H_factors || !a || !b || !proof_out || !proof_len || n == 0 || n > (1u << 24)) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    sc ws;
+    std::vector<sc> gf, hf, av, bv;
+    if (!sc_from_canonical(ws, w) || !load_canonical(gf, G_factors, n) || !load_canonical(hf, H_factors, n) || !load_canonical(av, a, n) ||
+        !load_canonical(bv, b, n))
+        return BBP_ERR_FORMAT;
+    std::vector<uint8_t> out;
+    int rc = ipp_create_generic(ctx, t->tr, ws, gf.data(), hf.data(), av.data(), bv.data(), (uint32_t)n, out);
+    if (rc) return rc;
+    const size_t cap = *proof_len;
+    *proof_len = out.size();
+    if (cap < out.size()) return BBP_ERR_INPUT;
+    memcpy(proof_out, out.data(), out.size());
+    return BBP_OK;
+}
+
 // ---------------------------------------------------------------- test hooks
 int bbp_test_fe(bbp_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, int op, uint8_t *out) {
     if (!ctx || !a || !b || !out || n == 0) return BBP_ERR_INPUT;

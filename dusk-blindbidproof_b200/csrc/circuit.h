@@ -63,6 +63,11 @@ struct circuit_template {
     // CSR over target rows: rows [0,n1) = wL, [n1,2n1) = wR, [2n1,3n1) = wO, [3n1,3n1+m) = wV.
     // entry = constraint index j | sign bit (bit 31 set: subtract z^(j+1))
     std::vector<uint32_t> row_ptr, entries;
+    // generic circuits only (empty for the blind-bid template, whose variable coefficients are all +-1): per entry the
+    // index of the term's coefficient in the public value table (0 = one), and that table itself ([0] = 1, then the
+    // circuit's coefficients and constants: it belongs to the circuit, not to the proof)
+    std::vector<uint32_t> coef;
+    std::vector<sc> coef_table;
     // constant terms (verifier only): wc = - sum sign * z^(j+1) * pub[idx];  entry j | sign<<31, paired with idx
     std::vector<uint32_t> const_j, const_idx;
 };
@@ -270,6 +275,73 @@ inline std::shared_ptr<const circuit_template> blindbid_template(uint32_t n_comm
         tpl->row_ptr[r + 1] = (uint32_t)tpl->entries.size();
     }
     cache[key] = tpl;
+    return tpl;
+}
+
+// ---- generic circuits: the flattened form of a bulletproofs ConstraintSystem ---------------------------------------
+// What `ConstraintSystem::{multiply, constrain}` (src/gadgets.rs:30,53 and every other call site) leave behind is a list
+// of linear constraints over (Variable, Scalar) terms; `multiply` additionally allocates one multiplier and contributes
+// its two constraints  left - L_i = 0,  right - R_i = 0  (bulletproofs 1.0.4 r1cs/prover.rs, verifier.rs). A caller
+// that recorded its circuit hands the constraints over in CSR form: constraint j owns terms con_ptr[j] .. con_ptr[j+1],
+// term t = (term_var[t] = kind << 28 | index, term_coeff[32 t ..] = canonical scalar), kinds as var_kind plus VK_ONE.
+enum : uint32_t { VK_ONE = 4 };
+// returns nullptr on malformed input (index out of range, non-canonical coefficient, unknown kind)
+inline std::shared_ptr<const circuit_template> generic_template(uint32_t n_mul, uint32_t n_commit, uint32_t n_con, const uint32_t *con_ptr,
+                                                                const uint32_t *term_var, const uint8_t *term_coeff) {
+    auto tpl = std::make_shared<circuit_template>();
+    tpl->n_commit = n_commit; tpl->n_toggle = 0; tpl->m = n_commit; tpl->n1 = n_mul; tpl->q = n_con;
+    tpl->coef_table.push_back(sc_one());
+    const sc one = sc_one(), minus_one = sc_neg(sc_one());
+    std::map<std::vector<uint8_t>, uint32_t> known;   // coefficient bytes -> table index
+    auto table_index = [&](const sc &c, const uint8_t *bytes) -> uint32_t {
+        if (sc_eq(c, one)) return 0;
+        std::vector<uint8_t> key(bytes, bytes + 32);
+        auto it = known.find(key);
+        if (it != known.end()) return it->second;
+        uint32_t idx = (uint32_t)tpl->coef_table.size();
+        tpl->coef_table.push_back(c);
+        known.emplace(std::move(key), idx);
+        return idx;
+    };
+    const size_t n_rows = 3 * (size_t)n_mul + n_commit;
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> rows(n_rows);   // (entry, coefficient index)
+    if (n_con && con_ptr[0] != 0) return nullptr;
+    bool any_coef = false;
+    for (uint32_t j = 0; j < n_con; j++) {
+        if (con_ptr[j + 1] < con_ptr[j]) return nullptr;
+        for (uint32_t t = con_ptr[j]; t < con_ptr[j + 1]; t++) {
+            const uint32_t kind = term_var[t] >> 28, idx = term_var[t] & 0x0fffffffu;
+            sc c;
+            if (!sc_from_canonical(c, term_coeff + 32 * (size_t)t)) return nullptr;
+            if (sc_iszero(c)) continue;   // contributes nothing to any flattened weight
+            if (kind == VK_ONE) {
+                tpl->const_j.push_back(j);
+                tpl->const_idx.push_back(table_index(c, term_coeff + 32 * (size_t)t));
+                continue;
+            }
+            size_t row;
+            bool neg = false;
+            switch (kind) {
+                case VK_LEFT: if (idx >= n_mul) return nullptr; row = idx; break;
+                case VK_RIGHT: if (idx >= n_mul) return nullptr; row = (size_t)n_mul + idx; break;
+                case VK_OUT: if (idx >= n_mul) return nullptr; row = 2 * (size_t)n_mul + idx; break;
+                case VK_COMMITTED: if (idx >= n_commit) return nullptr; row = 3 * (size_t)n_mul + idx; neg = true; break;   // wV -= z^(j+1) c
+                default: return nullptr;
+            }
+            uint32_t ci = 0;
+            if (sc_eq(c, minus_one)) neg = !neg;
+            else ci = table_index(c, term_coeff + 32 * (size_t)t);
+            any_coef = any_coef || ci != 0;
+            rows[row].push_back({j | (neg ? 0x80000000u : 0u), ci});
+        }
+    }
+    tpl->n_pub = (uint32_t)tpl->coef_table.size();
+    tpl->row_ptr.assign(n_rows + 1, 0);
+    for (size_t r = 0; r < n_rows; r++) {
+        for (auto &e : rows[r]) { tpl->entries.push_back(e.first); tpl->coef.push_back(e.second); }
+        tpl->row_ptr[r + 1] = (uint32_t)tpl->entries.size();
+    }
+    if (!any_coef) tpl->coef.clear();
     return tpl;
 }
 

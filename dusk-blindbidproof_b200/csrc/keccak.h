@@ -297,6 +297,22 @@ class merlin_rng_builder {
 class merlin_transcript {
   public:
     explicit merlin_transcript(const char *label) : s_("Merlin v1.0") { append_message("dom-sep", label, strlen(label)); }
+    // labels and messages as (pointer, length) pairs: what the C ABI's bbp_transcript_* entry points receive
+    merlin_transcript(const void *label, size_t label_len) : s_("Merlin v1.0") { append_message_l("dom-sep", 7, label, label_len); }
+    void append_message_l(const void *label, size_t label_len, const void *msg, size_t n) {
+        uint8_t len[4];
+        put_le32(len, (uint32_t)n);
+        s_.meta_ad(label, label_len, false);
+        s_.meta_ad(len, 4, true);
+        s_.ad(msg, n, false);
+    }
+    void challenge_bytes_l(const void *label, size_t label_len, uint8_t *dest, size_t n) {
+        uint8_t len[4];
+        put_le32(len, (uint32_t)n);
+        s_.meta_ad(label, label_len, false);
+        s_.meta_ad(len, 4, true);
+        s_.prf(dest, n, false);
+    }
     void append_message(const char *label, const void *msg, size_t n) {
         uint8_t len[4];
         put_le32(len, (uint32_t)n);
@@ -318,6 +334,7 @@ class merlin_transcript {
     }
     merlin_rng_builder build_rng() const { return merlin_rng_builder(s_); }
     void export_state(uint8_t out[208]) const { s_.export_state(out); }   // hand-off to the device-side replay
+    void import_state(const uint8_t in[208]) { s_.import_state(in); }
 
     void domain_sep(const char *name) { append_message("dom-sep", name, strlen(name)); }
     void r1cs_domain_sep() { domain_sep("r1cs v1"); }

@@ -231,6 +231,7 @@ struct host_buf {
 struct dev_template {
     std::shared_ptr<const circuit_template> tpl;
     uint32_t *row_ptr = nullptr, *entries = nullptr, *const_j = nullptr, *const_idx = nullptr;
+    uint32_t *coef = nullptr;      // generic circuits only: coefficient index per entry (sc_kernels.cuh: flatten_term)
     uint32_t n_long = 0, long_rows[BBP_MAX_LONG] = {};   // the longest CSR rows among wL / wR / wO (sc_kernels.cuh: flatten_long_rows)
 };
 
@@ -280,7 +281,7 @@ inline proto_state *proto_get(bbp_ctx *ctx) {
 
 void proto_release(proto_state *ps) {
     if (!ps) return;
-    for (auto &kv : ps->templates) { cudaFree(kv.second.row_ptr); cudaFree(kv.second.entries); cudaFree(kv.second.const_j); cudaFree(kv.second.const_idx); }
+    for (auto &kv : ps->templates) { cudaFree(kv.second.row_ptr); cudaFree(kv.second.entries); cudaFree(kv.second.const_j); cudaFree(kv.second.const_idx); cudaFree(kv.second.coef); }
     cudaFree(ps->comb); cudaFree(ps->wtable); cudaFree(ps->wtable2); cudaFree(ps->colmap); cudaFree(ps->ipp_colmap); cudaFree(ps->dtable);
     ps->sm_partial.release(); ps->lane_partials.release();
     ps->fext.release(); ps->ftab.release();
@@ -321,6 +322,8 @@ inline int proto_tables(bbp_ctx *ctx) {
     return 0;
 }
 
+inline int template_upload(bbp_ctx *ctx, dev_template &dt);
+inline void template_free(dev_template &dt);
 inline int proto_template(bbp_ctx *ctx, uint32_t n_commit, uint32_t n_toggle, dev_template **out) {
     proto_state *ps = proto_get(ctx);
     uint64_t key = ((uint64_t)n_commit << 32) | n_toggle;
@@ -328,11 +331,26 @@ inline int proto_template(bbp_ctx *ctx, uint32_t n_commit, uint32_t n_toggle, de
     if (it == ps->templates.end()) {
         if (ps->templates.size() >= TEMPLATE_CACHE_MAX) {   // keyed by request-chosen counts: bounded (no call holds a pointer across calls)
             BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-            for (auto &kv : ps->templates) { cudaFree(kv.second.row_ptr); cudaFree(kv.second.entries); cudaFree(kv.second.const_j); cudaFree(kv.second.const_idx); }
+            for (auto &kv : ps->templates) template_free(kv.second);
             ps->templates.clear();
         }
         dev_template dt;
         dt.tpl = blindbid_template(n_commit, n_toggle);
+        int urc = template_upload(ctx, dt);
+        if (urc) return urc;
+        it = ps->templates.emplace(key, dt).first;
+    }
+    *out = &it->second;
+    return 0;
+}
+inline void template_free(dev_template &dt) {
+    cudaFree(dt.row_ptr); cudaFree(dt.entries); cudaFree(dt.const_j); cudaFree(dt.const_idx); cudaFree(dt.coef);
+    dt.row_ptr = dt.entries = dt.const_j = dt.const_idx = dt.coef = nullptr;
+}
+// uploads dt.tpl's CSR; fills the device pointers and the long-row list
+inline int template_upload(bbp_ctx *ctx, dev_template &dt) {
+    {
+        {
         const circuit_template &t = *dt.tpl;
         BBP_CUDA_OK(cudaMalloc(&dt.row_ptr, t.row_ptr.size() * 4));
         BBP_CUDA_OK(cudaMalloc(&dt.entries, std::max<size_t>(t.entries.size(), 1) * 4));
@@ -342,6 +360,10 @@ inline int proto_template(bbp_ctx *ctx, uint32_t n_commit, uint32_t n_toggle, de
         BBP_CUDA_OK(cudaMemcpyAsync(dt.entries, t.entries.data(), t.entries.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         BBP_CUDA_OK(cudaMemcpyAsync(dt.const_j, t.const_j.data(), t.const_j.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         BBP_CUDA_OK(cudaMemcpyAsync(dt.const_idx, t.const_idx.data(), t.const_idx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (!t.coef.empty()) {
+            BBP_CUDA_OK(cudaMalloc(&dt.coef, t.coef.size() * 4));
+            BBP_CUDA_OK(cudaMemcpyAsync(dt.coef, t.coef.data(), t.coef.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        }
         BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
         {
             std::vector<std::pair<uint32_t, uint32_t>> lens;   // (length, row) of rows above the threshold, longest first
@@ -353,9 +375,8 @@ inline int proto_template(bbp_ctx *ctx, uint32_t n_commit, uint32_t n_toggle, de
             dt.n_long = (uint32_t)std::min<size_t>(lens.size(), BBP_MAX_LONG);
             for (uint32_t k = 0; k < dt.n_long; k++) dt.long_rows[k] = lens[k].second;
         }
-        it = ps->templates.emplace(key, dt).first;
+        }
     }
-    *out = &it->second;
     return 0;
 }
 
@@ -380,6 +401,7 @@ inline int msm_gens_small(bbp_ctx *ctx, const sc *d_scalars, uint32_t slot_len, 
 inline int pedersen_commit_host(bbp_ctx *ctx, const sc *vals, size_t n, uint8_t *out) {
     proto_state *ps = proto_get(ctx);
     int rc;
+    if (n == 0) return 0;   // a circuit without commitments
     if ((rc = ps->commit_in.ensure(n * 64)) || (rc = ps->commit_out.ensure(n * 32))) return rc;
     if ((rc = h2d(ctx, ps->commit_in.p, vals, n * 64))) return rc;
     if (n <= 64 && small_msm_ok(2 * n)) {
@@ -613,37 +635,49 @@ struct prove_job {
     std::vector<uint8_t> commitments, t_c;   // 4 x 32, L x 32
 };
 
-// a toggle index beyond the list makes every toggle bit zero (the reference: `x as u64 == toggle`); the device witness
-// kernel handles that as well, this only guards the uint32 narrowing
-inline bool J0_toggle_in_range(const std::vector<prove_job> &jobs, const std::vector<size_t> &idx, uint32_t) {
-    for (size_t i : idx)
-        if (jobs[i].toggle > 0xfffffffeull) return false;
-    return true;
-}
+// What the R1CS prover core needs from its caller, per proof bi < B. All proofs of a call share one circuit template.
+// Two callers: the blind-bid driver (Proof::prove, src/blindbid/proof.rs:36-91: the circuit of src/gadgets.rs, witness by
+// the evaluator or by k_blindbid_witness) and the generic bulletproofs surface (bbp_r1cs_prove: circuit and witness
+// recorded by the caller through ConstraintSystem::{multiply, constrain}).
+struct prove_source {
+    uint32_t B = 0;
+    dev_template *dt = nullptr;
+    // committed values and their blindings (m each), the 32 external RNG bytes (RNG contract)
+    std::function<void(size_t, std::vector<sc> &, std::vector<sc> &, const uint8_t *&)> inputs;
+    // a fresh transcript positioned where Prover::new leaves it (label, then "r1cs v1"); the core owns it
+    std::function<merlin_transcript *(size_t)> transcript;
+    // host witness: writes a_L, a_R, a_O (n1 scalars each) given the committed values
+    std::function<void(size_t, const std::vector<sc> &, sc *, sc *, sc *)> witness;
+    // optional device witness of the blind-bid circuit (bb_L = list length, 0 = not available): fills
+    // (d, k, y_inv, seed, items[bb_L]) and the toggle index; false = this request cannot take the device path
+    uint32_t bb_L = 0;
+    std::function<bool(size_t, sc *, uint32_t *)> bb_witness_in;
+    // result: V (m x 32 B compressed), the proof bytes, the transcript as the proof leaves it
+    std::function<void(size_t, const uint8_t *, std::vector<uint8_t> &&, const merlin_transcript &)> done;
+    std::function<void(int)> fail_all;
+};
 
-// proves jobs[idx[0..B)] — all with the same list length L
-inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::vector<size_t> &idx) {
+// Prover::prove for S.B proofs over one circuit (bulletproofs 1.0.4 @ 4a05305 r1cs/prover.rs; call site src/blindbid/proof.rs:88)
+inline int prove_core(bbp_ctx *ctx, prove_source &S) {
     proto_state *ps = proto_get(ctx);
-    const uint32_t B = (uint32_t)idx.size();
-    const uint32_t L = (uint32_t)jobs[idx[0]].pub_list.size();
+    const uint32_t B = S.B;
     int rc;
     if ((rc = proto_tables(ctx))) return rc;
-    // the capacity check comes BEFORE the template is built: L is the caller's, the template costs O(L^2) to record
-    if (L > BLINDBID_MAX_TOGGLES || next_pow2_u32(blindbid_n1(L)) > ctx->gens_capacity || ctx->party_capacity < 1) {
-        for (size_t i : idx) jobs[i].status = BBP_ERR_INVALID_GENERATORS_LENGTH;   // bp_gens.gens_capacity < padded_n
-        return 0;
-    }
-    dev_template *dt;
-    if ((rc = proto_template(ctx, 4, L, &dt))) return rc;
+    dev_template *dt = S.dt;
     const circuit_template &T = *dt->tpl;
     const uint32_t n1 = T.n1, m = T.m, n = next_pow2_u32(n1), lg = log2_u32(n);
+    if (n > ctx->gens_capacity || ctx->party_capacity < 1) {
+        S.fail_all(BBP_ERR_INVALID_GENERATORS_LENGTH);   // bp_gens.gens_capacity < padded_n
+        return 0;
+    }
     const uint32_t gcols = ctx->gens_capacity * ctx->party_capacity, slot_len = 2 + 2 * gcols;
+    const uint32_t L = S.bb_L;
 
     struct hstate {
         std::unique_ptr<merlin_transcript> tr;
         std::unique_ptr<merlin_rng> rng;
-        evaluator ev;
-        std::vector<sc> pub, v;
+        std::vector<sc> v, bl;
+        const uint8_t *rng_seed = nullptr;
         r1cs_proof_host pf;
         sc i_bl, o_bl, s_bl, tbl[6];   // tbl[1] (t_2 blinding) comes from the device
     };
@@ -661,30 +695,23 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     const size_t wit_count = (size_t)B * (device_rng ? 3 : 5) * n1;
     if ((rc = ps->h_wit.ensure(wit_count * 32))) return rc;
     sc *wit = ps->h_wit.as<sc>();
-    // large batches evaluate the witness on the device too (one thread per proof, k_blindbid_witness); the host evaluator
-    // walks the generic gadget code and is the path for small batches
-    const bool device_witness = device_rng && J0_toggle_in_range(jobs, idx, L);
+    // large batches of the blind-bid circuit evaluate the witness on the device too (one thread per proof,
+    // k_blindbid_witness); the host path (the caller's evaluator, or its recorded assignments) serves the rest
+    bool device_witness = device_rng && L > 0 && (bool)S.bb_witness_in;
     std::vector<sc> commit_vals((size_t)B * m * 2), wit_in(device_witness ? (size_t)B * (4 + L) : 0);
     std::vector<uint32_t> toggles_u32(device_witness ? B : 0);
+    std::atomic<bool> all_device{true};
     parallel_for(B, [&](size_t bi) {
-        prove_job &J = jobs[idx[bi]];
         hstate &H = hs[bi];
-        H.v = {J.d, J.k, J.y, J.y_inv};
-        for (uint32_t i = 0; i < L; i++) H.v.push_back(sc_from_u64((uint64_t)i == J.toggle ? 1 : 0));
-        for (uint32_t i = 0; i < m; i++) { commit_vals[((size_t)bi * m + i) * 2] = H.v[i]; commit_vals[((size_t)bi * m + i) * 2 + 1] = J.blindings[i]; }
-        if (device_witness) {
-            sc *wi = &wit_in[bi * (4 + L)];
-            wi[0] = J.d; wi[1] = J.k; wi[2] = J.y_inv; wi[3] = J.seed;
-            for (uint32_t i = 0; i < L; i++) wi[4 + i] = J.pub_list[i];
-            toggles_u32[bi] = (uint32_t)J.toggle;
-            return;
-        }
-        fill_public_values(H.pub, J.seed, J.q, J.z_img, J.pub_list.data(), L);
-        H.ev.pub = H.pub.data();
-        H.ev.a_L = &wit[((size_t)0 * B + bi) * n1]; H.ev.a_R = &wit[((size_t)1 * B + bi) * n1]; H.ev.a_O = &wit[((size_t)2 * B + bi) * n1];
-        std::vector<sc> toggles(H.v.begin() + 4, H.v.end()), items(J.pub_list.begin(), J.pub_list.end());
-        proof_gadget(H.ev, H.v[0], H.v[1], H.v[3], J.q, J.z_img, J.seed, toggles, items);
+        S.inputs(bi, H.v, H.bl, H.rng_seed);
+        for (uint32_t i = 0; i < m; i++) { commit_vals[((size_t)bi * m + i) * 2] = H.v[i]; commit_vals[((size_t)bi * m + i) * 2 + 1] = H.bl[i]; }
+        if (device_witness && !S.bb_witness_in(bi, &wit_in[bi * (4 + L)], &toggles_u32[bi])) all_device = false;
     });
+    if (device_witness && !all_device) device_witness = false;
+    if (!device_witness)
+        parallel_for(B, [&](size_t bi) {
+            S.witness(bi, hs[bi].v, &wit[((size_t)0 * B + bi) * n1], &wit[((size_t)1 * B + bi) * n1], &wit[((size_t)2 * B + bi) * n1]);
+        });
     trace.mark("host_witness");
     std::vector<uint8_t> V((size_t)B * m * 32);
     if ((rc = pedersen_commit_host(ctx, commit_vals.data(), (size_t)B * m, V.data()))) return rc;
@@ -700,22 +727,18 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     uint8_t *rng_states = ps->h_states.p;
     std::vector<sc> vbl((size_t)B * m), blind3((size_t)B * 3);
     parallel_for(B, [&](size_t bi) {
-        prove_job &J = jobs[idx[bi]];
         hstate &H = hs[bi];
-        H.tr.reset(new merlin_transcript("BlindBidProofGadget"));   // src/blindbid/mod.rs:37
-        H.tr->r1cs_domain_sep();                                      // Prover::new
+        H.tr.reset(S.transcript(bi));                                 // Transcript::new(label), then Prover::new's "r1cs v1"
         for (uint32_t i = 0; i < m; i++) H.tr->append_point("V", &V[((size_t)bi * m + i) * 32]);
-        J.commitments.assign(&V[(size_t)bi * m * 32], &V[(size_t)bi * m * 32] + 4 * 32);
-        J.t_c.assign(&V[((size_t)bi * m + 4) * 32], &V[((size_t)bi * m + 4) * 32] + (size_t)L * 32);
         H.tr->append_u64("m", m);
         merlin_rng_builder rb = H.tr->build_rng();
         for (uint32_t i = 0; i < m; i++) {
             uint8_t b[32];
-            sc_tobytes(b, J.blindings[i]);
+            sc_tobytes(b, H.bl[i]);
             rb.rekey_with_witness_bytes("v_blinding", b, 32);
-            vbl[(size_t)bi * m + i] = J.blindings[i];
+            vbl[(size_t)bi * m + i] = H.bl[i];
         }
-        H.rng.reset(new merlin_rng(rb.finalize(J.rng_seed)));
+        H.rng.reset(new merlin_rng(rb.finalize(H.rng_seed)));
         H.i_bl = H.rng->random_scalar(); H.o_bl = H.rng->random_scalar(); H.s_bl = H.rng->random_scalar();
         blind3[bi * 3] = H.i_bl; blind3[bi * 3 + 1] = H.o_bl; blind3[bi * 3 + 2] = H.s_bl;
         auto W = [&](uint32_t k) { return &wit[((size_t)k * B + bi) * n1]; };
@@ -774,6 +797,12 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     SB.n_long = dt->n_long;
     memcpy(SB.long_rows, dt->long_rows, sizeof SB.long_rows);
     SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>();
+    SB.coef = dt->coef;
+    if (dt->coef) {   // generic circuit: its coefficient table, once (shared by the batch: n_pub = 0 -> stride 0)
+        if ((rc = ps->pub.ensure(T.coef_table.size() * 32)) || (rc = h2d(ctx, ps->pub.p, T.coef_table.data(), T.coef_table.size() * 32))) return rc;
+        SB.pub = ps->pub.as<sc>();
+        SB.n_pub = 0;
+    }
     const sc *dw = ps->wit.as<sc>();
     const size_t vs = (size_t)B * n1;
     SB.aL = dw; SB.aR = dw + vs; SB.aO = dw + 2 * vs; SB.sL = dw + 3 * vs; SB.sR = dw + 4 * vs;
@@ -885,12 +914,66 @@ inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::ve
     std::vector<sc> ab((size_t)B * 2);
     if ((rc = d2h_sync(ctx, ab.data(), ps->ab.p, ab.size() * 32))) return rc;
     for (uint32_t bi = 0; bi < B; bi++) {
-        prove_job &J = jobs[idx[bi]];
         hs[bi].pf.a = ab[bi * 2]; hs[bi].pf.b = ab[bi * 2 + 1];
-        J.proof = r1cs_to_bytes(hs[bi].pf, ps->proof_versioned != 0);
-        J.status = 0;
+        S.done(bi, &V[(size_t)bi * m * 32], r1cs_to_bytes(hs[bi].pf, ps->proof_versioned != 0), *hs[bi].tr);
     }
     return 0;
+}
+
+// proves jobs[idx[0..B)] — all with the same list length L: Proof::prove (src/blindbid/proof.rs:36-91) over prove_core
+inline int prove_group(bbp_ctx *ctx, std::vector<prove_job> &jobs, const std::vector<size_t> &idx) {
+    const uint32_t L = (uint32_t)jobs[idx[0]].pub_list.size();
+    // the capacity check comes BEFORE the template is built: L is the caller's, the template costs O(L^2) to record
+    if (L > BLINDBID_MAX_TOGGLES || next_pow2_u32(blindbid_n1(L)) > ctx->gens_capacity || ctx->party_capacity < 1) {
+        for (size_t i : idx) jobs[i].status = BBP_ERR_INVALID_GENERATORS_LENGTH;   // bp_gens.gens_capacity < padded_n
+        return 0;
+    }
+    int rc;
+    prove_source S;
+    S.B = (uint32_t)idx.size();
+    if ((rc = proto_template(ctx, 4, L, &S.dt))) return rc;
+    S.inputs = [&](size_t bi, std::vector<sc> &v, std::vector<sc> &bl, const uint8_t *&seed) {
+        prove_job &J = jobs[idx[bi]];
+        v = {J.d, J.k, J.y, J.y_inv};                                   // src/blindbid/proof.rs:55-58
+        for (uint32_t i = 0; i < L; i++) v.push_back(sc_from_u64((uint64_t)i == J.toggle ? 1 : 0));   // proof.rs:60-67
+        bl = J.blindings;
+        seed = J.rng_seed;
+    };
+    S.transcript = [](size_t) {
+        merlin_transcript *tr = new merlin_transcript("BlindBidProofGadget");   // src/blindbid/mod.rs:37
+        tr->r1cs_domain_sep();                                                    // Prover::new
+        return tr;
+    };
+    S.witness = [&](size_t bi, const std::vector<sc> &v, sc *aL, sc *aR, sc *aO) {
+        prove_job &J = jobs[idx[bi]];
+        std::vector<sc> pub;
+        fill_public_values(pub, J.seed, J.q, J.z_img, J.pub_list.data(), L);
+        evaluator ev;
+        ev.pub = pub.data();
+        ev.a_L = aL; ev.a_R = aR; ev.a_O = aO;
+        std::vector<sc> toggles(v.begin() + 4, v.end()), items(J.pub_list.begin(), J.pub_list.end());
+        proof_gadget(ev, v[0], v[1], v[3], J.q, J.z_img, J.seed, toggles, items);   // proof.rs:74-85
+    };
+    S.bb_L = L;
+    S.bb_witness_in = [&](size_t bi, sc *wi, uint32_t *toggle) {
+        prove_job &J = jobs[idx[bi]];
+        // a toggle index beyond the list makes every toggle bit zero (the reference: `x as u64 == toggle`); the device
+        // witness kernel handles that as well, this only guards the uint32 narrowing
+        if (J.toggle > 0xfffffffeull) return false;
+        wi[0] = J.d; wi[1] = J.k; wi[2] = J.y_inv; wi[3] = J.seed;
+        for (uint32_t i = 0; i < L; i++) wi[4 + i] = J.pub_list[i];
+        *toggle = (uint32_t)J.toggle;
+        return true;
+    };
+    S.done = [&](size_t bi, const uint8_t *V, std::vector<uint8_t> &&proof, const merlin_transcript &) {
+        prove_job &J = jobs[idx[bi]];
+        J.commitments.assign(V, V + 4 * 32);
+        J.t_c.assign(V + 4 * 32, V + (size_t)(4 + L) * 32);
+        J.proof = std::move(proof);
+        J.status = 0;
+    };
+    S.fail_all = [&](int st) { for (size_t i : idx) jobs[i].status = st; };
+    return prove_core(ctx, S);
 }
 
 // Lanes: sibling contexts of the same GPU that the 1024-request parts of a larger batch run on concurrently, one host
@@ -1001,6 +1084,11 @@ struct verify_prepared {
     // the first m + 11 + 2 lg entries are the dynamic points of the mega-check, the whole blob is what the transcript absorbs
     std::vector<uint8_t> blob;
     std::vector<sc> pub;
+    // generic circuits (bbp_r1cs_verify): the caller's template and the transcript state Verifier::new leaves behind
+    // (208 B, keccak.h export_state); tr_out, if set, receives the state after the last IPP challenge
+    dev_template *dt = nullptr;
+    const uint8_t *tr_state = nullptr;
+    uint8_t *tr_out = nullptr;
 };
 
 // Host part of Verifier::verify for one request: parse (FormatError), the structural checks the reference would panic
@@ -1047,6 +1135,7 @@ inline void verify_transcript_host(const verify_prepared &P, const uint8_t rng_s
     const uint8_t *blob = P.blob.data(), *pts = blob + 32 * (size_t)m, *lr = pts + 32 * 11, *scal = lr + 64 * (size_t)lg;
     merlin_transcript tr("BlindBidProofGadget");
     tr.r1cs_domain_sep();
+    if (P.tr_state) tr.import_state(P.tr_state);
     for (uint32_t i = 0; i < m; i++) tr.append_point("V", blob + 32 * (size_t)i);
     tr.append_u64("m", m);
     tr.append_point("A_I1", pts); tr.append_point("A_O1", pts + 32); tr.append_point("S1", pts + 64);
@@ -1066,6 +1155,7 @@ inline void verify_transcript_host(const verify_prepared &P, const uint8_t rng_s
         inv[j] = c[CH_UJ0 + j] = tr.challenge_scalar("u");
     }
     inv[lg] = y;
+    if (P.tr_out) tr.export_state(P.tr_out);
     merlin_rng rng = tr.build_rng().finalize(rng_seed);
     sc r = rng.random_scalar();
     sc_batch_invert(inv.data(), inv.size());
@@ -1096,8 +1186,8 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     const verify_prepared &P0 = prep[idx[0]];
     int rc;
     if ((rc = proto_tables(ctx))) return rc;
-    dev_template *dt;
-    if ((rc = proto_template(ctx, P0.nc, P0.nt, &dt))) return rc;
+    dev_template *dt = P0.dt;
+    if (!dt && (rc = proto_template(ctx, P0.nc, P0.nt, &dt))) return rc;
     const circuit_template &T = *dt->tpl;
     const uint32_t n1 = T.n1, m = T.m, n = P0.n, lg = P0.lg, gcols = ctx->gens_capacity * ctx->party_capacity, slot_len = 2 + 2 * gcols;
     const uint32_t ds = m + 11 + 2 * lg, blob_stride = 32 * (ds + 5);
@@ -1148,10 +1238,11 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     // Fiat-Shamir replay: on the device for large batches (one warp per request, ~0.2 ms whatever the batch), on the host
     // threads otherwise (~40 us per request per thread); BBP_DEVICE_TRANSCRIPT_MIN_BATCH overrides the crossover
     const char *tr_env = getenv("BBP_DEVICE_TRANSCRIPT_MIN_BATCH");
-    const bool device_replay = B >= (uint32_t)(tr_env ? atoi(tr_env) : (int)(8 * host_threads()));
+    const bool device_replay = !P0.tr_out && B >= (uint32_t)(tr_env ? atoi(tr_env) : (int)(8 * host_threads()));
     if (device_replay) {
         transcript_init init;
-        {
+        if (P0.tr_state) memcpy(init.state, P0.tr_state, sizeof init.state);   // one group = one circuit = one starting state
+        else {
             merlin_transcript tr("BlindBidProofGadget");   // src/blindbid/mod.rs:37
             tr.r1cs_domain_sep();                            // Verifier::new
             tr.export_state(init.state);
@@ -1200,6 +1291,7 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     memcpy(SB.long_rows, dt->long_rows, sizeof SB.long_rows);
     SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>();
     SB.pub = ps->pub.as<sc>(); SB.dyn_out = ps->dyn_sc.as<sc>(); SB.dyn_stride = ds; SB.stat = ps->stat.as<sc>();
+    SB.coef = dt->coef;
     SB.stab = ps->sG.as<sc>();
     SB.skip_ypow = 1;
     SB.dyn_done = 1;
@@ -1338,6 +1430,159 @@ inline int verify_batch(bbp_ctx *ctx, std::vector<verify_job> &jobs, const uint8
     // ANDs this flag over the ranks next to the identity test of the summed partials)
     for (auto &J : jobs) ok = ok && J.status == 0;
     if (all_ok) *all_ok = ok ? 1 : 0;
+    return 0;
+}
+
+
+// ================================================================ generic bulletproofs surface (layer 3)
+// What src/gadgets.rs and src/blindbid compile against: ConstraintSystem::{multiply, constrain} (gadgets.rs:53, 30),
+// Prover::{new, commit, prove} (blindbid/proof.rs:50, 57, 88), Verifier::{new, commit, verify} (blindbid/verify.rs:51, 57,
+// 88) and InnerProductProof::create underneath. The caller records its circuit (and, proving, its assignments) and hands
+// the flattened form over; the prover / verifier below are the same ones the blind-bid entry points run on.
+struct generic_cs {
+    std::shared_ptr<const circuit_template> tpl;
+};
+inline int generic_cs_build(generic_cs &out, uint32_t n_mul, uint32_t n_commit, uint32_t n_con, const uint32_t *con_ptr, const uint32_t *term_var,
+                            const uint8_t *term_coeff) {
+    if (n_mul == 0 || n_mul > (1u << 24) || n_commit > (1u << 24) || n_con > (1u << 28)) return BBP_ERR_INPUT;
+    out.tpl = generic_template(n_mul, n_commit, n_con, con_ptr, term_var, term_coeff);
+    return out.tpl ? 0 : BBP_ERR_FORMAT;
+}
+
+// Prover::prove over a recorded circuit. tr: the caller's transcript as Transcript::new(label) left it (Prover::new's
+// domain separator is applied here); on success it is advanced exactly as the Rust prover advances its &mut Transcript.
+inline int r1cs_prove_generic(bbp_ctx *ctx, merlin_transcript &tr, const generic_cs &cs, const sc *aL, const sc *aR, const sc *aO, const sc *v,
+                              const sc *v_blinding, const uint8_t rng_seed[32], uint8_t *V_out, std::vector<uint8_t> &proof, int *status) {
+    const circuit_template &T = *cs.tpl;
+    dev_template dt;
+    dt.tpl = cs.tpl;
+    int rc = template_upload(ctx, dt);
+    if (rc) { template_free(dt); return rc; }
+    prove_source S;
+    S.B = 1;
+    S.dt = &dt;
+    S.inputs = [&](size_t, std::vector<sc> &vv, std::vector<sc> &bl, const uint8_t *&seed) {
+        vv.assign(v, v + T.m); bl.assign(v_blinding, v_blinding + T.m); seed = rng_seed;
+    };
+    S.transcript = [&](size_t) {
+        merlin_transcript *t = new merlin_transcript(tr);
+        t->r1cs_domain_sep();   // Prover::new
+        return t;
+    };
+    S.witness = [&](size_t, const std::vector<sc> &, sc *l, sc *r, sc *o) {
+        memcpy(l, aL, (size_t)T.n1 * 32); memcpy(r, aR, (size_t)T.n1 * 32); memcpy(o, aO, (size_t)T.n1 * 32);
+    };
+    *status = BBP_ERR_CUDA;
+    S.done = [&](size_t, const uint8_t *V, std::vector<uint8_t> &&pf, const merlin_transcript &after) {
+        if (V_out) memcpy(V_out, V, (size_t)T.m * 32);
+        proof = std::move(pf);
+        tr = after;
+        *status = 0;
+    };
+    S.fail_all = [&](int st) { *status = st; };
+    rc = prove_core(ctx, S);
+    cudaStreamSynchronize(ctx->stream);
+    template_free(dt);
+    return rc;
+}
+
+// Verifier::verify over a recorded circuit: 0 = accept, BBP_ERR_* mirroring R1CSError otherwise
+inline int r1cs_verify_generic(bbp_ctx *ctx, merlin_transcript &tr, const generic_cs &cs, const uint8_t *proof, size_t proof_len, const uint8_t *V,
+                               const uint8_t rng_seed[32], int *status) {
+    const circuit_template &T = *cs.tpl;
+    proto_state *ps = proto_get(ctx);
+    std::vector<verify_job> jobs(1);
+    std::vector<verify_prepared> prep(1);
+    verify_job &J = jobs[0];
+    verify_prepared &P = prep[0];
+    memcpy(J.rng_seed, rng_seed, 32);
+    J.status = 0;
+    *status = 0;
+    r1cs_proof_host pf;
+    if (!r1cs_from_bytes(pf, proof, proof_len, ps->proof_versioned != 0)) { *status = BBP_ERR_FORMAT; return 0; }
+    P.m = T.m; P.n1 = T.n1; P.n = next_pow2_u32(T.n1); P.lg = log2_u32(P.n);
+    // the order of the checks is Verifier::verify's (see verify_prepare)
+    if (all_zero32(pf.A_I1) || all_zero32(pf.A_O1) || all_zero32(pf.S1)) { *status = BBP_ERR_VERIFICATION; return 0; }
+    if (P.n > ctx->gens_capacity || ctx->party_capacity < 1) { *status = BBP_ERR_INVALID_GENERATORS_LENGTH; return 0; }
+    if (all_zero32(pf.T_1) || all_zero32(pf.T_3) || all_zero32(pf.T_4) || all_zero32(pf.T_5) || all_zero32(pf.T_6)) { *status = BBP_ERR_VERIFICATION; return 0; }
+    const uint32_t lg_p = (uint32_t)(pf.LR.size() / 64);
+    if (lg_p >= 32 || P.n != (1u << lg_p)) { *status = BBP_ERR_VERIFICATION; return 0; }
+    for (uint32_t j = 0; j < 2 * lg_p; j++)
+        if (all_zero32(&pf.LR[32 * (size_t)j])) { *status = BBP_ERR_VERIFICATION; return 0; }
+    P.blob.resize((size_t)32 * (P.m + 11 + 2 * lg_p + 5));
+    uint8_t *o = P.blob.data();
+    memcpy(o, V, (size_t)P.m * 32); o += (size_t)P.m * 32;
+    const uint8_t *fixed_pts[11] = {pf.A_I1, pf.A_O1, pf.S1, pf.A_I2, pf.A_O2, pf.S2, pf.T_1, pf.T_3, pf.T_4, pf.T_5, pf.T_6};
+    for (int k = 0; k < 11; k++) { memcpy(o, fixed_pts[k], 32); o += 32; }
+    memcpy(o, pf.LR.data(), pf.LR.size()); o += pf.LR.size();
+    sc_tobytes(o, pf.t_x); sc_tobytes(o + 32, pf.t_x_blinding); sc_tobytes(o + 64, pf.e_blinding); sc_tobytes(o + 96, pf.a); sc_tobytes(o + 128, pf.b);
+    P.pub = T.coef_table;
+    P.live = true;
+    dev_template dt;
+    dt.tpl = cs.tpl;
+    int rc = template_upload(ctx, dt);
+    if (rc) { template_free(dt); return rc; }
+    uint8_t st_in[BBP_STROBE_STATE_BYTES], st_out[BBP_STROBE_STATE_BYTES];
+    {
+        merlin_transcript t0(tr);
+        t0.r1cs_domain_sep();   // Verifier::new
+        t0.export_state(st_in);
+    }
+    P.dt = &dt; P.tr_state = st_in; P.tr_out = st_out;
+    std::vector<size_t> idx(1, 0);
+    std::vector<uint8_t> verdicts;
+    rc = verify_group(ctx, jobs, prep, idx, false, nullptr, verdicts, nullptr);
+    template_free(dt);
+    if (rc) return rc;
+    tr.import_state(st_out);
+    *status = J.status;
+    return 0;
+}
+
+// InnerProductProof::create with Q = w * B (B = the Pedersen value base: how Prover::prove and RangeProof use it), over
+// the first n resident generators G, H of party 0. Output: L_0 R_0 .. L_{lg n - 1} R_{lg n - 1} a b.
+inline int ipp_create_generic(bbp_ctx *ctx, merlin_transcript &tr, const sc &w, const sc *Gf, const sc *Hf, const sc *a, const sc *b, uint32_t n,
+                              std::vector<uint8_t> &out) {
+    proto_state *ps = proto_get(ctx);
+    int rc;
+    if (n == 0 || (n & (n - 1)) || n > ctx->gens_capacity || ctx->party_capacity < 1) return BBP_ERR_INVALID_GENERATORS_LENGTH;
+    if ((rc = proto_tables(ctx))) return rc;
+    const uint32_t lg = log2_u32(n), gcols = ctx->gens_capacity * ctx->party_capacity, slot_len = 2 + 2 * gcols;
+    if ((rc = ps->chal.ensure((size_t)CH_N * 32)) || (rc = ps->a.ensure((size_t)n * 32)) || (rc = ps->b.ensure((size_t)n * 32)) ||
+        (rc = ps->sG.ensure((size_t)n * 32)) || (rc = ps->sH.ensure((size_t)n * 32)) || (rc = ps->slots.ensure((size_t)3 * slot_len * 32)) ||
+        (rc = ps->ab.ensure(64)) || (rc = ps->wit.ensure((size_t)4 * n * 32)))
+        return rc;
+    sc_batch SB;
+    memset(&SB, 0, sizeof SB);
+    SB.n_proofs = 1; SB.n1 = n; SB.n = n; SB.lg_n = lg; SB.gcols = gcols;
+    SB.chal = ps->chal.as<sc>(); SB.a = ps->a.as<sc>(); SB.b = ps->b.as<sc>(); SB.sG = ps->sG.as<sc>(); SB.sH = ps->sH.as<sc>();
+    SB.slots = ps->slots.as<sc>(); SB.ab_out = ps->ab.as<sc>();
+    sc *stage = ps->wit.as<sc>();
+    if ((rc = h2d(ctx, stage, a, (size_t)n * 32)) || (rc = h2d(ctx, stage + n, b, (size_t)n * 32)) || (rc = h2d(ctx, stage + 2 * (size_t)n, Gf, (size_t)n * 32)) ||
+        (rc = h2d(ctx, stage + 3 * (size_t)n, Hf, (size_t)n * 32)))
+        return rc;
+    std::vector<sc> chal(CH_N, sc_zero());
+    chal[CH_W] = w;
+    if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32))) return rc;
+    BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));   // the sources are pageable caller memory
+    k_ipp_load<<<1, BBP_SC_THREADS, 0, ctx->stream>>>(SB, stage, stage + n, stage + 2 * (size_t)n, stage + 3 * (size_t)n);
+    ctx->launches++;
+    tr.innerproduct_domain_sep(n);
+    out.assign((size_t)64 * lg + 64, 0);
+    phase_trace trace("ipp_create");
+    rc = ipp_rounds(ctx, SB, 1, chal, [&](uint32_t j, const std::vector<uint8_t> &lr) {
+        memcpy(&out[(size_t)64 * j], lr.data(), 64);
+        tr.append_point("L", lr.data());
+        tr.append_point("R", lr.data() + 32);
+        sc u = tr.challenge_scalar("u");
+        chal[CH_UJ] = u;
+        chal[CH_UJINV] = sc_invert(u);
+    }, trace);
+    if (rc) return rc;
+    sc ab[2];
+    if ((rc = d2h_sync(ctx, ab, ps->ab.p, 64))) return rc;
+    sc_tobytes(&out[(size_t)64 * lg], ab[0]);
+    sc_tobytes(&out[(size_t)64 * lg + 32], ab[1]);
     return 0;
 }
 

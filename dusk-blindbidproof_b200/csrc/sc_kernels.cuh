@@ -35,6 +35,8 @@ struct sc_batch {
     uint32_t gcols;                            // generator columns per family in the table (capacity x parties >= n): slot
                                                // layout [B, B_blinding, G[0..gcols), H[0..gcols)], slot length 2 + 2 gcols
     const uint32_t *row_ptr, *entries;         // circuit template CSR (shared by the batch)
+    const uint32_t *coef;                      // per entry: index into the proof's public value table of the term's coefficient
+                                               // (0 = one). nullptr when every variable coefficient is +-1 (the blind-bid circuit)
     uint32_t skip_ypow;                        // verifiers need only z^j and y^-i
     uint32_t n_long, long_rows[BBP_MAX_LONG];  // the few CSR rows long enough to be summed by the whole block (see flatten_long_rows)
     const uint32_t *const_j, *const_idx;       // constant terms (verifier)
@@ -156,12 +158,22 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_powers(sc_batch B) {
 }
 inline size_t k_powers_smem(uint32_t q, uint32_t n) { return (size_t)3 * (((q + 1 > n ? q + 1 : n) + 63) >> BBP_POW_LO_BITS) * sizeof(sc); }
 
+// one CSR entry: z^(j+1) times the term's coefficient (Montgomery form). Circuits recorded through the generic constraint
+// system carry arbitrary coefficients (pub[coef[e]], normal form); the blind-bid template has none (B.coef == nullptr).
+__device__ __forceinline__ sc flatten_term(const sc_batch &B, const sc *zpow, const sc *pub, uint32_t e, uint32_t v) {
+    sc zp = zpow[v & 0x7fffffffu];
+    if (B.coef) {
+        const uint32_t ci = B.coef[e];
+        if (ci) zp = mm(zp, sc_to_mont(pub[ci]));
+    }
+    return zp;
+}
 // signed sum of z powers over one CSR row (Montgomery form)
-__device__ __forceinline__ sc flatten_row(const sc_batch &B, const sc *zpow, uint32_t row) {
+__device__ __forceinline__ sc flatten_row(const sc_batch &B, const sc *zpow, uint32_t row, const sc *pub) {
     sc acc = sc_zero();
     for (uint32_t e = B.row_ptr[row]; e < B.row_ptr[row + 1]; e++) {
         uint32_t v = B.entries[e];
-        const sc &zp = zpow[v & 0x7fffffffu];
+        const sc zp = flatten_term(B, zpow, pub, e, v);
         acc = (v >> 31) ? sc_sub(acc, zp) : sc_add(acc, zp);
     }
     return acc;
@@ -170,13 +182,13 @@ __device__ __forceinline__ sc flatten_row(const sc_batch &B, const sc *zpow, uin
 // A wire that feeds many constraints has a long row (the blind-bid circuit has one a_O wire in 820 constraints and one in
 // 279, every other row has <= 19 entries); walked by one thread it would bound the whole block, so the rows listed in
 // B.long_rows are summed by all threads first and looked up afterwards.
-__device__ inline void flatten_long_rows(const sc_batch &B, const sc *zpow, sc *long_val, sc *smem) {
+__device__ inline void flatten_long_rows(const sc_batch &B, const sc *zpow, sc *long_val, sc *smem, const sc *pub) {
     for (uint32_t k = 0; k < B.n_long; k++) {
         const uint32_t row = B.long_rows[k];
         sc acc = sc_zero();
         for (uint32_t e = B.row_ptr[row] + threadIdx.x; e < B.row_ptr[row + 1]; e += BBP_SC_THREADS) {
             uint32_t v = B.entries[e];
-            const sc &zp = zpow[v & 0x7fffffffu];
+            const sc zp = flatten_term(B, zpow, pub, e, v);
             acc = (v >> 31) ? sc_sub(acc, zp) : sc_add(acc, zp);
         }
         acc = block_sum_sc(acc, smem);
@@ -184,10 +196,10 @@ __device__ inline void flatten_long_rows(const sc_batch &B, const sc *zpow, sc *
     }
     __syncthreads();
 }
-__device__ __forceinline__ sc flatten_row_l(const sc_batch &B, const sc *zpow, uint32_t row, const sc *long_val) {
+__device__ __forceinline__ sc flatten_row_l(const sc_batch &B, const sc *zpow, uint32_t row, const sc *long_val, const sc *pub) {
     for (uint32_t k = 0; k < B.n_long; k++)
         if (B.long_rows[k] == row) return long_val[k];
-    return flatten_row(B, zpow, row);
+    return flatten_row(B, zpow, row, pub);
 }
 
 // ---------------------------------------------------------------- prover: commitment scalar slots
@@ -270,10 +282,11 @@ __global__ void __launch_bounds__(BBP_SC_THREADS, 2) k_polys(sc_batch B) {
     const sc *zpow = B.zpow + (size_t)p * B.q, *ypow = B.ypow + (size_t)p * B.n, *yinv = B.yinvpow + (size_t)p * B.n;
     sc *poly = B.poly + (size_t)p * 6 * n1;
     __shared__ sc long_val[BBP_MAX_LONG];
-    flatten_long_rows(B, zpow, long_val, smem);
+    const sc *pub = B.pub ? B.pub + (size_t)p * B.n_pub : nullptr;   // coefficient table (generic circuits only)
+    flatten_long_rows(B, zpow, long_val, smem, pub);
     sc t1 = sc_zero(), t2 = t1, t3 = t1, t4 = t1, t5 = t1, t6 = t1;
     for (uint32_t i = t; i < n1; i += BBP_SC_THREADS) {
-        sc wL = flatten_row_l(B, zpow, i, long_val), wR = flatten_row_l(B, zpow, n1 + i, long_val), wO = flatten_row_l(B, zpow, 2 * n1 + i, long_val);
+        sc wL = flatten_row_l(B, zpow, i, long_val, pub), wR = flatten_row_l(B, zpow, n1 + i, long_val, pub), wO = flatten_row_l(B, zpow, 2 * n1 + i, long_val, pub);
         size_t k = (size_t)p * n1 + i;
         sc aL = sc_to_mont(B.aL[k]), aR = sc_to_mont(B.aR[k]), aO = sc_to_mont(B.aO[k]), sL = sc_to_mont(B.sL[k]), sR = sc_to_mont(B.sR[k]);
         sc l1 = sc_add(aL, mm(yinv[i], wR));
@@ -291,7 +304,7 @@ __global__ void __launch_bounds__(BBP_SC_THREADS, 2) k_polys(sc_batch B) {
     // t2_blinding = <wV, v_blinding>
     sc tb = sc_zero();
     for (uint32_t i = t; i < B.m; i += BBP_SC_THREADS) {
-        sc wV = flatten_row(B, zpow, 3 * n1 + i);
+        sc wV = flatten_row(B, zpow, 3 * n1 + i, pub);
         tb = sc_add(tb, mm(wV, sc_to_mont(B.vbl[(size_t)p * B.m + i])));
     }
     sc r[7] = {t1, t2, t3, t4, t5, t6, tb};
@@ -413,6 +426,16 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_ipp_round(sc_batch B, uint32
     }
 }
 
+// standalone InnerProductProof::create (bbp_ipp_create): a, b and the G / H factors arrive in normal form
+__global__ void __launch_bounds__(BBP_SC_THREADS) k_ipp_load(sc_batch B, const sc *__restrict__ a, const sc *__restrict__ b, const sc *__restrict__ gf,
+                                                             const sc *__restrict__ hf) {
+    const uint32_t p = blockIdx.x, n = B.n;
+    for (uint32_t k = threadIdx.x; k < n; k += BBP_SC_THREADS) {
+        const size_t o = (size_t)p * n + k;
+        B.a[o] = sc_to_mont(a[o]); B.b[o] = sc_to_mont(b[o]); B.sG[o] = sc_to_mont(gf[o]); B.sH[o] = sc_to_mont(hf[o]);
+    }
+}
+
 // Materialisation step of the hybrid IPP, run once when the vectors have shrunk to n_f = n >> j0: applies the pending
 // fold (challenge of round j0 - 1), then emits the compact scalars of F_G[k] = sum_e sG[k + n_f e] G[k + n_f e] (and F_H):
 // mat[fam][k][e], k < n_f, e < n / n_f — one MSM slot of n / n_f scalars per folded base — and resets the factors to 1.
@@ -521,7 +544,7 @@ __global__ void __launch_bounds__(BBP_SC_THREADS, 2) k_verify_scalars(sc_batch B
     }
     wc = block_sum_sc(wc, smem);
     sc delta = sc_zero();
-    flatten_long_rows(B, zpow, long_val, smem);
+    flatten_long_rows(B, zpow, long_val, smem, pub);
     sc *s_hi = s_hi_all;
     build_s_factors(s_lo, s_hi, uj, lg, lo_bits);
     // rho, a / b and uf are folded into four copies of the (small) high factor table, so that a column costs 8 products
@@ -543,7 +566,7 @@ __global__ void __launch_bounds__(BBP_SC_THREADS, 2) k_verify_scalars(sc_batch B
         const uint32_t lo = i & (n_lo - 1), hi = i >> lo_bits;   // reversed index n - 1 - i: (n_lo - 1 - lo, n_hi - 1 - hi)
         sc g, h;
         if (i < n1) {
-            sc wL = flatten_row_l(B, zpow, i, long_val), wR = flatten_row_l(B, zpow, n1 + i, long_val), wO = flatten_row_l(B, zpow, 2 * n1 + i, long_val);
+            sc wL = flatten_row_l(B, zpow, i, long_val, pub), wR = flatten_row_l(B, zpow, n1 + i, long_val, pub), wO = flatten_row_l(B, zpow, 2 * n1 + i, long_val, pub);
             const sc yi = yinv[i];
             sc ywR = mm(yi, wR);
             delta = sc_add(delta, mm(ywR, wL));
@@ -561,7 +584,7 @@ __global__ void __launch_bounds__(BBP_SC_THREADS, 2) k_verify_scalars(sc_batch B
     sc x2 = mm(xM, xM), rx2 = mm(rM, x2);
     if (!B.dyn_done) {
         for (uint32_t i = t; i < B.m; i += BBP_SC_THREADS) {
-            sc wV = flatten_row(B, zpow, 3 * n1 + i);
+            sc wV = flatten_row(B, zpow, 3 * n1 + i, pub);
             B.dyn_out[(size_t)p * B.dyn_stride + i] = sc_from_mont(mm(rhoM, mm(wV, rx2)));
         }
         // the transcript-dependent dynamic scalars (written unweighted by k_verify_transcript) take the batch weight here
@@ -604,6 +627,10 @@ __global__ void __launch_bounds__(64) k_dyn_weights(sc_batch B) {
                 sc zp = sc_mont_one();
                 for (uint32_t k = 0; k < 16; k++)
                     if ((ex >> k) & 1) zp = mm(zp, z2k[k]);
+                if (B.coef) {
+                    const uint32_t ci = B.coef[e];
+                    if (ci) zp = mm(zp, sc_to_mont(B.pub[(size_t)p * B.n_pub + ci]));
+                }
                 acc = (v >> 31) ? sc_sub(acc, zp) : sc_add(acc, zp);
             }
             const sc xM = sc_to_mont(ch[CH_X]);

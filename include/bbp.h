@@ -198,6 +198,59 @@ int bbp_pedersen_commit(bbp_ctx *ctx, const uint8_t *values, const uint8_t *blin
  * n_slots x slot_len x 32 B, column i multiplies generator i; out = n_slots x 32 B compressed */
 int bbp_msm_gens(bbp_ctx *ctx, const uint8_t *scalars, size_t slot_len, size_t n_slots, uint8_t *out);
 
+/* ---- L1: the bulletproofs surface under src/gadgets.rs and src/blindbid (third layer) ---------------------
+ * A Rust `ConstraintSystem` implementation over this ABI (rust/bbp/src/r1cs.rs) records what the gadgets do and hands the
+ * flattened circuit over; the prover / verifier are the ones the blind-bid entry points above run on. */
+
+/* merlin::Transcript — replaces `Transcript::new(b"BlindBidProofGadget")` at /root/reference/src/blindbid/mod.rs:37 and the
+ * `&mut Transcript` that Prover::new / Verifier::new borrow (src/blindbid/proof.rs:50, verify.rs:51). Labels and messages
+ * are (pointer, length) pairs. */
+typedef struct bbp_transcript bbp_transcript;
+bbp_transcript *bbp_transcript_new(const uint8_t *label, size_t label_len);
+bbp_transcript *bbp_transcript_clone(const bbp_transcript *t);
+void bbp_transcript_free(bbp_transcript *t);
+int bbp_transcript_append_message(bbp_transcript *t, const uint8_t *label, size_t label_len, const uint8_t *msg, size_t msg_len);
+int bbp_transcript_append_u64(bbp_transcript *t, const uint8_t *label, size_t label_len, uint64_t x);
+int bbp_transcript_challenge_bytes(bbp_transcript *t, const uint8_t *label, size_t label_len, uint8_t *out, size_t out_len);
+
+/* Variable kinds of bulletproofs::r1cs::Variable, packed as kind << 28 | index */
+#define BBP_VAR_COMMITTED 0u /* Variable::Committed(i): the i-th Prover::commit / Verifier::commit */
+#define BBP_VAR_MUL_LEFT 1u  /* Variable::MultiplierLeft(i) */
+#define BBP_VAR_MUL_RIGHT 2u /* Variable::MultiplierRight(i) */
+#define BBP_VAR_MUL_OUT 3u   /* Variable::MultiplierOutput(i) */
+#define BBP_VAR_ONE 4u       /* Variable::One() */
+
+/* The circuit as `ConstraintSystem::{multiply, constrain}` leave it (call sites /root/reference/src/gadgets.rs:30, 53-62,
+ * 80-85, 119-139): `multiply(l, r)` allocates multiplier i and contributes the two constraints l - L_i = 0, r - R_i = 0;
+ * `constrain(lc)` contributes lc = 0. Constraint j owns terms con_ptr[j] .. con_ptr[j + 1]; term t is
+ * (term_var[t], term_coeff[32 t .. 32 t + 32) canonical scalar). Constraint order = call order (it fixes the z powers). */
+typedef struct bbp_cs {
+    uint32_t n_multipliers;  /* >= 1 */
+    uint32_t n_commitments;  /* m */
+    uint32_t n_constraints;
+    const uint32_t *con_ptr; /* n_constraints + 1 entries, con_ptr[0] = 0 */
+    const uint32_t *term_var;
+    const uint8_t *term_coeff;
+} bbp_cs;
+
+/* Prover::prove — /root/reference/src/blindbid/proof.rs:50-88 (Prover::new, commit x m, gadgets, prove). `t` is the transcript
+ * as Transcript::new left it and is advanced exactly as the Rust prover advances its borrow. a_L / a_R / a_O: the
+ * multiplier assignments (n_multipliers x 32 B each), v / v_blinding: the committed values and their blindings (m x 32 B),
+ * rng_seed: the 32 external bytes of the RNG contract. V_out (m x 32 B, may be NULL) receives the commitments;
+ * proof_out / *proof_len: capacity in, length out (BBP_ERR_INPUT with the needed length if too small).
+ * Returns BBP_OK or an R1CSError mirror (BBP_ERR_INVALID_GENERATORS_LENGTH when the padded circuit exceeds the context). */
+int bbp_r1cs_prove(bbp_ctx *ctx, bbp_transcript *t, const bbp_cs *cs, const uint8_t *a_L, const uint8_t *a_R, const uint8_t *a_O, const uint8_t *v,
+                   const uint8_t *v_blinding, const uint8_t rng_seed[32], uint8_t *V_out, uint8_t *proof_out, size_t *proof_len);
+/* Verifier::verify — /root/reference/src/blindbid/verify.rs:51-88. V: the m commitments. BBP_OK = accept;
+ * BBP_ERR_FORMAT / BBP_ERR_VERIFICATION / BBP_ERR_INVALID_GENERATORS_LENGTH as the reference reports them. */
+int bbp_r1cs_verify(bbp_ctx *ctx, bbp_transcript *t, const bbp_cs *cs, const uint8_t *proof, size_t proof_len, const uint8_t *V,
+                    const uint8_t rng_seed[32]);
+/* InnerProductProof::create ([UP] bulletproofs inner_product_proof.rs; reached through Prover::prove, proof.rs:88) with
+ * Q = w * B, over the first n resident generators G, H (n a power of two <= gens_capacity). G_factors, H_factors, a, b:
+ * n x 32 B canonical scalars. Output: L_0 R_0 .. a b = 32 (2 lg n + 2) bytes. */
+int bbp_ipp_create(bbp_ctx *ctx, bbp_transcript *t, const uint8_t w[32], const uint8_t *G_factors, const uint8_t *H_factors, const uint8_t *a,
+                   const uint8_t *b, size_t n, uint8_t *proof_out, size_t *proof_len);
+
 /* ---- unit-test hooks (field / group primitives evaluated on the GPU; tests/ compares them with the oracle) ---------- */
 /* op: 0 mul, 1 add, 2 sub, 3 invert(a), 4 square(a), 5 neg(a); inputs are raw 256-bit limbs, output canonical */
 int bbp_test_fe(bbp_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, int op, uint8_t *out);

@@ -4,6 +4,8 @@
 //
 // Conventions: scalars are 32-byte little-endian, points are 32-byte compressed Ristretto unless a
 // function says "ext" (128 bytes = X,Y,Z,T as 4 canonical field encodings).
+#include <map>
+#include <string>
 #include "blindbid.h"
 #include "rangeproof.h"
 #include <chrono>
@@ -225,6 +227,96 @@ int orc_blindbid_verify(const uint8_t *proof, size_t proof_len, int versioned, c
         for (size_t i = 0; i < mega.size() && i < cap; i++) sc_tobytes(mega_scalars_out + 32 * i, mega[i]);
     }
     return rc;
+}
+
+// ---------------- generic R1CS (flattened circuits) and the standalone inner-product argument ----------------
+// The circuit as ConstraintSystem::{multiply, constrain} leave it (src/gadgets.rs:30,53): constraint j owns terms
+// con_ptr[j] .. con_ptr[j+1], term = (kind << 28 | index, coefficient). Feeds the oracle's generic prover / verifier
+// (r1cs.h) directly, so that the product's bbp_r1cs_prove / bbp_r1cs_verify can be compared on arbitrary circuits.
+static bool load_flat(std::vector<lincomb> &cons, size_t q, const uint32_t *con_ptr, const uint32_t *term_var, const uint8_t *term_coeff) {
+    cons.resize(q);
+    for (size_t j = 0; j < q; j++)
+        for (uint32_t t = con_ptr[j]; t < con_ptr[j + 1]; t++) {
+            uint32_t kind = term_var[t] >> 28, idx = term_var[t] & 0x0fffffffu;
+            if (kind > 4) return false;
+            sc c;
+            if (!sc_from_canonical(c, term_coeff + 32 * (size_t)t)) return false;
+            cons[j].terms.push_back({variable{(var_kind)kind, idx}, c});
+        }
+    return true;
+}
+static const bulletproof_gens &flat_gens(size_t cap) {
+    static std::map<size_t, bulletproof_gens *> cache;
+    auto it = cache.find(cap);
+    if (it == cache.end()) it = cache.emplace(cap, new bulletproof_gens(cap, 1)).first;
+    return *it->second;
+}
+int orc_r1cs_prove_flat(const uint8_t *label, size_t label_len, size_t gens_capacity, size_t n_mul, size_t m, size_t q, const uint32_t *con_ptr,
+                        const uint32_t *term_var, const uint8_t *term_coeff, const uint8_t *a_L, const uint8_t *a_R, const uint8_t *a_O,
+                        const uint8_t *v, const uint8_t *v_blinding, const uint8_t rng32[32], int versioned, uint8_t *V_out, uint8_t *proof_out,
+                        size_t *proof_len, uint8_t challenge_after[32]) {
+    std::string lbl((const char *)label, label_len);
+    transcript tr(lbl.c_str());
+    pedersen_gens pc;
+    prover P(pc, tr);
+    for (size_t i = 0; i < m; i++) {
+        bytes32 V;
+        P.commit(sc_load_reduced(v + 32 * i), sc_load_reduced(v_blinding + 32 * i), V);
+        memcpy(V_out + 32 * i, V.data(), 32);
+    }
+    for (size_t i = 0; i < n_mul; i++) {
+        P.a_L.push_back(sc_load_reduced(a_L + 32 * i)); P.a_R.push_back(sc_load_reduced(a_R + 32 * i)); P.a_O.push_back(sc_load_reduced(a_O + 32 * i));
+    }
+    if (!load_flat(P.constraints, q, con_ptr, term_var, term_coeff)) return R1CS_FORMAT_ERROR;
+    r1cs_proof out;
+    int rc = P.prove(flat_gens(gens_capacity), rng32, out);
+    if (rc != R1CS_OK) return rc;
+    std::vector<uint8_t> pb = r1cs_proof_to_bytes(out, versioned != 0);
+    if (pb.size() > *proof_len) return R1CS_FORMAT_ERROR;
+    memcpy(proof_out, pb.data(), pb.size());
+    *proof_len = pb.size();
+    if (challenge_after) tr.challenge_bytes("after", challenge_after, 32);   // pins the transcript state the proof leaves behind
+    return R1CS_OK;
+}
+int orc_r1cs_verify_flat(const uint8_t *label, size_t label_len, size_t gens_capacity, size_t n_mul, size_t m, size_t q, const uint32_t *con_ptr,
+                         const uint32_t *term_var, const uint8_t *term_coeff, const uint8_t *proof, size_t proof_len, int versioned,
+                         const uint8_t *V, const uint8_t rng32[32], uint8_t challenge_after[32]) {
+    std::string lbl((const char *)label, label_len);
+    transcript tr(lbl.c_str());
+    verifier ve(tr);
+    for (size_t i = 0; i < m; i++) {
+        bytes32 c;
+        memcpy(c.data(), V + 32 * i, 32);
+        ve.commit(c);
+    }
+    ve.num_vars = n_mul;
+    if (!load_flat(ve.constraints, q, con_ptr, term_var, term_coeff)) return R1CS_FORMAT_ERROR;
+    r1cs_proof p;
+    int rc = r1cs_proof_from_bytes(p, proof, proof_len, versioned != 0);
+    if (rc != R1CS_OK) return rc;
+    pedersen_gens pc;
+    rc = ve.verify(p, pc, flat_gens(gens_capacity), rng32);
+    if (rc == R1CS_OK && challenge_after) tr.challenge_bytes("after", challenge_after, 32);
+    return rc;
+}
+// InnerProductProof::create with Q = w * B over the first n generators of BulletproofGens::new(n, 1)
+int orc_ipp_create(const uint8_t *label, size_t label_len, const uint8_t w[32], const uint8_t *Gf, const uint8_t *Hf, const uint8_t *a,
+                   const uint8_t *b, size_t n, uint8_t *out, uint8_t challenge_after[32]) {
+    std::string lbl((const char *)label, label_len);
+    transcript tr(lbl.c_str());
+    pedersen_gens pc;
+    const bulletproof_gens &bp = flat_gens(n);
+    std::vector<sc> gf(n), hf(n), av(n), bv(n);
+    for (size_t i = 0; i < n; i++) {
+        gf[i] = sc_load_reduced(Gf + 32 * i); hf[i] = sc_load_reduced(Hf + 32 * i); av[i] = sc_load_reduced(a + 32 * i); bv[i] = sc_load_reduced(b + 32 * i);
+    }
+    std::vector<ge> G(bp.G[0].begin(), bp.G[0].begin() + n), H(bp.H[0].begin(), bp.H[0].begin() + n);
+    ge Q = ge_scalarmul(sc_load_reduced(w), pc.B);
+    ipp_proof pf = ipp_create(tr, Q, gf, hf, std::move(G), std::move(H), std::move(av), std::move(bv));
+    std::vector<uint8_t> bytes = ipp_to_bytes(pf);
+    memcpy(out, bytes.data(), bytes.size());
+    if (challenge_after) tr.challenge_bytes("after", challenge_after, 32);
+    return 0;
 }
 
 // ---------------- aggregated range proof (config 5) ----------------

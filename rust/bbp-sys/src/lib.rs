@@ -22,6 +22,28 @@ pub struct bbp_points {
 }
 
 #[repr(C)]
+pub struct bbp_transcript {
+    _private: [u8; 0],
+}
+
+pub const BBP_VAR_COMMITTED: u32 = 0;
+pub const BBP_VAR_MUL_LEFT: u32 = 1;
+pub const BBP_VAR_MUL_RIGHT: u32 = 2;
+pub const BBP_VAR_MUL_OUT: u32 = 3;
+pub const BBP_VAR_ONE: u32 = 4;
+
+/// Flattened constraint system (`include/bbp.h`: `bbp_cs`).
+#[repr(C)]
+pub struct bbp_cs {
+    pub n_multipliers: u32,
+    pub n_commitments: u32,
+    pub n_constraints: u32,
+    pub con_ptr: *const u32,
+    pub term_var: *const u32,
+    pub term_coeff: *const u8,
+}
+
+#[repr(C)]
 pub struct bbp_prove_req {
     pub d: *const u8,
     pub k: *const u8,
@@ -97,6 +119,16 @@ extern "C" {
     pub fn bbp_mimc_hash(left: *const u8, right: *const u8, out: *mut u8) -> c_int;
     pub fn bbp_mimc_constants(out: *mut u8) -> c_int;
     pub fn bbp_blindbid_circuit_shape(n_commitments: usize, n_toggles: usize, out: *mut usize) -> c_int;
+    // generic bulletproofs surface: transcript, R1CS prover / verifier, inner-product argument
+    pub fn bbp_transcript_new(label: *const u8, label_len: usize) -> *mut bbp_transcript;
+    pub fn bbp_transcript_clone(t: *const bbp_transcript) -> *mut bbp_transcript;
+    pub fn bbp_transcript_free(t: *mut bbp_transcript);
+    pub fn bbp_transcript_append_message(t: *mut bbp_transcript, label: *const u8, label_len: usize, msg: *const u8, msg_len: usize) -> c_int;
+    pub fn bbp_transcript_append_u64(t: *mut bbp_transcript, label: *const u8, label_len: usize, x: u64) -> c_int;
+    pub fn bbp_transcript_challenge_bytes(t: *mut bbp_transcript, label: *const u8, label_len: usize, out: *mut u8, out_len: usize) -> c_int;
+    pub fn bbp_r1cs_prove(ctx: *mut bbp_ctx, t: *mut bbp_transcript, cs: *const bbp_cs, a_l: *const u8, a_r: *const u8, a_o: *const u8, v: *const u8, v_blinding: *const u8, rng_seed: *const u8, v_out: *mut u8, proof_out: *mut u8, proof_len: *mut usize) -> c_int;
+    pub fn bbp_r1cs_verify(ctx: *mut bbp_ctx, t: *mut bbp_transcript, cs: *const bbp_cs, proof: *const u8, proof_len: usize, v: *const u8, rng_seed: *const u8) -> c_int;
+    pub fn bbp_ipp_create(ctx: *mut bbp_ctx, t: *mut bbp_transcript, w: *const u8, g_factors: *const u8, h_factors: *const u8, a: *const u8, b: *const u8, n: usize, proof_out: *mut u8, proof_len: *mut usize) -> c_int;
     // aggregated range proofs
     pub fn bbp_rangeproof_prove_multiple(ctx: *mut bbp_ctx, values: *const u64, blindings: *const u8, m: usize, nbits: usize, rng_seed: *const u8, proof_out: *mut u8, proof_len: *mut usize, commitments_out: *mut u8) -> c_int;
     pub fn bbp_rangeproof_verify_multiple(ctx: *mut bbp_ctx, proof: *const u8, proof_len: usize, commitments: *const u8, m: usize, nbits: usize, rng_seed: *const u8) -> c_int;

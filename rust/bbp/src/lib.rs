@@ -12,6 +12,8 @@ use curve25519_dalek::scalar::Scalar;
 use rand::RngCore;
 use std::ptr;
 
+pub mod r1cs;
+
 #[derive(Debug)]
 pub enum Error {
     InvalidGeneratorsLength,
@@ -23,7 +25,7 @@ pub enum Error {
     Other(i32),
 }
 
-fn check(rc: i32) -> Result<(), Error> {
+pub(crate) fn check(rc: i32) -> Result<(), Error> {
     match rc {
         sys::BBP_OK => Ok(()),
         sys::BBP_ERR_INVALID_GENERATORS_LENGTH => Err(Error::InvalidGeneratorsLength),
@@ -41,6 +43,12 @@ pub struct Context {
     raw: *mut sys::bbp_ctx,
 }
 unsafe impl Send for Context {}
+
+impl Context {
+    pub(crate) fn raw(&self) -> *mut sys::bbp_ctx {
+        self.raw
+    }
+}
 
 impl Drop for Context {
     fn drop(&mut self) {

@@ -30,3 +30,7 @@ def gpu_random_points(seed, n):
     test_gpu_primitives pins against the oracle and the libsodium golden vectors)."""
     stream = shake(b"bbp-bench-points" + seed.to_bytes(8, "little"), 64 * n)
     return backend().from_uniform_bytes(stream)
+
+
+def pkg():
+    return bbp_loader.load()

@@ -133,3 +133,45 @@ def blindbid_verify(proof, comm, tc, score, z_img, seed, pub_list, rng32, versio
     if want_mega:
         return rc, mega.raw[:32 * nm.value]
     return rc
+
+
+# ---- generic R1CS over flattened circuits, standalone inner-product argument (oracle side of tests/test_gpu_r1cs.py)
+def _flat_args(cs):
+    import array
+    con_ptr = (ctypes.c_uint32 * len(cs["con_ptr"]))(*cs["con_ptr"])
+    term_var = (ctypes.c_uint32 * max(1, len(cs["term_var"])))(*cs["term_var"])
+    return con_ptr, term_var
+
+
+def r1cs_prove_flat(label, gens_capacity, cs, a_L, a_R, a_O, v, v_blinding, rng32, versioned=1):
+    """cs = dict(n_mul, m, con_ptr[q+1], term_var[], term_coeff bytes). Returns (rc, proof, V, transcript challenge after)."""
+    con_ptr, term_var = _flat_args(cs)
+    m, q = cs["m"], len(cs["con_ptr"]) - 1
+    V = _buf(32 * max(1, m))
+    proof = _buf(4096)
+    plen = ctypes.c_size_t(4096)
+    after = _buf(32)
+    rc = lib().orc_r1cs_prove_flat(label, ctypes.c_size_t(len(label)), ctypes.c_size_t(gens_capacity), ctypes.c_size_t(cs["n_mul"]), ctypes.c_size_t(m),
+                                   ctypes.c_size_t(q), con_ptr, term_var, cs["term_coeff"], a_L, a_R, a_O, v, v_blinding, rng32, versioned, V, proof,
+                                   ctypes.byref(plen), after)
+    if rc != 0:
+        return rc, None, None, None
+    return 0, proof.raw[:plen.value], V.raw[:32 * m], after.raw
+
+
+def r1cs_verify_flat(label, gens_capacity, cs, proof, V, rng32, versioned=1):
+    con_ptr, term_var = _flat_args(cs)
+    m, q = cs["m"], len(cs["con_ptr"]) - 1
+    after = _buf(32)
+    rc = lib().orc_r1cs_verify_flat(label, ctypes.c_size_t(len(label)), ctypes.c_size_t(gens_capacity), ctypes.c_size_t(cs["n_mul"]), ctypes.c_size_t(m),
+                                    ctypes.c_size_t(q), con_ptr, term_var, cs["term_coeff"], proof, ctypes.c_size_t(len(proof)), versioned, V, rng32, after)
+    return rc, after.raw
+
+
+def ipp_create(label, w, Gf, Hf, a, b):
+    n = len(a) // 32
+    lg = n.bit_length() - 1
+    out = _buf(64 * lg + 64)
+    after = _buf(32)
+    lib().orc_ipp_create(label, ctypes.c_size_t(len(label)), w, Gf, Hf, a, b, ctypes.c_size_t(n), out, after)
+    return out.raw, after.raw

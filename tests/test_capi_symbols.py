@@ -62,3 +62,59 @@ def test_rust_sys_crate_matches_header():
     for must in ("bbp_init", "bbp_free", "bbp_blindbid_prove_batch", "bbp_blindbid_verify_each", "bbp_blindbid_verify_batch",
                  "bbp_msm_vartime", "bbp_msm_optional", "bbp_rangeproof_prove_multiple", "bbp_rangeproof_verify_multiple"):
         assert must in rust, must
+
+
+def _c_params(decl):
+    """parameter list of a C prototype -> coarse types ('ptr', 'u32', 'u64', 'usize', 'int')"""
+    inside = decl[decl.index("(") + 1:decl.rindex(")")]
+    out = []
+    for prm in [x.strip() for x in inside.split(",") if x.strip() and x.strip() != "void"]:
+        if "*" in prm or "[" in prm:
+            out.append("ptr")
+        elif "uint32_t" in prm:
+            out.append("u32")
+        elif "uint64_t" in prm:
+            out.append("u64")
+        elif "size_t" in prm:
+            out.append("usize")
+        elif re.search(r"\bint\b", prm):
+            out.append("int")
+        else:
+            out.append(prm)
+    return out
+
+
+def _rust_params(decl):
+    inside = decl[decl.index("(") + 1:decl.rindex(")")]
+    out = []
+    for prm in [x.strip() for x in inside.split(",") if x.strip()]:
+        ty = prm.split(":", 1)[1].strip()
+        out.append("ptr" if ty.startswith("*") else {"u32": "u32", "u64": "u64", "usize": "usize", "c_int": "int"}.get(ty, ty))
+    return out
+
+
+def test_rust_sys_crate_signatures_match_header():
+    """every Rust extern declaration has the header's parameter count, order and widths (pointer / u32 / u64 / usize /
+    int), and the same kind of return value — a swapped size_t / u32 or a missing argument fails here"""
+    hdr = re.sub(r"/\*.*?\*/", " ", open(os.path.join(ROOT, "include", "bbp.h")).read(), flags=re.S)
+    hdr = re.sub(r"^\s*#.*$", " ", hdr, flags=re.M)
+    c_decl = {}
+    for m in re.finditer(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(bbp_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        c_decl[m.group(2)] = (m.group(1).strip(), "(" + " ".join(m.group(3).split()) + ")")
+    src = open(os.path.join(ROOT, "rust", "bbp-sys", "src", "lib.rs")).read()
+    checked = 0
+    for m in re.finditer(r"pub fn (bbp_[a-z0-9_]+)\s*(\([^;]*?\))\s*(->\s*([^;]+))?;", src, flags=re.S):
+        name, params, ret = m.group(1), m.group(2), (m.group(4) or "").strip()
+        assert name in c_decl, name
+        c_ret, c_params = c_decl[name]
+        assert _rust_params(params) == _c_params(c_params), (name, _rust_params(params), _c_params(c_params))
+        want_ret = "ptr" if "*" in c_ret else ("" if c_ret.endswith("void") else {"int": "c_int", "uint64_t": "u64", "size_t": "usize"}[c_ret.split()[-1]])
+        got_ret = "ptr" if ret.startswith("*") else ret
+        assert got_ret == want_ret, (name, ret, c_ret)
+        checked += 1
+    assert checked >= 35
+    # the struct the generic surface passes by pointer has the header's field order
+    fields_c = re.search(r"typedef struct bbp_cs \{(.*?)\} bbp_cs;", hdr, flags=re.S).group(1)
+    names_c = re.findall(r"(\w+)\s*;", fields_c)
+    names_r = re.findall(r"pub (\w+):", re.search(r"pub struct bbp_cs \{(.*?)\}", src, flags=re.S).group(1))
+    assert names_c == names_r == ["n_multipliers", "n_commitments", "n_constraints", "con_ptr", "term_var", "term_coeff"]
