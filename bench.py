@@ -117,34 +117,74 @@ def oracle_lib():
     return orc.lib()
 
 
-def cpu_points_ext(lib, n, seed):
-    """n uniform points in extended coordinates via the oracle (test infrastructure)."""
-    st = shake(b"bbp-bench-points" + seed.to_bytes(8, "little"), 64 * n)
-    out = ctypes.create_string_buffer(128 * n)
-    one = ctypes.create_string_buffer(128)
-    for i in range(n):
-        lib.orc_ge_from_uniform_ext(one, st[64 * i:64 * i + 64])
-        out[128 * i:128 * i + 128] = one.raw
-    return out.raw
+BENCH_SEED = 1000        # rank r of the B200 arm uses BENCH_SEED + r; the CPU arm times rank 0's inputs
 
 
-def cpu_scalars(n, seed):
-    L = 2**252 + 27742317777372353535851937790883648493
-    st = shake(b"bbp-bench-scalars" + seed.to_bytes(8, "little"), 64 * n)
-    return b"".join((int.from_bytes(st[64 * i:64 * i + 64], "little") % L).to_bytes(32, "little") for i in range(n))
+def bench_scalars(n, seed):
+    """n uniform 252-bit scalars: the SHAKE256 stream with the top nibble of every 32-byte block cleared (both arms)"""
+    import numpy as np
+    raw = np.frombuffer(bytearray(shake(b"bbp-bench-scalars" + seed.to_bytes(8, "little"), 32 * n)), dtype=np.uint8).copy()
+    raw[31::32] &= 0x0f
+    return raw.tobytes()
 
 
-def cpu_msm_rate(n, threads, reps, base=1 << 14):
-    """points/s of the oracle Pippenger on `threads` host threads over n points (a `base`-point set tiled to n)."""
-    lib = oracle_lib()
-    pts = cpu_points_ext(lib, base, 0) * (n // base)
-    scs = cpu_scalars(n, 0)
+def bench_uniform_blocks(n, seed):
+    return shake(b"bbp-bench-points" + seed.to_bytes(8, "little"), 64 * n)
+
+
+def cpu_inputs(lib, n, seed, threads):
+    """the B200 arm's inputs for `seed`, built on the host: n DISTINCT uniform points (from_uniform_bytes of the same
+    SHAKE256 blocks, extended coordinates) and the same scalars"""
+    pts = ctypes.create_string_buffer(128 * n)
+    lib.orc_points_from_uniform_ext_mt(pts, bench_uniform_blocks(n, seed), ctypes.c_size_t(n), threads)
+    return pts.raw, bench_scalars(n, seed)
+
+
+def cpu_msm_rate(lib, pts, scs, n, threads, reps):
+    """(points/s, seconds, compressed result) of the oracle Pippenger on `threads` host threads, best of reps"""
     out = ctypes.create_string_buffer(32)
+    lib.orc_msm_ext.restype = ctypes.c_double
     best = None
     for _ in range(reps):
-        s = lib.orc_msm_ext(out, scs, pts, ctypes.c_size_t(n), threads)
-        best = s if best is None else min(best, s)
-    return n / best, best
+        sec = lib.orc_msm_ext(out, scs, pts, ctypes.c_size_t(n), threads)
+        best = sec if best is None else min(best, sec)
+    return n / best, best, out.raw
+
+
+def cpu_blindbid_rates(cores, L=8, rounds=1):
+    """oracle prove / verify on `cores` threads, one request per thread (ctypes releases the GIL); generators cached"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    bids = [orc.make_bid(5000 + i, L, i % L) for i in range(cores)]
+    bls = [orc.bid_blindings(5000 + i, L) for i in range(cores)]
+    orc.blindbid_prove(bids[0], bls[0], bytes(32))           # builds the oracle's generator cache
+    res = [None] * cores
+
+    def prove(i):
+        for _ in range(rounds):
+            res[i] = orc.blindbid_prove(bids[i], bls[i], bytes(32))
+
+    def verify(i):
+        _, p, c, tc = res[i]
+        for _ in range(rounds):
+            assert orc.blindbid_verify(p, c, tc, bids[i]["q"], bids[i]["z_img"], bids[i]["seed"], bids[i]["pub_list"], bytes(32)) == 0
+
+    out = {}
+    for name, fn in (("prove", prove), ("verify", verify)):
+        th = [threading.Thread(target=fn, args=(i,)) for i in range(cores)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        out[name] = cores * rounds / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    prove(0)
+    out["prove_1thread"] = rounds / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    verify(0)
+    out["verify_1thread"] = rounds / (time.perf_counter() - t0)
+    return out
 
 
 def run_reference(args, rank):
@@ -153,8 +193,8 @@ def run_reference(args, rank):
     cores = os.cpu_count() or 1
     n = 1 << LOG2_N
     lib = oracle_lib()
-    pts = cpu_points_ext(lib, 1 << 14, 0) * (n >> 14)
-    scs = cpu_scalars(n, 0)
+    lib.orc_msm_ext.restype = ctypes.c_double
+    pts, scs = cpu_inputs(lib, n, BENCH_SEED, cores)
     out = ctypes.create_string_buffer(32)
     for _ in range(args.warmup):
         lib.orc_msm_ext(out, scs[:32 << 16], pts[:128 << 16], ctypes.c_size_t(1 << 16), cores)
@@ -162,14 +202,22 @@ def run_reference(args, rank):
     for _ in range(args.steps):
         t += lib.orc_msm_ext(out, scs, pts, ctypes.c_size_t(n), cores)
     value = n * args.steps / t
-    sample = f"{args.steps} x one 2^{LOG2_N}-point Pippenger MSM (16384 distinct uniform points tiled), {cores} threads over point ranges"
+    sample = f"{args.steps} x one 2^{LOG2_N}-point Pippenger MSM over the B200 arm's rank-0 inputs (seed {BENCH_SEED}, 2^{LOG2_N} distinct uniform points), {cores} threads over point ranges"
+    bb = cpu_blindbid_rates(cores, 8, 2)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (GF(2^255-19), mod l)",
-        "data": "synthetic", "config": {"workload": f"ristretto255-msm-2^{LOG2_N}", "points": n},
+        "data": "synthetic", "config": {"workload": f"ristretto255-msm-2^{LOG2_N}", "points_per_gpu": n},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # the primary metric's two legs on the same host cores (the B200 arm reports them under the same keys)
+        "blindbid": {"list_len": 8,
+                     "prove": {"value": bb["prove"], "unit": "proofs/s", "cores": cores, "one_thread": bb["prove_1thread"]},
+                     "batch_verify": {"value": bb["verify"], "unit": "proofs/s", "cores": cores, "one_thread": bb["verify_1thread"],
+                                      "note": "per-request Verify::verify, one request per thread (the reference has no batch verification)"},
+                     "sample": f"2 rounds of {cores} independent requests, one per thread, oracle prover / verifier, generators cached (the reference rebuilds them per request: src/blindbid/mod.rs:36)"},
+        "msm_result": out.raw.hex(),
         "note": "CPU restatement (oracle/) of the reference's algorithm, not dalek AVX2: the Rust reference cannot be built in this image",
     }
     print(json.dumps(line), flush=True)
@@ -292,6 +340,52 @@ def run_blindbid(pkg, be, torch, dist, rank, world, n_prove=1024, n_verify=1024,
     verify_big_s = tmax((time.perf_counter() - t0) / reps)
     assert okb
     del prep_vbig
+    # BASELINE config 4 as stated: 1024 proofs IN TOTAL, sharded by proof range over the ranks (strong scaling)
+    n_total = 1024
+    lo, hi = pkg.sharding.shard_range(n_total, rank, world)
+    prep_strong = capi.PreparedVerify(items[lo:hi] if world > 1 else items[:n_total])
+    assert pkg.sharding.sharded_batch_verify(be, dist, prep_strong, batch_seed, d_partial, d_gather, d_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ok_s = pkg.sharding.sharded_batch_verify(be, dist, prep_strong, batch_seed, d_partial, d_gather, d_out)
+    torch.cuda.synchronize()
+    strong_s = tmax((time.perf_counter() - t0) / reps)
+    assert ok_s
+    # ... and with 1 / 16 corrupted proofs (single GPU: the failed combination is followed by the per-request pass that
+    # names the culprits; the sharded call reports the batch verdict only)
+    corrupted = {}
+    if world == 1:
+        for n_bad in (1, 16):
+            its = [dict(x) for x in items[:n_total]]
+            for k in range(n_bad):
+                pb = bytearray(its[(k * 61 + 7) % n_total]["proof"])
+                pb[-1 - 32 * (k % 2)] ^= 1                    # final a or b of the inner-product argument
+                its[(k * 61 + 7) % n_total]["proof"] = bytes(pb)
+            prep_bad = capi.PreparedVerify(its)
+            okb, stb = be.blindbid_verify_batch(prep_bad, batch_seed)
+            assert not okb and sum(1 for x in stb if x != 0) == n_bad
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                be.blindbid_verify_batch(prep_bad, batch_seed)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / reps
+            corrupted[f"{n_bad}_bad"] = {"value": n_total / dt, "unit": "proofs/s", "ms_per_batch": 1e3 * dt,
+                                         "note": "combined check fails -> one per-request pass; verdicts single out exactly the corrupted requests"}
+    # BASELINE config 3 sweep: list lengths x batch sizes, one GPU (rank 0's GPU at N > 1 is not re-measured)
+    sweep = []
+    if world == 1:
+        for Ls in (1, 8, 64, 202):
+            sb = [synth_bid(capi, 900000 + Ls * 1000 + i, Ls) for i in range(256)]
+            for Bs in (1, 16, 256):
+                pp = capi.PreparedProve(sb[:Bs])
+                be.blindbid_prove_prepared(pp)
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    be.blindbid_prove_prepared(pp)
+                dt = (time.perf_counter() - t0) / 2
+                assert all(o[0] == 0 for o in pp.results())
+                sweep.append({"L": Ls, "B": Bs, "ms": 1e3 * dt, "proofs_per_s": Bs / dt})
     # single-request latency through the one-shot entry points
     t0 = time.perf_counter()
     be.blindbid_prove(bids[0])
@@ -301,7 +395,11 @@ def run_blindbid(pkg, be, torch, dist, rank, world, n_prove=1024, n_verify=1024,
     lat_v = time.perf_counter() - t0
     proof_bytes = len(items[0]["proof"])
     return {
-        "list_len": L,
+        "list_len": L, "n_gpus": world,
+        "batch_verify_1024_total": {"value": n_total / strong_s, "unit": "proofs/s", "ms_per_batch": 1e3 * strong_s, "proofs_per_gpu": hi - lo if world > 1 else n_total,
+                                    "scaling": "strong", "note": "BASELINE configs[3]: 1024 proofs in total, proof-range shards, all-gather of 256 B partial sums"},
+        "batch_verify_1024_corrupted": corrupted,
+        "prove_config3_sweep": sweep,
         "prove": {"value": world * n_prove / prove_s, "unit": "proofs/s", "batch_per_gpu": n_prove, "ms_per_batch": 1e3 * prove_s,
                   "gpu_launches_per_batch": prove_launches, "parallelism": "replicas" if world > 1 else "1 GPU",
                   "call": "bbp_blindbid_prove_batch (host requests in, proof bytes out)"},
@@ -357,32 +455,74 @@ def run_rangeproof(pkg, torch, dist, rank, world, device, n_proofs=256, m=64, nb
             "range_statements_per_s_prove": world * n_proofs * m / prove_s}
 
 
-def cpu_blindbid_rates(cores, L=8):
-    """oracle prove / verify on `cores` threads, one request per thread (ctypes releases the GIL)"""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import orc
-    bids = [orc.make_bid(5000 + i, L, i % L) for i in range(cores)]
-    bls = [orc.bid_blindings(5000 + i, L) for i in range(cores)]
-    orc.blindbid_prove(bids[0], bls[0], bytes(32))           # builds the oracle's generator cache
-    res = [None] * cores
+# ------------------------------------------------------------------------------------------------ checks and leg rooflines
+def check_sharded_msm(pkg, be, torch, dist, rank, world, stream, n_chk=1 << 14):
+    """Outside every timer: a point-range sharded MSM of world x 2^14 points through the same sharded path, compared on rank
+    0 with (a) one MSM of its own over the concatenated slices and (b) the CPU oracle. Returns the verdict string."""
+    def inputs(r):
+        return (be.from_uniform_bytes(shake(b"bbp-shard-check-points" + r.to_bytes(4, "little"), 64 * n_chk)),
+                bench_scalars(n_chk, 77000 + r))
+    pts_c, scs = inputs(rank)
+    table = be.points_from_compressed(pts_c)[0] if hasattr(be, "points_from_compressed") else None
+    if table is None:
+        ext, _ = be.decompress(pts_c)
+        table = be.points_from_extended(ext)
+    d_s = torch.frombuffer(bytearray(scs), dtype=torch.uint8).cuda()
+    d_ext = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    d_g = torch.zeros(128 * world, dtype=torch.uint8, device="cuda")
+    d_o = torch.zeros(32, dtype=torch.uint8, device="cuda")
+    with torch.cuda.stream(stream):
+        pkg.sharding.sharded_msm(be, dist, d_s, n_chk, table, d_ext, d_g, d_o)
+    torch.cuda.synchronize()
+    got = bytes(d_o.cpu().numpy())
+    table.free()
+    verdict = "not checked on this rank"
+    if rank == 0:
+        allp, alls = b"", b""
+        for r in range(world):
+            p_r, s_r = inputs(r)
+            allp += p_r
+            alls += s_r
+        own = be.msm_optional(alls, allp)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import orc
+        want = orc.msm(alls, allp, threads=os.cpu_count() or 1)
+        assert got == own, "sharded MSM differs from the single-GPU MSM over the concatenated slices"
+        assert got == want, "sharded MSM differs from the CPU oracle"
+        verdict = "oracle-equal"
+    return {"verdict": verdict, "points": world * n_chk, "what": "sum_compress(all-gathered partials) == single-GPU MSM == CPU oracle, outside the timers"}
 
-    def prove(i):
-        res[i] = orc.blindbid_prove(bids[i], bls[i], bytes(32))
 
-    def verify(i):
-        _, p, c, tc = res[i]
-        assert orc.blindbid_verify(p, c, tc, bids[i]["q"], bids[i]["z_img"], bids[i]["seed"], bids[i]["pub_list"], bytes(32)) == 0
+def prove_alg_imads(L=8):
+    """Algorithmic bucket work of ONE blind-bid proof as this prover computes it, in SURVEY.md §8d units: mixed additions
+    (7M = 1008 IMAD-eq) = scalar terms x windows. Commitments A_I1 / A_O1 / S1: 5 n1 + 3 terms over the 24-window table;
+    IPP rounds 0..3 over the original generators: 2 (n + 1) terms x 24 windows each; materialisation of the folded bases:
+    2 n terms x 43 windows; rounds 4..10 over the folded bases: 2 (n_j + 1) terms x 51 windows; V / T commitments: 128
+    comb additions each. (The reference's folding form would cost 2 x 2047 x 382 k IMAD on top)"""
+    n1 = 16 * 90 + 3 * L + 2
+    n = 1 << (n1 - 1).bit_length()
+    adds = (5 * n1 + 3) * 24 + 4 * 2 * (n + 1) * 24 + 2 * n * 43 + sum(2 * ((128 >> k) + 1) for k in range(7)) * 51 + (4 + L + 5) * 128
+    return adds * 7 * M_IMAD
 
-    out = {}
-    for name, fn in (("prove", prove), ("verify", verify)):
-        th = [threading.Thread(target=fn, args=(i,)) for i in range(cores)]
-        t0 = time.perf_counter()
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-        out[name] = cores / (time.perf_counter() - t0)
-    return out
+
+def verify_alg_imads(batch, L=8):
+    """scalar assembly ~ 3 x 4098 mod-l products x 300 IMAD per proof, plus the proof's share of the
+    combined MSM: (34 + L + 3) own points and 4098 / batch static columns at W x 7M with the W of a 2^20-point MSM (16)."""
+    return 3 * 4098 * 300 + ((37 + L) + 4098.0 / batch) * 16 * 7 * M_IMAD
+
+
+def add_leg_rooflines(bb, peak_imad):
+    for key, alg in (("prove", prove_alg_imads(bb["list_len"])), ("prove_large_batch", prove_alg_imads(bb["list_len"]))):
+        if key in bb:
+            ach = alg * bb[key]["value"] / bb.get("n_gpus", 1)
+            bb[key]["roofline"] = {"bound": "int32-multiply", "achieved": ach / 1e12, "peak": peak_imad / 1e12, "unit": "T IMAD-eq/s", "frac": ach / peak_imad,
+                                   "imad_eq_per_proof": alg, "formula": "bench.py: prove_alg_imads (mixed additions of the no-fold prover x 1008)"}
+    for key in ("batch_verify", "batch_verify_large"):
+        if key in bb:
+            alg = verify_alg_imads(bb[key]["batch_per_gpu"], bb["list_len"])
+            ach = alg * bb[key]["value"] / bb.get("n_gpus", 1)
+            bb[key]["roofline"] = {"bound": "int32-multiply", "achieved": ach / 1e12, "peak": peak_imad / 1e12, "unit": "T IMAD-eq/s", "frac": ach / peak_imad,
+                                   "imad_eq_per_proof": alg, "formula": "bench.py: verify_alg_imads (SURVEY.md §8d: 3.7 M scalar assembly + MSM share)"}
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -404,18 +544,14 @@ def run_b200(args, rank, world):
 
     with torch.cuda.stream(stream):
         # synthetic inputs: every rank owns a different slice of the N*2^20-point problem
-        seed = 1000 + rank
-        uni = shake(b"bbp-bench-points" + seed.to_bytes(8, "little"), 64 * n)
-        pts_c = be.from_uniform_bytes(uni)
+        seed = BENCH_SEED + rank
+        pts_c = be.from_uniform_bytes(bench_uniform_blocks(n, seed))
         ext, valid = be.decompress(pts_c)
         assert all(valid)
         table = be.points_from_extended(ext)
-        # uniform scalars mod l: 64-byte blocks are reduced on the GPU by the MSM's own recoder, which accepts any
-        # 256-bit value; keep 253-bit uniform values by masking the SHAKE stream (statistically identical buckets)
-        raw = bytearray(shake(b"bbp-bench-scalars" + seed.to_bytes(8, "little"), 32 * n))
-        for i in range(31, 32 * n, 32):
-            raw[i] &= 0x0f
-        scalars = bytes(raw)
+        # uniform 252-bit scalars: the SHAKE stream with the top nibble cleared (statistically identical buckets to
+        # values reduced mod l); the CPU arm times exactly these inputs (rank 0's)
+        scalars = bench_scalars(n, seed)
         d_scalars = torch.frombuffer(bytearray(scalars), dtype=torch.uint8).cuda()
         # independent MSM steps alternate between the lanes of the context (bbp_lane: sibling contexts with their own stream,
         # engine and scratch), so the latency-bound tail of one step (bucket reduction, Horner chain) overlaps the next
@@ -456,7 +592,12 @@ def run_b200(args, rank, world):
             want = be.msm_points(scalars, table)
             assert all(bytes(o.cpu().numpy()) == want for o in d_outs), "device and host MSM entry points disagree"
 
+        sharded_check = None
+        if world > 1:
+            sharded_check = check_sharded_msm(pkg, be, torch, dist, rank, world, stream)
+
         peak_wide, peak_per_clk = be.int_peak()  # IMAD.WIDE.U32: per second (power-capped loop) and per SM clock, measured now
+        _, peak_pair_per_clk = be.int_peak_pairs()   # the same as mad.lo.cc / madc.hi pairs (ptxas fuses them: must agree)
         n_sm = torch.cuda.get_device_properties(local).multi_processor_count
         sampler = ClockSampler(local)
         sampler.start()
@@ -471,6 +612,22 @@ def run_b200(args, rank, world):
         barrier()
         ms = e0.elapsed_time(e1)
         launches = be.launch_count() - l0
+        # sustained: the same steps back to back for >= 2 s with the clock / power trace (the timed region above is a burst)
+        sustained = None
+        if args.sustained_s > 0:
+            sus_steps = max(args.steps, int(args.sustained_s / (ms / args.steps * 1e-3)))
+            sus = ClockSampler(local)
+            sus.start()
+            barrier()
+            e0.record(stream)
+            for i in range(sus_steps):
+                step(i)
+            join_lanes()
+            e1.record(stream)
+            barrier()
+            sus_ms = e0.elapsed_time(e1)
+            sus_clocks = sus.stop()
+            sustained = {"seconds": sus_ms * 1e-3, "steps": sus_steps, "ms_per_step": sus_ms / sus_steps, "clocks": sus_clocks}
         # per-stage timing of the same step (events between the MSM's kernels, on the same stream)
         be.set_profiling(1)
         stage = [0.0] * 7
@@ -523,17 +680,19 @@ def run_b200(args, rank, world):
         # the same call shape over COMPRESSED points (optional_multiscalar_mul: 32 B per point, decompressed on the GPU)
         e2e_c_s1, rc_ = e2e_time(call_cmp, 1)
         e2e_c_s, rc2 = e2e_time(call_cmp, EC)
+        gpu_result = bytes(d_out.cpu().numpy())
         if world == 1:
-            assert r == bytes(d_out.cpu().numpy()) and r2 == r and rc_ == r and rc2 == r
+            assert r == gpu_result and r2 == r and rc_ == r and rc2 == r
         clocks = sampler.stop()
         table.free()
         blindbid = None if args.no_blindbid else run_blindbid(pkg, be, torch, dist, rank, world)
         rangeproof = None if args.no_blindbid else run_rangeproof(pkg, torch, dist, rank, world, local)
 
-    t_ms = torch.tensor([ms, e2e_s * 1e3, e2e_c_s * 1e3, e2e_s1 * 1e3, e2e_c_s1 * 1e3], dtype=torch.float64, device="cuda")
+    t_ms = torch.tensor([ms, e2e_s * 1e3, e2e_c_s * 1e3, e2e_s1 * 1e3, e2e_c_s1 * 1e3, sustained["ms_per_step"] if sustained else 0.0],
+                        dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, e2e_c_ms, e2e_ms1, e2e_c_ms1 = t_ms.tolist()   # e2e_*: seconds -> ms PER CALL
+    ms, e2e_ms, e2e_c_ms, e2e_ms1, e2e_c_ms1, sus_ms_step = t_ms.tolist()   # e2e_*: seconds -> ms PER CALL
     if rank == 0:
         value = n * world * args.steps / (ms * 1e-3)
         e2e_value = n * world / (e2e_ms * 1e-3)
@@ -542,7 +701,7 @@ def run_b200(args, rank, world):
         # x the SM clock sampled while the MSM steps ran (the multiplier loop itself is power-capped to a lower clock, so
         # its per-second figure is below what a mixed kernel can reach and is reported separately as peak_sustained).
         sm_hz = 1e6 * (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0)
-        peak_imad = 2.0 * peak_per_clk * n_sm * sm_hz
+        peak_imad = 2.0 * max(peak_per_clk, peak_pair_per_clk) * n_sm * sm_hz
         achieved = accumulate_imads(n, plan["c"], plan["W"]) / (acc_ms * 1e-3)
         traffic = None
         try:
@@ -570,27 +729,45 @@ def run_b200(args, rank, world):
             "roofline": {"bound": "int32-multiply", "kernel": "k_accumulate", "achieved": achieved / 1e12, "peak": peak_imad / 1e12,
                          "unit": "T IMAD-eq/s", "frac": achieved / peak_imad, "traffic": traffic,
                          "kernel_ms": acc_ms, "peak_source": "bbp_int_peak measured in this run: IMAD.WIDE.U32 issue rate per SM clock (clock64) x 2 IMAD-eq x SMs x SM clock sampled during the MSM steps",
-                         "peak_per_clk_per_sm_wide": peak_per_clk, "peak_sustained": 2.0 * peak_wide / 1e12,
+                         "peak_per_clk_per_sm_wide": peak_per_clk, "peak_per_clk_per_sm_pairs": peak_pair_per_clk, "peak_sustained": 2.0 * peak_wide / 1e12,
                          "peak_sustained_note": "same loop in IMAD-eq per wall-clock second: a pure multiplier loop is power-capped to ~1.45 GHz",
                          "whole_msm_frac": msm_imads(n, plan["c"], plan["W"]) / (ms / args.steps * 1e-3) / peak_imad,
                          "hbm_gather_gbs": plan["W"] * n * 96 / (acc_ms * 1e-3) / 1e9},
             "stage_ms": dict(zip(["recode", "scan", "scatter", "accumulate", "reduce_level1", "reduce_merge", "combine"], [round(x, 4) for x in stage])),
             "clocks": clocks,
         }
+        if sustained is not None:
+            sustained["value"] = n * world / (sus_ms_step * 1e-3)
+            sustained["unit"] = UNIT
+            sustained["whole_msm_frac"] = msm_imads(n, plan["c"], plan["W"]) / (sus_ms_step * 1e-3) / \
+                (2.0 * max(peak_per_clk, peak_pair_per_clk) * n_sm * 1e6 * (sustained["clocks"].get("sm_mhz") or 1965.0))
+            line["sustained"] = sustained
+        if sharded_check is not None:
+            line["sharded_check"] = sharded_check
         if blindbid is not None:
+            add_leg_rooflines(blindbid, peak_imad)
             line["blindbid"] = blindbid
         if rangeproof is not None:
             line["rangeproof_m64"] = rangeproof
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            rate, secs = cpu_msm_rate(n, cores, 3)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"the same 2^{LOG2_N}-point MSM (16384 distinct uniform points tiled) through oracle/msm.h's Pippenger, "
-                                              f"{cores} threads over point ranges, best of 3, {secs:.2f} s each (~{3 * secs * cores:.0f} CPU-seconds)"}
+            lib = oracle_lib()
+            c_pts, c_scs = cpu_inputs(lib, n, BENCH_SEED, cores)
+            rate, secs, c_res = cpu_msm_rate(lib, c_pts, c_scs, n, cores, 3)
+            rate1, secs1, _ = cpu_msm_rate(lib, c_pts, c_scs, n, 1, 1)
+            assert c_res == gpu_result, "CPU port and GPU disagree on the benchmark MSM"
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "one_thread": rate1,
+                                    "result_equal_to_gpu": True,
+                                    "sample": f"the SAME inputs as the GPU arm (seed {BENCH_SEED}, 2^{LOG2_N} distinct uniform points) through oracle/msm.h's Pippenger: "
+                                              f"{cores} threads over point ranges, best of 3, {secs:.2f} s each; 1 thread once, {secs1:.2f} s"}
             if blindbid is not None:
                 r = cpu_blindbid_rates(cores)
-                line["cpu_baseline"]["blindbid"] = {"prove_proofs_per_s": r["prove"], "verify_proofs_per_s": r["verify"], "list_len": 8,
-                                                    "sample": f"{cores} independent requests, one per thread, oracle prover / verifier (generators cached)"}
+                line["cpu_baseline"]["blindbid"] = {"prove_proofs_per_s": r["prove"], "verify_proofs_per_s": r["verify"],
+                                                    "prove_proofs_per_s_1thread": r["prove_1thread"], "verify_proofs_per_s_1thread": r["verify_1thread"],
+                                                    "published_reference_s_per_op": 0.261,
+                                                    "list_len": 8,
+                                                    "sample": f"{cores} independent requests, one per thread, oracle prover / verifier (generators cached; the reference "
+                                                              "rebuilds them per request); published: 0.261 s per prove+verify on an i7-8559U (BASELINE.md)"}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -605,6 +782,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--msm-lanes", type=int, default=4, help="lanes the resident MSM steps alternate over (1 = no pipelining, max 8)")
     ap.add_argument("--e2e-callers", type=int, default=2, help="concurrent caller threads of the host-buffer MSM leg (one lane each)")
+    ap.add_argument("--sustained-s", type=float, default=2.0, help="length of the sustained MSM sub-leg in seconds (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-blindbid", action="store_true", help="skip the blind-bid prove / batch-verify legs")
     args = ap.parse_args()

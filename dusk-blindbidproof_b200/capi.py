@@ -192,6 +192,12 @@ class Backend:
         _chk(lib().bbp_int_peak(self.ctx, ctypes.byref(v), ctypes.byref(c)), "bbp_int_peak")
         return v.value, c.value
 
+    def int_peak_pairs(self):
+        """the same as mad.lo.cc / madc.hi pairs: (pairs per second sustained, pairs per SM clock per SM)"""
+        v, c = ctypes.c_double(), ctypes.c_double()
+        _chk(lib().bbp_int_peak_pairs(self.ctx, ctypes.byref(v), ctypes.byref(c)), "bbp_int_peak_pairs")
+        return v.value, c.value
+
     def msm_vartime(self, scalars, points_ext):
         out = _out(32)
         _chk(lib().bbp_msm_vartime(self.ctx, scalars, points_ext, _sz(len(scalars) // 32), out), "bbp_msm_vartime")

@@ -95,8 +95,8 @@ int bbp_msm_plan(size_t n, uint32_t out[4]) {
     out[0] = sh.c; out[1] = sh.W; out[2] = sh.S; out[3] = sh.B;
     return BBP_OK;
 }
-int bbp_int_peak(bbp_ctx *ctx, double *wide_mads_per_s, double *wide_mads_per_clk_per_sm) {
-    if (!ctx || !wide_mads_per_s) return BBP_ERR_INPUT;
+static int int_peak_run(bbp_ctx *ctx, int pairs, double *per_s, double *per_clk_per_sm) {
+    if (!ctx || !per_s) return BBP_ERR_INPUT;
     cudaSetDevice(ctx->device);
     cudaDeviceProp prop;
     BBP_CUDA_OK(cudaGetDeviceProperties(&prop, ctx->device));
@@ -112,7 +112,8 @@ int bbp_int_peak(bbp_ctx *ctx, double *wide_mads_per_s, double *wide_mads_per_cl
     double best_per_clk = 0;
     for (int rep = 0; rep < 6; rep++) {
         cudaEventRecord(e0, ctx->stream);
-        k_int_peak<<<blocks, threads, 0, ctx->stream>>>(d, rep + 1, d_cyc);
+        if (pairs) k_int_peak_pair<<<blocks, threads, 0, ctx->stream>>>(d, rep + 1, d_cyc);
+        else k_int_peak<<<blocks, threads, 0, ctx->stream>>>(d, rep + 1, d_cyc);
         cudaEventRecord(e1, ctx->stream);
         if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); cudaFree(d_cyc); return BBP_ERR_CUDA; }
         float ms;
@@ -128,10 +129,12 @@ int bbp_int_peak(bbp_ctx *ctx, double *wide_mads_per_s, double *wide_mads_per_cl
     }
     ctx->launches += 6;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d); cudaFree(d_cyc);
-    *wide_mads_per_s = (double)blocks * threads * (double)BBP_PEAK_ITERS * BBP_PEAK_ILP / (best * 1e-3);
-    if (wide_mads_per_clk_per_sm) *wide_mads_per_clk_per_sm = best_per_clk;
+    *per_s = (double)blocks * threads * (double)BBP_PEAK_ITERS * BBP_PEAK_ILP / (best * 1e-3);
+    if (per_clk_per_sm) *per_clk_per_sm = best_per_clk;
     return BBP_OK;
 }
+int bbp_int_peak(bbp_ctx *ctx, double *wide_mads_per_s, double *wide_mads_per_clk_per_sm) { return int_peak_run(ctx, 0, wide_mads_per_s, wide_mads_per_clk_per_sm); }
+int bbp_int_peak_pairs(bbp_ctx *ctx, double *pairs_per_s, double *pairs_per_clk_per_sm) { return int_peak_run(ctx, 1, pairs_per_s, pairs_per_clk_per_sm); }
 
 // ---------------------------------------------------------------- base tables
 int bbp_points_from_compressed(bbp_ctx *ctx, const uint8_t *points, size_t n, bbp_points **out, int *all_valid) {

@@ -147,6 +147,32 @@ __global__ void __launch_bounds__(1024, 2) k_int_peak(uint32_t *out, uint32_t se
     if (threadIdx.x == 0) cycles[blockIdx.x] = (unsigned long long)(c1 - c0);
 }
 
+// the same measurement on the instruction pair the field multiplier is actually written in: mad.lo.cc.u32 / madc.hi.u32 on
+// a 64-bit accumulator (ptxas fuses the pair into one IMAD.WIDE.U32; if it ever did not, this variant would show it)
+__global__ void __launch_bounds__(1024, 2) k_int_peak_pair(uint32_t *out, uint32_t seed, unsigned long long *cycles) {
+    uint32_t lo[BBP_PEAK_ILP], hi[BBP_PEAK_ILP];
+    uint32_t x = seed + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < BBP_PEAK_ILP; i++) { lo[i] = x + i; hi[i] = seed * 3 + blockIdx.x + 7 * i; }
+    __syncthreads();
+    long long c0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < BBP_PEAK_ITERS; it += 4) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int i = 0; i < BBP_PEAK_ILP; i++)
+                asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(lo[i]), "+r"(hi[i]) : "r"(lo[(i + 1) % BBP_PEAK_ILP] | 1u), "r"(x));
+        }
+    }
+    long long c1 = clock64();
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < BBP_PEAK_ILP; i++) r ^= lo[i] ^ hi[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = (unsigned long long)(c1 - c0);
+}
+
 // sum of n (<= 1024) extended points, compressed: the local tail of a sharded MSM after the all-gather of the
 // per-GPU partial sums. One warp: lane sums, then a shuffle-free tree through shared memory.
 __global__ void __launch_bounds__(32) k_sum_compress(const uint8_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ out) {

@@ -69,6 +69,8 @@ int bbp_msm_plan(size_t n, uint32_t out[4]);
  * per second (a pure multiplier loop runs power-capped at ~1.45 GHz) and the rate per SM clock (from clock64), which is the
  * architectural issue rate and does not depend on the clock the chip happened to hold */
 int bbp_int_peak(bbp_ctx *ctx, double *wide_mads_per_s, double *wide_mads_per_clk_per_sm);
+/* the same loop written as the mad.lo.cc.u32 / madc.hi.u32 pairs of the field multiplier (one pair = one 32x32+64 product) */
+int bbp_int_peak_pairs(bbp_ctx *ctx, double *pairs_per_s, double *pairs_per_clk_per_sm);
 
 /* ---- generators (bulletproofs PedersenGens / BulletproofGens, used at src/blindbid/mod.rs:35-36) ------------------- */
 /* compressed B, B_blinding */

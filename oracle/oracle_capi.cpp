@@ -5,6 +5,7 @@
 // Conventions: scalars are 32-byte little-endian, points are 32-byte compressed Ristretto unless a
 // function says "ext" (128 bytes = X,Y,Z,T as 4 canonical field encodings).
 #include <map>
+#include <thread>
 #include <string>
 #include "blindbid.h"
 #include "rangeproof.h"
@@ -138,6 +139,18 @@ double orc_msm_ext(uint8_t out[32], const uint8_t *scalars, const uint8_t *point
     auto t1 = std::chrono::steady_clock::now();
     ge_compress(out, r);
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// n uniform points from n 64-byte blocks (from_uniform_bytes), extended coordinates, on `threads` host threads: builds the
+// CPU arm's inputs of bench.py (the same SHAKE256 stream the GPU arm maps to the group with its own codec)
+void orc_points_from_uniform_ext_mt(uint8_t *out, const uint8_t *in, size_t n, int threads) {
+    if (threads < 1) threads = 1;
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++)
+        th.emplace_back([=] {
+            for (size_t i = n * t / threads; i < n * (t + 1) / threads; i++) ge_to_ext(out + 128 * i, ge_from_uniform_bytes(in + 64 * i));
+        });
+    for (auto &x : th) x.join();
 }
 
 // ---------------- generators / constants ----------------
