@@ -536,7 +536,9 @@ def run_b200(args, rank, world):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a bounded collective timeout: a rank that falls out of step ends the run in minutes, not in the default ten
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     be = pkg.Backend(device=local, gens_capacity=2048, party_capacity=1)
     stream = torch.cuda.ExternalStream(be.stream(), device=local)
     n = 1 << LOG2_N
@@ -616,6 +618,10 @@ def run_b200(args, rank, world):
         sustained = None
         if args.sustained_s > 0:
             sus_steps = max(args.steps, int(args.sustained_s / (ms / args.steps * 1e-3)))
+            if dist is not None:   # every rank must run the same number of steps (each step is a collective)
+                t_steps = torch.tensor([sus_steps], dtype=torch.int64, device="cuda")
+                dist.all_reduce(t_steps, op=dist.ReduceOp.MIN)
+                sus_steps = int(t_steps.item())
             sus = ClockSampler(local)
             sus.start()
             barrier()

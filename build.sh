@@ -9,4 +9,9 @@ if [ ! -f $OUT ] || [ -n "$(find $SRC include -newer $OUT -type f | head -1)" ];
   $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xptxas -v -Xcompiler -fPIC -shared \
     -o $OUT $SRC/bbp_capi.cu 2> build_ptxas.log || { tail -50 build_ptxas.log; exit 1; }
 fi
+# the Unix-socket server shell (plain C++ over the C ABI)
+SRV=dusk-blindbidproof_b200/bbp-blindbid-server
+if [ ! -f $SRV ] || [ $SRC/server/bbp_server.cpp -nt $SRV ] || [ $OUT -nt $SRV ]; then
+  g++ -O2 -std=c++17 -pthread -o $SRV $SRC/server/bbp_server.cpp -Ldusk-blindbidproof_b200 -lbbp_b200 -Wl,-rpath,'$ORIGIN'
+fi
 make -s -C oracle liboracle.so

@@ -323,6 +323,75 @@ def _generic_methods():
     return dict(r1cs_prove=r1cs_prove, r1cs_verify=r1cs_verify, ipp_create=ipp_create)
 
 
+# ---------------------------------------------------------------------------------------------- outer boundary: TLV codec
+def wire_prove_request(scalars7, pub_list, toggle):
+    """the request frame of opcode 1 (d, k, y, y_inv, q, z_img, seed as 7 x 32 bytes)"""
+    out = _out(64 + 40 * (8 + len(pub_list) // 32))
+    n = ctypes.c_size_t(len(out))
+    _chk(lib().bbp_wire_encode_prove_request(scalars7, pub_list, _sz(len(pub_list) // 32), ctypes.c_uint64(toggle), out, ctypes.byref(n)), "bbp_wire_encode_prove_request")
+    return out.raw[:n.value]
+
+
+def wire_proof_blob(proof, commitments, t_c):
+    out = _out(len(proof) + 40 * (4 + (len(commitments) + len(t_c)) // 32))
+    n = ctypes.c_size_t(len(out))
+    _chk(lib().bbp_wire_encode_proof_blob(proof, _sz(len(proof)), commitments, _sz(len(commitments) // 32), t_c, _sz(len(t_c) // 32), out, ctypes.byref(n)),
+         "bbp_wire_encode_proof_blob")
+    return out.raw[:n.value]
+
+
+def wire_decode_proof_blob(blob):
+    proof, comm, tc = _out(len(blob)), _out(len(blob)), _out(len(blob))
+    pl, nc, nt = ctypes.c_size_t(len(blob)), ctypes.c_size_t(len(blob) // 32), ctypes.c_size_t(len(blob) // 32)
+    _chk(lib().bbp_wire_decode_proof_blob(blob, _sz(len(blob)), proof, ctypes.byref(pl), comm, ctypes.byref(nc), tc, ctypes.byref(nt)), "bbp_wire_decode_proof_blob")
+    return proof.raw[:pl.value], comm.raw[:32 * nc.value], tc.raw[:32 * nt.value]
+
+
+def wire_verify_request(blob, score, z_img, seed, pub_list):
+    out = _out(len(blob) + 200 + 40 * (len(pub_list) // 32))
+    n = ctypes.c_size_t(len(out))
+    _chk(lib().bbp_wire_encode_verify_request(blob, _sz(len(blob)), score, z_img, seed, pub_list, _sz(len(pub_list) // 32), out, ctypes.byref(n)),
+         "bbp_wire_encode_verify_request")
+    return out.raw[:n.value]
+
+
+def wire_frame(buf):
+    """(status, header length, payload length): status 1 complete, 0 incomplete, < 0 malformed"""
+    h, p = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    st = lib().bbp_wire_frame_len(buf, _sz(len(buf)), ctypes.byref(h), ctypes.byref(p))
+    return st, h.value, p.value
+
+
+def wire_parse(payload):
+    """(opcode or status, handle); the handle must go to wire_free"""
+    h = ctypes.c_void_p()
+    op = lib().bbp_wire_parse(payload, _sz(len(payload)), ctypes.byref(h))
+    return op, h
+
+
+def wire_free(h):
+    lib().bbp_wire_request_free.restype = None
+    lib().bbp_wire_request_free(h)
+
+
+def wire_execute(backend, handles, seed32=None):
+    """bbp_wire_execute over parsed requests; returns the list of reply frames (None = nothing is written)"""
+    n = len(handles)
+    arr = (ctypes.c_void_p * n)(*[h.value for h in handles])
+    replies = (ctypes.c_void_p * n)()
+    lens = (ctypes.c_size_t * n)()
+    _chk(lib().bbp_wire_execute(backend.ctx, _sz(n), arr, seed32, replies, lens), "bbp_wire_execute")
+    out = []
+    lib().bbp_wire_reply_free.restype = None
+    for i in range(n):
+        if replies[i]:
+            out.append(ctypes.string_at(replies[i], lens[i]))
+            lib().bbp_wire_reply_free(ctypes.c_void_p(replies[i]))
+        else:
+            out.append(None)
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- blind-bid entry points
 class ProveReq(ctypes.Structure):
     _fields_ = [(n, ctypes.c_char_p) for n in ("d", "k", "y", "y_inv", "q", "z_img", "seed", "pub_list")] + [

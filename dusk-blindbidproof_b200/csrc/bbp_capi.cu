@@ -7,6 +7,7 @@
 #include "ctx.cuh"
 #include "msm.cuh"
 #include "protocol.cuh"
+#include "wire.h"
 #include "rangeproof.cuh"
 
 using namespace bbp;
@@ -336,6 +337,175 @@ int bbp_from_uniform_bytes(bbp_ctx *ctx, const uint8_t *bytes64, size_t n, uint8
     ctx->launches += 2;
     BBP_CUDA_OK(cudaMemcpyAsync(out_compressed, ctx->d_out + n * 128, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
     BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return BBP_OK;
+}
+
+// ---------------------------------------------------------------- outer boundary: TLV codec + batched execution
+struct bbp_wire_request {
+    wire::request R;
+    bool malformed = false;   // opcode 2 with a body the reference's readers reject: answered with 0x00 (futures/main.rs:95-101)
+};
+
+int bbp_wire_frame_len(const uint8_t *buf, size_t len, size_t *hdr_len, size_t *payload_len) {
+    if (!buf || !hdr_len || !payload_len) return BBP_ERR_INPUT;
+    size_t hdr;
+    uint64_t pl;
+    if (len == 0) return 0;
+    if (!wire::tlv_header(buf, len, &hdr, &pl)) {
+        int w = buf[0];
+        return (w == 1 || w == 2 || w == 4 || w == 8) ? 0 : BBP_ERR_FORMAT;   // known tag, header not complete yet: need more bytes
+    }
+    if (pl > (1ull << 30)) return BBP_ERR_FORMAT;   // a request is a few kilobytes; refuse absurd lengths before buffering them
+    *hdr_len = hdr;
+    *payload_len = (size_t)pl;
+    return len - hdr >= pl ? 1 : 0;
+}
+
+int bbp_wire_parse(const uint8_t *payload, size_t len, bbp_wire_request **out) {
+    if (!payload || !out) return BBP_ERR_INPUT;
+    *out = nullptr;
+    bbp_wire_request *w = new (std::nothrow) bbp_wire_request();
+    if (!w) return BBP_ERR_INPUT;
+    int op = wire::parse_request(payload, len, w->R);
+    if (op < 0 && len >= 1 && payload[0] == wire::OP_VERIFY) { w->malformed = true; op = wire::OP_VERIFY; }
+    if (op <= 0) { delete w; return op < 0 ? BBP_ERR_FORMAT : 0; }
+    *out = w;
+    return op;
+}
+void bbp_wire_request_free(bbp_wire_request *r) { delete r; }
+void bbp_wire_reply_free(uint8_t *reply) { free(reply); }
+
+// n x len random bytes: SHAKE256(seed || LE64(index)) when a seed is given (tests), the OS generator otherwise
+static bool wire_entropy(const uint8_t *seed32, uint64_t index, uint8_t *out, size_t len) {
+    if (seed32) {
+        keccak_sponge sp = shake256_new();
+        sp.absorb(seed32, 32);
+        uint8_t ix[8];
+        for (int i = 0; i < 8; i++) ix[i] = (uint8_t)(index >> (8 * i));
+        sp.absorb(ix, 8);
+        sp.squeeze(out, len);
+        return true;
+    }
+    FILE *f = fopen("/dev/urandom", "rb");
+    if (!f) return false;
+    bool ok = fread(out, 1, len, f) == len;
+    fclose(f);
+    return ok;
+}
+
+int bbp_wire_execute(bbp_ctx *ctx, size_t n, bbp_wire_request *const *reqs, const uint8_t *seed32, uint8_t **replies, size_t *reply_lens) {
+    if (!ctx || !reqs || !replies || !reply_lens || n == 0) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    std::vector<prove_job> pj;
+    std::vector<verify_job> vj;
+    std::vector<size_t> pmap, vmap;
+    for (size_t i = 0; i < n; i++) {
+        replies[i] = nullptr;
+        reply_lens[i] = 0;
+        if (!reqs[i]) continue;
+        const wire::request &R = reqs[i]->R;
+        const size_t L = R.pub_list.size() / 32;
+        if (R.opcode == wire::OP_PROVE) {
+            prove_job J;
+            // serde rejects non-canonical scalars (proof.rs:100-106); an empty list panics in the reference (gadgets.rs:103)
+            if (L == 0 || !sc_from_canonical(J.d, R.scalars[0]) || !sc_from_canonical(J.k, R.scalars[1]) || !sc_from_canonical(J.y, R.scalars[2]) ||
+                !sc_from_canonical(J.y_inv, R.scalars[3]) || !sc_from_canonical(J.q, R.scalars[4]) || !sc_from_canonical(J.z_img, R.scalars[5]) ||
+                !sc_from_canonical(J.seed, R.scalars[6]))
+                continue;
+            J.pub_list.resize(L);
+            for (size_t k = 0; k < L; k++) J.pub_list[k] = sc_from_bits(R.pub_list.data() + 32 * k);   // Bid::from (bid.rs:20-29)
+            J.toggle = R.toggle;
+            // the randomness the reference takes from thread_rng (proof.rs:53,64 and TranscriptRngBuilder::finalize)
+            std::vector<uint8_t> rnd(64 * (4 + L) + 32);
+            if (!wire_entropy(seed32, i, rnd.data(), rnd.size())) return BBP_ERR_INPUT;
+            J.blindings.resize(4 + L);
+            for (size_t k = 0; k < 4 + L; k++) J.blindings[k] = sc_from_wide(rnd.data() + 64 * k);   // Scalar::random
+            memcpy(J.rng_seed, rnd.data() + 64 * (4 + L), 32);
+            pmap.push_back(i);
+            pj.push_back(std::move(J));
+        } else if (R.opcode == wire::OP_VERIFY) {
+            verify_job J;
+            bool ok = !reqs[i]->malformed && sc_from_canonical(J.score, R.scalars[0]) && sc_from_canonical(J.z_img, R.scalars[1]) &&
+                      sc_from_canonical(J.seed, R.scalars[2]);
+            if (!ok) {
+                wire::bytes rep = wire::verify_reply(false);
+                replies[i] = (uint8_t *)malloc(rep.size());
+                if (!replies[i]) return BBP_ERR_INPUT;
+                memcpy(replies[i], rep.data(), rep.size());
+                reply_lens[i] = rep.size();
+                continue;
+            }
+            J.proof = R.proof; J.commitments = R.commitments; J.t_c = R.t_c;
+            J.pub_list.resize(L);
+            for (size_t k = 0; k < L; k++) J.pub_list[k] = sc_from_bits(R.pub_list.data() + 32 * k);   // verify.rs:112-116
+            if (!wire_entropy(seed32, i, J.rng_seed, 32)) return BBP_ERR_INPUT;
+            vmap.push_back(i);
+            vj.push_back(std::move(J));
+        }
+    }
+    if (!pj.empty()) {
+        int rc = prove_batch(ctx, pj);
+        if (rc) return rc;
+        for (size_t k = 0; k < pj.size(); k++) {
+            const prove_job &J = pj[k];
+            if (J.status) continue;   // prove-side error: nothing is written (futures/main.rs:15-25, 83-86)
+            wire::bytes rep = wire::prove_reply(J.proof.data(), J.proof.size(), J.commitments.data(), J.commitments.size() / 32, J.t_c.data(), J.t_c.size() / 32);
+            replies[pmap[k]] = (uint8_t *)malloc(rep.size());
+            if (!replies[pmap[k]]) return BBP_ERR_INPUT;
+            memcpy(replies[pmap[k]], rep.data(), rep.size());
+            reply_lens[pmap[k]] = rep.size();
+        }
+    }
+    if (!vj.empty()) {
+        uint8_t batch_seed[32];
+        if (!wire_entropy(seed32, ~0ull, batch_seed, 32)) return BBP_ERR_INPUT;
+        int ok = 0;
+        // one random linear combination for all pending verifications; on failure the library re-checks per request, so
+        // every client gets the verdict Verify::verify would have given it
+        int rc = verify_batch(ctx, vj, batch_seed, &ok, false, nullptr);
+        if (rc) return rc;
+        for (size_t k = 0; k < vj.size(); k++) {
+            wire::bytes rep = wire::verify_reply(vj[k].status == 0);
+            replies[vmap[k]] = (uint8_t *)malloc(rep.size());
+            if (!replies[vmap[k]]) return BBP_ERR_INPUT;
+            memcpy(replies[vmap[k]], rep.data(), rep.size());
+            reply_lens[vmap[k]] = rep.size();
+        }
+    }
+    return BBP_OK;
+}
+
+static int wire_copy_out(const wire::bytes &b, uint8_t *out, size_t *out_len) {
+    const size_t cap = *out_len;
+    *out_len = b.size();
+    if (cap < b.size()) return BBP_ERR_INPUT;
+    memcpy(out, b.data(), b.size());
+    return BBP_OK;
+}
+int bbp_wire_encode_prove_request(const uint8_t *scalars7, const uint8_t *pub_list, size_t L, uint64_t toggle, uint8_t *out, size_t *out_len) {
+    if (!scalars7 || (!pub_list && L) || !out || !out_len) return BBP_ERR_INPUT;
+    uint8_t sc7[7][32];
+    memcpy(sc7, scalars7, sizeof sc7);
+    return wire_copy_out(wire::prove_request(sc7, pub_list, L, toggle), out, out_len);
+}
+int bbp_wire_encode_verify_request(const uint8_t *proof_blob, size_t blob_len, const uint8_t score[32], const uint8_t z_img[32], const uint8_t seed[32],
+                                   const uint8_t *pub_list, size_t L, uint8_t *out, size_t *out_len) {
+    if (!proof_blob || !score || !z_img || !seed || (!pub_list && L) || !out || !out_len) return BBP_ERR_INPUT;
+    return wire_copy_out(wire::verify_request(proof_blob, blob_len, score, z_img, seed, pub_list, L), out, out_len);
+}
+int bbp_wire_encode_proof_blob(const uint8_t *proof, size_t proof_len, const uint8_t *commitments, size_t nc, const uint8_t *t_c, size_t nt, uint8_t *out,
+                               size_t *out_len) {
+    if (!proof || (!commitments && nc) || (!t_c && nt) || !out || !out_len) return BBP_ERR_INPUT;
+    return wire_copy_out(wire::proof_blob(proof, proof_len, commitments, nc, t_c, nt), out, out_len);
+}
+int bbp_wire_decode_proof_blob(const uint8_t *blob, size_t blob_len, uint8_t *proof_out, size_t *proof_len, uint8_t *commitments_out, size_t *nc,
+                               uint8_t *t_c_out, size_t *nt) {
+    if (!blob || !proof_out || !proof_len || !commitments_out || !nc || !t_c_out || !nt) return BBP_ERR_INPUT;
+    wire::bytes p, c, t;
+    if (!wire::parse_proof_blob(blob, blob_len, p, c, t)) return BBP_ERR_FORMAT;
+    if (p.size() > *proof_len || c.size() / 32 > *nc || t.size() / 32 > *nt) { *proof_len = p.size(); *nc = c.size() / 32; *nt = t.size() / 32; return BBP_ERR_INPUT; }
+    memcpy(proof_out, p.data(), p.size()); memcpy(commitments_out, c.data(), c.size()); memcpy(t_c_out, t.data(), t.size());
+    *proof_len = p.size(); *nc = c.size() / 32; *nt = t.size() / 32;
     return BBP_OK;
 }
 

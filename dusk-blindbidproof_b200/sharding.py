@@ -41,17 +41,40 @@ def sharded_msm(be, dist, d_scalars, n_local, table, d_ext, d_gather, d_out):
     be.sum_compress_device(d_gather.data_ptr(), world, d_out.data_ptr())
 
 
+_PART = 256            # two extended points (static | dynamic partial sums)
+_ROW = _PART + 16      # + this rank's local flag, padded to a 16-byte multiple
+
+
 def sharded_batch_verify(be, dist, items, batch_seed, d_partial, d_gather, d_out):
     """Proof-range sharded batch verification: items = this rank's requests. Returns True iff the combined mega-check
-    over ALL ranks' requests is the identity (every rank returns the same verdict)."""
+    over ALL ranks' requests is the identity AND every rank accepted all of its requests locally (every rank returns the
+    same verdict). One collective and one device -> host read per call: the rank's local flag (requests refused on the
+    host, or with a point that does not decompress, never enter a partial sum, so the identity test alone would accept
+    them) travels in the same all-gather row as its 256-byte partial sums."""
     world = 1 if dist is None else dist.get_world_size()
     if world == 1:
         ok, _ = be.blindbid_verify_batch(items, batch_seed)
         return ok
-    local_ok, _ = be.blindbid_verify_batch_partial(items, batch_seed, d_partial.data_ptr())
-    gather_partials(dist, d_partial, d_gather)
-    be.sum_compress_device(d_gather.data_ptr(), 2 * world, d_out.data_ptr())
-    return combine_verdicts(dist, local_ok, d_out)
+    buf = getattr(be, "_shard_bufs", None)
+    if buf is None or buf[0].device != d_out.device or buf[1].numel() != _ROW * world:
+        dev = d_out.device
+        buf = (torch.zeros(_ROW, dtype=torch.uint8, device=dev), torch.zeros(_ROW * world, dtype=torch.uint8, device=dev),
+               torch.zeros(_PART * world, dtype=torch.uint8, device=dev), torch.zeros(32 + world, dtype=torch.uint8, device=dev),
+               torch.zeros(32 + world, dtype=torch.uint8).pin_memory() if dev.type == "cuda" else torch.zeros(32 + world, dtype=torch.uint8))
+        be._shard_bufs = buf
+    row, rows, parts, res, h_res = buf
+    local_ok, _ = be.blindbid_verify_batch_partial(items, batch_seed, row.data_ptr())
+    row[_PART] = 1 if local_ok else 0
+    dist.all_gather_into_tensor(rows, row)
+    rv = rows.view(world, _ROW)
+    parts.view(world, _PART).copy_(rv[:, :_PART])
+    be.sum_compress_device(parts.data_ptr(), 2 * world, res.data_ptr())
+    res[32:].copy_(rv[:, _PART])
+    h_res.copy_(res, non_blocking=True)
+    if res.is_cuda:
+        torch.cuda.current_stream().synchronize()
+    out = bytes(h_res.numpy())
+    return out[:32] == bytes(32) and all(out[32:])
 
 
 def combine_verdicts(dist, local_ok, d_out):

@@ -253,6 +253,36 @@ int bbp_r1cs_verify(bbp_ctx *ctx, bbp_transcript *t, const bbp_cs *cs, const uin
 int bbp_ipp_create(bbp_ctx *ctx, bbp_transcript *t, const uint8_t w[32], const uint8_t *G_factors, const uint8_t *H_factors, const uint8_t *a,
                    const uint8_t *b, size_t n, uint8_t *proof_out, size_t *proof_len);
 
+/* ---- outer (process) boundary: TLV request / reply codec and batched execution ---------------------------------------------
+ * The reference serves one TLV frame per Unix-socket connection, payload byte 0 = opcode (/root/reference/src/futures/main.rs:64-110):
+ * opcode 1 = prove (body: /root/reference/src/blindbid/proof.rs:97-114, reply :118-143), opcode 2 = verify (body:
+ * /root/reference/src/blindbid/verify.rs:91-128, reply: one byte). csrc/server/bbp_server.cpp is the socket shell over these
+ * entry points; it coalesces concurrent requests into one bbp_wire_execute call. The byte-level framing belongs to the crate
+ * dusk-tlv @ 5be856b, whose source is absent: csrc/wire.h implements the recollected form and marks it UNPINNED. */
+typedef struct bbp_wire_request bbp_wire_request;
+/* is buf[0..len) a complete frame? 1 = yes (*hdr_len + *payload_len bytes), 0 = more bytes needed, BBP_ERR_FORMAT = bad tag / absurd length */
+int bbp_wire_frame_len(const uint8_t *buf, size_t len, size_t *hdr_len, size_t *payload_len);
+/* parses the PAYLOAD of a request frame. Returns the opcode (1 prove, 2 verify; a verify body the reference's readers would
+ * reject still yields a request, answered 0x00 as at futures/main.rs:95-101), 0 for an unknown opcode and BBP_ERR_FORMAT for a
+ * malformed prove body (both: the reference writes nothing). *out must be released with bbp_wire_request_free. */
+int bbp_wire_parse(const uint8_t *payload, size_t len, bbp_wire_request **out);
+void bbp_wire_request_free(bbp_wire_request *r);
+/* Executes n parsed requests at once: every prove request in ONE bbp_blindbid_prove_batch, every verify request in ONE
+ * bbp_blindbid_verify_batch (per-request verdicts). replies[i] = the complete reply frame (release with bbp_wire_reply_free), or
+ * NULL when the reference would write nothing (prove-side error). seed32 = NULL: blindings and RNG seeds come from the OS, as
+ * the reference takes them from thread_rng; non-NULL: derived from it (reproducible tests). */
+int bbp_wire_execute(bbp_ctx *ctx, size_t n, bbp_wire_request *const *reqs, const uint8_t *seed32, uint8_t **replies, size_t *reply_lens);
+void bbp_wire_reply_free(uint8_t *reply);
+/* client-side encoders: the frames a client (the Go node) sends, and the proof blob inside a verify request / prove reply.
+ * out_len: capacity in, length out (BBP_ERR_INPUT with the needed length if too small). scalars7 = d,k,y,y_inv,q,z_img,seed. */
+int bbp_wire_encode_prove_request(const uint8_t *scalars7, const uint8_t *pub_list, size_t L, uint64_t toggle, uint8_t *out, size_t *out_len);
+int bbp_wire_encode_verify_request(const uint8_t *proof_blob, size_t blob_len, const uint8_t score[32], const uint8_t z_img[32], const uint8_t seed[32],
+                                   const uint8_t *pub_list, size_t L, uint8_t *out, size_t *out_len);
+int bbp_wire_encode_proof_blob(const uint8_t *proof, size_t proof_len, const uint8_t *commitments, size_t nc, const uint8_t *t_c, size_t nt, uint8_t *out,
+                               size_t *out_len);
+int bbp_wire_decode_proof_blob(const uint8_t *blob, size_t blob_len, uint8_t *proof_out, size_t *proof_len, uint8_t *commitments_out, size_t *nc,
+                               uint8_t *t_c_out, size_t *nt);
+
 /* ---- unit-test hooks (field / group primitives evaluated on the GPU; tests/ compares them with the oracle) ---------- */
 /* op: 0 mul, 1 add, 2 sub, 3 invert(a), 4 square(a), 5 neg(a); inputs are raw 256-bit limbs, output canonical */
 int bbp_test_fe(bbp_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, int op, uint8_t *out);

@@ -22,6 +22,10 @@ pub struct bbp_points {
 }
 
 #[repr(C)]
+pub struct bbp_wire_request {
+    _private: [u8; 0],
+}
+#[repr(C)]
 pub struct bbp_transcript {
     _private: [u8; 0],
 }
@@ -129,6 +133,12 @@ extern "C" {
     pub fn bbp_r1cs_prove(ctx: *mut bbp_ctx, t: *mut bbp_transcript, cs: *const bbp_cs, a_l: *const u8, a_r: *const u8, a_o: *const u8, v: *const u8, v_blinding: *const u8, rng_seed: *const u8, v_out: *mut u8, proof_out: *mut u8, proof_len: *mut usize) -> c_int;
     pub fn bbp_r1cs_verify(ctx: *mut bbp_ctx, t: *mut bbp_transcript, cs: *const bbp_cs, proof: *const u8, proof_len: usize, v: *const u8, rng_seed: *const u8) -> c_int;
     pub fn bbp_ipp_create(ctx: *mut bbp_ctx, t: *mut bbp_transcript, w: *const u8, g_factors: *const u8, h_factors: *const u8, a: *const u8, b: *const u8, n: usize, proof_out: *mut u8, proof_len: *mut usize) -> c_int;
+    // outer boundary: TLV codec + batched execution
+    pub fn bbp_wire_frame_len(buf: *const u8, len: usize, hdr_len: *mut usize, payload_len: *mut usize) -> c_int;
+    pub fn bbp_wire_parse(payload: *const u8, len: usize, out: *mut *mut bbp_wire_request) -> c_int;
+    pub fn bbp_wire_request_free(r: *mut bbp_wire_request);
+    pub fn bbp_wire_execute(ctx: *mut bbp_ctx, n: usize, reqs: *const *mut bbp_wire_request, seed32: *const u8, replies: *mut *mut u8, reply_lens: *mut usize) -> c_int;
+    pub fn bbp_wire_reply_free(reply: *mut u8);
     // aggregated range proofs
     pub fn bbp_rangeproof_prove_multiple(ctx: *mut bbp_ctx, values: *const u64, blindings: *const u8, m: usize, nbits: usize, rng_seed: *const u8, proof_out: *mut u8, proof_len: *mut usize, commitments_out: *mut u8) -> c_int;
     pub fn bbp_rangeproof_verify_multiple(ctx: *mut bbp_ctx, proof: *const u8, proof_len: usize, commitments: *const u8, m: usize, nbits: usize, rng_seed: *const u8) -> c_int;

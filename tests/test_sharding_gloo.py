@@ -77,3 +77,79 @@ def test_gather_partials_world2_gloo():
         assert p.exitcode == 0
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] and r[2] for r in res)
+
+
+class _FakeBackend:
+    """stands in for the GPU backend on CPU tensors: the partial sums come from the oracle, everything else (row packing,
+    the single all-gather, flag handling, the verdict) is the product's sharding.sharded_batch_verify"""
+
+    def __init__(self, orc, partial_points, local_ok):
+        self.orc, self.partial, self.local_ok = orc, partial_points, local_ok
+
+    def blindbid_verify_batch_partial(self, items, seed, ptr):
+        ctypes.memmove(ptr, self.partial, 256)
+        return self.local_ok, []
+
+    def sum_compress_device(self, ptr, n, out_ptr):
+        pts = ctypes.string_at(ptr, 128 * n)
+        comp = ctypes.create_string_buffer(32)
+        cs = []
+        for i in range(n):
+            self.orc.lib().orc_ge_compress_ext(comp, pts[128 * i:128 * i + 128])
+            cs.append(comp.raw)
+        total = self.orc.msm(b"".join((1).to_bytes(32, "little") for _ in cs), b"".join(cs), algo=0)
+        ctypes.memmove(out_ptr, total, 32)
+
+
+def _verify_worker(rank, world, port, case, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bbp_loader
+    import orc
+    sh = bbp_loader.load().sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # rank 0 contributes (P, Q), rank 1 contributes (-P, -Q) [case "identity"] or (-P, Q) [case "nonzero"]
+    P, Q = orc.random_points(3, 2)[:32], orc.random_points(3, 2)[32:]
+    neg = (orc.L_ORDER - 1).to_bytes(32, "little")
+    ext = ctypes.create_string_buffer(128)
+
+    def ext_of(scalar, point):
+        c = orc.msm(scalar, point, algo=0)
+        assert orc.lib().orc_ge_decompress_ext(ext, c) == 1
+        return ext.raw
+
+    one = (1).to_bytes(32, "little")
+    if rank == 0:
+        partial = ext_of(one, P) + ext_of(one, Q)
+    else:
+        partial = ext_of(neg, P) + ext_of(one if case == "nonzero" else neg, Q)
+    local_ok = not (case == "flag" and rank == 1)
+    be = _FakeBackend(orc, partial, local_ok)
+    d_out = torch.zeros(32, dtype=torch.uint8)
+    verdict = sh.sharded_batch_verify(be, dist, [], bytes(32), None, None, d_out)
+    q.put((rank, verdict))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case,want", [("identity", True), ("nonzero", False), ("flag", False)])
+def test_sharded_batch_verify_world2_gloo(case, want):
+    """the sharded verdict over gloo, world size 2: partial sums that cancel -> accept; that do not -> reject; that cancel
+    while one rank refused a request locally -> reject (the flag rides in the same all-gather row)"""
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_verify_worker, args=(r, world, port, case, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [v for _, v in sorted(res)] == [want, want]
