@@ -394,6 +394,8 @@ def run_blindbid(pkg, be, torch, dist, rank, world, n_prove=1024, n_verify=1024,
     assert be.blindbid_verify(items[0]) == 0
     lat_v = time.perf_counter() - t0
     proof_bytes = len(items[0]["proof"])
+    torch.cuda.synchronize()
+    be.__dict__.pop("_shard_bufs", None)      # cached device tensors of the sharded call: released while the stream exists
     return {
         "list_len": L, "n_gpus": world,
         "batch_verify_1024_total": {"value": n_total / strong_s, "unit": "proofs/s", "ms_per_batch": 1e3 * strong_s, "proofs_per_gpu": hi - lo if world > 1 else n_total,
@@ -448,11 +450,59 @@ def run_rangeproof(pkg, torch, dist, rank, world, device, n_proofs=256, m=64, nb
         vst = be.rangeproof_verify_batch(proofs, Vs, m, nbits, vseeds)
     verify_s = tmax((time.perf_counter() - t0) / reps)
     assert vst == [0] * n_proofs
-    be.close()
-    return {"parties": m, "bits": nbits, "ipp_len": m * nbits, "proof_bytes": len(proofs[0]), "batch_per_gpu": n_proofs,
-            "prove": {"value": world * n_proofs / prove_s, "unit": "aggregated proofs/s", "ms_per_batch": 1e3 * prove_s},
-            "verify": {"value": world * n_proofs / verify_s, "unit": "aggregated proofs/s", "ms_per_batch": 1e3 * verify_s},
-            "range_statements_per_s_prove": world * n_proofs * m / prove_s}
+    sharded = None
+    if world > 1:
+        # BASELINE config 5 "stressing the 2^12-point IPP at N GPUs" (SURVEY.md §8e row 4): all ranks prove the SAME batch
+        # cooperatively — rank r owns the generator columns i = r (mod N); one all-gather of the partial L / R sums per round
+        n_sh = 64
+        s_vals = [[int.from_bytes(shake(b"rp-sh-v" + bytes([k & 255, i]), 8), "little") for i in range(m)] for k in range(n_sh)]
+        s_bls = b"".join(le32(int.from_bytes(shake(b"rp-sh-bl" + bytes([k & 255, i]), 64), "little") % LO) for k in range(n_sh) for i in range(m))
+        s_seeds = b"".join(hashlib.sha256(b"rpsh%d" % k).digest() for k in range(n_sh))
+        st, plain, _ = be.rangeproof_prove_batch(s_vals, s_bls, m, nbits, s_seeds)
+        t0 = time.perf_counter()
+        be.rangeproof_prove_batch(s_vals, s_bls, m, nbits, s_seeds)
+        plain_s = tmax(time.perf_counter() - t0)
+        stats = pkg.sharding.enable_sharded_ipp(be, dist)
+        with torch.cuda.stream(torch.cuda.ExternalStream(be.stream())):
+            st, shp, _ = be.rangeproof_prove_batch(s_vals, s_bls, m, nbits, s_seeds)
+            assert shp == plain, "sharded inner-product argument changed the proof bytes"
+            dist.barrier()
+            stats["allgathers"] = 0
+            t0 = time.perf_counter()
+            be.rangeproof_prove_batch(s_vals, s_bls, m, nbits, s_seeds)
+            torch.cuda.synchronize()
+            sh_s = tmax(time.perf_counter() - t0)
+            # the bare collective at the size one round exchanges (2 x 128 B per proof per rank), stream-ordered, device-timed
+            buf_s = torch.zeros(2 * n_sh * 128, dtype=torch.uint8, device="cuda")
+            buf_r = torch.zeros(2 * n_sh * 128 * world, dtype=torch.uint8, device="cuda")
+            for _ in range(5):
+                dist.all_gather_into_tensor(buf_r, buf_s)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(50):
+                dist.all_gather_into_tensor(buf_r, buf_s)
+            e1.record()
+            torch.cuda.synchronize()
+            ag_us = tmax(e0.elapsed_time(e1) * 1e3 / 50)
+        pkg.sharding.disable_sharded_ipp(be)
+        sharded = {"value": n_sh / sh_s, "unit": "aggregated proofs/s (one batch of %d proved cooperatively by all %d GPUs)" % (n_sh, world),
+                   "ms_per_batch": 1e3 * sh_s, "same_batch_on_one_gpu_ms": 1e3 * plain_s, "rounds": stats["allgathers"],
+                   "bytes_per_rank_per_round": stats["bytes_per_rank"], "allgather_us_per_round": ag_us,
+                   "proof_bytes_equal_to_single_gpu": True,
+                   "note": "strided column partition i mod N of G / H; a, b, the factors and c_L / c_R are replicated (128 KB per proof); "
+                           "latency-bound by construction: replicas (the `prove` figure above) are the throughput configuration"}
+    if world == 1:
+        be.close()
+    # at N > 1 the context stays alive until the process exits: NCCL has seen its stream (the sharded leg's all-gathers are
+    # ordered on it) and still holds events on it when the process group is torn down
+    out = {"parties": m, "bits": nbits, "ipp_len": m * nbits, "proof_bytes": len(proofs[0]), "batch_per_gpu": n_proofs,
+           "prove": {"value": world * n_proofs / prove_s, "unit": "aggregated proofs/s", "ms_per_batch": 1e3 * prove_s},
+           "verify": {"value": world * n_proofs / verify_s, "unit": "aggregated proofs/s", "ms_per_batch": 1e3 * verify_s},
+           "range_statements_per_s_prove": world * n_proofs * m / prove_s}
+    if sharded is not None:
+        out["sharded_ipp"] = sharded
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ checks and leg rooflines

@@ -81,6 +81,10 @@ class Backend:
         self.device = device
 
     def close(self):
+        # device tensors cached on this object (sharding.py) were used on the context's stream: they must be released while
+        # that stream still exists (torch records an event on every stream a tensor was used on when it frees it)
+        for k in ("_shard_bufs", "_ipp_views", "_ipp_allgather"):
+            self.__dict__.pop(k, None)
         if self.ctx:
             if getattr(self, "_owner", None) is None:   # lanes belong to the context that created them
                 lib().bbp_free(self.ctx)
@@ -191,6 +195,10 @@ class Backend:
         v, c = ctypes.c_double(), ctypes.c_double()
         _chk(lib().bbp_int_peak(self.ctx, ctypes.byref(v), ctypes.byref(c)), "bbp_int_peak")
         return v.value, c.value
+
+    def set_ipp_shard(self, rank, world, allgather=None, emulate=0):
+        """bbp_set_ipp_shard: allgather = a ctypes callback (sharding.enable_sharded_ipp builds it over torch.distributed)"""
+        _chk(lib().bbp_set_ipp_shard(self.ctx, ctypes.c_uint32(rank), ctypes.c_uint32(world), allgather, None, int(emulate)), "bbp_set_ipp_shard")
 
     def int_peak_pairs(self):
         """the same as mad.lo.cc / madc.hi pairs: (pairs per second sustained, pairs per SM clock per SM)"""

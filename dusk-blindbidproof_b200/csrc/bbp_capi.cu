@@ -509,6 +509,13 @@ int bbp_wire_decode_proof_blob(const uint8_t *blob, size_t blob_len, uint8_t *pr
     return BBP_OK;
 }
 
+int bbp_set_ipp_shard(bbp_ctx *ctx, uint32_t rank, uint32_t world, bbp_allgather_fn allgather, void *user, int emulate) {
+    if (!ctx || world == 0 || rank >= world || (world > 1 && !allgather) || emulate < 0 || emulate > 64 || world > 64) return BBP_ERR_INPUT;
+    ctx->shard_rank = rank; ctx->shard_world = world; ctx->shard_allgather = allgather; ctx->shard_user = user;
+    ctx->shard_emulate = world == 1 ? emulate : 0;
+    return BBP_OK;
+}
+
 // ---------------------------------------------------------------- generic bulletproofs surface
 struct bbp_transcript {
     merlin_transcript tr;

@@ -173,6 +173,15 @@ __global__ void __launch_bounds__(1024, 2) k_int_peak_pair(uint32_t *out, uint32
     if (threadIdx.x == 0) cycles[blockIdx.x] = (unsigned long long)(c1 - c0);
 }
 
+// sharded IPP: slot s of every rank's partial sums (rank-major, n_slots x 128 B per rank) -> one compressed point per slot
+__global__ void __launch_bounds__(64) k_sum_ranks_compress(const uint8_t *__restrict__ in, uint32_t n_slots, uint32_t world, uint32_t *__restrict__ out) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    ge acc = ge_load(in + 128 * (size_t)s);
+    for (uint32_t r = 1; r < world; r++) acc = ge_add(acc, ge_load(in + 128 * ((size_t)r * n_slots + s)));
+    ge_compress_words(out + 8 * (size_t)s, acc);
+}
+
 // sum of n (<= 1024) extended points, compressed: the local tail of a sharded MSM after the all-gather of the
 // per-GPU partial sums. One warp: lane sums, then a shuffle-free tree through shared memory.
 __global__ void __launch_bounds__(32) k_sum_compress(const uint8_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ out) {

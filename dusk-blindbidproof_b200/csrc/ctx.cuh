@@ -37,6 +37,14 @@ struct bbp_ctx {
     // sibling contexts on the same device (own streams, scratch and tables) that large batched prove calls are split
     // over, one host thread each, so that one lane's host phases and round trips hide behind the others' kernels
     std::vector<bbp_ctx *> lanes;
+    // sharded inner-product argument: this context owns the generator columns i = shard_rank (mod
+    // shard_world); after every round's MSM the per-rank partial sums are exchanged through the caller's all-gather
+    // (NCCL via torch.distributed in the Python host; stream-ordered on `stream`). shard_emulate: all shards computed here
+    // one after the other, no collective (single-GPU tests of the partition).
+    uint32_t shard_rank = 0, shard_world = 1;
+    int shard_emulate = 0;
+    bbp_allgather_fn shard_allgather = nullptr;
+    void *shard_user = nullptr;
     // staging
     uint8_t *d_in = nullptr, *d_out = nullptr, *d_scratch = nullptr;
     size_t cap_in = 0, cap_out = 0, cap_scratch = 0;

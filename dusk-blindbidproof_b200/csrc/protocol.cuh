@@ -248,7 +248,7 @@ struct proto_state {
     uint32_t *colmap = nullptr;    // compact slot -> generator column map of the materialisation MSM
     uint32_t colmap_n = 0, colmap_gcols = 0;
     uint8_t *dtable = nullptr;     // digit-multiple table of the latency path (small_msm.cuh), built on first use
-    dev_buf sm_partial, lane_partials;
+    dev_buf sm_partial, lane_partials, shard_gather;
     uint32_t *ipp_colmap = nullptr;   // early IPP rounds, compact slots: lg n maps of 2 (1 + n) generator columns (L slot, R slot)
     uint32_t ipp_colmap_n = 0, ipp_colmap_gcols = 0;
     dev_buf fext, ftab;            // materialised folded bases: extended, then niels (+ B at the tail)
@@ -283,7 +283,7 @@ void proto_release(proto_state *ps) {
     if (!ps) return;
     for (auto &kv : ps->templates) { cudaFree(kv.second.row_ptr); cudaFree(kv.second.entries); cudaFree(kv.second.const_j); cudaFree(kv.second.const_idx); cudaFree(kv.second.coef); }
     cudaFree(ps->comb); cudaFree(ps->wtable); cudaFree(ps->wtable2); cudaFree(ps->colmap); cudaFree(ps->ipp_colmap); cudaFree(ps->dtable);
-    ps->sm_partial.release(); ps->lane_partials.release();
+    ps->sm_partial.release(); ps->lane_partials.release(); ps->shard_gather.release();
     ps->fext.release(); ps->ftab.release();
     dev_buf *all[] = {&ps->chal, &ps->zpow, &ps->ypow, &ps->yinvpow, &ps->wit, &ps->vbl, &ps->blind3, &ps->poly, &ps->tout, &ps->a, &ps->b, &ps->sG, &ps->sH,
                       &ps->slots, &ps->ab, &ps->pub, &ps->dyn_sc, &ps->dyn_pts, &ps->dyn_niels, &ps->stat, &ps->stat_red, &ps->msm_out, &ps->msm_ext,
@@ -464,7 +464,11 @@ inline int ipp_rounds(bbp_ctx *ctx, sc_batch &SB, uint32_t P, std::vector<sc> &c
     const uint32_t n = SB.n, lg = SB.lg_n, gcols = SB.gcols, slot_len = 2 + 2 * gcols;
     const char *hyb_env = getenv("BBP_IPP_HYBRID");   // 0 = never, 2 = always (tests), default: batches of >= 32
     const int hyb = hyb_env ? atoi(hyb_env) : 1;
-    const bool hybrid = hyb && n >= 4 * IPP_NF && (P >= 32 || hyb == 2);   // small batches are launch bound: fewer, larger rounds win
+    const uint32_t shard_G = ctx->shard_world > 1 ? ctx->shard_world : (ctx->shard_emulate > 1 ? (uint32_t)ctx->shard_emulate : 1);
+    const bool sharded = shard_G > 1;
+    if (sharded && ctx->shard_world > 1 && !ctx->shard_allgather) return BBP_ERR_INPUT;
+    // sharded: every round's L_j / R_j stay MSMs over the ORIGINAL generators, so that the column partition never moves
+    const bool hybrid = !sharded && hyb && n >= 4 * IPP_NF && (P >= 32 || hyb == 2);   // small batches are launch bound: fewer, larger rounds win
     const char *nf_env = getenv("BBP_IPP_NF");   // tuning knob (power of two, 16 .. n / 4)
     const uint32_t nf = nf_env ? (uint32_t)atoi(nf_env) : IPP_NF;
     const uint32_t j0 = hybrid ? lg - log2_u32(nf) : lg;
@@ -472,7 +476,9 @@ inline int ipp_rounds(bbp_ctx *ctx, sc_batch &SB, uint32_t P, std::vector<sc> &c
     std::vector<uint8_t> lr((size_t)P * 64);
     SB.fac_n = n; SB.late = 0;
     const char *cp_env = getenv("BBP_IPP_COMPACT");
-    SB.compact = (cp_env ? atoi(cp_env) : 1) && n >= 4;
+    SB.compact = !sharded && (cp_env ? atoi(cp_env) : 1) && n >= 4;
+    SB.shard_G = shard_G; SB.shard_g = ctx->shard_world > 1 ? ctx->shard_rank : 0;
+    if (sharded && ((rc = ps->msm_ext.ensure((size_t)2 * P * 128)) || (rc = ps->shard_gather.ensure((size_t)shard_G * 2 * P * 128)))) return rc;
     const uint32_t cslot = 1 + n;
     if (SB.compact && (ps->ipp_colmap_n != n || ps->ipp_colmap_gcols != gcols)) {
         // round j, slot s (0 = L, 1 = R), entry e: e = 0 -> B; then n/2 G columns and n/2 H columns, block by block
@@ -533,7 +539,28 @@ inline int ipp_rounds(bbp_ctx *ctx, sc_batch &SB, uint32_t P, std::vector<sc> &c
         }
         k_ipp_round<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB, j, mode);
         ctx->launches++;
-        if (!SB.late && SB.compact && small_msm_ok((size_t)2 * P * cslot)) {
+        if (sharded) {
+            // this rank's columns -> 2 P partial sums (extended); all ranks' partials -> gather buffer; local sum + compression.
+            // a, b, the factors and c_L / c_R are replicated (128 KB per proof: cheaper to recompute than to exchange), so the only
+            // traffic per round is 2 x 128 B per proof per GPU and every rank derives the same challenge from the same bytes
+            const size_t part_bytes = (size_t)2 * P * 128;
+            if (ctx->shard_world > 1) {
+                if ((rc = msm_gens_device(ctx, SB.slots, slot_len, 2 * P, nullptr, ps->msm_ext.p))) return rc;
+                if (ctx->shard_allgather(ctx->shard_user, ps->msm_ext.p, ps->shard_gather.p, part_bytes)) return BBP_ERR_NCCL;
+            } else {
+                for (uint32_t g = 0; g < shard_G; g++) {   // emulation: the shards one after the other on this GPU
+                    if (g) {
+                        SB.shard_g = g;
+                        k_ipp_round<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB, j, mode | 2);   // slots only: the fold was applied above
+                        ctx->launches++;
+                    }
+                    if ((rc = msm_gens_device(ctx, SB.slots, slot_len, 2 * P, nullptr, ps->shard_gather.p + g * part_bytes))) return rc;
+                }
+                SB.shard_g = 0;
+            }
+            k_sum_ranks_compress<<<(2 * P + 63) / 64, 64, 0, ctx->stream>>>(ps->shard_gather.p, 2 * P, shard_G, ps->msm_out.as<uint32_t>());
+            ctx->launches++;
+        } else if (!SB.late && SB.compact && small_msm_ok((size_t)2 * P * cslot)) {
             if ((rc = msm_gens_small(ctx, SB.slots, cslot, 2 * P, ps->ipp_colmap + (size_t)j * 2 * cslot, 2, ps->msm_out.p, nullptr))) return rc;
         } else if (!SB.late && SB.compact) {
             msm_shape sh = msm_engine::make_shape(2 * P * cslot, cslot, cslot, true, WT_C, WT_W, (uint32_t)ctx->n_gens);

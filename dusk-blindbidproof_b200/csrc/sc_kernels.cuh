@@ -65,6 +65,7 @@ struct sc_batch {
     uint32_t compact;                          // early rounds: 1 = slots hold only the non-zero half of the columns
                                                // ([B | n/2 G terms | n/2 H terms], addressed through a per-round column map)
     sc *mat;                                   // [n_proofs][2 n] compact scalars of the materialisation MSM
+    uint32_t shard_g, shard_G;                 // sharded IPP: only generator columns i = shard_g (mod shard_G) get scalars (G = 0 / 1: all)
     // aggregated range proofs (bulletproofs RangeProof::prove_multiple / verify_multiple)
     const uint64_t *rp_values;                 // [n_proofs][rp_m]
     uint32_t rp_bits, rp_m;                    // n = rp_bits * rp_m
@@ -399,15 +400,17 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_ipp_round(sc_batch B, uint32
     // slot layout: early rounds [B, B_bl, G[0..gc), H[0..gc)]; late rounds [F_G[0..fn), F_H[0..fn), B]
     const uint32_t gc = B.late ? fn : B.gcols, hdr = B.late ? 0 : 2, slot_len = B.late ? 2 * fn + 1 : 2 + 2 * gc;
     sc *sl = B.slots + (size_t)(2 * p) * slot_len, *sr = sl + slot_len;
+    const bool sharded = B.shard_G > 1;
     if (t == 0) {
         sc wM = sc_to_mont(ch[CH_W]);
         uint32_t bpos = B.late ? 2 * fn : 0;
-        sl[bpos] = sc_from_mont(mm(cl, wM)); sr[bpos] = sc_from_mont(mm(cr, wM));
+        const bool own_q = !sharded || B.shard_g == 0;   // the c * Q term belongs to shard 0
+        sl[bpos] = own_q ? sc_from_mont(mm(cl, wM)) : sc_zero(); sr[bpos] = own_q ? sc_from_mont(mm(cr, wM)) : sc_zero();
         if (!B.late) { sl[1] = sc_zero(); sr[1] = sc_zero(); }
     }
     for (uint32_t i = t; i < gc; i += BBP_SC_THREADS) {
         sc zero = sc_zero();
-        if (i >= fn) {    // generator columns beyond the vector length are unused
+        if (i >= fn || (sharded && i % B.shard_G != B.shard_g)) {    // columns beyond the vector length, or another shard's
             sl[hdr + i] = zero; sr[hdr + i] = zero; sl[hdr + gc + i] = zero; sr[hdr + gc + i] = zero;
             continue;
         }

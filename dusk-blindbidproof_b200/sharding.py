@@ -86,3 +86,56 @@ def combine_verdicts(dist, local_ok, d_out):
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     return bool(flag.item()) and bytes(d_out.cpu().numpy()) == bytes(32)
+
+
+# ---- sharded inner-product argument (BASELINE config 5 at N GPUs) ------------------------------------
+class _DevicePtr:
+    """a raw device pointer as a __cuda_array_interface__ object (zero-copy view for torch.as_tensor)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def enable_sharded_ipp(be, dist):
+    """Every rank calls this once and then drives the SAME proving call with the SAME inputs: rank r computes the MSM terms of
+    the generator columns i = r (mod world) and after each round's MSM the ranks exchange their partial sums (2 x 128 B per
+    proof) with one all-gather, issued from the library through the callback built here. Returns the per-call statistics
+    dict (number of all-gathers, bytes)."""
+    import ctypes
+    world, rank = dist.get_world_size(), dist.get_rank()
+    stats = {"allgathers": 0, "bytes_per_rank": 0}
+    views = {}
+    be._ipp_views = views                         # dropped by disable_sharded_ipp, while the backend's stream still exists
+    stream = torch.cuda.ExternalStream(be.stream())
+    proto = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+
+    def allgather(user, send, recv, nbytes):
+        try:
+            key = (send, recv, nbytes)
+            if key not in views:
+                views[key] = (torch.as_tensor(_DevicePtr(send, nbytes), device="cuda"), torch.as_tensor(_DevicePtr(recv, nbytes * world), device="cuda"))
+            s, r = views[key]
+            with torch.cuda.stream(stream):      # ordered after the MSM kernels the library queued on its own stream
+                dist.all_gather_into_tensor(r, s)
+            stats["allgathers"] += 1
+            stats["bytes_per_rank"] = nbytes
+            return 0
+        except Exception:                         # never let an exception cross the C frame
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    cb = proto(allgather)
+    be._ipp_allgather = cb                        # keeps the callback alive as long as the backend
+    be.set_ipp_shard(rank, world, cb)
+    return stats
+
+
+def disable_sharded_ipp(be):
+    """must run before the backend is closed: the zero-copy views were used on the backend's stream, and torch records an
+    event on every stream a tensor was used on when it frees it"""
+    be.set_ipp_shard(0, 1, None)
+    torch.cuda.synchronize()
+    views = getattr(be, "_ipp_views", None)
+    if views is not None:
+        views.clear()

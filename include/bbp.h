@@ -283,6 +283,18 @@ int bbp_wire_encode_proof_blob(const uint8_t *proof, size_t proof_len, const uin
 int bbp_wire_decode_proof_blob(const uint8_t *blob, size_t blob_len, uint8_t *proof_out, size_t *proof_len, uint8_t *commitments_out, size_t *nc,
                                uint8_t *t_c_out, size_t *nt);
 
+/* ---- sharded inner-product argument (BASELINE config 5 at N GPUs) ---------------------------------------
+ * After bbp_set_ipp_shard every InnerProductProof::create this context runs (range proofs, R1CS proofs, bbp_ipp_create) is
+ * computed cooperatively by `world` contexts, one per GPU, that are all driven with the SAME inputs: context `rank` owns the
+ * generator columns i = rank (mod world) (a strided partition, so that the folding pairs (i, i + n / 2) never straddle ranks)
+ * and after each round's MSM the ranks exchange their 2 x 128-byte partial sums per proof through `allgather` (called on the
+ * calling host thread; the copy must be ordered on bbp_stream(ctx); 0 = ok). Every rank then sums the partials, compresses
+ * L_j / R_j and derives the same challenge, so all ranks return byte-identical proofs — identical to the single-GPU proof.
+ * world = 1 switches it off. emulate > 1 (with world = 1) computes that many shards one after the other on this GPU without
+ * any collective: the single-GPU test of the partition. */
+typedef int (*bbp_allgather_fn)(void *user, const void *send_device, void *recv_device, size_t bytes_per_rank);
+int bbp_set_ipp_shard(bbp_ctx *ctx, uint32_t rank, uint32_t world, bbp_allgather_fn allgather, void *user, int emulate);
+
 /* ---- unit-test hooks (field / group primitives evaluated on the GPU; tests/ compares them with the oracle) ---------- */
 /* op: 0 mul, 1 add, 2 sub, 3 invert(a), 4 square(a), 5 neg(a); inputs are raw 256-bit limbs, output canonical */
 int bbp_test_fe(bbp_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, int op, uint8_t *out);

@@ -3,6 +3,7 @@ the oracle's under the same blindings / rng stream, identical accept / reject de
 config-5 shape (m = 64 parties x 64 bits: 4096-element IPP, 1056-byte proof)."""
 import ctypes
 import hashlib
+import os
 
 import pytest
 
@@ -98,3 +99,40 @@ def test_rangeproof_config5_shape(hybrid, device_rng, monkeypatch):
         swapped = [Vs[1], Vs[0], Vs[2]]
         assert be.rangeproof_verify_batch(proofs, swapped, 64, 64, RNG * 3) == [-3, -3, 0]
     be.close()
+
+
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_sharded_ipp_partition_gives_identical_proofs(shards, monkeypatch):
+    """BASELINE config 5's sharded inner-product argument, the partition emulated on one GPU (bbp_set_ipp_shard(emulate)):
+    generator columns i = g (mod G) per shard, per-round sum of the shards' partial L / R points -> the proof bytes of the
+    unsharded prover and of the oracle (m = 64 x 64 bits: 4096-element IPP, 12 rounds)."""
+    be = backend(64, 64)
+    seeds = [hashlib.sha256(b"sh%d" % i).digest() for i in range(2)]
+    vals = [[from_le(hashlib.shake_256(b"sh-v" + bytes([i, k])).digest(8)) for i in range(64)] for k in range(2)]
+    bls = [blindings(64, b"sh-bl%d" % k) for k in range(2)]
+    st, plain, Vs = be.rangeproof_prove_batch(vals, b"".join(bls), 64, 64, b"".join(seeds))
+    assert st == [0, 0]
+    l0 = be.launch_count()
+    be.set_ipp_shard(0, 1, None, emulate=shards)
+    st, sharded, Vs2 = be.rangeproof_prove_batch(vals, b"".join(bls), 64, 64, b"".join(seeds))
+    be.set_ipp_shard(0, 1, None, emulate=0)
+    assert st == [0, 0] and sharded == plain and Vs2 == Vs
+    assert be.launch_count() - l0 > 12 * shards            # one MSM per shard and round actually ran
+    rc, proof, V = oracle_prove(vals[1], 64, bls[1], seeds[1])
+    assert rc == 0 and sharded[1] == proof
+    be.close()
+
+
+def test_sharded_ipp_two_ranks_nccl():
+    """the same over NCCL: two processes, one GPU each, identical inputs, per-round all-gather of the partial sums; every rank
+    returns the single-GPU proof. Needs two devices (skipped on a one-GPU box)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sharded_ipp_worker.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", script], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("SHARDED-IPP-OK") == 2
