@@ -396,18 +396,20 @@ inline int d2h_sync(bbp_ctx *ctx, void *dst, const void *src, size_t bytes) {
 
 // n commitments v*B + r*B_blinding; vals = n x (value, blinding) reduced scalars on the host; out = n x 32 B on the host
 inline bool small_msm_ok(size_t total_terms);
+inline bool ct_commit();
 inline int msm_gens_small(bbp_ctx *ctx, const sc *d_scalars, uint32_t slot_len, uint32_t n_slots, const uint32_t *colmap, uint32_t colmap_slots,
-                          uint8_t *d_out_compressed, uint8_t *d_out_ext);
+                          uint8_t *d_out_compressed, uint8_t *d_out_ext, bool uniform);
 inline int pedersen_commit_host(bbp_ctx *ctx, const sc *vals, size_t n, uint8_t *out) {
     proto_state *ps = proto_get(ctx);
     int rc;
     if (n == 0) return 0;   // a circuit without commitments
     if ((rc = ps->commit_in.ensure(n * 64)) || (rc = ps->commit_out.ensure(n * 32))) return rc;
     if ((rc = h2d(ctx, ps->commit_in.p, vals, n * 64))) return rc;
-    if (n <= 64 && small_msm_ok(2 * n)) {
+    if (ct_commit() || (n <= 64 && small_msm_ok(2 * n))) {
         // a handful of commitments (one request's V or T points): the comb kernel is a 128-addition chain per thread
-        // (~0.4 ms); as two-column slots [B, B_blinding] of the latency path the additions spread over four warps
-        if ((rc = msm_gens_small(ctx, ps->commit_in.as<sc>(), 2, (uint32_t)n, nullptr, 0, ps->commit_out.p, nullptr))) return rc;
+        // (~0.4 ms); as two-column slots [B, B_blinding] of the latency path the additions spread over four warps.
+        // BBP_CT_COMMIT: every batch size, uniform instruction stream (values and blindings are secret)
+        if ((rc = msm_gens_small(ctx, ps->commit_in.as<sc>(), 2, (uint32_t)n, nullptr, 0, ps->commit_out.p, nullptr, ct_commit()))) return rc;
         return d2h_sync(ctx, out, ps->commit_out.p, n * 32);
     }
     k_pedersen_commit<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ps->commit_in.as<sc>(), ps->comb, ps->commit_out.as<uint32_t>(), (uint32_t)n);
@@ -425,8 +427,12 @@ inline bool small_msm_ok(size_t total_terms) {
     const char *e = getenv("BBP_SMALL_MSM_MAX");
     return total_terms <= (size_t)(e ? atol(e) : 66000);
 }
+// BBP_CT_COMMIT=1: MSMs whose scalars are SECRET (the V / T Pedersen commitments, A_I1 / A_O1 / S1 — what the reference
+// computes with dalek's constant-time multiscalar_mul) take the digit-table path with a uniform
+// instruction stream whatever their size, instead of the variable-time bucket engine. Read per call.
+inline bool ct_commit() { const char *e = getenv("BBP_CT_COMMIT"); return e && atoi(e) != 0; }
 inline int msm_gens_small(bbp_ctx *ctx, const sc *d_scalars, uint32_t slot_len, uint32_t n_slots, const uint32_t *colmap, uint32_t colmap_slots,
-                          uint8_t *d_out_compressed, uint8_t *d_out_ext) {
+                          uint8_t *d_out_compressed, uint8_t *d_out_ext, bool uniform = false) {
     proto_state *ps = proto_get(ctx);
     if (!ps->dtable) {
         const size_t entries = (size_t)SM_W * ctx->n_gens;
@@ -438,16 +444,18 @@ inline int msm_gens_small(bbp_ctx *ctx, const sc *d_scalars, uint32_t slot_len, 
     int rc;
     if ((rc = ps->sm_partial.ensure((size_t)n_slots * chunks * 128))) return rc;
     k_small_msm_partial<<<dim3(chunks, n_slots), SM_THREADS, 0, ctx->stream>>>(d_scalars, slot_len, ps->dtable, (uint32_t)ctx->n_gens, colmap,
-                                                                                 colmap_slots ? colmap_slots : 1, ps->sm_partial.p);
+                                                                                 colmap_slots ? colmap_slots : 1, ps->sm_partial.p, uniform ? 1u : 0u);
     k_small_msm_final<<<n_slots, SM_THREADS, 0, ctx->stream>>>(ps->sm_partial.p, chunks, d_out_ext, d_out_compressed);
     ctx->launches += 2;
     BBP_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-inline int msm_gens_device(bbp_ctx *ctx, const sc *d_scalars, uint32_t slot_len, uint32_t n_slots, uint8_t *d_out_compressed, uint8_t *d_out_ext) {
+inline int msm_gens_device(bbp_ctx *ctx, const sc *d_scalars, uint32_t slot_len, uint32_t n_slots, uint8_t *d_out_compressed, uint8_t *d_out_ext,
+                           bool secret = false) {
     proto_state *ps = proto_get(ctx);
     if (slot_len > ctx->n_gens || !ps->wtable) return BBP_ERR_INVALID_GENERATORS_LENGTH;
+    if (secret && ct_commit()) return msm_gens_small(ctx, d_scalars, slot_len, n_slots, nullptr, 0, d_out_compressed, d_out_ext, true);
     if (small_msm_ok((size_t)n_slots * slot_len)) return msm_gens_small(ctx, d_scalars, slot_len, n_slots, nullptr, 0, d_out_compressed, d_out_ext);
     msm_shape sh = msm_engine::make_shape(n_slots * slot_len, slot_len, slot_len, true, WT_C, WT_W, (uint32_t)ctx->n_gens);
     return ctx->msm.run(sh, (const uint8_t *)d_scalars, ps->wtable, d_out_ext, d_out_compressed);
@@ -839,11 +847,11 @@ inline int prove_core(bbp_ctx *ctx, prove_source &S) {
     // ---- phase 2 (GPU): A_I1, A_O1, S1
     k_commit_slots<<<2 * B, BBP_SC_THREADS, 0, ctx->stream>>>(SB, 0, 2, 0);
     ctx->launches++;
-    if ((rc = msm_gens_device(ctx, SB.slots, slot_len, 2 * B, ps->msm_out.p, nullptr))) return rc;
+    if ((rc = msm_gens_device(ctx, SB.slots, slot_len, 2 * B, ps->msm_out.p, nullptr, true))) return rc;   // witness scalars: secret
     if (device_rng) BBP_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ps->ev_rng, 0));
     k_commit_slots<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB, 2, 1, 2 * B);
     ctx->launches++;
-    if ((rc = msm_gens_device(ctx, SB.slots + (size_t)2 * B * slot_len, slot_len, B, ps->msm_out.p + (size_t)2 * B * 32, nullptr))) return rc;
+    if ((rc = msm_gens_device(ctx, SB.slots + (size_t)2 * B * slot_len, slot_len, B, ps->msm_out.p + (size_t)2 * B * 32, nullptr, true))) return rc;
     std::vector<uint8_t> pts((size_t)B * 3 * 32);
     if ((rc = d2h_sync(ctx, pts.data(), ps->msm_out.p, pts.size()))) return rc;
     trace.mark("gpu_A_S_msm");

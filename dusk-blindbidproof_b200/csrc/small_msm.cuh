@@ -61,7 +61,7 @@ __device__ inline ge sm_block_fold(ge acc, ge *sh) {
 // Entry e of a slot multiplies generator column colmap[(slot % colmap_slots) * slot_len + e] (or e without a map).
 __global__ void __launch_bounds__(SM_THREADS) k_small_msm_partial(const sc *__restrict__ scalars, uint32_t slot_len, const uint8_t *__restrict__ table,
                                                                    uint32_t n_gens, const uint32_t *__restrict__ colmap, uint32_t colmap_slots,
-                                                                   uint8_t *__restrict__ partial) {
+                                                                   uint8_t *__restrict__ partial, uint32_t uniform) {
     __shared__ ge sh[SM_THREADS];
     // the window group is the warp index, so that a warp's lanes (32 different terms) all add at the same windows
     const uint32_t slot = blockIdx.y, t = threadIdx.x, g = t >> 5;
@@ -70,7 +70,30 @@ __global__ void __launch_bounds__(SM_THREADS) k_small_msm_partial(const sc *__re
     if (e < slot_len) {
         sc s = scalars[(size_t)slot * slot_len + e];
         if (s.v[7] >> 29) s = sc_reduce_words(s.v);   // callers of the raw MSM surface may pass any 256-bit value; the recoding needs < 2^253
-        if (!sc_iszero(s)) {
+        if (uniform) {
+            // secret scalars (BBP_CT_COMMIT): the same instruction stream and the same number of table reads for every
+            // scalar value — no zero-scalar exit, no zero-digit skip; a zero digit reads entry 16 and its sum is discarded
+            // by a limb-wise select. (The table ADDRESS still depends on the digit; see DESIGN.md §constant time.)
+            const uint32_t col = colmap ? colmap[(size_t)(slot % colmap_slots) * slot_len + e] : e;
+            uint32_t carry = 0;
+#pragma unroll 1
+            for (uint32_t w = 0; w < SM_W; w++) {
+                uint32_t v = sm_bits5(s.v, SM_C * w) + carry;
+                carry = v > SM_D ? 1u : 0u;
+                int d = (int)v - (int)(carry << SM_C);
+                if ((w & (SM_GROUPS - 1)) == g) {      // public: depends on the window index only
+                    uint32_t a = (uint32_t)(d < 0 ? -d : d);
+                    const uint32_t keep = 0u - (uint32_t)(d != 0);
+                    niels q = niels_load_ro(table + 96 * (((size_t)w * n_gens + col) * SM_D + ((a - 1) & (SM_D - 1))));
+                    ge sum = ge_madd(acc, q, d < 0);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        acc.X.v[k] = (sum.X.v[k] & keep) | (acc.X.v[k] & ~keep); acc.Y.v[k] = (sum.Y.v[k] & keep) | (acc.Y.v[k] & ~keep);
+                        acc.Z.v[k] = (sum.Z.v[k] & keep) | (acc.Z.v[k] & ~keep); acc.T.v[k] = (sum.T.v[k] & keep) | (acc.T.v[k] & ~keep);
+                    }
+                }
+            }
+        } else if (!sc_iszero(s)) {
             const uint32_t col = colmap ? colmap[(size_t)(slot % colmap_slots) * slot_len + e] : e;
             uint32_t carry = 0;
 #pragma unroll 1

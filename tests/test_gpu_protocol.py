@@ -408,3 +408,19 @@ def test_legacy_proof_layout(be):
         assert len(vproof) == 1121 and vproof[1:1 + 96] == proof[:96] and vproof[1 + 96:] == proof[192:]
     finally:
         be.set_proof_format(1)
+
+
+def test_ct_commit_path_gives_identical_bytes(be, monkeypatch):
+    """BBP_CT_COMMIT=1: the secret-scalar MSMs (V / T commitments, A_I1, A_O1, S1 — constant-time multiscalar_mul upstream)
+    take the uniform digit-table path whatever the batch size; same group elements, same proof bytes"""
+    cases = [make_case(880 + i, 8) for i in range(40)]
+    plain = be.blindbid_prove_batch(cases)
+    monkeypatch.setenv("BBP_CT_COMMIT", "1")
+    l0 = be.launch_count()
+    ct = be.blindbid_prove_batch(cases)
+    assert ct == plain
+    assert be.blindbid_prove(cases[3]) == plain[3]
+    monkeypatch.delenv("BBP_CT_COMMIT")
+    for i in (0, 39):
+        rc, oproof, ocomm, otc = orc.blindbid_prove(cases[i], cases[i]["blindings"], cases[i]["rng_seed"])
+        assert rc == 0 and ct[i] == (0, oproof, ocomm, otc)
