@@ -435,7 +435,9 @@ int bbp_wire_execute(bbp_ctx *ctx, size_t n, bbp_wire_request *const *reqs, cons
                 reply_lens[i] = rep.size();
                 continue;
             }
-            J.proof = R.proof; J.commitments = R.commitments; J.t_c = R.t_c;
+            J.proof = R.proof.data(); J.proof_len = R.proof.size();
+            J.commitments = R.commitments.data(); J.n_commitments = R.commitments.size() / 32;
+            J.t_c = R.t_c.data(); J.n_t_c = R.t_c.size() / 32;
             J.pub_list.resize(L);
             for (size_t k = 0; k < L; k++) J.pub_list[k] = sc_from_bits(R.pub_list.data() + 32 * k);   // verify.rs:112-116
             if (!wire_entropy(seed32, i, J.rng_seed, 32)) return BBP_ERR_INPUT;
@@ -754,9 +756,9 @@ static int load_verify_jobs(size_t n, bbp_verify_req *reqs, std::vector<verify_j
         R.status = BBP_ERR_INPUT;
         if (!R.proof || !R.commitments || !R.t_c || !R.score || !R.z_img || !R.seed || (!R.pub_list && R.L) || !R.rng_seed) return;
         verify_job &J = all[i];
-        J.proof.assign(R.proof, R.proof + R.proof_len);
-        J.commitments.assign(R.commitments, R.commitments + 32 * R.n_commitments);
-        J.t_c.assign(R.t_c, R.t_c + 32 * R.n_t_c);
+        J.proof = R.proof; J.proof_len = R.proof_len;                      // views: the caller's buffers outlive the call
+        J.commitments = R.commitments; J.n_commitments = R.n_commitments;
+        J.t_c = R.t_c; J.n_t_c = R.n_t_c;
         // serde-decoded in the reference (src/blindbid/verify.rs:100-102): canonical encodings only
         if (!sc_from_canonical(J.score, R.score) || !sc_from_canonical(J.z_img, R.z_img) || !sc_from_canonical(J.seed, R.seed)) { R.status = BBP_ERR_FORMAT; return; }
         J.pub_list.resize(R.L);

@@ -60,6 +60,7 @@ struct circuit_template {
     uint32_t q = 0;           // constraints
     uint32_t m = 0;           // commitments
     uint32_t n_pub = 0;       // length of the public value table
+    uint32_t n_pub_shared = 0;   // its first entries that are the same for every proof of the circuit (blind bid: 1 + MiMC constants)
     // CSR over target rows: rows [0,n1) = wL, [n1,2n1) = wR, [2n1,3n1) = wO, [3n1,3n1+m) = wV.
     // entry = constraint index j | sign bit (bit 31 set: subtract z^(j+1))
     std::vector<uint32_t> row_ptr, entries;
@@ -249,6 +250,7 @@ inline std::shared_ptr<const circuit_template> blindbid_template(uint32_t n_comm
     tpl->n_commit = n_commit; tpl->n_toggle = n_toggle;
     tpl->m = n_commit + n_toggle;
     tpl->n_pub = PV_ITEM + n_toggle;
+    tpl->n_pub_shared = PV_SEED;
     recorder rec(tpl.get());
     rec.n_mul_cap = 4 * 4 * MIMC_ROUNDS + 3 * n_toggle + 2;
     std::vector<sym_lc> toggles, items;

@@ -248,7 +248,7 @@ struct proto_state {
     uint32_t *colmap = nullptr;    // compact slot -> generator column map of the materialisation MSM
     uint32_t colmap_n = 0, colmap_gcols = 0;
     uint8_t *dtable = nullptr;     // digit-multiple table of the latency path (small_msm.cuh), built on first use
-    dev_buf sm_partial, lane_partials, shard_gather;
+    dev_buf sm_partial, lane_partials, shard_gather, pub_shared;
     uint32_t *ipp_colmap = nullptr;   // early IPP rounds, compact slots: lg n maps of 2 (1 + n) generator columns (L slot, R slot)
     uint32_t ipp_colmap_n = 0, ipp_colmap_gcols = 0;
     dev_buf fext, ftab;            // materialised folded bases: extended, then niels (+ B at the tail)
@@ -283,7 +283,7 @@ void proto_release(proto_state *ps) {
     if (!ps) return;
     for (auto &kv : ps->templates) { cudaFree(kv.second.row_ptr); cudaFree(kv.second.entries); cudaFree(kv.second.const_j); cudaFree(kv.second.const_idx); cudaFree(kv.second.coef); }
     cudaFree(ps->comb); cudaFree(ps->wtable); cudaFree(ps->wtable2); cudaFree(ps->colmap); cudaFree(ps->ipp_colmap); cudaFree(ps->dtable);
-    ps->sm_partial.release(); ps->lane_partials.release(); ps->shard_gather.release();
+    ps->sm_partial.release(); ps->lane_partials.release(); ps->shard_gather.release(); ps->pub_shared.release();
     ps->fext.release(); ps->ftab.release();
     dev_buf *all[] = {&ps->chal, &ps->zpow, &ps->ypow, &ps->yinvpow, &ps->wit, &ps->vbl, &ps->blind3, &ps->poly, &ps->tout, &ps->a, &ps->b, &ps->sG, &ps->sH,
                       &ps->slots, &ps->ab, &ps->pub, &ps->dyn_sc, &ps->dyn_pts, &ps->dyn_niels, &ps->stat, &ps->stat_red, &ps->msm_out, &ps->msm_ext,
@@ -301,6 +301,15 @@ void proto_release(proto_state *ps) {
 inline int proto_tables(bbp_ctx *ctx) {
     proto_state *ps = proto_get(ctx);
     if (ctx->n_gens < 2) return BBP_ERR_INVALID_GENERATORS_LENGTH;
+    if (!ps->pub_shared.p) {   // public values every blind-bid proof shares: 1 and the 90 MiMC round constants (circuit.h: PV_ONE, PV_MIMC)
+        std::vector<sc> sh(PV_SEED);
+        sh[PV_ONE] = sc_one();
+        for (uint32_t i = 0; i < MIMC_ROUNDS; i++) sh[PV_MIMC + i] = mimc_constants()[i];
+        int prc = ps->pub_shared.ensure(sh.size() * 32);
+        if (prc) return prc;
+        BBP_CUDA_OK(cudaMemcpyAsync(ps->pub_shared.p, sh.data(), sh.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
+        BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));   // the source is a local
+    }
     if (!ps->comb) {
         BBP_CUDA_OK(cudaMalloc(&ps->comb, (size_t)BBP_COMB_ENTRIES * 96));
         k_build_comb<<<1, 128, 0, ctx->stream>>>(ctx->d_gens_ext, ps->comb);
@@ -1105,7 +1114,9 @@ inline int prove_batch(bbp_ctx *ctx, std::vector<prove_job> &jobs) {
 
 // ================================================================ verifier
 struct verify_job {
-    std::vector<uint8_t> proof, commitments, t_c;   // R1CSProof bytes, nc x 32, nt x 32
+    // views into the caller's request (valid for the duration of the call): R1CSProof bytes, nc x 32, nt x 32
+    const uint8_t *proof = nullptr, *commitments = nullptr, *t_c = nullptr;
+    size_t proof_len = 0, n_commitments = 0, n_t_c = 0;
     sc score, z_img, seed;
     std::vector<sc> pub_list;
     uint8_t rng_seed[32];
@@ -1132,8 +1143,8 @@ struct verify_prepared {
 inline void verify_prepare(bbp_ctx *ctx, verify_job &J, verify_prepared &P, bool versioned) {
     P.live = false;
     r1cs_proof_host pf;
-    if (!r1cs_from_bytes(pf, J.proof.data(), J.proof.size(), versioned)) { J.status = BBP_ERR_FORMAT; return; }
-    P.nc = (uint32_t)(J.commitments.size() / 32); P.nt = (uint32_t)(J.t_c.size() / 32);
+    if (!r1cs_from_bytes(pf, J.proof, J.proof_len, versioned)) { J.status = BBP_ERR_FORMAT; return; }
+    P.nc = (uint32_t)std::min<size_t>(J.n_commitments, 0xffffffffu); P.nt = (uint32_t)std::min<size_t>(J.n_t_c, 0xffffffffu);
     // the reference indexes vars[0], vars[1], vars[3] and toggle[0], items[i] (panics otherwise: SURVEY.md §5)
     if (P.nc < 4 || P.nt < 1 || J.pub_list.size() < P.nt) { J.status = BBP_ERR_FORMAT; return; }
     if (P.nc > BLINDBID_MAX_COMMITMENTS) { J.status = BBP_ERR_INPUT; return; }   // no reference counterpart: bounds the per-request work
@@ -1153,13 +1164,17 @@ inline void verify_prepare(bbp_ctx *ctx, verify_job &J, verify_prepared &P, bool
         if (all_zero32(&pf.LR[32 * (size_t)j])) { J.status = BBP_ERR_VERIFICATION; return; }
     P.blob.resize((size_t)32 * (P.m + 11 + 2 * lg_p + 5));
     uint8_t *o = P.blob.data();
-    memcpy(o, J.commitments.data(), (size_t)P.nc * 32); o += (size_t)P.nc * 32;
-    memcpy(o, J.t_c.data(), (size_t)P.nt * 32); o += (size_t)P.nt * 32;
+    memcpy(o, J.commitments, (size_t)P.nc * 32); o += (size_t)P.nc * 32;
+    memcpy(o, J.t_c, (size_t)P.nt * 32); o += (size_t)P.nt * 32;
     const uint8_t *fixed_pts[11] = {pf.A_I1, pf.A_O1, pf.S1, pf.A_I2, pf.A_O2, pf.S2, pf.T_1, pf.T_3, pf.T_4, pf.T_5, pf.T_6};
     for (int k = 0; k < 11; k++) { memcpy(o, fixed_pts[k], 32); o += 32; }
     memcpy(o, pf.LR.data(), pf.LR.size()); o += pf.LR.size();
     sc_tobytes(o, pf.t_x); sc_tobytes(o + 32, pf.t_x_blinding); sc_tobytes(o + 64, pf.e_blinding); sc_tobytes(o + 96, pf.a); sc_tobytes(o + 128, pf.b);
-    fill_public_values(P.pub, J.seed, J.score, J.z_img, J.pub_list.data(), P.nt);
+    // the per-proof part of the public value table (circuit.h: PV_SEED ..): seed, score, z_img, items. The 91 entries before
+    // it (1 and the MiMC constants) are the same for every proof and live on the device once (proto_tables)
+    P.pub.resize(3 + (size_t)P.nt);
+    P.pub[0] = J.seed; P.pub[1] = J.score; P.pub[2] = J.z_img;
+    for (uint32_t i = 0; i < P.nt; i++) P.pub[3 + i] = J.pub_list[i];
     P.live = true;
 }
 
@@ -1231,7 +1246,8 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     event_timeline tl;
 
     // ---- upload blobs, seeds, public values; decompress the dynamic points; replay the transcripts
-    if ((rc = ps->h_wit.ensure((size_t)B * (blob_stride + 32 + (size_t)T.n_pub * 32) + 32))) return rc;
+    const uint32_t n_pub_own = T.n_pub - T.n_pub_shared;   // per-proof public values (the shared prefix is resident: ps->pub_shared)
+    if ((rc = ps->h_wit.ensure((size_t)B * (blob_stride + 32 + (size_t)n_pub_own * 32) + 32))) return rc;
     uint8_t *h_blobs = ps->h_wit.p, *h_seeds = h_blobs + (size_t)B * blob_stride;   // B request seeds, then the batch seed
     sc *h_pub = (sc *)(h_seeds + (size_t)(B + 1) * 32);
     if (combined) memcpy(h_seeds + (size_t)B * 32, batch_seed, 32); else memset(h_seeds + (size_t)B * 32, 0, 32);
@@ -1239,9 +1255,9 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
         const verify_prepared &P = prep[idx[bi]];
         memcpy(h_blobs + bi * blob_stride, P.blob.data(), blob_stride);
         memcpy(h_seeds + bi * 32, jobs[idx[bi]].rng_seed, 32);
-        memcpy(h_pub + bi * T.n_pub, P.pub.data(), (size_t)T.n_pub * 32);
+        memcpy(h_pub + bi * n_pub_own, P.pub.data(), (size_t)n_pub_own * 32);
     });
-    if ((rc = ps->dyn_pts.ensure((size_t)B * blob_stride)) || (rc = ps->rng_states.ensure((size_t)(B + 1) * 32)) || (rc = ps->pub.ensure((size_t)B * T.n_pub * 32)) ||
+    if ((rc = ps->dyn_pts.ensure((size_t)B * blob_stride)) || (rc = ps->rng_states.ensure((size_t)(B + 1) * 32)) || (rc = ps->pub.ensure((size_t)B * n_pub_own * 32)) ||
         (rc = ps->bw_digests.ensure((size_t)(B / 32 + 1) * 32)) || (rc = ps->dyn_niels.ensure((size_t)B * ds * 96)) || (rc = ps->valid.ensure((size_t)B * ds)) || (rc = ps->chal.ensure((size_t)B * CH_N * 32)) ||
         (rc = ps->dyn_sc.ensure((size_t)B * ds * 32)) || (rc = ps->zpow.ensure((size_t)B * T.q * 32)) || (rc = ps->ypow.ensure((size_t)B * n * 32)) ||
         (rc = ps->yinvpow.ensure((size_t)B * n * 32)) || (rc = ps->stat.ensure((size_t)B * slot_len * 32)) || (rc = ps->sG.ensure((size_t)B * n * 32)) ||
@@ -1250,7 +1266,7 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     trace.mark("stage");
     tl.mark("start", ctx->stream);
     if ((rc = h2d(ctx, ps->dyn_pts.p, h_blobs, (size_t)B * blob_stride)) || (rc = h2d(ctx, ps->rng_states.p, h_seeds, (size_t)(B + 1) * 32)) ||
-        (rc = h2d(ctx, ps->pub.p, h_pub, (size_t)B * T.n_pub * 32)))
+        (rc = h2d(ctx, ps->pub.p, h_pub, (size_t)B * n_pub_own * 32)))
         return rc;
     // Two streams: the variable-base MSM over the requests' own points (decompression, then the bucket engine) runs on the
     // side stream; transcript replay, weights, power tables, scalar assembly and the static-base MSM run on the main one.
@@ -1326,6 +1342,7 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     memcpy(SB.long_rows, dt->long_rows, sizeof SB.long_rows);
     SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>();
     SB.pub = ps->pub.as<sc>(); SB.dyn_out = ps->dyn_sc.as<sc>(); SB.dyn_stride = ds; SB.stat = ps->stat.as<sc>();
+    SB.n_pub = n_pub_own; SB.n_pub_shared = T.n_pub_shared; SB.pub_shared = ps->pub_shared.as<sc>();
     SB.coef = dt->coef;
     SB.stab = ps->sG.as<sc>();
     SB.skip_ypow = 1;

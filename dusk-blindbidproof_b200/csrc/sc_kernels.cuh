@@ -53,7 +53,9 @@ struct sc_batch {
     sc *slots;                                 // MSM scalar slots, 2 + 2n scalars each (normal form)
     sc *ab_out;                                // [n_proofs][2] final a, b
     // verifier
-    const sc *pub;                             // [n_proofs][n_pub] public value tables (normal form)
+    const sc *pub;                             // [n_proofs][n_pub] public value tables (normal form): table indices >= n_pub_shared
+    const sc *pub_shared;                      // [n_pub_shared] the table's prefix that every proof shares (blind bid: 1, MiMC constants)
+    uint32_t n_pub_shared;
     sc *dyn_out;                               // [n_proofs][dyn_stride]: first m entries = rho * wV[i] * r * x^2 (written here)
     uint32_t dyn_stride;
     uint32_t dyn_done;                         // 1: k_dyn_weights has already written dyn_out (k_verify_scalars leaves it alone)
@@ -159,13 +161,17 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_powers(sc_batch B) {
 }
 inline size_t k_powers_smem(uint32_t q, uint32_t n) { return (size_t)3 * (((q + 1 > n ? q + 1 : n) + 63) >> BBP_POW_LO_BITS) * sizeof(sc); }
 
+// entry ci of a proof's public value table: the shared prefix lives once, the rest per proof
+__device__ __forceinline__ sc pub_value(const sc_batch &B, const sc *pub, uint32_t ci) {
+    return ci < B.n_pub_shared ? B.pub_shared[ci] : pub[ci - B.n_pub_shared];
+}
 // one CSR entry: z^(j+1) times the term's coefficient (Montgomery form). Circuits recorded through the generic constraint
 // system carry arbitrary coefficients (pub[coef[e]], normal form); the blind-bid template has none (B.coef == nullptr).
 __device__ __forceinline__ sc flatten_term(const sc_batch &B, const sc *zpow, const sc *pub, uint32_t e, uint32_t v) {
     sc zp = zpow[v & 0x7fffffffu];
     if (B.coef) {
         const uint32_t ci = B.coef[e];
-        if (ci) zp = mm(zp, sc_to_mont(pub[ci]));
+        if (ci) zp = mm(zp, sc_to_mont(pub_value(B, pub, ci)));
     }
     return zp;
 }
@@ -542,7 +548,7 @@ __global__ void __launch_bounds__(BBP_SC_THREADS, 2) k_verify_scalars(sc_batch B
     const sc *pub = B.pub + (size_t)p * B.n_pub;
     for (uint32_t e = t; e < B.n_const; e += BBP_SC_THREADS) {
         uint32_t v = B.const_j[e];
-        sc term = mm(zpow[v & 0x7fffffffu], sc_to_mont(pub[B.const_idx[e]]));
+        sc term = mm(zpow[v & 0x7fffffffu], sc_to_mont(pub_value(B, pub, B.const_idx[e])));
         wc = (v >> 31) ? sc_add(wc, term) : sc_sub(wc, term);
     }
     wc = block_sum_sc(wc, smem);
@@ -632,7 +638,7 @@ __global__ void __launch_bounds__(64) k_dyn_weights(sc_batch B) {
                     if ((ex >> k) & 1) zp = mm(zp, z2k[k]);
                 if (B.coef) {
                     const uint32_t ci = B.coef[e];
-                    if (ci) zp = mm(zp, sc_to_mont(B.pub[(size_t)p * B.n_pub + ci]));
+                    if (ci) zp = mm(zp, sc_to_mont(pub_value(B, B.pub + (size_t)p * B.n_pub, ci)));
                 }
                 acc = (v >> 31) ? sc_sub(acc, zp) : sc_add(acc, zp);
             }
