@@ -43,6 +43,25 @@ def msm_imads(n, c, W):
     return W * (n * 7 * M_IMAD + 2 * (1 << (c - 1)) * 8 * M_IMAD) + (W - 1) * c * (4 * M_IMAD + 4 * S_IMAD) + W * 8 * M_IMAD
 
 
+def msm_window_plan(n):
+    """window bits / windows the engine picks for a one-slot variable-base MSM of n points (msm.cuh: make_shape; the B200 arm
+    asserts that the library agrees)"""
+    c = 4
+    while c < 16 and (n >> (c + 4)) >= 1:
+        c += 1
+    return c, 253 // c + 1
+
+
+def bench_config(n, world, lanes):
+    """the `config` object of the line — both arms print the same one (the reference arm runs on the B200 arm's config)"""
+    c, W = msm_window_plan(n)
+    return {"workload": f"ristretto255-msm-2^{LOG2_N}", "points_per_gpu": n, "window_bits": c, "windows": W,
+            "l2": "inputs (134 MB bases+scalars, 128 MB sort buffers) exceed the 126 MB L2; no explicit flush",
+            "pipelining": f"independent MSM steps alternate over {lanes} lanes (bbp_lane: sibling contexts, own stream + scratch) of each GPU; "
+                          "ms_per_step is the average with that overlap, stage_ms / roofline are one step alone" if lanes > 1 else "none",
+            "parallelism": f"point-range shards x{world}, all-gather of 128 B partial sums" if world > 1 else "1 GPU"}
+
+
 def accumulate_imads(n, c, W):
     """bucket accumulation alone: one 7M mixed addition per (point, window) pair"""
     return W * n * 7 * M_IMAD
@@ -207,7 +226,7 @@ def run_reference(args, rank):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (GF(2^255-19), mod l)",
-        "data": "synthetic", "config": {"workload": f"ristretto255-msm-2^{LOG2_N}", "points_per_gpu": n},
+        "data": "synthetic", "config": bench_config(n, max(1, args.gpus), max(1, args.msm_lanes)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -593,6 +612,7 @@ def run_b200(args, rank, world):
     stream = torch.cuda.ExternalStream(be.stream(), device=local)
     n = 1 << LOG2_N
     plan = pkg.Backend.msm_plan(n)
+    assert (plan["c"], plan["W"]) == msm_window_plan(n), "bench.py's window plan is out of step with the library's"
 
     with torch.cuda.stream(stream):
         # synthetic inputs: every rank owns a different slice of the N*2^20-point problem
@@ -769,11 +789,7 @@ def run_b200(args, rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (GF(2^255-19), mod l)", "data": "synthetic",
-            "config": {"workload": f"ristretto255-msm-2^{LOG2_N}", "points_per_gpu": n, "window_bits": plan["c"], "windows": plan["W"],
-                       "l2": "inputs (134 MB bases+scalars, 128 MB sort buffers) exceed the 126 MB L2; no explicit flush",
-                       "pipelining": f"independent MSM steps alternate over {L} lanes (bbp_lane: sibling contexts, own stream + scratch) of each GPU; "
-                                     "ms_per_step is the average with that overlap, stage_ms / roofline are one step alone" if L > 1 else "none",
-                       "parallelism": f"point-range shards x{world}, all-gather of 128 B partial sums" if world > 1 else "1 GPU"},
+            "config": bench_config(n, world, L),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (32 + 128), "d2h_bytes_per_step": 32,
                     "call": "bbp_msm_vartime(host scalars, host extended points) incl. niels table build",
                     "callers": f"{EC} concurrent caller threads per GPU, one lane each" if EC > 1 else "1 caller",

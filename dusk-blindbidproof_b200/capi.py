@@ -305,6 +305,14 @@ def _cs_struct(cs):
     return st, (con_ptr, term_var)
 
 
+def cs_shape(cs):
+    """host-only bbp_cs_shape: (status, [multipliers, constraints, commitments, padded n, coefficient-table entries])"""
+    st, keep = _cs_struct(cs)
+    out = (ctypes.c_size_t * 5)()
+    rc = lib().bbp_cs_shape(ctypes.byref(st), out)
+    return rc, list(out)
+
+
 def _generic_methods():
     def r1cs_prove(self, transcript, cs, a_L, a_R, a_O, v, v_blinding, rng_seed):
         """Prover::prove over a flattened circuit; returns (status, proof, V). The transcript is advanced."""

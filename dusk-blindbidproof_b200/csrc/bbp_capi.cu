@@ -553,6 +553,15 @@ static bool load_canonical(std::vector<sc> &out, const uint8_t *in, size_t n) {
     return true;
 }
 
+int bbp_cs_shape(const bbp_cs *cs, size_t out[5]) {
+    if (!cs || !out || !cs->con_ptr || (cs->n_constraints && cs->con_ptr[cs->n_constraints] && (!cs->term_var || !cs->term_coeff))) return BBP_ERR_INPUT;
+    generic_cs G;
+    int rc = generic_cs_build(G, cs->n_multipliers, cs->n_commitments, cs->n_constraints, cs->con_ptr, cs->term_var, cs->term_coeff);
+    if (rc) return rc;
+    out[0] = G.tpl->n1; out[1] = G.tpl->q; out[2] = G.tpl->m; out[3] = next_pow2_u32(G.tpl->n1); out[4] = G.tpl->coef_table.size();
+    return BBP_OK;
+}
+
 int bbp_r1cs_prove(bbp_ctx *ctx, bbp_transcript *t, const bbp_cs *cs, const uint8_t *a_L, const uint8_t *a_R, const uint8_t *a_O, const uint8_t *v,
                    const uint8_t *v_blinding, const uint8_t rng_seed[32], uint8_t *V_out, uint8_t *proof_out, size_t *proof_len) {
     if (!ctx || !t || !cs || !a_L || !a_R || !a_O || !rng_seed || !proof_out || !proof_len) return BBP_ERR_INPUT;

@@ -250,6 +250,10 @@ int bbp_r1cs_verify(bbp_ctx *ctx, bbp_transcript *t, const bbp_cs *cs, const uin
 /* InnerProductProof::create ([UP] bulletproofs inner_product_proof.rs; reached through Prover::prove, proof.rs:88) with
  * Q = w * B, over the first n resident generators G, H (n a power of two <= gens_capacity). G_factors, H_factors, a, b:
  * n x 32 B canonical scalars. Output: L_0 R_0 .. a b = 32 (2 lg n + 2) bytes. */
+/* host-only: validates a flattened circuit the way bbp_r1cs_prove / _verify will and reports its shape: out = {multipliers,
+ * constraints, commitments, padded length n = next power of two, entries of the coefficient table (1 = every variable
+ * coefficient is +-1)}. BBP_ERR_FORMAT: index out of range, unknown variable kind, non-canonical coefficient. */
+int bbp_cs_shape(const bbp_cs *cs, size_t out[5]);
 int bbp_ipp_create(bbp_ctx *ctx, bbp_transcript *t, const uint8_t w[32], const uint8_t *G_factors, const uint8_t *H_factors, const uint8_t *a,
                    const uint8_t *b, size_t n, uint8_t *proof_out, size_t *proof_len);
 

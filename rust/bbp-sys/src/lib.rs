@@ -130,6 +130,7 @@ extern "C" {
     pub fn bbp_transcript_append_message(t: *mut bbp_transcript, label: *const u8, label_len: usize, msg: *const u8, msg_len: usize) -> c_int;
     pub fn bbp_transcript_append_u64(t: *mut bbp_transcript, label: *const u8, label_len: usize, x: u64) -> c_int;
     pub fn bbp_transcript_challenge_bytes(t: *mut bbp_transcript, label: *const u8, label_len: usize, out: *mut u8, out_len: usize) -> c_int;
+    pub fn bbp_cs_shape(cs: *const bbp_cs, out: *mut usize) -> c_int;
     pub fn bbp_r1cs_prove(ctx: *mut bbp_ctx, t: *mut bbp_transcript, cs: *const bbp_cs, a_l: *const u8, a_r: *const u8, a_o: *const u8, v: *const u8, v_blinding: *const u8, rng_seed: *const u8, v_out: *mut u8, proof_out: *mut u8, proof_len: *mut usize) -> c_int;
     pub fn bbp_r1cs_verify(ctx: *mut bbp_ctx, t: *mut bbp_transcript, cs: *const bbp_cs, proof: *const u8, proof_len: usize, v: *const u8, rng_seed: *const u8) -> c_int;
     pub fn bbp_ipp_create(ctx: *mut bbp_ctx, t: *mut bbp_transcript, w: *const u8, g_factors: *const u8, h_factors: *const u8, a: *const u8, b: *const u8, n: usize, proof_out: *mut u8, proof_len: *mut usize) -> c_int;
