@@ -267,13 +267,20 @@ BBP_DEV void fe_sq_wide(uint32_t *r, const uint32_t *a) {
           "r"(t[13]), "r"(t[14]), "r"(t[15]));
 }
 
-// 512-bit value -> fe: lo + 38*hi, then fold the small overflow twice
+// 512-bit value -> fe: lo + 38*hi, then fold the small overflow twice.
+// The fold is eight 32x32+64 products by 38. BBP_FOLD_SHIFT builds the alternative 38 hi = (hi << 5) + (hi << 2) + (hi << 1)
+// (three funnel-shifted copies and three carry chains on the ALU pipe, 8 of the 72 wide products of a multiplication off the
+// FMA-heavy pipe, which ncu shows 84 % busy in the bucket accumulation against 42 % for the ALU pipe). Measured on the 2^20
+// MSM it is SLOWER — k_accumulate 1.10 -> 1.23 ms: 54 dependent ALU instructions per multiplication cost more issue slots
+// and latency than the 8 multiplier slots they free — so the multiplier form stays the default.
 BBP_DEV fe fe_reduce_wide(const uint32_t *r) {
     fe o;
-    uint32_t lo[8], od[8];
+    uint32_t lo[8], top;
+#ifndef BBP_FOLD_SHIFT
+    uint32_t od[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) lo[i] = r[i];
-    uint32_t top = mad4_cc(lo, r[8], r[10], r[12], r[14], 38u);
+    top = mad4_cc(lo, r[8], r[10], r[12], r[14], 38u);
     mul4(od, r[9], r[11], r[13], r[15], 38u);
     asm("add.cc.u32 %0, %0, %8;\n\t"
         "addc.cc.u32 %1, %1, %9;\n\t"
@@ -285,7 +292,45 @@ BBP_DEV fe fe_reduce_wide(const uint32_t *r) {
         "addc.u32 %7, %7, %15;"
         : "+&r"(lo[1]), "+&r"(lo[2]), "+&r"(lo[3]), "+&r"(lo[4]), "+&r"(lo[5]), "+&r"(lo[6]), "+&r"(lo[7]), "+&r"(top)
         : "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
-    // top <= 39; lo += 38*top
+#else
+    uint32_t s[9];
+    // lo + (hi << 1)
+#pragma unroll
+    for (int i = 1; i < 8; i++) s[i] = __funnelshift_l(r[7 + i], r[8 + i], 1);
+    s[0] = r[8] << 1; s[8] = r[15] >> 31;
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, %25, 0;"
+        : "=&r"(lo[0]), "=&r"(lo[1]), "=&r"(lo[2]), "=&r"(lo[3]), "=&r"(lo[4]), "=&r"(lo[5]), "=&r"(lo[6]), "=&r"(lo[7]), "=&r"(top)
+        : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(s[0]), "r"(s[1]), "r"(s[2]), "r"(s[3]), "r"(s[4]), "r"(s[5]), "r"(s[6]), "r"(s[7]), "r"(s[8]));
+    // + (hi << 2), + (hi << 5)
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+        const int k = pass ? 5 : 2;
+#pragma unroll
+        for (int i = 1; i < 8; i++) s[i] = __funnelshift_l(r[7 + i], r[8 + i], k);
+        s[0] = r[8] << k; s[8] = r[15] >> (32 - k);
+        asm("add.cc.u32 %0, %0, %9;\n\t"
+            "addc.cc.u32 %1, %1, %10;\n\t"
+            "addc.cc.u32 %2, %2, %11;\n\t"
+            "addc.cc.u32 %3, %3, %12;\n\t"
+            "addc.cc.u32 %4, %4, %13;\n\t"
+            "addc.cc.u32 %5, %5, %14;\n\t"
+            "addc.cc.u32 %6, %6, %15;\n\t"
+            "addc.cc.u32 %7, %7, %16;\n\t"
+            "addc.u32 %8, %8, %17;"
+            : "+&r"(lo[0]), "+&r"(lo[1]), "+&r"(lo[2]), "+&r"(lo[3]), "+&r"(lo[4]), "+&r"(lo[5]), "+&r"(lo[6]), "+&r"(lo[7]), "+&r"(top)
+            : "r"(s[0]), "r"(s[1]), "r"(s[2]), "r"(s[3]), "r"(s[4]), "r"(s[5]), "r"(s[6]), "r"(s[7]), "r"(s[8]));
+    }
+#endif
+    // top <= 39 (multiplier form) / <= 38 (shift form); lo += 38*top
     uint32_t t = top * 38u, c2;
     asm("add.cc.u32 %0, %0, %9;\n\t"
         "addc.cc.u32 %1, %1, 0;\n\t"
