@@ -393,8 +393,16 @@ static bool wire_entropy(const uint8_t *seed32, uint64_t index, uint8_t *out, si
     return ok;
 }
 
+static int wire_execute_impl(bbp_ctx *ctx, size_t n, bbp_wire_request *const *reqs, const uint8_t *seed32, uint8_t **replies, size_t *reply_lens);
 int bbp_wire_execute(bbp_ctx *ctx, size_t n, bbp_wire_request *const *reqs, const uint8_t *seed32, uint8_t **replies, size_t *reply_lens) {
     if (!ctx || !reqs || !replies || !reply_lens || n == 0) return BBP_ERR_INPUT;
+    for (size_t i = 0; i < n; i++) { replies[i] = nullptr; reply_lens[i] = 0; }
+    int rc = wire_execute_impl(ctx, n, reqs, seed32, replies, reply_lens);
+    if (rc)   // no partial results: whatever was encoded before the failure is released
+        for (size_t i = 0; i < n; i++) { free(replies[i]); replies[i] = nullptr; reply_lens[i] = 0; }
+    return rc;
+}
+static int wire_execute_impl(bbp_ctx *ctx, size_t n, bbp_wire_request *const *reqs, const uint8_t *seed32, uint8_t **replies, size_t *reply_lens) {
     cudaSetDevice(ctx->device);
     std::vector<prove_job> pj;
     std::vector<verify_job> vj;

@@ -389,6 +389,23 @@ inline int template_upload(bbp_ctx *ctx, dev_template &dt) {
     return 0;
 }
 
+// k_powers / k_verify_scalars take their small tables in dynamic shared memory; circuits beyond the blind-bid sizes can need
+// more than the 48 KB a kernel gets without opting in
+inline int sc_kernels_smem_opt_in(uint32_t q, uint32_t n, uint32_t lg) {
+    static std::mutex mu;
+    static size_t cur_p = 0, cur_v = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    const size_t p = k_powers_smem(q, n), v = k_verify_scalars_smem(n, lg);
+    if (p > cur_p && p + 8192 > 48 * 1024) {
+        BBP_CUDA_OK(cudaFuncSetAttribute(k_powers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p));
+        cur_p = p;
+    }
+    if (v > cur_v && v + 20480 > 48 * 1024) {
+        BBP_CUDA_OK(cudaFuncSetAttribute(k_verify_scalars, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v));
+        cur_v = v;
+    }
+    return 0;
+}
 inline uint32_t next_pow2_u32(uint32_t n) { uint32_t p = 1; while (p < n) p <<= 1; return p; }
 inline uint32_t log2_u32(uint32_t n) { uint32_t l = 0; while ((1u << l) < n) l++; return l; }
 
@@ -884,6 +901,7 @@ inline int prove_core(bbp_ctx *ctx, prove_source &S) {
     if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32))) return rc;
 
     // ---- phase 4 (GPU): power tables, flattened constraints, l / r polynomials, t_1 .. t_6
+    if ((rc = sc_kernels_smem_opt_in(SB.q, SB.n, SB.lg_n))) return rc;
     k_powers<<<B, BBP_SC_THREADS, k_powers_smem(SB.q, SB.n), ctx->stream>>>(SB);
     k_polys<<<B, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
     ctx->launches += 2;
@@ -1366,6 +1384,7 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
         if (two_streams) BBP_CUDA_OK(cudaEventRecord(ps->ev_up, side));
         tl.mark("side:dyn_msm", side);
     }
+    if ((rc = sc_kernels_smem_opt_in(SB.q, SB.n, SB.lg_n))) return rc;
     k_powers<<<B, BBP_SC_THREADS, k_powers_smem(SB.q, SB.n), ctx->stream>>>(SB);
     tl.mark("powers", ctx->stream);
     k_verify_scalars<<<B, BBP_SC_THREADS, k_verify_scalars_smem(SB.n, SB.lg_n), ctx->stream>>>(SB);
@@ -1496,7 +1515,9 @@ struct generic_cs {
 };
 inline int generic_cs_build(generic_cs &out, uint32_t n_mul, uint32_t n_commit, uint32_t n_con, const uint32_t *con_ptr, const uint32_t *term_var,
                             const uint8_t *term_coeff) {
-    if (n_mul == 0 || n_mul > (1u << 24) || n_commit > (1u << 24) || n_con > (1u << 28)) return BBP_ERR_INPUT;
+    // the power tables address z^(j+1), j < q, and y^i, i < n, through 16-bit two-level indices (sc_kernels.cuh: k_powers,
+    // k_dyn_weights): q + 1 and the padded n must not exceed 65536
+    if (n_mul == 0 || n_mul > (1u << 16) || n_commit > (1u << 16) || n_con >= (1u << 16)) return BBP_ERR_INPUT;
     out.tpl = generic_template(n_mul, n_commit, n_con, con_ptr, term_var, term_coeff);
     return out.tpl ? 0 : BBP_ERR_FORMAT;
 }

@@ -125,3 +125,22 @@ def test_standalone_ipp_matches_oracle(be, capi, n):
     got = be.ipp_create(tr, w, gf, hf, a, b)
     assert got == want
     assert tr.challenge_bytes(b"after", 32) == after
+
+
+def test_generic_circuit_beyond_blindbid_size(gpu_pkg, capi):
+    """2502 multipliers -> padded n = 4096 (lg n = 12, more than any blind-bid circuit): proof bytes == oracle, verifies"""
+    be = gpu_pkg.Backend(device=0, gens_capacity=4096, party_capacity=1)
+    cs = example_circuit(77, 2500)
+    flat = cs.flatten()
+    assert capi.cs_shape(flat)[1][:4] == [2502, 5007, 3, 4096]
+    aL, aR, aO, v = cs.witness()
+    bl, rng = blindings(b"big", 3), hashlib.sha256(b"big").digest()
+    rc, oproof, oV, oafter = orc.r1cs_prove_flat(b"big circuit", 4096, flat, aL, aR, aO, v, bl, rng)
+    tr = capi.Transcript(b"big circuit")
+    st, proof, V = be.r1cs_prove(tr, flat, aL, aR, aO, v, bl, rng)
+    assert rc == 0 == st and (proof, V) == (oproof, oV) and tr.challenge_bytes(b"after", 32) == oafter
+    assert len(proof) == 1 + 32 * 11 + 64 * 12 + 64
+    assert be.r1cs_verify(capi.Transcript(b"big circuit"), flat, proof, V, rng) == 0
+    bad = bytearray(proof); bad[500] ^= 2
+    assert be.r1cs_verify(capi.Transcript(b"big circuit"), flat, bytes(bad), V, rng) == orc.r1cs_verify_flat(b"big circuit", 4096, flat, bytes(bad), V, rng)[0] != 0
+    be.close()
