@@ -256,7 +256,7 @@ struct proto_state {
         msm_out, msm_ext, flags, valid, commit_in, commit_out, rng_states, rng_raw, bw_digests;
     host_buf h_wit, h_states;
     cudaStream_t rng_stream = nullptr;   // the device TranscriptRng chain runs beside the A_I1 / A_O1 commitments
-    cudaEvent_t ev_up = nullptr, ev_rng = nullptr, ev_dyn = nullptr;
+    cudaEvent_t ev_up = nullptr, ev_rng = nullptr, ev_dyn = nullptr, ev_head = nullptr, ev_pow = nullptr;
     int proof_versioned = 1;       // R1CSProof::to_bytes layout (SURVEY.md §8c risk R1): 1 = leading phase byte, 0 = legacy 14-point form
 };
 
@@ -270,6 +270,8 @@ inline int proto_side_stream(proto_state *ps) {
         BBP_CUDA_OK(cudaEventCreateWithFlags(&ps->ev_up, cudaEventDisableTiming));
         BBP_CUDA_OK(cudaEventCreateWithFlags(&ps->ev_rng, cudaEventDisableTiming));
         BBP_CUDA_OK(cudaEventCreateWithFlags(&ps->ev_dyn, cudaEventDisableTiming));
+        BBP_CUDA_OK(cudaEventCreateWithFlags(&ps->ev_head, cudaEventDisableTiming));
+        BBP_CUDA_OK(cudaEventCreateWithFlags(&ps->ev_pow, cudaEventDisableTiming));
     }
     return 0;
 }
@@ -294,6 +296,8 @@ void proto_release(proto_state *ps) {
     if (ps->ev_up) cudaEventDestroy(ps->ev_up);
     if (ps->ev_rng) cudaEventDestroy(ps->ev_rng);
     if (ps->ev_dyn) cudaEventDestroy(ps->ev_dyn);
+    if (ps->ev_head) cudaEventDestroy(ps->ev_head);
+    if (ps->ev_pow) cudaEventDestroy(ps->ev_pow);
     delete ps;
 }
 
@@ -1308,6 +1312,26 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     // threads otherwise (~40 us per request per thread); BBP_DEVICE_TRANSCRIPT_MIN_BATCH overrides the crossover
     const char *tr_env = getenv("BBP_DEVICE_TRANSCRIPT_MIN_BATCH");
     const bool device_replay = !P0.tr_out && B >= (uint32_t)(tr_env ? atoi(tr_env) : (int)(8 * host_threads()));
+    sc_batch SB;
+    memset(&SB, 0, sizeof SB);
+    SB.n_proofs = B; SB.n1 = n1; SB.q = T.q; SB.m = m; SB.n = n; SB.lg_n = lg; SB.n_pub = T.n_pub; SB.gcols = gcols;
+    SB.row_ptr = dt->row_ptr; SB.entries = dt->entries; SB.const_j = dt->const_j; SB.const_idx = dt->const_idx; SB.n_const = (uint32_t)T.const_j.size();
+    SB.n_long = dt->n_long;
+    memcpy(SB.long_rows, dt->long_rows, sizeof SB.long_rows);
+    SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>();
+    SB.pub = ps->pub.as<sc>(); SB.dyn_out = ps->dyn_sc.as<sc>(); SB.dyn_stride = ds; SB.stat = ps->stat.as<sc>();
+    SB.n_pub = n_pub_own; SB.n_pub_shared = T.n_pub_shared; SB.pub_shared = ps->pub_shared.as<sc>();
+    SB.coef = dt->coef;
+    SB.stab = ps->sG.as<sc>();
+    SB.skip_ypow = 1;
+    SB.dyn_done = 1;
+    // BBP_VERIFY_SPLIT=1: split replay — phase 1 ends with y, z and y^-1, which is all k_powers needs; the tables are then built
+    // on the side stream while phase 2 (a latency chain of ~25 permutations and an inversion) runs here. Measured SLOWER
+    // (1024 proofs: 2.6 -> 3.1 ms): the second inversion costs ~0.1 ms and the wide k_powers blocks keep phase 2's warps off
+    // the SMs until they drain; kept as an experiment knob, off by default.
+    const char *sp_env = getenv("BBP_VERIFY_SPLIT");
+    const bool split = two_streams && device_replay && !keccak_per_thread() && sp_env && atoi(sp_env) == 1;
+    if ((rc = sc_kernels_smem_opt_in(SB.q, SB.n, SB.lg_n))) return rc;
     if (device_replay) {
         transcript_init init;
         if (P0.tr_state) memcpy(init.state, P0.tr_state, sizeof init.state);   // one group = one circuit = one starting state
@@ -1319,9 +1343,22 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
         if (keccak_per_thread())
             k_verify_transcript<<<(B + 31) / 32, 32, 0, ctx->stream>>>(init, ps->dyn_pts.p, blob_stride, ps->rng_states.p, B, m, lg, (uint64_t)n,
                                                                        ps->chal.as<sc>(), ps->dyn_sc.as<sc>(), ds);
-        else   // one warp per request
+        else if (!split)   // one warp per request
             k_verify_transcript_warp<<<(B + 3) / 4, 128, 0, ctx->stream>>>(init, ps->dyn_pts.p, blob_stride, ps->rng_states.p, B, m, lg, (uint64_t)n,
-                                                                           ps->chal.as<sc>(), ps->dyn_sc.as<sc>(), ds);
+                                                                           ps->chal.as<sc>(), ps->dyn_sc.as<sc>(), ds, 0, nullptr);
+        else {
+            if ((rc = ps->rng_raw.ensure((size_t)B * BBP_STROBE_STATE_BYTES))) return rc;
+            k_verify_transcript_warp<<<(B + 3) / 4, 128, 0, ctx->stream>>>(init, ps->dyn_pts.p, blob_stride, ps->rng_states.p, B, m, lg, (uint64_t)n,
+                                                                           ps->chal.as<sc>(), ps->dyn_sc.as<sc>(), ds, 1, ps->rng_raw.p);
+            BBP_CUDA_OK(cudaEventRecord(ps->ev_head, ctx->stream));
+            BBP_CUDA_OK(cudaStreamWaitEvent(side, ps->ev_head, 0));
+            k_powers<<<B, BBP_SC_THREADS, k_powers_smem(SB.q, SB.n), side>>>(SB);
+            BBP_CUDA_OK(cudaEventRecord(ps->ev_pow, side));
+            tl.mark("side:powers", side);
+            k_verify_transcript_warp<<<(B + 3) / 4, 128, 0, ctx->stream>>>(init, ps->dyn_pts.p, blob_stride, ps->rng_states.p, B, m, lg, (uint64_t)n,
+                                                                           ps->chal.as<sc>(), ps->dyn_sc.as<sc>(), ds, 2, ps->rng_raw.p);
+            ctx->launches += 2;
+        }
         ctx->launches++;
     } else {
         // pinned staging: the copies below are asynchronous and nothing waits for them before the end of the group
@@ -1352,19 +1389,6 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
                                                               ps->rng_states.p + (size_t)B * 32, combined ? 1u : 0u);
     ctx->launches++;
 
-    sc_batch SB;
-    memset(&SB, 0, sizeof SB);
-    SB.n_proofs = B; SB.n1 = n1; SB.q = T.q; SB.m = m; SB.n = n; SB.lg_n = lg; SB.n_pub = T.n_pub; SB.gcols = gcols;
-    SB.row_ptr = dt->row_ptr; SB.entries = dt->entries; SB.const_j = dt->const_j; SB.const_idx = dt->const_idx; SB.n_const = (uint32_t)T.const_j.size();
-    SB.n_long = dt->n_long;
-    memcpy(SB.long_rows, dt->long_rows, sizeof SB.long_rows);
-    SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>();
-    SB.pub = ps->pub.as<sc>(); SB.dyn_out = ps->dyn_sc.as<sc>(); SB.dyn_stride = ds; SB.stat = ps->stat.as<sc>();
-    SB.n_pub = n_pub_own; SB.n_pub_shared = T.n_pub_shared; SB.pub_shared = ps->pub_shared.as<sc>();
-    SB.coef = dt->coef;
-    SB.stab = ps->sG.as<sc>();
-    SB.skip_ypow = 1;
-    SB.dyn_done = 1;
     k_dyn_weights<<<B, 64, 0, ctx->stream>>>(SB);
     ctx->launches++;
     tl.mark("weights", ctx->stream);
@@ -1384,8 +1408,8 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
         if (two_streams) BBP_CUDA_OK(cudaEventRecord(ps->ev_up, side));
         tl.mark("side:dyn_msm", side);
     }
-    if ((rc = sc_kernels_smem_opt_in(SB.q, SB.n, SB.lg_n))) return rc;
-    k_powers<<<B, BBP_SC_THREADS, k_powers_smem(SB.q, SB.n), ctx->stream>>>(SB);
+    if (split) BBP_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ps->ev_pow, 0));
+    else k_powers<<<B, BBP_SC_THREADS, k_powers_smem(SB.q, SB.n), ctx->stream>>>(SB);
     tl.mark("powers", ctx->stream);
     k_verify_scalars<<<B, BBP_SC_THREADS, k_verify_scalars_smem(SB.n, SB.lg_n), ctx->stream>>>(SB);
     if (combined && B >= 32)

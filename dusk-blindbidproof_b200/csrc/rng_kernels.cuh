@@ -582,33 +582,62 @@ __global__ void __launch_bounds__(32) k_verify_transcript(transcript_init init, 
 // The same replay with one WARP per request (strobe_warp / keccak_warp): the ~50 permutations and ~60 transcript operations
 // of a request run lane-parallel; the scalar arithmetic that follows (challenge reductions, one batched inversion, the
 // dynamic-point weights) is computed redundantly by every lane (uniform control flow) and stored by lane 0. 4 requests per block.
+// x^-1 in the Montgomery domain (x^(l-2), square and multiply over the constant exponent)
+__device__ __noinline__ sc sc_invert_mont(sc accM) {
+    sc inv = sc_to_mont(sc_one());
+#pragma unroll 1
+    for (int i = 252; i >= 0; i--) {
+        inv = mm(inv, inv);
+        uint32_t e = sc_l_limb(i >> 5);
+        if (i < 32) e = sc_l_limb(0) - 2;
+        if ((e >> (i & 31)) & 1) inv = mm(inv, accM);
+    }
+    return inv;
+}
+
+// phase 0: the whole replay in one launch. phase 1: up to the challenges y, z (plus y^-1) — everything k_powers needs — then the
+// sponge is parked in `states` (208 B per request); phase 2: the rest, resumed from there. With the split the power tables
+// are built on a second stream while the (latency-bound) remainder of the replay runs.
 __global__ void __launch_bounds__(128) k_verify_transcript_warp(transcript_init init, const uint8_t *__restrict__ blobs, uint32_t blob_stride,
                                                                 const uint8_t *__restrict__ seeds, uint32_t n_req, uint32_t m, uint32_t lg, uint64_t n_ipp,
-                                                                sc *__restrict__ chal, sc *__restrict__ dyn, uint32_t dyn_stride) {
+                                                                sc *__restrict__ chal, sc *__restrict__ dyn, uint32_t dyn_stride, uint32_t phase,
+                                                                uint8_t *__restrict__ states) {
     __shared__ uint64_t sm_state[4][26];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t p = blockIdx.x * 4 + warp;
     if (p >= n_req) return;   // whole warps leave together
     strobe_warp S;
     S.attach((uint8_t *)sm_state[warp], lane);
-    S.load(init.state);
     const bool lead = lane == 0;
     const uint8_t *blob = blobs + (size_t)p * blob_stride;
     const uint8_t *pts = blob + 32 * (size_t)m;                   // A_I1 ...
     const uint8_t *lr = pts + 32 * 11;
     const uint8_t *scal = lr + 64 * (size_t)lg;                   // t_x, t_x_blinding, e_blinding, a, b
     sc *c = chal + (size_t)p * CH_N;
-    for (uint32_t i = 0; i < m; i++) S.append_message(BBP_LBL("V"), blob + 32 * (size_t)i, 32);
-    S.append_u64(BBP_LBL("m"), m);
-    S.append_message(BBP_LBL("A_I1"), pts, 32);
-    S.append_message(BBP_LBL("A_O1"), pts + 32, 32);
-    S.append_message(BBP_LBL("S1"), pts + 64, 32);
-    S.append_message(BBP_LBL("dom-sep"), (const uint8_t *)"r1cs-1phase", 11);
-    S.append_message(BBP_LBL("A_I2"), pts + 96, 32);
-    S.append_message(BBP_LBL("A_O2"), pts + 128, 32);
-    S.append_message(BBP_LBL("S2"), pts + 160, 32);
-    sc y = S.challenge_scalar(BBP_LBL("y"));
-    sc z = S.challenge_scalar(BBP_LBL("z"));
+    sc y, z;
+    if (phase != 2) {
+        S.load(init.state);
+        for (uint32_t i = 0; i < m; i++) S.append_message(BBP_LBL("V"), blob + 32 * (size_t)i, 32);
+        S.append_u64(BBP_LBL("m"), m);
+        S.append_message(BBP_LBL("A_I1"), pts, 32);
+        S.append_message(BBP_LBL("A_O1"), pts + 32, 32);
+        S.append_message(BBP_LBL("S1"), pts + 64, 32);
+        S.append_message(BBP_LBL("dom-sep"), (const uint8_t *)"r1cs-1phase", 11);
+        S.append_message(BBP_LBL("A_I2"), pts + 96, 32);
+        S.append_message(BBP_LBL("A_O2"), pts + 128, 32);
+        S.append_message(BBP_LBL("S2"), pts + 160, 32);
+        y = S.challenge_scalar(BBP_LBL("y"));
+        z = S.challenge_scalar(BBP_LBL("z"));
+        if (phase == 1) {
+            sc yinv = sc_from_mont(sc_invert_mont(sc_to_mont(y)));
+            if (lead) { c[CH_Y] = y; c[CH_Z] = z; c[CH_YINV] = yinv; }
+            S.store(states + (size_t)p * BBP_STROBE_STATE_BYTES, 0);
+            return;
+        }
+    } else {
+        S.load(states + (size_t)p * BBP_STROBE_STATE_BYTES);
+        y = c[CH_Y]; z = c[CH_Z];
+    }
     S.append_message(BBP_LBL("T_1"), pts + 192, 32);
     S.append_message(BBP_LBL("T_3"), pts + 224, 32);
     S.append_message(BBP_LBL("T_4"), pts + 256, 32);
@@ -636,24 +665,22 @@ __global__ void __launch_bounds__(128) k_verify_transcript_warp(transcript_init 
     }
     __syncwarp();                          // lane 0's stores to c[] are read back by every lane below
     sc pre_y = acc;
-    acc = mm(acc, sc_to_mont(y));
+    if (phase == 0) acc = mm(acc, sc_to_mont(y));   // phase 2: y^-1 was computed by phase 1, only the u_j are inverted here
     // verifier randomness: transcript.build_rng().finalize(rng_seed) -> one scalar
     S.meta_ad_label(BBP_LBL("rng"));
     S.key32(seeds + 32 * (size_t)p);
     uint32_t rw[16];
     S.fill64(rw);
     sc r = sc_from_wide_words(rw);
-    // acc = (prod u_j * y) R ; invert once: x^(l-2) in the Montgomery domain
-    sc inv = sc_to_mont(sc_one());
-#pragma unroll 1
-    for (int i = 252; i >= 0; i--) {
-        inv = mm(inv, inv);
-        uint32_t e = sc_l_limb(i >> 5);
-        if (i < 32) e = sc_l_limb(0) - 2;
-        if ((e >> (i & 31)) & 1) inv = mm(inv, acc);
+    // acc = (prod u_j [* y]) R ; invert once: x^(l-2) in the Montgomery domain
+    sc inv = sc_invert_mont(acc);
+    sc yinv;
+    if (phase == 0) {
+        yinv = sc_from_mont(mm(inv, pre_y));
+        inv = mm(inv, sc_to_mont(y));
+    } else {
+        yinv = c[CH_YINV];
     }
-    sc yinv = sc_from_mont(mm(inv, pre_y));
-    inv = mm(inv, sc_to_mont(y));
     sc *d = dyn + (size_t)p * dyn_stride + m;
 #pragma unroll 1
     for (uint32_t j = lg; j-- > 0;) {
