@@ -49,6 +49,10 @@ std::condition_variable g_cv;
 std::deque<pending> g_queue;
 std::atomic<bool> g_stop{false};
 std::atomic<uint64_t> g_served{0}, g_batches{0};
+std::atomic<int> g_open{0};                 // connections being read or waiting for their reply
+const size_t MAX_REQUEST = 16u << 20;       // a request is a few kilobytes (L = 202: ~10 KB); refuse absurd frames before buffering them
+const int MAX_OPEN = 8192;                  // one reader thread per connection: bounded
+const int READ_TIMEOUT_S = 30;              // a client that connects and stays silent does not hold a thread forever
 
 bool read_exact(int fd, uint8_t *buf, size_t n) {
     while (n) {
@@ -70,7 +74,15 @@ bool write_all(int fd, const uint8_t *buf, size_t n) {
 }
 
 // one connection: read the request frame, parse it, queue it (TlvReader::next, futures/main.rs:68-76)
+struct open_guard {   // counts the connection out when its reader gives up (queued requests are counted out by the executor)
+    bool armed = true;
+    ~open_guard() { if (armed) g_open--; }
+};
+
 void reader_thread(int fd) {
+    open_guard guard;
+    timeval tv = {READ_TIMEOUT_S, 0};
+    setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof tv);
     uint8_t head[9];
     size_t hdr = 0, pl = 0;
     // tag byte, then the length field it announces (csrc/wire.h: tlv_header)
@@ -81,6 +93,7 @@ void reader_thread(int fd) {
         close(fd);
         return;
     }
+    if (pl > MAX_REQUEST) { LOG(L_ERROR, "Error resolving the request: frame of %zu bytes refused", pl); close(fd); return; }
     std::vector<uint8_t> payload(pl);
     if (pl && !read_exact(fd, payload.data(), pl)) {
         LOG(L_ERROR, "Error resolving the request: unexpected end of the request frame");
@@ -95,6 +108,7 @@ void reader_thread(int fd) {
         return;
     }
     LOG(L_TRACE, "request queued (opcode %d)", op);
+    guard.armed = false;
     {
         std::lock_guard<std::mutex> lock(g_mu);
         g_queue.push_back({fd, req});
@@ -134,6 +148,7 @@ void executor_thread(bbp_ctx *ctx, unsigned window_us, size_t max_batch) {
                 LOG(L_ERROR, "Error resolving the request: no reply is written");
             }
             close(batch[i].fd);
+            g_open--;
             bbp_wire_reply_free(replies[i]);
             bbp_wire_request_free(batch[i].req);
         }
@@ -202,6 +217,8 @@ int main(int argc, char **argv) {
     while (!g_stop) {
         int fd = accept(srv, nullptr, nullptr);
         if (fd < 0) { if (g_stop) break; continue; }
+        if (g_open.load() >= MAX_OPEN) { LOG(L_WARN, "too many open connections: refused"); close(fd); continue; }
+        g_open++;
         std::thread(reader_thread, fd).detach();
     }
     g_stop = true;
