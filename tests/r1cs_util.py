@@ -95,3 +95,38 @@ def example_circuit(seed, n_extra=5):
         cur = c2
     cs.constrain(acc - LC.const(acc_val))
     return cs
+
+
+def random_circuit(seed, n_mul, n_commit, n_free):
+    """a random satisfiable circuit: n_mul multipliers whose inputs are random linear combinations (random 252-bit
+    coefficients, small ones, +-1 and constants mixed) of everything allocated so far, plus n_free extra constraints that are
+    satisfied by construction (a random combination minus its own value)."""
+    import random
+    rnd = random.Random(seed)
+    cs = Recorder([rnd.getrandbits(rnd.choice([1, 64, 252])) for _ in range(n_commit)])
+    pool = [cs.committed(i) for i in range(n_commit)]
+
+    def coeff():
+        k = rnd.random()
+        if k < 0.35:
+            return 1
+        if k < 0.5:
+            return L_ORDER - 1
+        if k < 0.7:
+            return rnd.randrange(2, 1000)
+        return rnd.getrandbits(252) % L_ORDER
+
+    def random_lc():
+        lc = LC.const(rnd.getrandbits(200)) if rnd.random() < 0.4 or not pool else LC()
+        for _ in range(rnd.randrange(1, 5)):
+            if pool:
+                lc = lc + rnd.choice(pool).scale(coeff())
+        return lc
+
+    for _ in range(n_mul):
+        l, r, o = cs.multiply(random_lc(), random_lc())
+        pool += [l, r, o]
+    for _ in range(n_free):
+        lc = random_lc()
+        cs.constrain(lc - LC.const(cs.eval(lc)))
+    return cs

@@ -7,7 +7,7 @@ import pytest
 
 import orc
 from orc import L_ORDER, from_le, le
-from r1cs_util import LC, Recorder, example_circuit
+from r1cs_util import LC, Recorder, example_circuit, random_circuit
 
 pytestmark = pytest.mark.gpu
 
@@ -144,3 +144,25 @@ def test_generic_circuit_beyond_blindbid_size(gpu_pkg, capi):
     bad = bytearray(proof); bad[500] ^= 2
     assert be.r1cs_verify(capi.Transcript(b"big circuit"), flat, bytes(bad), V, rng) == orc.r1cs_verify_flat(b"big circuit", 4096, flat, bytes(bad), V, rng)[0] != 0
     be.close()
+
+
+@pytest.mark.parametrize("seed,n_mul,n_commit,n_free", [(1, 1, 0, 0), (2, 3, 1, 2), (3, 17, 4, 9), (4, 64, 2, 30), (5, 200, 7, 100), (6, 333, 0, 5)])
+def test_random_circuits_match_oracle(be, capi, seed, n_mul, n_commit, n_free):
+    """random satisfiable circuits (random / small / +-1 coefficients, constants, every variable kind on both sides): proof
+    bytes and commitments equal the oracle's, both verifiers accept, and a wrong witness is rejected by both"""
+    cs = random_circuit(seed, n_mul, n_commit, n_free)
+    flat = cs.flatten()
+    aL, aR, aO, v = cs.witness()
+    bl = blindings(b"rc%d" % seed, flat["m"])
+    rng = hashlib.sha256(b"rc%d" % seed).digest()
+    label = b"random circuit"
+    rc, oproof, oV, oafter = orc.r1cs_prove_flat(label, 2048, flat, aL, aR, aO, v, bl, rng)
+    tr = capi.Transcript(label)
+    st, proof, V = be.r1cs_prove(tr, flat, aL, aR, aO, v, bl, rng)
+    assert rc == 0 == st and (proof, V) == (oproof, oV) and tr.challenge_bytes(b"after", 32) == oafter
+    assert be.r1cs_verify(capi.Transcript(label), flat, proof, V, rng) == 0 == orc.r1cs_verify_flat(label, 2048, flat, proof, V, rng)[0]
+    if n_mul > 1:
+        cs.aL[1] = (cs.aL[1] + 1) % L_ORDER
+        aL2 = cs.witness()[0]
+        st, p2, V2 = be.r1cs_prove(capi.Transcript(label), flat, aL2, aR, aO, v, bl, rng)
+        assert st == 0 and be.r1cs_verify(capi.Transcript(label), flat, p2, V2, rng) == orc.r1cs_verify_flat(label, 2048, flat, p2, V2, rng)[0] == -3
