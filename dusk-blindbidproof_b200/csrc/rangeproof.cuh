@@ -325,8 +325,13 @@ inline int rp_verify_group(bbp_ctx *ctx, std::vector<rp_verify_job> &jobs, uint3
         merlin_rng vrng = tr.build_rng().finalize(J.rng_seed);
         sc c = vrng.random_scalar();
         sc rho = vrng.random_scalar();
+        // one inversion for everything that has to be inverted: the u_j, y, and the denominators y - 1, z - 1 of the two
+        // geometric series below (a zero denominator — probability 2^-252 — is replaced by one and its series summed directly)
+        const sc ym1 = sc_sub(y, sc_one()), zm1 = sc_sub(z, sc_one());
         std::vector<sc> all(uj);
         all.push_back(y);
+        all.push_back(sc_iszero(ym1) ? sc_one() : ym1);
+        all.push_back(sc_iszero(zm1) ? sc_one() : zm1);
         std::vector<sc> pre(all.size()), allinv(all.size());
         sc acc = sc_one();
         for (size_t k = 0; k < all.size(); k++) { pre[k] = acc; acc = sc_mul(acc, all[k]); }
@@ -339,15 +344,15 @@ inline int rp_verify_group(bbp_ctx *ctx, std::vector<rp_verify_job> &jobs, uint3
         for (size_t j = 0; j < lg_p; j++) { ch[CH_UJ0 + j] = uj[j]; ch[CH_UJ0 + lg_p + j] = allinv[j]; }
         // B and B_blinding coefficients
         sc zz = sc_mul(z, z);
-        // 1 + base + ... + base^(cnt-1): geometric series in closed form for long ranges (cnt = n m = 4096 for y), plain loop otherwise
-        auto sum_pow = [&](const sc &base, size_t cnt) {
-            sc bm1 = sc_sub(base, sc_one());
-            if (cnt >= 64 && !sc_iszero(bm1)) return sc_mul(sc_sub(sc_pow_u64(base, cnt), sc_one()), sc_invert(bm1));
+        // 1 + base + ... + base^(cnt-1): geometric series in closed form (cnt = n m = 4096 for y), plain loop for short ranges
+        auto sum_pow = [&](const sc &base, const sc &bm1, const sc &bm1_inv, size_t cnt) {
+            if (cnt >= 64 && !sc_iszero(bm1)) return sc_mul(sc_sub(sc_pow_u64(base, cnt), sc_one()), bm1_inv);
             sc s = sc_zero(), e = sc_one();
             for (size_t k = 0; k < cnt; k++) { s = sc_add(s, e); e = sc_mul(e, base); }
             return s;
         };
-        sc sum_y = sum_pow(y, nm), sum_2 = sum_pow(sc_from_u64(2), nbits), sum_z = sum_pow(z, m);
+        sc sum_y = sum_pow(y, ym1, allinv[lg_p + 1], nm), sum_z = sum_pow(z, zm1, allinv[lg_p + 2], m);
+        sc sum_2 = nbits >= 64 ? sc_sub(sc_pow_u64(sc_from_u64(2), nbits), sc_one()) : sc_from_u64((1ull << nbits) - 1);   // 2^n - 1
         sc delta = sc_sub(sc_mul(sc_sub(z, zz), sum_y), sc_mul(sc_mul(sc_mul(zz, z), sum_2), sum_z));
         ch[CH_TX] = sc_add(sc_mul(w, sc_sub(t_x, sc_mul(a, b))), sc_mul(c, sc_sub(delta, t_x)));
         ch[CH_TXBL] = sc_sub(sc_neg(e_bl), sc_mul(c, t_x_bl));
