@@ -888,7 +888,8 @@ inline int prove_core(bbp_ctx *ctx, prove_source &S) {
 
     // ---- phase 3 (host): y, z
     std::vector<sc> chal((size_t)B * CH_N, sc_zero());
-    parallel_for(B, [&](size_t bi) {
+    parallel_chunks(B, [&](size_t lo_, size_t hi_) {
+    for (size_t bi = lo_; bi < hi_; bi++) {
         hstate &H = hs[bi];
         r1cs_proof_host &P = H.pf;
         if (device_rng) H.rng->import_state(&rng_states[bi * BBP_STROBE_STATE_BYTES]);
@@ -900,7 +901,13 @@ inline int prove_core(bbp_ctx *ctx, prove_source &S) {
         sc *c = &chal[bi * CH_N];
         c[CH_Y] = H.tr->challenge_scalar("y");
         c[CH_Z] = H.tr->challenge_scalar("z");
-        c[CH_YINV] = sc_invert(c[CH_Y]);
+        c[CH_YINV] = c[CH_Y];
+    }
+    // y^-1 for the whole chunk with one exponentiation (Montgomery's trick), like the u_j of the IPP rounds
+    std::vector<sc> inv(hi_ - lo_);
+    for (size_t bi = lo_; bi < hi_; bi++) inv[bi - lo_] = chal[bi * CH_N + CH_Y];
+    sc_batch_invert(inv.data(), inv.size());
+    for (size_t bi = lo_; bi < hi_; bi++) chal[bi * CH_N + CH_YINV] = inv[bi - lo_];
     });
     if ((rc = h2d(ctx, ps->chal.p, chal.data(), chal.size() * 32))) return rc;
 
