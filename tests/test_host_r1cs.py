@@ -49,3 +49,26 @@ def test_transcript_object_merlin_vector_on_cpu():
     t = capi.Transcript(b"test protocol")
     t.append_message(b"some label", b"some data")
     assert t.challenge_bytes(b"challenge", 32).hex() == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+
+
+def test_cs_shape_on_random_garbage():
+    """random term lists are either accepted with a consistent shape or refused — never a crash"""
+    import random
+    rnd = random.Random(99)
+    ok = refused = 0
+    for _ in range(300):
+        n_mul, m, q = rnd.randrange(1, 9), rnd.randrange(0, 4), rnd.randrange(0, 12)
+        con_ptr = [0]
+        for _ in range(q):
+            con_ptr.append(con_ptr[-1] + rnd.randrange(0, 5))
+        nt = con_ptr[-1]
+        term_var = [(rnd.randrange(0, 6) << 28) | rnd.randrange(0, 10) for _ in range(nt)]
+        coeff = b"".join(le(rnd.choice([0, 1, L_ORDER - 1, rnd.getrandbits(252) % L_ORDER, L_ORDER + rnd.randrange(3)]) % (1 << 256)) for _ in range(nt))
+        rc, shape = capi.cs_shape(dict(n_mul=n_mul, m=m, con_ptr=con_ptr, term_var=term_var, term_coeff=coeff or b"\0"))
+        if rc == 0:
+            ok += 1
+            assert shape[:3] == [n_mul, q, m]
+        else:
+            refused += 1
+            assert rc == capi.BBP_ERR_FORMAT
+    assert ok > 5 and refused > 5

@@ -76,3 +76,41 @@ def test_proof_blob_roundtrip_and_verify_request():
     op, h = capi.wire_parse(frame[hdr:-5])
     assert op == 2
     capi.wire_free(h)
+
+
+def test_parsers_survive_random_and_mutated_input():
+    """robustness of the outer boundary's parsers on the CPU: random bytes, truncations and single-byte mutations of valid
+    frames never crash, never read out of bounds (the process would die under the allocator's guard pages sooner or later)
+    and always come back with a definite answer"""
+    import random
+    rnd = random.Random(1234)
+    scalars = b"".join(sc(i + 1) for i in range(7))
+    pub = b"".join(sc(100 + i) for i in range(6))
+    blob = capi.wire_proof_blob(bytes(range(256)) * 4 + b"\x09" * 97, b"".join(sc(i + 7) for i in range(4)), b"".join(sc(i + 70) for i in range(6)))
+    valid = [capi.wire_prove_request(scalars, pub, 2), capi.wire_verify_request(blob, sc(1), sc(2), sc(3), pub)]
+    seen = set()
+    for frame in valid:
+        st, hdr, pl = capi.wire_frame(frame)
+        payload = frame[hdr:]
+        for cut in list(range(0, min(len(payload), 80))) + [len(payload) - k for k in range(1, 40)]:
+            op, h = capi.wire_parse(payload[:cut]) if cut > 0 else (capi.BBP_ERR_INPUT, None)
+            seen.add(op)
+            if h is not None and op > 0:
+                capi.wire_free(h)
+        for _ in range(400):
+            m = bytearray(payload)
+            for _ in range(rnd.randrange(1, 4)):
+                m[rnd.randrange(len(m))] = rnd.randrange(256)
+            op, h = capi.wire_parse(bytes(m))
+            seen.add(op)
+            if op > 0:
+                capi.wire_free(h)
+    for _ in range(300):
+        junk = bytes(rnd.randrange(256) for _ in range(rnd.randrange(1, 200)))
+        st, hdr, pl = capi.wire_frame(junk)
+        assert st in (0, 1) or st < 0
+        op, h = capi.wire_parse(junk)
+        seen.add(op)
+        if op > 0:
+            capi.wire_free(h)
+    assert {1, 2, 0} <= seen and any(x < 0 for x in seen)
