@@ -253,7 +253,7 @@ struct proto_state {
     uint32_t ipp_colmap_n = 0, ipp_colmap_gcols = 0;
     dev_buf fext, ftab;            // materialised folded bases: extended, then niels (+ B at the tail)
     dev_buf chal, zpow, ypow, yinvpow, wit, vbl, blind3, poly, tout, a, b, sG, sH, slots, ab, pub, dyn_sc, dyn_pts, dyn_niels, stat, stat_red,
-        msm_out, msm_ext, flags, valid, commit_in, commit_out, rng_states, rng_raw, bw_digests;
+        msm_out, msm_ext, flags, valid, commit_in, commit_out, rng_states, rng_raw, bw_digests, rp_blobs, rp_chal0, rp_dyn0;
     host_buf h_wit, h_states;
     cudaStream_t rng_stream = nullptr;   // the device TranscriptRng chain runs beside the A_I1 / A_O1 commitments
     cudaEvent_t ev_up = nullptr, ev_rng = nullptr, ev_dyn = nullptr, ev_head = nullptr, ev_pow = nullptr;
@@ -289,7 +289,7 @@ void proto_release(proto_state *ps) {
     ps->fext.release(); ps->ftab.release();
     dev_buf *all[] = {&ps->chal, &ps->zpow, &ps->ypow, &ps->yinvpow, &ps->wit, &ps->vbl, &ps->blind3, &ps->poly, &ps->tout, &ps->a, &ps->b, &ps->sG, &ps->sH,
                       &ps->slots, &ps->ab, &ps->pub, &ps->dyn_sc, &ps->dyn_pts, &ps->dyn_niels, &ps->stat, &ps->stat_red, &ps->msm_out, &ps->msm_ext,
-                      &ps->flags, &ps->valid, &ps->commit_in, &ps->commit_out, &ps->rng_states, &ps->rng_raw, &ps->bw_digests};
+                      &ps->flags, &ps->valid, &ps->commit_in, &ps->commit_out, &ps->rng_states, &ps->rng_raw, &ps->bw_digests, &ps->rp_blobs, &ps->rp_chal0, &ps->rp_dyn0};
     for (dev_buf *b : all) b->release();
     ps->h_wit.release(); ps->h_states.release();
     if (ps->rng_stream) cudaStreamDestroy(ps->rng_stream);

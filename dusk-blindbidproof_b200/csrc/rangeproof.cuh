@@ -272,6 +272,129 @@ struct rp_verify_job {
     int status = 0;
 };
 
+// The same for large batches, with the replay on the device (rng_kernels.cuh: k_rp_verify_transcript_warp): the host keeps
+// the format checks and the packing, everything per-proof that costs time — ~40 Keccak permutations, an inversion, ~300
+// scalar products — runs one warp per proof. One stream, one synchronisation per pass.
+inline int rp_verify_group_device(bbp_ctx *ctx, std::vector<rp_verify_job> &jobs, uint32_t nbits, uint32_t m) {
+    proto_state *ps = proto_get(ctx);
+    const uint32_t nm = nbits * m, lg = log2_u32(nm);
+    const uint32_t gcols = ctx->gens_capacity * ctx->party_capacity, slot_len = 2 + 2 * gcols, ds = 4 + 2 * lg + m;
+    const size_t proof_len = (size_t)32 * (9 + 2 * lg), blob_stride = (size_t)32 * m + proof_len;
+    int rc;
+    if ((rc = proto_tables(ctx))) return rc;
+    std::vector<size_t> live;
+    // host: FormatError / VerificationError checks that need no arithmetic (RangeProof::from_bytes, validate_and_append_point)
+    for (size_t i = 0; i < jobs.size(); i++) {
+        rp_verify_job &J = jobs[i];
+        const uint8_t *pf = J.proof.data();
+        const size_t len = J.proof.size();
+        J.status = BBP_ERR_FORMAT;
+        if (len % 32 != 0 || len < 7 * 32) continue;
+        sc t;
+        if (!sc_from_canonical(t, pf + 128) || !sc_from_canonical(t, pf + 160) || !sc_from_canonical(t, pf + 192)) continue;
+        const size_t ne = (len - 224) / 32;
+        if (ne < 2 || (ne - 2) % 2 != 0) continue;
+        const size_t lg_p = (ne - 2) / 2;
+        if (lg_p >= 32) continue;
+        if (!sc_from_canonical(t, pf + 224 + 64 * lg_p) || !sc_from_canonical(t, pf + 224 + 64 * lg_p + 32)) continue;
+        J.status = BBP_ERR_VERIFICATION;
+        if (all_zero32(pf) || all_zero32(pf + 32) || all_zero32(pf + 64) || all_zero32(pf + 96)) continue;
+        if (nm != ((size_t)1 << lg_p)) continue;
+        bool ident = false;
+        for (size_t j = 0; j < 2 * lg_p; j++) ident = ident || all_zero32(pf + 224 + 32 * j);
+        if (ident || J.commitments.size() != (size_t)32 * m) continue;
+        live.push_back(i);
+    }
+    const uint32_t P = (uint32_t)live.size();
+    if (!P) return 0;
+    // pinned staging: blobs (commitments | proof), seeds, dynamic points (A S T_1 T_2 | L_j | R_j | V_j)
+    if ((rc = ps->h_wit.ensure((size_t)P * (blob_stride + 32 + (size_t)ds * 32)))) return rc;
+    uint8_t *h_blobs = ps->h_wit.p, *h_seeds = h_blobs + (size_t)P * blob_stride, *h_pts = h_seeds + (size_t)P * 32;
+    parallel_for(P, [&](size_t k) {
+        const rp_verify_job &J = jobs[live[k]];
+        const uint8_t *pf = J.proof.data(), *LR = pf + 224;
+        uint8_t *bl = h_blobs + k * blob_stride, *pp = h_pts + k * (size_t)ds * 32;
+        memcpy(bl, J.commitments.data(), (size_t)32 * m);
+        memcpy(bl + (size_t)32 * m, pf, proof_len);
+        memcpy(h_seeds + k * 32, J.rng_seed, 32);
+        memcpy(pp, pf, 128);
+        for (uint32_t j = 0; j < lg; j++) {
+            memcpy(pp + (size_t)(4 + j) * 32, LR + 64 * (size_t)j, 32);
+            memcpy(pp + (size_t)(4 + lg + j) * 32, LR + 64 * (size_t)j + 32, 32);
+        }
+        memcpy(pp + (size_t)(4 + 2 * lg) * 32, J.commitments.data(), (size_t)32 * m);
+    });
+    const size_t voff = ((size_t)P * ds + 3) & ~(size_t)3;
+    if ((rc = ps->dyn_pts.ensure((size_t)P * ds * 32)) || (rc = ps->dyn_niels.ensure((size_t)P * ds * 96)) || (rc = ps->valid.ensure(voff + 4)) ||
+        (rc = ps->rp_blobs.ensure((size_t)P * blob_stride)) || (rc = ps->rng_states.ensure((size_t)P * 32)) || (rc = ps->rp_chal0.ensure((size_t)P * CH_N * 32)) ||
+        (rc = ps->rp_dyn0.ensure((size_t)P * ds * 32)) || (rc = ps->chal.ensure((size_t)P * CH_N * 32)) || (rc = ps->dyn_sc.ensure((size_t)P * ds * 32)) ||
+        (rc = ps->zpow.ensure(32)) || (rc = ps->ypow.ensure((size_t)P * nm * 32)) || (rc = ps->yinvpow.ensure((size_t)P * nm * 32)) ||
+        (rc = ps->stat.ensure((size_t)P * slot_len * 32)) || (rc = ps->stat_red.ensure((size_t)P * slot_len * 32)) || (rc = ps->msm_ext.ensure((size_t)2 * P * 128)) ||
+        (rc = ps->flags.ensure(P)) || (rc = ps->sG.ensure((size_t)P * nm * 32)))
+        return rc;
+    if ((rc = h2d(ctx, ps->rp_blobs.p, h_blobs, (size_t)P * blob_stride)) || (rc = h2d(ctx, ps->rng_states.p, h_seeds, (size_t)P * 32)) ||
+        (rc = h2d(ctx, ps->dyn_pts.p, h_pts, (size_t)P * ds * 32)))
+        return rc;
+    int *d_all = (int *)(ps->valid.p + voff);
+    BBP_CUDA_OK(cudaMemsetAsync(d_all, 1, 4, ctx->stream));
+    k_decompress_to_niels<<<(P * ds + 127) / 128, 128, 0, ctx->stream>>>(ps->dyn_pts.as<uint32_t>(), ps->dyn_niels.p, P * ds, d_all, ps->valid.p);
+    transcript_init init;
+    {
+        merlin_transcript tr("bbp-rangeproof");
+        tr.rangeproof_domain_sep(nbits, m);
+        tr.export_state(init.state);
+    }
+    k_rp_verify_transcript_warp<<<(P + 3) / 4, 128, 0, ctx->stream>>>(init, ps->rp_blobs.p, (uint32_t)blob_stride, ps->rng_states.p, P, m, nbits, lg,
+                                                                      ps->rp_chal0.as<sc>(), ps->rp_dyn0.as<sc>(), ds);
+    ctx->launches += 2;
+    std::vector<uint8_t> valid((size_t)P * ds), fl;
+    auto pass = [&](bool combined) -> int {
+        int r;
+        const uint32_t n_groups = combined ? 1 : P;
+        k_rp_apply_weights<<<P, 128, 0, ctx->stream>>>(ps->rp_chal0.as<sc>(), ps->rp_dyn0.as<sc>(), ps->valid.p, ds, P, combined ? 1u : 0u, ps->chal.as<sc>(),
+                                                       ps->dyn_sc.as<sc>());
+        sc_batch SB;
+        memset(&SB, 0, sizeof SB);
+        SB.n_proofs = P; SB.n = nm; SB.lg_n = lg; SB.gcols = gcols; SB.rp_bits = nbits; SB.rp_m = m; SB.q = 0;
+        SB.chal = ps->chal.as<sc>(); SB.zpow = ps->zpow.as<sc>(); SB.ypow = ps->ypow.as<sc>(); SB.yinvpow = ps->yinvpow.as<sc>(); SB.stat = ps->stat.as<sc>();
+        SB.stab = ps->sG.as<sc>();
+        SB.skip_ypow = 1;
+        k_powers<<<P, BBP_SC_THREADS, k_powers_smem(SB.q, SB.n), ctx->stream>>>(SB);
+        k_rp_verify_scalars<<<P, BBP_SC_THREADS, 0, ctx->stream>>>(SB);
+        if (combined && P >= 32)
+            k_stat_reduce_wide<<<dim3((slot_len + 15) / 16, 1), 256, 0, ctx->stream>>>(SB.stat, P, slot_len, ps->stat_red.as<sc>());
+        else
+            k_stat_reduce<<<dim3((slot_len + BBP_SC_THREADS - 1) / BBP_SC_THREADS, n_groups), BBP_SC_THREADS, 0, ctx->stream>>>(SB.stat, combined ? P : 1, slot_len,
+                                                                                                                                 ps->stat_red.as<sc>());
+        ctx->launches += 4;
+        uint8_t *ext = ps->msm_ext.p;
+        if ((r = msm_gens_device(ctx, ps->stat_red.as<sc>(), slot_len, n_groups, nullptr, ext))) return r;
+        msm_shape sh = msm_engine::make_shape(P * ds, combined ? P * ds : ds, P * ds, false, 0, 0, 0);
+        if ((r = ctx->msm.run(sh, ps->dyn_sc.p, ps->dyn_niels.p, ext + (size_t)n_groups * 128, nullptr))) return r;
+        k_group_sum_identity<<<(n_groups + 63) / 64, 64, 0, ctx->stream>>>(ext, n_groups, 2, n_groups, ps->flags.p, nullptr);
+        ctx->launches++;
+        fl.resize(n_groups);
+        BBP_CUDA_OK(cudaMemcpyAsync(valid.data(), ps->valid.p, valid.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        return d2h_sync(ctx, fl.data(), ps->flags.p, n_groups);
+    };
+    auto alive = [&](uint32_t k) {
+        for (uint32_t t = 0; t < ds; t++) if (!valid[(size_t)k * ds + t]) return false;
+        return true;
+    };
+    const char *cb_env = getenv("BBP_RP_COMBINED");   // 0 = always the per-request pass (tests run both)
+    const bool try_combined = P >= 2 && (cb_env ? atoi(cb_env) != 0 : true);
+    if (try_combined) {
+        if ((rc = pass(true))) return rc;
+        if (fl[0]) {   // the combination is the identity: every live request verifies
+            for (uint32_t k = 0; k < P; k++) jobs[live[k]].status = alive(k) ? 0 : BBP_ERR_VERIFICATION;
+            return 0;
+        }
+    }
+    if ((rc = pass(false))) return rc;
+    for (uint32_t k = 0; k < P; k++) jobs[live[k]].status = (alive(k) && fl[k]) ? 0 : BBP_ERR_VERIFICATION;
+    return 0;
+}
+
 // every job independently (one mega-check each); all jobs share (nbits, m)
 inline int rp_verify_group(bbp_ctx *ctx, std::vector<rp_verify_job> &jobs, uint32_t nbits, uint32_t m) {
     proto_state *ps = proto_get(ctx);
@@ -281,6 +404,11 @@ inline int rp_verify_group(bbp_ctx *ctx, std::vector<rp_verify_job> &jobs, uint3
     if (ctx->gens_capacity != nbits || ctx->party_capacity < m) {
         for (auto &J : jobs) J.status = BBP_ERR_INVALID_GENERATORS_LENGTH;
         return 0;
+    }
+    {   // large batches replay their transcripts on the device (same crossover knob as the blind-bid verifier)
+        const char *tr_env = getenv("BBP_DEVICE_TRANSCRIPT_MIN_BATCH");
+        if (jobs.size() >= (size_t)(tr_env ? atoi(tr_env) : (int)(8 * host_threads())) && !keccak_per_thread())
+            return rp_verify_group_device(ctx, jobs, nbits, m);
     }
     if ((rc = proto_tables(ctx))) return rc;
     std::vector<size_t> live;

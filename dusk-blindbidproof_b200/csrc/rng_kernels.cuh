@@ -716,6 +716,157 @@ __global__ void __launch_bounds__(128) k_verify_transcript_warp(transcript_init 
 }
 
 
+// ---------------------------------------------------------------- aggregated range proofs: verifier replay, one warp per proof
+// RangeProof::verify_multiple's Fiat-Shamir replay and O(m + lg n) scalar work (rangeproof.cuh: rp_verify_group restates it
+// on the host for small batches): challenges y, z, x, w, u_j, the verifier's two random scalars c and rho, one batched
+// inversion of (u_j, y, y - 1, z - 1), delta(y, z), the B / B_blinding coefficients and the dynamic-point scalars. Everything
+// is written UNWEIGHTED (chal0 / dyn0); k_rp_apply_weights applies the per-pass weight. blob = commitments (m x 32) | proof.
+__global__ void __launch_bounds__(128) k_rp_verify_transcript_warp(transcript_init init, const uint8_t *__restrict__ blobs, uint32_t blob_stride,
+                                                                   const uint8_t *__restrict__ seeds, uint32_t n_req, uint32_t m, uint32_t nbits, uint32_t lg,
+                                                                   sc *__restrict__ chal0, sc *__restrict__ dyn0, uint32_t ds) {
+    __shared__ uint64_t sm_state[4][26];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t p = blockIdx.x * 4 + warp;
+    if (p >= n_req) return;   // whole warps leave together
+    strobe_warp S;
+    S.attach((uint8_t *)sm_state[warp], lane);
+    S.load(init.state);
+    const bool lead = lane == 0;
+    const uint8_t *blob = blobs + (size_t)p * blob_stride;
+    const uint8_t *pf = blob + 32 * (size_t)m;            // A S T_1 T_2 | t_x t_x_blinding e_blinding | L_0 R_0 .. | a b
+    const uint8_t *LR = pf + 224;
+    const uint64_t nm = (uint64_t)nbits * m;
+    sc *c = chal0 + (size_t)p * CH_N;
+    sc *d = dyn0 + (size_t)p * ds;
+    for (uint32_t j = 0; j < m; j++) S.append_message(BBP_LBL("V"), blob + 32 * (size_t)j, 32);
+    S.append_message(BBP_LBL("A"), pf, 32);
+    S.append_message(BBP_LBL("S"), pf + 32, 32);
+    const sc y = S.challenge_scalar(BBP_LBL("y"));
+    const sc z = S.challenge_scalar(BBP_LBL("z"));
+    S.append_message(BBP_LBL("T_1"), pf + 64, 32);
+    S.append_message(BBP_LBL("T_2"), pf + 96, 32);
+    const sc x = S.challenge_scalar(BBP_LBL("x"));
+    S.append_message(BBP_LBL("t_x"), pf + 128, 32);
+    S.append_message(BBP_LBL("t_x_blinding"), pf + 160, 32);
+    S.append_message(BBP_LBL("e_blinding"), pf + 192, 32);
+    const sc w = S.challenge_scalar(BBP_LBL("w"));
+    S.append_message(BBP_LBL("dom-sep"), (const uint8_t *)"ipp v1", 6);
+    S.append_u64(BBP_LBL("n"), nm);
+    // prefix products for the batched inversion, in the Montgomery domain: u_0 .. u_{lg-1}, y, y - 1, z - 1
+    sc acc = sc_to_mont(sc_one());
+    for (uint32_t j = 0; j < lg; j++) {
+        S.append_message(BBP_LBL("L"), LR + 64 * (size_t)j, 32);
+        S.append_message(BBP_LBL("R"), LR + 64 * (size_t)j + 32, 32);
+        sc uj = S.challenge_scalar(BBP_LBL("u"));
+        if (lead) {
+            c[CH_UJ0 + j] = uj;
+            c[CH_UJ0 + lg + j] = acc;      // prefix (Montgomery form), replaced by the inverse below
+        }
+        acc = mm(acc, sc_to_mont(uj));
+    }
+    __syncwarp();
+    // verifier randomness once every proof byte has been absorbed: c merges the two equations, rho weighs the request
+    S.meta_ad_label(BBP_LBL("rng"));
+    S.key32(seeds + 32 * (size_t)p);
+    uint32_t rw[16];
+    S.fill64(rw);
+    const sc cc = sc_from_wide_words(rw);
+    S.fill64(rw);
+    const sc rho = sc_from_wide_words(rw);
+    const sc one = sc_one();
+    sc ym1 = sc_sub(y, one), zm1 = sc_sub(z, one);
+    const bool y_is_1 = sc_iszero(ym1), z_is_1 = sc_iszero(zm1);
+    if (y_is_1) ym1 = one;
+    if (z_is_1) zm1 = one;
+    const sc yM = sc_to_mont(y), ym1M = sc_to_mont(ym1), zm1M = sc_to_mont(zm1);
+    const sc pre_y = acc;
+    acc = mm(acc, yM);
+    const sc pre_ym1 = acc;
+    acc = mm(acc, ym1M);
+    const sc pre_zm1 = acc;
+    acc = mm(acc, zm1M);
+    sc inv = sc_invert_mont(acc);
+    const sc zm1_inv = mm(inv, pre_zm1);           // Montgomery form
+    inv = mm(inv, zm1M);
+    const sc ym1_inv = mm(inv, pre_ym1);
+    inv = mm(inv, ym1M);
+    const sc yinv = sc_from_mont(mm(inv, pre_y));
+    inv = mm(inv, yM);
+    sc *dl = d + 4, *dr = d + 4 + lg;
+#pragma unroll 1
+    for (uint32_t j = lg; j-- > 0;) {
+        sc uj = c[CH_UJ0 + j];
+        sc ujinv = sc_from_mont(mm(inv, c[CH_UJ0 + lg + j]));
+        inv = mm(inv, sc_to_mont(uj));
+        sc w_l = sc_mul(uj, uj), w_r = sc_mul(ujinv, ujinv);
+        __syncwarp();
+        if (lead) { c[CH_UJ0 + lg + j] = ujinv; dl[j] = w_l; dr[j] = w_r; }
+    }
+    // geometric series: 1 + b + .. + b^(cnt-1) = (b^cnt - 1) / (b - 1) for cnt >= 64 and b != 1, summed directly otherwise
+    const sc zM = sc_to_mont(z);
+    sc sum_y, sum_z;
+    if (nm >= 64 && !y_is_1) {
+        sc e = yM;
+        for (uint64_t k = 1; k < nm; k <<= 1) e = mm(e, e);      // n m is a power of two: y^(n m) by squarings
+        sum_y = sc_from_mont(mm(sc_sub(e, sc_to_mont(one)), ym1_inv));
+    } else {
+        sc s = sc_zero(), e = sc_to_mont(one);
+        for (uint64_t k = 0; k < nm; k++) { s = sc_add(s, e); e = mm(e, yM); }
+        sum_y = sc_from_mont(s);
+    }
+    {
+        sc s = sc_zero(), e = sc_to_mont(one);
+        for (uint32_t k = 0; k < m; k++) { s = sc_add(s, e); e = mm(e, zM); }   // e = z^m afterwards
+        sum_z = (m >= 64 && !z_is_1) ? sc_from_mont(mm(sc_sub(e, sc_to_mont(one)), zm1_inv)) : sc_from_mont(s);
+    }
+    sc sum_2 = sc_zero();
+    if (nbits >= 64) { sum_2.v[0] = 0xffffffffu; sum_2.v[1] = 0xffffffffu; }   // 2^64 - 1 (the protocol's widest range)
+    else { const uint64_t v = (1ull << nbits) - 1; sum_2.v[0] = (uint32_t)v; sum_2.v[1] = (uint32_t)(v >> 32); }
+    const sc zz = sc_mul(z, z);
+    const sc delta = sc_sub(sc_mul(sc_sub(z, zz), sum_y), sc_mul(sc_mul(sc_mul(zz, z), sum_2), sum_z));
+    sc t_x, t_x_bl, e_bl, a, b;
+    const uint32_t *sw = (const uint32_t *)(pf + 128);
+    for (int k = 0; k < 8; k++) { t_x.v[k] = sw[k]; t_x_bl.v[k] = sw[8 + k]; e_bl.v[k] = sw[16 + k]; }
+    const uint32_t *abw = (const uint32_t *)(LR + 64 * (size_t)lg);
+    for (int k = 0; k < 8; k++) { a.v[k] = abw[k]; b.v[k] = abw[8 + k]; }
+    const sc tx_coef = sc_add(sc_mul(w, sc_sub(t_x, sc_mul(a, b))), sc_mul(cc, sc_sub(delta, t_x)));
+    const sc txbl_coef = sc_sub(sc_neg(e_bl), sc_mul(cc, t_x_bl));
+    // commitment weights c z^(2+j)
+    sc ez = sc_mul(cc, zz);
+    for (uint32_t j = 0; j < m; j++) {
+        if (lead) d[4 + 2 * lg + j] = ez;
+        ez = sc_mul(ez, z);
+    }
+    if (!lead) return;
+    c[CH_Y] = y; c[CH_YINV] = yinv; c[CH_Z] = z; c[CH_X] = x; c[CH_W] = w; c[CH_A] = a; c[CH_B] = b; c[CH_R] = rho; c[CH_RHO] = one;
+    c[CH_TX] = tx_coef; c[CH_TXBL] = txbl_coef;
+    c[CH_U] = sc_zero(); c[CH_UJ] = sc_zero(); c[CH_UJINV] = sc_zero(); c[CH_EBL] = sc_zero();
+    d[0] = one; d[1] = x; d[2] = sc_mul(cc, x); d[3] = sc_mul(cc, sc_mul(x, x));
+}
+
+// per-pass weights of a range-proof verification: rho_k (combined pass) or 1 (per-request pass), 0 for a request with a point
+// that did not decompress; applied to the B / B_blinding coefficients and the dynamic scalars, CH_RHO for k_rp_verify_scalars
+__global__ void __launch_bounds__(128) k_rp_apply_weights(const sc *__restrict__ chal0, const sc *__restrict__ dyn0, const uint8_t *__restrict__ valid,
+                                                          uint32_t ds, uint32_t n_req, uint32_t combined, sc *__restrict__ chal, sc *__restrict__ dyn) {
+    const uint32_t p = blockIdx.x, t = threadIdx.x;
+    __shared__ uint32_t dead;
+    if (t == 0) dead = 0;
+    __syncthreads();
+    for (uint32_t k = t; k < ds; k += blockDim.x)
+        if (!valid[(size_t)p * ds + k]) dead = 1;
+    __syncthreads();
+    const sc *c0 = chal0 + (size_t)p * CH_N;
+    const sc rho = dead ? sc_zero() : (combined ? c0[CH_R] : sc_one());
+    sc *c = chal + (size_t)p * CH_N;
+    for (uint32_t k = t; k < CH_N; k += blockDim.x) {
+        sc v = c0[k];
+        if (k == CH_RHO) v = rho;
+        else if (k == CH_TX || k == CH_TXBL) v = sc_mul(rho, v);
+        c[k] = v;
+    }
+    for (uint32_t k = t; k < ds; k += blockDim.x) dyn[(size_t)p * ds + k] = sc_mul(rho, dyn0[(size_t)p * ds + k]);
+}
+
 // ---------------------------------------------------------------- batch-verification weights on the device
 // The random linear combination of a batch verification needs one secret, proof-binding weight per request. Deriving them
 // on the host meant a device -> host -> device round trip in the middle of every batch (the digests r_i come out of the

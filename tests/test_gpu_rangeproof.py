@@ -36,7 +36,11 @@ def backend(nbits, parties):
     return bbp_loader.load().Backend(device=0, gens_capacity=nbits, party_capacity=parties)
 
 
-def test_rangeproof_small_matches_oracle():
+@pytest.mark.parametrize("replay", ["host", "device"])
+def test_rangeproof_small_matches_oracle(replay, monkeypatch):
+    # the verifier's transcript replay runs on the host for small batches and one warp per proof on the device for large
+    # ones (BBP_DEVICE_TRANSCRIPT_MIN_BATCH is the crossover): force each, same verdicts
+    monkeypatch.setenv("BBP_DEVICE_TRANSCRIPT_MIN_BATCH", "1000000" if replay == "host" else "1")
     be = backend(8, 4)
     seed = b"\x07" * 32
     for values in ([0, 255, 17, 128], [3, 200], [77]):
@@ -91,8 +95,9 @@ def test_rangeproof_config5_shape(hybrid, device_rng, monkeypatch):
     assert want_bad[1] != 0
     # batches are first checked as ONE random linear combination (accept all if it is the identity), then per request if
     # that fails; BBP_RP_COMBINED=0 goes straight to the per-request pass: same verdicts either way
-    for combined in ("1", "0"):
+    for combined, replay_min in (("1", "1000000"), ("0", "1000000"), ("1", "1"), ("0", "1")):
         monkeypatch.setenv("BBP_RP_COMBINED", combined)
+        monkeypatch.setenv("BBP_DEVICE_TRANSCRIPT_MIN_BATCH", replay_min)   # host / device transcript replay
         assert be.rangeproof_verify_batch(proofs, Vs, 64, 64, RNG * 3) == [0, 0, 0]
         assert be.rangeproof_verify_batch(bad, Vs, 64, 64, RNG * 3) == want_bad
         # a commitment swapped between two requests breaks both
