@@ -853,7 +853,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--msm-lanes", type=int, default=4, help="lanes the resident MSM steps alternate over (1 = no pipelining, max 8)")
-    ap.add_argument("--e2e-callers", type=int, default=2, help="concurrent caller threads of the host-buffer MSM leg (one lane each)")
+    ap.add_argument("--e2e-callers", type=int, default=4, help="concurrent caller threads of the host-buffer MSM leg (one lane each)")
     ap.add_argument("--sustained-s", type=float, default=2.0, help="length of the sustained MSM sub-leg in seconds (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-blindbid", action="store_true", help="skip the blind-bid prove / batch-verify legs")

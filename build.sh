@@ -14,4 +14,8 @@ SRV=dusk-blindbidproof_b200/bbp-blindbid-server
 if [ ! -f $SRV ] || [ $SRC/server/bbp_server.cpp -nt $SRV ] || [ $OUT -nt $SRV ]; then
   g++ -O2 -std=c++17 -pthread -o $SRV $SRC/server/bbp_server.cpp -Ldusk-blindbidproof_b200 -lbbp_b200 -Wl,-rpath,'$ORIGIN'
 fi
+LG=dusk-blindbidproof_b200/bbp-loadgen   # replays request frames against the server, one connection per request (tools/server_bench.py)
+if [ ! -f $LG ] || [ $SRC/server/bbp_loadgen.cpp -nt $LG ]; then
+  g++ -O2 -std=c++17 -pthread -o $LG $SRC/server/bbp_loadgen.cpp
+fi
 make -s -C oracle liboracle.so

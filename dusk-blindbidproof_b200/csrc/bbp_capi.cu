@@ -1,6 +1,8 @@
 // C ABI of the B200 backend (include/bbp.h): context, resident generator tables, base tables, MSM entry points,
 // point codecs and the primitive test hooks. The protocol layer (R1CS prove / verify, blind-bid drivers) lives in
 // r1cs.cuh / blindbid.cuh and is exported from the bottom of this translation unit.
+#include <sys/random.h>
+#include <cerrno>
 #include "../../include/bbp.h"
 #include <time.h>
 #include "codec.cuh"
@@ -376,19 +378,31 @@ void bbp_wire_request_free(bbp_wire_request *r) { delete r; }
 void bbp_wire_reply_free(uint8_t *reply) { free(reply); }
 
 // n x len random bytes: SHAKE256(seed || LE64(index)) when a seed is given (tests), the OS generator otherwise
-static bool wire_entropy(const uint8_t *seed32, uint64_t index, uint8_t *out, size_t len) {
-    if (seed32) {
-        keccak_sponge sp = shake256_new();
-        sp.absorb(seed32, 32);
-        uint8_t ix[8];
-        for (int i = 0; i < 8; i++) ix[i] = (uint8_t)(index >> (8 * i));
-        sp.absorb(ix, 8);
-        sp.squeeze(out, len);
-        return true;
+// randomness of request `index` of one bbp_wire_execute call: SHAKE256(seed || LE64(index)). seed is the caller's (tests:
+// reproducible replies) or 32 bytes of OS entropy drawn ONCE per call (wire_os_seed) — opening the entropy device per
+// request cost ~15 us each and was the server's throughput bound.
+static void wire_entropy(const uint8_t *seed32, uint64_t index, uint8_t *out, size_t len) {
+    keccak_sponge sp = shake256_new();
+    sp.absorb(seed32, 32);
+    uint8_t ix[8];
+    for (int i = 0; i < 8; i++) ix[i] = (uint8_t)(index >> (8 * i));
+    sp.absorb(ix, 8);
+    sp.squeeze(out, len);
+}
+static bool wire_os_seed(uint8_t out[32]) {
+    size_t got = 0;
+    while (got < 32) {
+        ssize_t r = getrandom(out + got, 32 - got, 0);
+        if (r < 0) {
+            if (errno == EINTR) continue;
+            break;
+        }
+        got += (size_t)r;
     }
-    FILE *f = fopen("/dev/urandom", "rb");
+    if (got == 32) return true;
+    FILE *f = fopen("/dev/urandom", "rb");   // kernels without the system call
     if (!f) return false;
-    bool ok = fread(out, 1, len, f) == len;
+    bool ok = fread(out, 1, 32, f) == 32;
     fclose(f);
     return ok;
 }
@@ -404,6 +418,11 @@ int bbp_wire_execute(bbp_ctx *ctx, size_t n, bbp_wire_request *const *reqs, cons
 }
 static int wire_execute_impl(bbp_ctx *ctx, size_t n, bbp_wire_request *const *reqs, const uint8_t *seed32, uint8_t **replies, size_t *reply_lens) {
     cudaSetDevice(ctx->device);
+    uint8_t os_seed[32];
+    if (!seed32) {
+        if (!wire_os_seed(os_seed)) return BBP_ERR_INPUT;
+        seed32 = os_seed;
+    }
     std::vector<prove_job> pj;
     std::vector<verify_job> vj;
     std::vector<size_t> pmap, vmap;
@@ -425,7 +444,7 @@ static int wire_execute_impl(bbp_ctx *ctx, size_t n, bbp_wire_request *const *re
             J.toggle = R.toggle;
             // the randomness the reference takes from thread_rng (proof.rs:53,64 and TranscriptRngBuilder::finalize)
             std::vector<uint8_t> rnd(64 * (4 + L) + 32);
-            if (!wire_entropy(seed32, i, rnd.data(), rnd.size())) return BBP_ERR_INPUT;
+            wire_entropy(seed32, i, rnd.data(), rnd.size());
             J.blindings.resize(4 + L);
             for (size_t k = 0; k < 4 + L; k++) J.blindings[k] = sc_from_wide(rnd.data() + 64 * k);   // Scalar::random
             memcpy(J.rng_seed, rnd.data() + 64 * (4 + L), 32);
@@ -448,7 +467,7 @@ static int wire_execute_impl(bbp_ctx *ctx, size_t n, bbp_wire_request *const *re
             J.t_c = R.t_c.data(); J.n_t_c = R.t_c.size() / 32;
             J.pub_list.resize(L);
             for (size_t k = 0; k < L; k++) J.pub_list[k] = sc_from_bits(R.pub_list.data() + 32 * k);   // verify.rs:112-116
-            if (!wire_entropy(seed32, i, J.rng_seed, 32)) return BBP_ERR_INPUT;
+            wire_entropy(seed32, i, J.rng_seed, 32);
             vmap.push_back(i);
             vj.push_back(std::move(J));
         }
@@ -468,7 +487,7 @@ static int wire_execute_impl(bbp_ctx *ctx, size_t n, bbp_wire_request *const *re
     }
     if (!vj.empty()) {
         uint8_t batch_seed[32];
-        if (!wire_entropy(seed32, ~0ull, batch_seed, 32)) return BBP_ERR_INPUT;
+        wire_entropy(seed32, ~0ull, batch_seed, 32);
         int ok = 0;
         // one random linear combination for all pending verifications; on failure the library re-checks per request, so
         // every client gets the verdict Verify::verify would have given it

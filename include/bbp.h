@@ -273,8 +273,9 @@ int bbp_wire_parse(const uint8_t *payload, size_t len, bbp_wire_request **out);
 void bbp_wire_request_free(bbp_wire_request *r);
 /* Executes n parsed requests at once: every prove request in ONE bbp_blindbid_prove_batch, every verify request in ONE
  * bbp_blindbid_verify_batch (per-request verdicts). replies[i] = the complete reply frame (release with bbp_wire_reply_free), or
- * NULL when the reference would write nothing (prove-side error). seed32 = NULL: blindings and RNG seeds come from the OS, as
- * the reference takes them from thread_rng; non-NULL: derived from it (reproducible tests). */
+ * NULL when the reference would write nothing (prove-side error). Request i's blindings and RNG seed are SHAKE256(seed || LE64(i)):
+ * seed32 = NULL draws seed from the OS once per call (getrandom), as the reference takes its randomness from thread_rng;
+ * non-NULL uses the caller's 32 bytes (reproducible tests). */
 int bbp_wire_execute(bbp_ctx *ctx, size_t n, bbp_wire_request *const *reqs, const uint8_t *seed32, uint8_t **replies, size_t *reply_lens);
 void bbp_wire_reply_free(uint8_t *reply);
 /* client-side encoders: the frames a client (the Go node) sends, and the proof blob inside a verify request / prove reply.
