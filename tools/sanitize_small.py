@@ -34,4 +34,13 @@ be = pkg.Backend(device=0, gens_capacity=8, party_capacity=4)
 bl = b"".join((7 + i).to_bytes(32, "little") for i in range(4))
 rc, pf, V = be.rangeproof_prove([1, 2, 3, 255], bl, 8, bytes(32)); assert rc == 0
 assert be.rangeproof_verify(pf, V, 8, bytes(32)) == 0
+# a batch that does not fill the replay kernel's last block (5 proofs, 4 warps per block), one proof corrupted
+vals = [[(3 * k + j) & 255 for j in range(4)] for k in range(5)]
+st, pfs, Vs = be.rangeproof_prove_batch(vals, bl * 5, 4, 8, bytes(range(32)) * 5)
+assert st == [0] * 5
+assert be.rangeproof_verify_batch(pfs, Vs, 4, 8, bytes(32) * 5) == [0] * 5
+pfs[3] = pfs[3][:150] + bytes([pfs[3][150] ^ 1]) + pfs[3][151:]
+got = be.rangeproof_verify_batch(pfs, Vs, 4, 8, bytes(32) * 5)
+assert got[3] != 0 and [got[i] for i in (0, 1, 2, 4)] == [0] * 4, got
+be.close()
 print("sanitize_small ok")
