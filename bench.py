@@ -371,8 +371,8 @@ def run_blindbid(pkg, be, torch, dist, rank, world, n_prove=1024, n_verify=1024,
     torch.cuda.synchronize()
     strong_s = tmax((time.perf_counter() - t0) / reps)
     assert ok_s
-    # ... and with 1 / 16 corrupted proofs (single GPU: the failed combination is followed by the per-request pass that
-    # names the culprits; the sharded call reports the batch verdict only)
+    # ... and with 1 / 16 corrupted proofs (single GPU: the failed combination is narrowed down in runs of 8, then the
+    # per-request pass names the culprits; the sharded call reports the batch verdict only)
     corrupted = {}
     if world == 1:
         for n_bad in (1, 16):
@@ -390,7 +390,7 @@ def run_blindbid(pkg, be, torch, dist, rank, world, n_prove=1024, n_verify=1024,
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / reps
             corrupted[f"{n_bad}_bad"] = {"value": n_total / dt, "unit": "proofs/s", "ms_per_batch": 1e3 * dt,
-                                         "note": "combined check fails -> one per-request pass; verdicts single out exactly the corrupted requests"}
+                                         "note": "combined check fails -> runs of 8 re-combined from the resident state -> per-request pass over the failing runs; verdicts single out exactly the corrupted requests"}
     # BASELINE config 3 sweep: list lengths x batch sizes, one GPU (rank 0's GPU at N > 1 is not re-measured)
     sweep = []
     if world == 1:

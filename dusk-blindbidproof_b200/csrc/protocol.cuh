@@ -255,6 +255,7 @@ struct proto_state {
     dev_buf chal, zpow, ypow, yinvpow, wit, vbl, blind3, poly, tout, a, b, sG, sH, slots, ab, pub, dyn_sc, dyn_pts, dyn_niels, stat, stat_red,
         msm_out, msm_ext, flags, valid, commit_in, commit_out, rng_states, rng_raw, bw_digests, rp_blobs, rp_chal0, rp_dyn0;
     host_buf h_wit, h_states;
+    uint32_t resident_B = 0, resident_ds = 0;   // requests / dynamic points per request of the last combined verification pass (verify_regroup_pass)
     cudaStream_t rng_stream = nullptr;   // the device TranscriptRng chain runs beside the A_I1 / A_O1 commitments
     cudaEvent_t ev_up = nullptr, ev_rng = nullptr, ev_dyn = nullptr, ev_head = nullptr, ev_pow = nullptr;
     int proof_versioned = 1;       // R1CSProof::to_bytes layout (SURVEY.md §8c risk R1): 1 = leading phase byte, 0 = legacy 14-point form
@@ -1258,6 +1259,8 @@ inline void verify_transcript_host(const verify_prepared &P, const uint8_t rng_s
 // digest per request — the verifier scalar r that request's own transcript yields after absorbing the whole proof, so it
 // binds every proof byte — keyed with batch_seed. Verdicts: 1 = mega-check is the identity.
 // Requests with a point that fails to decompress get status VERIFICATION and weight zero.
+// A combined pass leaves its per-request state (weighted static rows, weighted dynamic scalars, decompressed points) on the
+// context: verify_regroup_pass re-combines it in runs.
 inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector<verify_prepared> &prep, const std::vector<size_t> &idx, bool combined,
                         const uint8_t *batch_seed, std::vector<uint8_t> &verdicts, uint8_t *d_partial_ext /* combined: 2 x 128 B, optional */) {
     proto_state *ps = proto_get(ctx);
@@ -1270,7 +1273,8 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     const circuit_template &T = *dt->tpl;
     const uint32_t n1 = T.n1, m = T.m, n = P0.n, lg = P0.lg, gcols = ctx->gens_capacity * ctx->party_capacity, slot_len = 2 + 2 * gcols;
     const uint32_t ds = m + 11 + 2 * lg, blob_stride = 32 * (ds + 5);
-    const uint32_t n_groups = combined ? 1 : B;
+    const uint32_t gsz = combined ? B : 1;   // requests per verdict
+    const uint32_t n_groups = (B + gsz - 1) / gsz;
     phase_trace trace(combined ? "verify_group(combined)" : "verify_group(each)");
     event_timeline tl;
 
@@ -1301,7 +1305,7 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     // side stream; transcript replay, weights, power tables, scalar assembly and the static-base MSM run on the main one.
     // The side stream only waits for the weighted dynamic scalars (k_dyn_weights). If the static-base MSM itself needs
     // the bucket engine (per-request checks of a large group, or the latency path switched off) both share the main stream.
-    const uint32_t n_stat_slots = combined ? 1 : B;
+    const uint32_t n_stat_slots = n_groups;
     const char *ds_env = getenv("BBP_VERIFY_STREAMS");   // 1 = everything on the main stream (tests compare both)
     const bool two_streams = small_msm_ok((size_t)n_stat_slots * slot_len) && !(ds_env && atoi(ds_env) == 1);
     cudaStream_t side = ctx->stream;
@@ -1400,7 +1404,7 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     ctx->launches++;
     tl.mark("weights", ctx->stream);
     uint8_t *ext = ps->msm_ext.p;
-    const uint32_t dyn_total = B * ds, per_slot = combined ? dyn_total : ds;
+    const uint32_t dyn_total = B * ds, per_slot = gsz * ds;
     {   // dynamic bases: one variable-base slot per group, on the side stream
         if (two_streams) {
             BBP_CUDA_OK(cudaEventRecord(ps->ev_dyn, ctx->stream));
@@ -1419,11 +1423,11 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     else k_powers<<<B, BBP_SC_THREADS, k_powers_smem(SB.q, SB.n), ctx->stream>>>(SB);
     tl.mark("powers", ctx->stream);
     k_verify_scalars<<<B, BBP_SC_THREADS, k_verify_scalars_smem(SB.n, SB.lg_n), ctx->stream>>>(SB);
-    if (combined && B >= 32)
-        k_stat_reduce_wide<<<dim3((slot_len + 15) / 16, n_groups), 256, 0, ctx->stream>>>(SB.stat, B, slot_len, ps->stat_red.as<sc>());
+    if (gsz >= 32)
+        k_stat_reduce_wide<<<dim3((slot_len + 15) / 16, n_groups), 256, 0, ctx->stream>>>(SB.stat, gsz, slot_len, ps->stat_red.as<sc>(), B);
     else
-        k_stat_reduce<<<dim3((slot_len + BBP_SC_THREADS - 1) / BBP_SC_THREADS, n_groups), BBP_SC_THREADS, 0, ctx->stream>>>(SB.stat, combined ? B : 1, slot_len,
-                                                                                                                             ps->stat_red.as<sc>());
+        k_stat_reduce<<<dim3((slot_len + BBP_SC_THREADS - 1) / BBP_SC_THREADS, n_groups), BBP_SC_THREADS, 0, ctx->stream>>>(SB.stat, gsz, slot_len,
+                                                                                                                             ps->stat_red.as<sc>(), B);
     ctx->launches += 3;
     tl.mark("scalars+reduce", ctx->stream);
     // static bases: one fixed-table slot per group
@@ -1432,7 +1436,7 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     if (two_streams) BBP_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ps->ev_up, 0));   // join: the dynamic-base sum
     k_group_sum_identity<<<(n_groups + 63) / 64, 64, 0, ctx->stream>>>(ext, n_groups, 2, n_groups, ps->flags.p, nullptr);
     ctx->launches++;
-    if (combined && d_partial_ext) BBP_CUDA_OK(cudaMemcpyAsync(d_partial_ext, ext, 256, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (combined && n_groups == 1 && d_partial_ext) BBP_CUDA_OK(cudaMemcpyAsync(d_partial_ext, ext, 256, cudaMemcpyDeviceToDevice, ctx->stream));
     std::vector<uint8_t> fl(n_groups), valid((size_t)B * ds);
     BBP_CUDA_OK(cudaMemcpyAsync(valid.data(), ps->valid.p, valid.size(), cudaMemcpyDeviceToHost, ctx->stream));
     trace.mark("launched");
@@ -1440,6 +1444,8 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
     if ((rc = d2h_sync(ctx, fl.data(), ps->flags.p, n_groups))) return rc;
     trace.mark("sync");
     tl.report(combined ? "verify_group(combined)" : "verify_group(each)");
+    ps->resident_B = combined ? B : 0;   // what verify_regroup_pass may re-combine
+    ps->resident_ds = ds;
     verdicts.assign(n_groups, 0);
     for (uint32_t g = 0; g < n_groups; g++) verdicts[g] = fl[g];
     for (uint32_t bi = 0; bi < B; bi++) {
@@ -1449,6 +1455,34 @@ inline int verify_group(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector
         else if (!combined) jobs[idx[bi]].status = fl[bi] ? 0 : BBP_ERR_VERIFICATION;
     }
     return 0;
+}
+
+// Narrowing pass after a failed combination: the B requests the last combined verify_group call on THIS context checked are
+// re-combined in consecutive runs of g (the same weights; ceil(B / g) verdicts) from the state that call left in HBM — the
+// weighted static rows (ps->stat), the weighted dynamic scalars and the decompressed points — so it costs two small MSMs
+// and no upload, replay or scalar assembly.
+inline int verify_regroup_pass(bbp_ctx *ctx, uint32_t B, uint32_t g, std::vector<uint8_t> &verdicts) {
+    proto_state *ps = proto_get(ctx);
+    if (!B || !g || ps->resident_B != B) return BBP_ERR_INPUT;
+    const uint32_t ds = ps->resident_ds, gcols = ctx->gens_capacity * ctx->party_capacity, slot_len = 2 + 2 * gcols, n_groups = (B + g - 1) / g;
+    int rc;
+    if ((rc = ps->stat_red.ensure((size_t)n_groups * slot_len * 32)) || (rc = ps->msm_ext.ensure((size_t)2 * n_groups * 128)) || (rc = ps->flags.ensure(n_groups)))
+        return rc;
+    if (g >= 32)
+        k_stat_reduce_wide<<<dim3((slot_len + 15) / 16, n_groups), 256, 0, ctx->stream>>>(ps->stat.as<sc>(), g, slot_len, ps->stat_red.as<sc>(), B);
+    else
+        k_stat_reduce<<<dim3((slot_len + BBP_SC_THREADS - 1) / BBP_SC_THREADS, n_groups), BBP_SC_THREADS, 0, ctx->stream>>>(ps->stat.as<sc>(), g, slot_len,
+                                                                                                                             ps->stat_red.as<sc>(), B);
+    ctx->launches++;
+    uint8_t *ext = ps->msm_ext.p;
+    if ((rc = msm_gens_device(ctx, ps->stat_red.as<sc>(), slot_len, n_groups, nullptr, ext))) return rc;
+    msm_shape sh = msm_engine::make_shape(B * ds, g * ds, B * ds, false, 0, 0, 0);
+    if ((rc = ctx->msm.run(sh, ps->dyn_sc.p, ps->dyn_niels.p, ext + (size_t)n_groups * 128, nullptr))) return rc;
+    k_group_sum_identity<<<(n_groups + 63) / 64, 64, 0, ctx->stream>>>(ext, n_groups, 2, n_groups, ps->flags.p, nullptr);
+    ctx->launches++;
+    verdicts.assign(n_groups, 0);
+    ps->resident_B = 0;   // stat_red / msm_ext were reused; the per-request state itself is still intact but one narrowing pass is all there is
+    return d2h_sync(ctx, verdicts.data(), ps->flags.p, n_groups);
 }
 
 inline void verify_prepare_all(bbp_ctx *ctx, std::vector<verify_job> &jobs, std::vector<verify_prepared> &prep, std::map<uint64_t, std::vector<size_t>> &groups) {
@@ -1474,6 +1508,13 @@ inline int verify_each(bbp_ctx *ctx, std::vector<verify_job> &jobs) {
         std::vector<uint8_t> verdicts;
         return verify_group(c, jobs, prep, parts[i], false, nullptr, verdicts, nullptr);
     });
+}
+
+// run length of the narrowing pass after a failed combination (BBP_VERIFY_REGROUP, 0 / 1 = off: per-request pass at once)
+inline uint32_t verify_regroup() {
+    const char *e = getenv("BBP_VERIFY_REGROUP");
+    int v = e ? atoi(e) : 8;
+    return v < 0 ? 0u : (uint32_t)v;
 }
 
 // Batch verification: one random linear combination of the mega-checks of all requests of a
@@ -1504,10 +1545,25 @@ inline int verify_batch(bbp_ctx *ctx, std::vector<verify_job> &jobs, const uint8
         int r = verify_group(c, jobs, prep, parts[i], true, batch_seed, verdicts, partial_only ? ps0->lane_partials.p + 256 * i : nullptr);
         if (r) return r;
         part_ok[i] = verdicts[0];
-        if (!verdicts[0] && !partial_only) {   // the combination failed: find the culprits with one per-request pass
-            for (size_t k : parts[i]) jobs[k].status = 0;
+        if (!verdicts[0] && !partial_only) {
+            // The combination failed: find the culprits. A per-request pass over the whole part costs ~12 us per request
+            // (4098 static columns each); with few culprits it is cheaper to re-combine runs of g requests first (same
+            // weights, ceil(B / g) verdicts, from the state the combined pass left on this lane) and to check one by one only
+            // the runs that fail.
+            const std::vector<size_t> *suspects = &parts[i];
+            std::vector<size_t> narrowed;
+            const uint32_t g = verify_regroup();
+            if (g >= 2 && parts[i].size() >= 4 * (size_t)g) {
+                std::vector<uint8_t> vg;
+                if ((r = verify_regroup_pass(c, (uint32_t)parts[i].size(), g, vg))) return r;
+                for (size_t k = 0; k < parts[i].size(); k++)
+                    if (!vg[k / g]) narrowed.push_back(parts[i][k]);
+                // every run passing while their sum fails cannot happen; if it does, trust nothing and check everyone
+                if (!narrowed.empty()) suspects = &narrowed;
+            }
+            for (size_t k : *suspects) jobs[k].status = 0;
             std::vector<uint8_t> v2;
-            if ((r = verify_group(c, jobs, prep, parts[i], false, nullptr, v2, nullptr))) return r;
+            if ((r = verify_group(c, jobs, prep, *suspects, false, nullptr, v2, nullptr))) return r;
         }
         return 0;
     });

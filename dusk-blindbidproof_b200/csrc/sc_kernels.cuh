@@ -759,24 +759,29 @@ __global__ void __launch_bounds__(BBP_SC_THREADS) k_rp_verify_scalars(sc_batch B
 // sums the per-proof static-base scalars over groups of `group_size` consecutive proofs -> one slot of slot_len scalars
 // per group (normal form). group_size = 1 converts each proof's slot for an individual check; group_size = n_proofs
 // builds the single combined slot of a batch verification.
-__global__ void __launch_bounds__(BBP_SC_THREADS) k_stat_reduce(const sc *__restrict__ stat, uint32_t group_size, uint32_t slot_len, sc *__restrict__ out) {
+// total: rows in stat; the last group may be shorter than group_size
+__global__ void __launch_bounds__(BBP_SC_THREADS) k_stat_reduce(const sc *__restrict__ stat, uint32_t group_size, uint32_t slot_len, sc *__restrict__ out,
+                                                                uint32_t total = 0xffffffffu) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
     if (i >= slot_len) return;
     sc acc = sc_zero();
     const sc *base = stat + (size_t)g * group_size * slot_len;
-    for (uint32_t p = 0; p < group_size; p++) acc = sc_add(acc, base[(size_t)p * slot_len + i]);
+    const uint32_t cnt = min(group_size, total - min(total, g * group_size));
+    for (uint32_t p = 0; p < cnt; p++) acc = sc_add(acc, base[(size_t)p * slot_len + i]);
     out[(size_t)g * slot_len + i] = sc_from_mont(acc);
 }
 
 // the same for large groups: 16 columns x 16 proof slices per block, so that a batch-wide sum is not 4098 threads walking
 // the whole batch one proof at a time
-__global__ void __launch_bounds__(256) k_stat_reduce_wide(const sc *__restrict__ stat, uint32_t group_size, uint32_t slot_len, sc *__restrict__ out) {
+__global__ void __launch_bounds__(256) k_stat_reduce_wide(const sc *__restrict__ stat, uint32_t group_size, uint32_t slot_len, sc *__restrict__ out,
+                                                          uint32_t total = 0xffffffffu) {
     __shared__ sc part[16][16];
     const uint32_t col = threadIdx.x & 15, slice = threadIdx.x >> 4, i = blockIdx.x * 16 + col, g = blockIdx.y;
     sc acc = sc_zero();
     if (i < slot_len) {
         const sc *base = stat + (size_t)g * group_size * slot_len + i;
-        for (uint32_t p = slice; p < group_size; p += 16) acc = sc_add(acc, base[(size_t)p * slot_len]);
+        const uint32_t cnt = min(group_size, total - min(total, g * group_size));
+        for (uint32_t p = slice; p < cnt; p += 16) acc = sc_add(acc, base[(size_t)p * slot_len]);
     }
     part[slice][col] = acc;
     __syncthreads();

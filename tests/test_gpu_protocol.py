@@ -341,6 +341,38 @@ def test_batch_verify_equals_and_of_singles(be, part, monkeypatch):
     assert st == be.blindbid_verify_each(its)
 
 
+@pytest.mark.parametrize("regroup", ["8", "5", "0"])
+def test_failed_combination_is_narrowed_by_runs(be, regroup, monkeypatch):
+    """After a failed combined check the batch is re-combined in runs of g requests (BBP_VERIFY_REGROUP, default 8; 0 = off)
+    and only the failing runs are checked request by request: the verdicts must be those of the per-request path, with a
+    ragged last run (37 = 4 x 8 + 5), culprits in the first and the last run, and a request whose point does not
+    decompress (weight zero: its run still passes)."""
+    monkeypatch.setenv("BBP_VERIFY_REGROUP", regroup)
+    n = 37
+    cases = [make_case(900 + i, 2) for i in range(n)]
+    outs = be.blindbid_prove_batch(cases)
+    assert all(o[0] == 0 for o in outs)
+    items = [verify_item(b, p, c, t, i) for i, (b, (st, p, c, t)) in enumerate(zip(cases, outs))]
+    ok, st = be.blindbid_verify_batch(items, seed32("runs0"))
+    assert ok and st == [0] * n
+    its = [dict(x) for x in items]
+    for b, pos in ((3, -1), (36, 1 + 32 * 8)):
+        p = bytearray(its[b]["proof"]); p[pos] ^= 1; its[b]["proof"] = bytes(p)
+    p = bytearray(its[10]["proof"]); p[1] |= 1; its[10]["proof"] = bytes(p)      # A_I1 is no longer a point encoding
+    ok, st = be.blindbid_verify_batch(its, seed32("runs1"))
+    assert not ok
+    assert [i for i, s in enumerate(st) if s != 0] == [3, 10, 36]
+    assert st == be.blindbid_verify_each(its)
+    for b in (3, 10, 36):
+        assert oracle_verify(its[b]) == st[b]
+    # every request bad: every run fails, everyone is checked alone
+    its = [dict(x) for x in items]
+    for b in range(n):
+        p = bytearray(its[b]["proof"]); p[-1] ^= 2; its[b]["proof"] = bytes(p)
+    ok, st = be.blindbid_verify_batch(its, seed32("runs2"))
+    assert not ok and all(s != 0 for s in st) and st == be.blindbid_verify_each(its)
+
+
 @pytest.mark.parametrize("n", [1, 31, 32, 33, 100, 1024])
 def test_batch_weights_are_the_documented_shake_tree(be, n):
     """The weights of a batch verification's random linear combination are derived on the device (rng_kernels.cuh:
