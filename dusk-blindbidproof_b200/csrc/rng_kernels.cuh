@@ -595,6 +595,76 @@ __device__ __noinline__ sc sc_invert_mont(sc accM) {
     return inv;
 }
 
+// The same for PUBLIC values (the verifier's challenges): binary extended Euclid (HAC 14.61) on 256-bit integers — about
+// 350 halvings and 180 subtractions of 8 limbs (~19 k instructions) instead of 265 Montgomery products (~61 k). Variable
+// time, which the verifier may be; every lane of the warp computes the same value, so the data-dependent loops do not
+// diverge. Input and output in the Montgomery domain like sc_invert_mont; 0 -> 0 as x^(l-2) gives.
+__device__ __forceinline__ void u256_shr1(uint32_t *a) {
+#pragma unroll
+    for (int i = 0; i < 7; i++) a[i] = __funnelshift_r(a[i], a[i + 1], 1);
+    a[7] >>= 1;
+}
+// x / 2 mod l for x < l: (x + (x odd ? l : 0)) >> 1
+__device__ __forceinline__ void sc_half(uint32_t *x) {
+    const uint32_t m = 0u - (x[0] & 1u);
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32 %7, %7, %15;"
+        : "+&r"(x[0]), "+&r"(x[1]), "+&r"(x[2]), "+&r"(x[3]), "+&r"(x[4]), "+&r"(x[5]), "+&r"(x[6]), "+&r"(x[7])
+        : "r"(sc_l_limb(0) & m), "r"(sc_l_limb(1) & m), "r"(sc_l_limb(2) & m), "r"(sc_l_limb(3) & m), "r"(sc_l_limb(4) & m), "r"(sc_l_limb(5) & m),
+          "r"(sc_l_limb(6) & m), "r"(sc_l_limb(7) & m));
+    u256_shr1(x);
+}
+// t = a - b over 256 bits; returns the borrow (1 when a < b)
+__device__ __forceinline__ uint32_t u256_sub(uint32_t *t, const uint32_t *a, const uint32_t *b) {
+    uint32_t bw;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=&r"(t[0]), "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]), "=&r"(bw)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return bw & 1u;
+}
+__device__ __forceinline__ bool u256_is_one(const uint32_t *a) {
+    return (a[0] ^ 1u | a[1] | a[2] | a[3] | a[4] | a[5] | a[6] | a[7]) == 0;
+}
+__device__ __noinline__ sc sc_invert_mont_vartime(sc accM) {
+    sc a = sc_from_mont(accM);   // < l
+    if (sc_iszero(a)) return a;
+    uint32_t u[8], v[8], t[8];
+    sc x1 = sc_one(), x2 = sc_zero();
+#pragma unroll
+    for (int i = 0; i < 8; i++) { u[i] = a.v[i]; v[i] = sc_l_limb(i); }
+#pragma unroll 1
+    while (!u256_is_one(u) && !u256_is_one(v)) {
+#pragma unroll 1
+        while (!(u[0] & 1u)) { u256_shr1(u); sc_half(x1.v); }
+#pragma unroll 1
+        while (!(v[0] & 1u)) { u256_shr1(v); sc_half(x2.v); }
+        if (!u256_sub(t, u, v)) {      // u >= v
+#pragma unroll
+            for (int i = 0; i < 8; i++) u[i] = t[i];
+            x1 = sc_sub(x1, x2);
+        } else {
+            u256_sub(v, v, u);
+            x2 = sc_sub(x2, x1);
+        }
+    }
+    return sc_to_mont(u256_is_one(u) ? x1 : x2);
+}
+
 // phase 0: the whole replay in one launch. phase 1: up to the challenges y, z (plus y^-1) — everything k_powers needs — then the
 // sponge is parked in `states` (208 B per request); phase 2: the rest, resumed from there. With the split the power tables
 // are built on a second stream while the (latency-bound) remainder of the replay runs.
@@ -629,7 +699,7 @@ __global__ void __launch_bounds__(128) k_verify_transcript_warp(transcript_init 
         y = S.challenge_scalar(BBP_LBL("y"));
         z = S.challenge_scalar(BBP_LBL("z"));
         if (phase == 1) {
-            sc yinv = sc_from_mont(sc_invert_mont(sc_to_mont(y)));
+            sc yinv = sc_from_mont(sc_invert_mont_vartime(sc_to_mont(y)));
             if (lead) { c[CH_Y] = y; c[CH_Z] = z; c[CH_YINV] = yinv; }
             S.store(states + (size_t)p * BBP_STROBE_STATE_BYTES, 0);
             return;
@@ -672,8 +742,8 @@ __global__ void __launch_bounds__(128) k_verify_transcript_warp(transcript_init 
     uint32_t rw[16];
     S.fill64(rw);
     sc r = sc_from_wide_words(rw);
-    // acc = (prod u_j [* y]) R ; invert once: x^(l-2) in the Montgomery domain
-    sc inv = sc_invert_mont(acc);
+    // acc = (prod u_j [* y]) R ; invert once, in the Montgomery domain
+    sc inv = sc_invert_mont_vartime(acc);   // public challenges: binary Euclid instead of x^(l-2)
     sc yinv;
     if (phase == 0) {
         yinv = sc_from_mont(mm(inv, pre_y));
@@ -785,7 +855,7 @@ __global__ void __launch_bounds__(128) k_rp_verify_transcript_warp(transcript_in
     acc = mm(acc, ym1M);
     const sc pre_zm1 = acc;
     acc = mm(acc, zm1M);
-    sc inv = sc_invert_mont(acc);
+    sc inv = sc_invert_mont_vartime(acc);   // public challenges: binary Euclid instead of x^(l-2)
     const sc zm1_inv = mm(inv, pre_zm1);           // Montgomery form
     inv = mm(inv, zm1M);
     const sc ym1_inv = mm(inv, pre_ym1);
