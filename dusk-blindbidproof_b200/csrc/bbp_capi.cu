@@ -278,7 +278,7 @@ static int msm_oneshot(bbp_ctx *ctx, const uint8_t *scalars, const uint8_t *poin
     uint8_t res[32];
     BBP_CUDA_OK(cudaMemcpyAsync(res, ctx->d_out, 32, cudaMemcpyDeviceToHost, ctx->stream));
     if (compressed) BBP_CUDA_OK(cudaMemcpyAsync(&h_valid, d_valid, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    BBP_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    if ((rc = wait_stream(ctx))) return rc;
     trace.mark("h2d+table+msm+d2h");
     if (!h_valid) return BBP_ERR_DECOMPRESS;   // optional_multiscalar_mul -> None; out untouched
     memcpy(out, res, 32);

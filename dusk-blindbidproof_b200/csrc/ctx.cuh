@@ -23,6 +23,7 @@ struct bbp_ctx {
     cudaStream_t copy_stream = nullptr;    // one-shot MSMs: point upload (copy_stream) and table build (conv_stream) overlap
     cudaStream_t conv_stream = nullptr;    // the scalar-side pipeline; uploads are never queued behind a conversion kernel
     cudaEvent_t ev_table = nullptr, ev_start = nullptr, ev_chunk[8] = {};
+    cudaEvent_t ev_block = nullptr;   // cudaEventBlockingSync: waits that put the host thread to sleep (wait_stream)
     bbp::msm_engine msm;
     uint64_t launches = 0;
     // generators: index 0 = B, 1 = B_blinding, then G[party 0][0..cap), G[party 1][..), ..., then all H the same way, so
@@ -91,6 +92,7 @@ struct bbp_ctx {
         for (auto &e : ev_chunk) BBP_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         BBP_CUDA_OK(cudaEventCreateWithFlags(&ev_table, cudaEventDisableTiming));
         BBP_CUDA_OK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+        BBP_CUDA_OK(cudaEventCreateWithFlags(&ev_block, cudaEventDisableTiming | cudaEventBlockingSync));
         msm.stream = stream;
         gens_capacity = gens_cap;
         party_capacity = gens_cap ? party_cap : 0;
@@ -146,6 +148,8 @@ struct bbp_ctx {
         conv_stream = nullptr;
         if (ev_table) cudaEventDestroy(ev_table);
         if (ev_start) cudaEventDestroy(ev_start);
+        if (ev_block) cudaEventDestroy(ev_block);
+        ev_block = nullptr;
         if (stream) cudaStreamDestroy(stream);
         stream = nullptr; copy_stream = nullptr; ev_table = ev_start = nullptr;
     }
