@@ -3,7 +3,7 @@ codecs, prove + verify with the device-side RNG / witness / transcript / hybrid-
 import hashlib, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))   # orc: the oracle is the checker here, as in the tests beside this script
 os.environ["BBP_DEVICE_RNG_MIN_BATCH"] = "1"
 os.environ["BBP_DEVICE_TRANSCRIPT_MIN_BATCH"] = "1"
 os.environ["BBP_IPP_HYBRID"] = "2"
