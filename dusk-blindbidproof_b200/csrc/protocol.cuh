@@ -235,7 +235,13 @@ struct dev_template {
     uint32_t n_long = 0, long_rows[BBP_MAX_LONG] = {};   // the longest CSR rows among wL / wR / wO (sc_kernels.cuh: flatten_long_rows)
 };
 
-static const uint32_t WT_C = 11, WT_W = 24;   // window table over the generators: 24 windows of 11 bits (264 >= 254 bits)
+// window table over the generators: 24 windows of 11 bits (264 >= 254 bits). BBP_WT_C (10 .. 14) is a tuning knob, read once.
+static const uint32_t WT_C = [] {
+    const char *e = getenv("BBP_WT_C");
+    int v = e ? atoi(e) : 11;
+    return (uint32_t)((v >= 10 && v <= 14) ? v : 11);
+}();
+static const uint32_t WT_W = (253 + WT_C) / WT_C;
 static const uint32_t WT2_C = 6, WT2_W = 43;   // second table, small windows: 32 buckets per slot, for the many tiny slots of the
                                                // IPP materialisation MSM (16 scalars each)
 static const uint32_t IPP_NF = 128;            // hybrid IPP: folded bases are materialised when the vectors reach this length
