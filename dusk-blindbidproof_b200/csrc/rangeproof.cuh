@@ -272,6 +272,28 @@ struct rp_verify_job {
     int status = 0;
 };
 
+// The checks of RangeProof::from_bytes and verify_multiple that look at bytes only: lengths, canonical scalars
+// (FormatError), identity points among A, S, T_1, T_2, L_j, R_j (validate_and_append_point), the number of L / R pairs
+// against n * m and the number of commitments (VerificationError). 1 = the proof goes on to the transcript replay.
+inline int rp_byte_checks(const rp_verify_job &J, uint32_t nm, uint32_t m) {
+    const uint8_t *pf = J.proof.data();
+    const size_t len = J.proof.size();
+    if (len % 32 != 0 || len < 7 * 32) return BBP_ERR_FORMAT;
+    sc t;
+    if (!sc_from_canonical(t, pf + 128) || !sc_from_canonical(t, pf + 160) || !sc_from_canonical(t, pf + 192)) return BBP_ERR_FORMAT;
+    const size_t ne = (len - 224) / 32;
+    if (ne < 2 || (ne - 2) % 2 != 0) return BBP_ERR_FORMAT;
+    const size_t lg_p = (ne - 2) / 2;
+    if (lg_p >= 32) return BBP_ERR_FORMAT;
+    if (!sc_from_canonical(t, pf + 224 + 64 * lg_p) || !sc_from_canonical(t, pf + 224 + 64 * lg_p + 32)) return BBP_ERR_FORMAT;
+    if (all_zero32(pf) || all_zero32(pf + 32) || all_zero32(pf + 64) || all_zero32(pf + 96)) return BBP_ERR_VERIFICATION;
+    if (nm != ((size_t)1 << lg_p)) return BBP_ERR_VERIFICATION;
+    for (size_t j = 0; j < 2 * lg_p; j++)
+        if (all_zero32(pf + 224 + 32 * j)) return BBP_ERR_VERIFICATION;
+    if (J.commitments.size() != (size_t)32 * m) return BBP_ERR_VERIFICATION;
+    return 1;
+}
+
 // The same for large batches, with the replay on the device (rng_kernels.cuh: k_rp_verify_transcript_warp): the host keeps
 // the format checks and the packing, everything per-proof that costs time — ~40 Keccak permutations, an inversion, ~300
 // scalar products — runs one warp per proof. One stream, one synchronisation per pass.
@@ -285,25 +307,8 @@ inline int rp_verify_group_device(bbp_ctx *ctx, std::vector<rp_verify_job> &jobs
     std::vector<size_t> live;
     // host: FormatError / VerificationError checks that need no arithmetic (RangeProof::from_bytes, validate_and_append_point)
     for (size_t i = 0; i < jobs.size(); i++) {
-        rp_verify_job &J = jobs[i];
-        const uint8_t *pf = J.proof.data();
-        const size_t len = J.proof.size();
-        J.status = BBP_ERR_FORMAT;
-        if (len % 32 != 0 || len < 7 * 32) continue;
-        sc t;
-        if (!sc_from_canonical(t, pf + 128) || !sc_from_canonical(t, pf + 160) || !sc_from_canonical(t, pf + 192)) continue;
-        const size_t ne = (len - 224) / 32;
-        if (ne < 2 || (ne - 2) % 2 != 0) continue;
-        const size_t lg_p = (ne - 2) / 2;
-        if (lg_p >= 32) continue;
-        if (!sc_from_canonical(t, pf + 224 + 64 * lg_p) || !sc_from_canonical(t, pf + 224 + 64 * lg_p + 32)) continue;
-        J.status = BBP_ERR_VERIFICATION;
-        if (all_zero32(pf) || all_zero32(pf + 32) || all_zero32(pf + 64) || all_zero32(pf + 96)) continue;
-        if (nm != ((size_t)1 << lg_p)) continue;
-        bool ident = false;
-        for (size_t j = 0; j < 2 * lg_p; j++) ident = ident || all_zero32(pf + 224 + 32 * j);
-        if (ident || J.commitments.size() != (size_t)32 * m) continue;
-        live.push_back(i);
+        jobs[i].status = rp_byte_checks(jobs[i], nm, m);
+        if (jobs[i].status == 1) live.push_back(i);
     }
     const uint32_t P = (uint32_t)live.size();
     if (!P) return 0;
@@ -418,17 +423,14 @@ inline int rp_verify_group(bbp_ctx *ctx, std::vector<rp_verify_job> &jobs, uint3
         rp_verify_job &J = jobs[i];
         const uint8_t *pf = J.proof.data();
         size_t len = J.proof.size();
-        J.status = BBP_ERR_FORMAT;
-        if (len % 32 != 0 || len < 7 * 32) return;
+        J.status = rp_byte_checks(J, nm, m);
+        if (J.status != 1) return;
+        J.status = BBP_ERR_VERIFICATION;   // until the replay below has gone through
         sc t_x, t_x_bl, e_bl, a, b;
-        if (!sc_from_canonical(t_x, pf + 128) || !sc_from_canonical(t_x_bl, pf + 160) || !sc_from_canonical(e_bl, pf + 192)) return;
-        size_t ne = (len - 224) / 32;
-        if (ne < 2 || (ne - 2) % 2 != 0) return;
-        size_t lg_p = (ne - 2) / 2;
-        if (lg_p >= 32) return;
+        sc_from_canonical(t_x, pf + 128); sc_from_canonical(t_x_bl, pf + 160); sc_from_canonical(e_bl, pf + 192);
+        const size_t lg_p = ((len - 224) / 32 - 2) / 2;
         const uint8_t *LR = pf + 224;
-        if (!sc_from_canonical(a, LR + 64 * lg_p) || !sc_from_canonical(b, LR + 64 * lg_p + 32)) return;
-        J.status = BBP_ERR_VERIFICATION;
+        sc_from_canonical(a, LR + 64 * lg_p); sc_from_canonical(b, LR + 64 * lg_p + 32);
         merlin_transcript tr("bbp-rangeproof");
         tr.rangeproof_domain_sep(nbits, m);
         for (uint32_t j = 0; j < m; j++) tr.append_point("V", &J.commitments[32 * (size_t)j]);
