@@ -160,6 +160,10 @@ class Backend:
     def sum_compress_device(self, ext_dev_ptr, n, out_dev_ptr):
         _chk(lib().bbp_sum_compress_device(self.ctx, ctypes.c_void_p(ext_dev_ptr), _sz(n), ctypes.c_void_p(out_dev_ptr)), "bbp_sum_compress_device")
 
+    def sharded_verdict_device(self, rows_dev_ptr, world, row_stride, out_dev_ptr):
+        _chk(lib().bbp_sharded_verdict_device(self.ctx, ctypes.c_void_p(rows_dev_ptr), _sz(world), _sz(row_stride), ctypes.c_void_p(out_dev_ptr)),
+             "bbp_sharded_verdict_device")
+
     def msm_vartime_ptr(self, scalars_host_ptr, points_ext_host_ptr, n):
         """bbp_msm_vartime on raw host pointers (e.g. pinned torch tensors)."""
         out = _out(32)

@@ -209,6 +209,15 @@ int bbp_sum_compress_device(bbp_ctx *ctx, const void *points_ext_device, size_t 
     return BBP_OK;
 }
 
+int bbp_sharded_verdict_device(bbp_ctx *ctx, const void *rows_device, size_t world, size_t row_stride, void *out_device) {
+    if (!ctx || !rows_device || !out_device || world == 0 || world > 4096 || row_stride < 257) return BBP_ERR_INPUT;
+    cudaSetDevice(ctx->device);
+    k_sharded_verdict<<<1, 32, 0, ctx->stream>>>((const uint8_t *)rows_device, (uint32_t)world, (uint32_t)row_stride, (uint8_t *)out_device);
+    ctx->launches++;
+    BBP_CUDA_OK(cudaGetLastError());
+    return BBP_OK;
+}
+
 int bbp_msm_points_batched(bbp_ctx *ctx, const uint8_t *scalars, size_t n_per_slot, size_t n_slots, const bbp_points *points, uint8_t *out) {
     if (!ctx || !scalars || !points || !out || n_per_slot == 0 || n_slots == 0 || n_per_slot != points->n) return BBP_ERR_INPUT;
     size_t n = n_per_slot * n_slots;

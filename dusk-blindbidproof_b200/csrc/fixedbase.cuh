@@ -76,4 +76,26 @@ __global__ void __launch_bounds__(32) k_partial_fold(const uint8_t *__restrict__
     ge_store(out + 128 * (size_t)g, acc);
 }
 
+// Verdict of a proof-range sharded batch verification after the all-gather: rows[r] = rank r's two extended partial sums
+// (2 x 128 B) followed by its local flag byte. out[0] = 1 iff every flag is set and the sum of the 2 x world points is the
+// Ristretto identity — tested in extended coordinates, no compression (its field exponentiation was most of the old
+// sum-and-compress tail). One warp: lane sums, then a tree through shared memory.
+__global__ void __launch_bounds__(32) k_sharded_verdict(const uint8_t *__restrict__ rows, uint32_t world, uint32_t row_stride, uint8_t *__restrict__ out) {
+    __shared__ uint4 sm_u4[32 * 8];
+    uint8_t *sm = (uint8_t *)sm_u4;
+    const uint32_t lane = threadIdx.x;
+    ge acc = ge_identity();
+    bool ok = true;
+    for (uint32_t i = lane; i < 2 * world; i += 32) acc = ge_add(acc, ge_load(rows + (size_t)(i >> 1) * row_stride + 128 * (i & 1)));
+    for (uint32_t r = lane; r < world; r += 32) ok = ok && rows[(size_t)r * row_stride + 256] != 0;
+    ge_store(sm + 128 * lane, acc);
+    __syncwarp();
+    for (uint32_t stride = 16; stride >= 1; stride >>= 1) {
+        if (lane < stride) ge_store(sm + 128 * lane, ge_add(ge_load(sm + 128 * lane), ge_load(sm + 128 * (lane + stride))));
+        __syncwarp();
+    }
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) out[0] = (all_ok && ge_is_identity(ge_load(sm))) ? 1 : 0;
+}
+
 }  // namespace bbp

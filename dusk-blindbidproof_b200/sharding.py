@@ -58,23 +58,23 @@ def sharded_batch_verify(be, dist, items, batch_seed, d_partial, d_gather, d_out
     buf = getattr(be, "_shard_bufs", None)
     if buf is None or buf[0].device != d_out.device or buf[1].numel() != _ROW * world:
         dev = d_out.device
+        pin = dev.type == "cuda"
         buf = (torch.zeros(_ROW, dtype=torch.uint8, device=dev), torch.zeros(_ROW * world, dtype=torch.uint8, device=dev),
-               torch.zeros(_PART * world, dtype=torch.uint8, device=dev), torch.zeros(32 + world, dtype=torch.uint8, device=dev),
-               torch.zeros(32 + world, dtype=torch.uint8).pin_memory() if dev.type == "cuda" else torch.zeros(32 + world, dtype=torch.uint8))
+               torch.zeros(16, dtype=torch.uint8, device=dev),
+               torch.zeros(16, dtype=torch.uint8).pin_memory() if pin else torch.zeros(16, dtype=torch.uint8),
+               torch.zeros(16, dtype=torch.uint8).pin_memory() if pin else torch.zeros(16, dtype=torch.uint8))
         be._shard_bufs = buf
-    row, rows, parts, res, h_res = buf
+    row, rows, res, h_res, h_flag = buf
     local_ok, _ = be.blindbid_verify_batch_partial(items, batch_seed, row.data_ptr())
-    row[_PART] = 1 if local_ok else 0
+    h_flag[0] = 1 if local_ok else 0
+    row[_PART:].copy_(h_flag, non_blocking=True)
     dist.all_gather_into_tensor(rows, row)
-    rv = rows.view(world, _ROW)
-    parts.view(world, _PART).copy_(rv[:, :_PART])
-    be.sum_compress_device(parts.data_ptr(), 2 * world, res.data_ptr())
-    res[32:].copy_(rv[:, _PART])
+    # one launch: sum of the 2 x world partial sums, identity test in extended coordinates, AND of the flags
+    be.sharded_verdict_device(rows.data_ptr(), world, _ROW, res.data_ptr())
     h_res.copy_(res, non_blocking=True)
     if res.is_cuda:
         torch.cuda.current_stream().synchronize()
-    out = bytes(h_res.numpy())
-    return out[:32] == bytes(32) and all(out[32:])
+    return bool(h_res[0].item())
 
 
 def combine_verdicts(dist, local_ok, d_out):

@@ -163,8 +163,13 @@ int bbp_blindbid_verify_batch(bbp_ctx *ctx, size_t n, bbp_verify_req *reqs, cons
  * partial sums (2 x 128 B extended points: static-base part, dynamic part) in HBM at partial_ext_device for the all-gather;
  * Requests rejected before the combination (malformed proof, identity point, point that fails to decompress) do not
  * enter the partial sum: they clear *local_ok and set reqs[i].status. The whole batch verifies iff EVERY rank reports
- * *local_ok = 1 AND the sum of all GPUs' partials is the identity (bbp_sum_compress_device -> 32 zero bytes). */
+ * *local_ok = 1 AND the sum of all GPUs' partials is the identity (bbp_sharded_verdict_device, or bbp_sum_compress_device ->
+ * 32 zero bytes). */
 int bbp_blindbid_verify_batch_partial(bbp_ctx *ctx, size_t n, bbp_verify_req *reqs, const uint8_t batch_seed[32], void *partial_ext_device, int *local_ok);
+/* the verdict after the all-gather, in one launch on the context's stream (no synchronisation): rows_device = world rows of
+ * row_stride (>= 257) bytes, row r = rank r's 2 x 128 B partial sums followed by its local flag byte; out_device[0] = 1 iff
+ * every flag is set and the sum of all 2 x world points is the identity (extended-coordinate test, no compression). */
+int bbp_sharded_verdict_device(bbp_ctx *ctx, const void *rows_device, size_t world, size_t row_stride, void *out_device);
 /* native MiMC-x^7 hash the circuit constrains (src/gadgets.rs:37-68) and its constants (src/blindbid/mod.rs:7-24): host helpers */
 int bbp_mimc_hash(const uint8_t left[32], const uint8_t right[32], uint8_t out[32]);
 int bbp_mimc_constants(uint8_t out[90 * 32]);

@@ -120,6 +120,7 @@ extern "C" {
     pub fn bbp_blindbid_verify_each(ctx: *mut bbp_ctx, n: usize, reqs: *mut bbp_verify_req) -> c_int;
     pub fn bbp_blindbid_verify_batch(ctx: *mut bbp_ctx, n: usize, reqs: *mut bbp_verify_req, batch_seed: *const u8, all_ok: *mut c_int) -> c_int;
     pub fn bbp_blindbid_verify_batch_partial(ctx: *mut bbp_ctx, n: usize, reqs: *mut bbp_verify_req, batch_seed: *const u8, partial_ext_device: *mut c_void, local_ok: *mut c_int) -> c_int;
+    pub fn bbp_sharded_verdict_device(ctx: *mut bbp_ctx, rows_device: *const c_void, world: usize, row_stride: usize, out_device: *mut c_void) -> c_int;
     pub fn bbp_mimc_hash(left: *const u8, right: *const u8, out: *mut u8) -> c_int;
     pub fn bbp_mimc_constants(out: *mut u8) -> c_int;
     pub fn bbp_blindbid_circuit_shape(n_commitments: usize, n_toggles: usize, out: *mut usize) -> c_int;

@@ -79,8 +79,19 @@ def test_proof_range_sharded_batch_verify(ranks, part, monkeypatch):
             local.append(ok)
         d_out = torch.zeros(32, dtype=torch.uint8, device="cuda")
         ctxs[0].sum_compress_device(torch.cat(partials).data_ptr(), 2 * world, d_out.data_ptr())
+        # the one-launch verdict the product path uses (rows = partial sums | flag byte | padding): identity test without
+        # compression AND the flags; must agree with sum-and-compress + the host-side AND
+        rows = torch.zeros(world, 272, dtype=torch.uint8, device="cuda")
+        for r in range(world):
+            rows[r, :256] = partials[r]
+            rows[r, 256] = 1 if local[r] else 0
+        d_v = torch.full((16,), 7, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        ctxs[0].sharded_verdict_device(rows.data_ptr(), world, 272, d_v.data_ptr())
         ctxs[0].sync()
-        return bytes(d_out.cpu().numpy()) == bytes(32), local
+        is_identity = bytes(d_out.cpu().numpy()) == bytes(32)
+        assert int(d_v[0].item()) == (1 if is_identity and all(local) else 0)
+        return is_identity, local
 
     ok, local = run(items)
     assert ok and all(local)

@@ -90,15 +90,18 @@ class _FakeBackend:
         ctypes.memmove(ptr, self.partial, 256)
         return self.local_ok, []
 
-    def sum_compress_device(self, ptr, n, out_ptr):
-        pts = ctypes.string_at(ptr, 128 * n)
+    def sharded_verdict_device(self, rows_ptr, world, row_stride, out_ptr):
+        # what k_sharded_verdict computes, with the oracle's group arithmetic: every flag set and the points sum to the identity
         comp = ctypes.create_string_buffer(32)
-        cs = []
-        for i in range(n):
-            self.orc.lib().orc_ge_compress_ext(comp, pts[128 * i:128 * i + 128])
-            cs.append(comp.raw)
+        cs, flags = [], []
+        for r in range(world):
+            row = ctypes.string_at(rows_ptr + r * row_stride, row_stride)
+            flags.append(row[256])
+            for k in range(2):
+                self.orc.lib().orc_ge_compress_ext(comp, row[128 * k:128 * k + 128])
+                cs.append(comp.raw)
         total = self.orc.msm(b"".join((1).to_bytes(32, "little") for _ in cs), b"".join(cs), algo=0)
-        ctypes.memmove(out_ptr, total, 32)
+        ctypes.memmove(out_ptr, bytes([1 if all(flags) and total == bytes(32) else 0]), 1)
 
 
 def _verify_worker(rank, world, port, case, q):
