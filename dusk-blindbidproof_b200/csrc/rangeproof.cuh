@@ -358,6 +358,26 @@ inline int rp_verify_group_device(bbp_ctx *ctx, std::vector<rp_verify_job> &jobs
         const uint32_t n_groups = combined ? 1 : P;
         k_rp_apply_weights<<<P, 128, 0, ctx->stream>>>(ps->rp_chal0.as<sc>(), ps->rp_dyn0.as<sc>(), ps->valid.p, ds, P, combined ? 1u : 0u, ps->chal.as<sc>(),
                                                        ps->dyn_sc.as<sc>());
+        // The variable-base MSM over the requests' own points needs nothing but the weighted dynamic scalars: it runs on the
+        // side stream beside the power tables, the scalar assembly and the static-base MSM — as long as the latter takes the
+        // digit-table path (one combined slot); the bucket engine has one set of scratch buffers, so otherwise both stay here.
+        const char *st_env = getenv("BBP_VERIFY_STREAMS");
+        const bool two_streams = small_msm_ok((size_t)n_groups * slot_len) && !(st_env && atoi(st_env) == 1);
+        {
+            uint8_t *ext_dyn = ps->msm_ext.p + (size_t)n_groups * 128;
+            msm_shape sh = msm_engine::make_shape(P * ds, combined ? P * ds : ds, P * ds, false, 0, 0, 0);
+            if (two_streams) {
+                if ((r = proto_side_stream(ps))) return r;
+                BBP_CUDA_OK(cudaEventRecord(ps->ev_dyn, ctx->stream));
+                BBP_CUDA_OK(cudaStreamWaitEvent(ps->rng_stream, ps->ev_dyn, 0));
+                cudaStream_t engine_stream = ctx->msm.stream;
+                ctx->msm.stream = ps->rng_stream;
+                r = ctx->msm.run(sh, ps->dyn_sc.p, ps->dyn_niels.p, ext_dyn, nullptr);
+                ctx->msm.stream = engine_stream;
+                if (r) return r;
+                BBP_CUDA_OK(cudaEventRecord(ps->ev_up, ps->rng_stream));
+            } else if ((r = ctx->msm.run(sh, ps->dyn_sc.p, ps->dyn_niels.p, ext_dyn, nullptr))) return r;
+        }
         sc_batch SB;
         memset(&SB, 0, sizeof SB);
         SB.n_proofs = P; SB.n = nm; SB.lg_n = lg; SB.gcols = gcols; SB.rp_bits = nbits; SB.rp_m = m; SB.q = 0;
@@ -374,8 +394,7 @@ inline int rp_verify_group_device(bbp_ctx *ctx, std::vector<rp_verify_job> &jobs
         ctx->launches += 4;
         uint8_t *ext = ps->msm_ext.p;
         if ((r = msm_gens_device(ctx, ps->stat_red.as<sc>(), slot_len, n_groups, nullptr, ext))) return r;
-        msm_shape sh = msm_engine::make_shape(P * ds, combined ? P * ds : ds, P * ds, false, 0, 0, 0);
-        if ((r = ctx->msm.run(sh, ps->dyn_sc.p, ps->dyn_niels.p, ext + (size_t)n_groups * 128, nullptr))) return r;
+        if (two_streams) BBP_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ps->ev_up, 0));   // join: the dynamic-base sum
         k_group_sum_identity<<<(n_groups + 63) / 64, 64, 0, ctx->stream>>>(ext, n_groups, 2, n_groups, ps->flags.p, nullptr);
         ctx->launches++;
         fl.resize(n_groups);
