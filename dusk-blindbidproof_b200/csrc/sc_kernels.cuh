@@ -527,7 +527,7 @@ __device__ inline void build_s_factors(sc *s_lo, sc *s_hi, const sc *uj, uint32_
 // Results stay in Montgomery form; k_stat_reduce sums them over the batch and converts.
 #define BBP_S_LO_BITS 8      // s_lo has min(n, 256) entries: with i = t + 256 k its index is constant per thread
 #define BBP_S_MAX_HI 256     // n <= 65536
-__global__ void __launch_bounds__(BBP_SC_THREADS, 2) k_verify_scalars(sc_batch B) {
+__global__ void __launch_bounds__(BBP_SC_THREADS, 3) k_verify_scalars(sc_batch B) {
     __shared__ sc smem[BBP_SC_THREADS];
     __shared__ sc uj[64];
     __shared__ sc long_val[BBP_MAX_LONG];
